@@ -1,0 +1,392 @@
+// api.cu -- C ABI (include/cpimh.h) for the filter and the coupled-chain driver: configuration checks, HBM
+// workspaces, launches.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include "host_common.h"
+
+namespace cpimh {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const ModelEntry* find_entry(int model, int dim) {
+  const ModelEntry* (*tables[])(int*) = {entries_gss, entries_ar, entries_sv, entries_sk, entries_lorenz};
+  for (auto tf : tables) {
+    int n = 0;
+    const ModelEntry* e = tf(&n);
+    for (int i = 0; i < n; i++)
+      if (e[i].model == model && e[i].dim == dim) return &e[i];
+  }
+  return nullptr;
+}
+
+int api_n_init(const cpimh_config& c) {
+  switch (c.model) {
+    case CPIMH_MODEL_GSS: return 1;
+    case CPIMH_MODEL_AR: case CPIMH_MODEL_LORENZ: return c.dim;
+    case CPIMH_MODEL_LEVY_SV: return 3;
+    default: return 0;
+  }
+}
+int api_n_trans(const cpimh_config& c) {
+  switch (c.model) {
+    case CPIMH_MODEL_GSS: return 1;
+    case CPIMH_MODEL_AR: case CPIMH_MODEL_LORENZ: return c.dim;
+    case CPIMH_MODEL_LEVY_SV: return 2;
+    case CPIMH_MODEL_SK: return 2 * c.sk_max_events;
+    default: return 0;
+  }
+}
+
+// host-side model precompute: model$precompute(theta) (R/model_get_ar.R:41-44) and the density constant of
+// dmvnorm_transpose_cholesky (src/mvnorm.cpp:120-121), evaluated the reference's way (a loop of log(L_ii)).
+std::vector<double> api_precompute(const cpimh_config& c) {
+  std::vector<double> pre;
+  if (c.model == CPIMH_MODEL_AR) {
+    const int d = c.dim;
+    pre.resize((size_t)d * d + 1);
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < d; j++) pre[i + (size_t)j * d] = pow(c.theta[0], 1 + abs(i - j));   // src/create_A_.cpp:10
+    double hl = 0;
+    for (int i = 0; i < d; i++) hl += log(c.theta[1]);
+    pre[(size_t)d * d] = -(hl) - (d * CPIMH_HALF_LOG_2PI_TRUNC);
+  } else if (c.model == CPIMH_MODEL_LORENZ) {
+    double hl = 0;
+    for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);
+    pre.push_back(-(hl) - (c.dim * CPIMH_HALF_LOG_2PI_TRUNC));
+  }
+  return pre;
+}
+
+int api_validate(cpimh_config* cp) {
+  cpimh_config& c = *cp;
+  CPIMH_REQUIRE(c.model >= CPIMH_MODEL_GSS && c.model <= CPIMH_MODEL_LORENZ, "unknown model id %d", c.model);
+  if (c.model == CPIMH_MODEL_GSS) { if (c.dim == 0) c.dim = 1; if (c.dim_y == 0) c.dim_y = 1; }
+  if (c.model == CPIMH_MODEL_LEVY_SV) { if (c.dim == 0) c.dim = 2; if (c.dim_y == 0) c.dim_y = 1; }
+  if (c.model == CPIMH_MODEL_SK) { if (c.dim == 0) c.dim = 4; if (c.dim_y == 0) c.dim_y = 2; }
+  if ((c.model == CPIMH_MODEL_AR || c.model == CPIMH_MODEL_LORENZ) && c.dim_y == 0) c.dim_y = c.dim;
+  CPIMH_REQUIRE(c.nparticles >= 1, "nparticles must be >= 1 (got %d)", c.nparticles);
+  CPIMH_REQUIRE(c.nobs >= 1 && c.nobs < (1 << 20), "nobs must be in [1, 2^20) (got %d)", c.nobs);
+  CPIMH_REQUIRE(find_entry(c.model, c.dim) != nullptr,
+                "model %d with dimension %d has no compiled kernel (see csrc/model_*.cu for the instantiated dimensions)", c.model, c.dim);
+  if (c.model == CPIMH_MODEL_SK) CPIMH_REQUIRE(c.dim_y == 2, "stochastic kinetic model has dim_y = 2");
+  if (c.model == CPIMH_MODEL_AR || c.model == CPIMH_MODEL_LORENZ) CPIMH_REQUIRE(c.dim_y == c.dim, "dim_y must equal dim for this model");
+  if (c.model == CPIMH_MODEL_LEVY_SV) {
+    double rate = c.theta[4] * c.theta[2] * c.theta[2] / c.theta[3];
+    CPIMH_REQUIRE(rate > 0 && rate <= 64.0, "Levy SV jump rate lambda*xi^2/omega^2 = %g outside (0, 64]", rate);
+  }
+  if (c.sk_max_events <= 0) c.sk_max_events = 64;
+  if (c.substeps <= 0) c.substeps = 1;
+  return CPIMH_OK;
+}
+
+// launch geometry shared by the filter and the chain kernels
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, Geometry* g) {
+  int dev = 0;
+  CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CPIMH_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  CPIMH_REQUIRE(prop.major >= 10, "libcpimh is built for sm_100a (Blackwell); device %d is sm_%d%d", dev, prop.major, prop.minor);
+  const int N = c.nparticles;
+  g->num_sms = prop.multiProcessorCount;
+  g->Npad = (N + 31) & ~31;
+  CPIMH_REQUIRE(N <= 65535, "the CTA-per-filter kernel supports N <= 65535 particles (got %d)", N);
+  int threads = c.threads_per_filter > 0 ? c.threads_per_filter : next_pow2((N + 7) / 8);
+  threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
+  threads = (threads + 31) & ~31;
+  g->threads = threads;
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  long long Mwant;
+  if (!c.store_paths) Mwant = 32;
+  else if (c.tree_capacity > 0) Mwant = c.tree_capacity < 3LL * N ? 3LL * N : c.tree_capacity;   // src/tree.cpp:7-9
+  else { Mwant = 10LL * N * c.dim; if (Mwant < 3LL * N) Mwant = 3LL * N; if (Mwant > 12LL * N) Mwant = 12LL * N; }   // R/CPF.R:17, capped
+  Mwant = (Mwant + 31) & ~31LL;
+  if (c.tree_capacity <= 0 && c.store_paths) {
+    // prefer a capacity that lets two CTAs share an SM; never below 8N automatically
+    const size_t half = (size_t)(prop.sharedMemPerMultiprocessor / 2) - 1024;
+    while (Mwant > 8LL * N && pf_smem_bytes(g->Npad, (int)Mwant, e->npre) > half && pf_smem_bytes(g->Npad, (int)(8LL * N + 31) & ~31, e->npre) <= half) Mwant -= 32LL * ((N + 31) / 32);
+    if (Mwant < ((8LL * N + 31) & ~31LL)) Mwant = (8LL * N + 31) & ~31LL;
+  }
+  g->M = (int)Mwant;
+  g->smem = pf_smem_bytes(g->Npad, g->M, e->npre);
+  CPIMH_REQUIRE(g->smem <= max_smem, "filter with N=%d, tree capacity %d needs %zu bytes of shared memory per CTA (limit %zu); lower tree_capacity or N",
+                N, g->M, g->smem, max_smem);
+  int bps = 0;
+  int rc = chains ? e->occupancy_chains(threads, g->smem, &bps) : e->occupancy_pf(threads, g->smem, &bps);
+  if (rc) return rc;
+  CPIMH_REQUIRE(bps >= 1, "kernel cannot be resident with %d threads and %zu bytes of shared memory", threads, g->smem);
+  g->blocks_per_sm = bps;
+  return CPIMH_OK;
+}
+
+}  // namespace cpimh
+
+using namespace cpimh;
+
+// ============================================================================ filter handle
+struct cpimh_pf {
+  cpimh_config cfg;
+  const ModelEntry* entry;
+  Geometry geo;
+  int64_t maxB, lastB;
+  int record_anc;
+  int64_t launches, bytes;
+  DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, logz, logz_t, traj, path_index, status, normw, leaf_out, anc_rec;
+  DevBuf inj_init, inj_trans, inj_resample, inj_shuffle, inj_path;
+  bool have_inj[5];
+  int npre;
+};
+
+extern "C" {
+
+const char* cpimh_last_error(void) { return g_err; }
+int cpimh_version(void) { return CPIMH_VERSION_MAJOR * 100 + CPIMH_VERSION_MINOR; }
+void cpimh_config_default(cpimh_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->store_paths = 1; cfg->substeps = 1; cfg->sk_max_events = 64;
+}
+int cpimh_model_n_init(const cpimh_config* cfg) { return api_n_init(*cfg); }
+int cpimh_model_n_trans(const cpimh_config* cfg) { cpimh_config c = *cfg; if (c.sk_max_events <= 0) c.sk_max_events = 64; return api_n_trans(c); }
+int cpimh_device_count(int* count) { CPIMH_CUDA_CHECK(cudaGetDeviceCount(count)); return CPIMH_OK; }
+int cpimh_set_device(int device) { CPIMH_CUDA_CHECK(cudaSetDevice(device)); return CPIMH_OK; }
+
+int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** out) {
+  CPIMH_REQUIRE(cfg_in && out, "null argument");
+  CPIMH_REQUIRE(max_filters >= 1, "max_filters must be >= 1");
+  cpimh_config cfg = *cfg_in;
+  int rc = api_validate(&cfg);
+  if (rc) return rc;
+  const ModelEntry* e = find_entry(cfg.model, cfg.dim);
+  Geometry g;
+  rc = api_plan_geometry(cfg, e, false, &g);
+  if (rc) return rc;
+  cpimh_pf* h = new cpimh_pf();
+  h->cfg = cfg; h->entry = e; h->geo = g; h->maxB = max_filters; h->lastB = 0; h->record_anc = 0; h->launches = 0; h->bytes = 0;
+  memset(h->have_inj, 0, sizeof(h->have_inj));
+  const int D = cfg.dim, N = cfg.nparticles, T = cfg.nobs;
+  std::vector<double> pre = api_precompute(cfg);
+  h->npre = (int)pre.size();
+  const size_t B = (size_t)max_filters;
+  auto A = [&](DevBuf& b, size_t n) { return b.alloc(n, &h->bytes); };
+  rc = A(h->obs, sizeof(double) * (size_t)T * cfg.dim_y);
+  if (!rc) rc = A(h->theta, sizeof(double) * CPIMH_MAX_THETA);
+  if (!rc) rc = A(h->pre, sizeof(double) * (pre.size() + 1));
+  if (!rc) rc = A(h->xbuf, sizeof(double) * B * 2 * D * g.Npad);
+  if (!rc && cfg.store_paths) {
+    rc = A(h->a_star, sizeof(int) * B * g.M);
+    if (!rc) rc = A(h->o_star, sizeof(int) * B * g.M);
+    if (!rc) rc = A(h->x_star, sizeof(double) * B * D * g.M);
+    if (!rc) rc = A(h->traj, sizeof(double) * B * (T + 1) * D);
+    if (!rc) rc = A(h->leaf_out, sizeof(int) * B * N);
+  }
+  if (!rc) rc = A(h->logz, sizeof(double) * B);
+  if (!rc) rc = A(h->logz_t, sizeof(double) * B * T);
+  if (!rc) rc = A(h->path_index, sizeof(int) * B);
+  if (!rc) rc = A(h->status, sizeof(int) * B);
+  if (!rc) rc = A(h->normw, sizeof(double) * B * N);
+  if (rc) { cpimh_pf_destroy(h); return rc; }
+  cudaError_t ce = cudaMemcpy(h->theta.p, cfg.theta, sizeof(double) * CPIMH_MAX_THETA, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess && !pre.empty()) ce = cudaMemcpy(h->pre.p, pre.data(), sizeof(double) * pre.size(), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { set_error("cudaMemcpy failed: %s", cudaGetErrorString(ce)); cpimh_pf_destroy(h); return CPIMH_ERR_CUDA; }
+  *out = h;
+  return CPIMH_OK;
+}
+
+int cpimh_pf_destroy(cpimh_pf* h) {
+  if (!h) return CPIMH_OK;
+  DevBuf* all[] = {&h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->logz, &h->logz_t, &h->traj, &h->path_index,
+                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
+  for (auto b : all) b->release();
+  delete h;
+  return CPIMH_OK;
+}
+
+}  // extern "C"
+namespace cpimh {
+int api_upload_obs(const cpimh_config& cfg, const double* obs_host, void* dst) {
+  const int T = cfg.nobs, dy = cfg.dim_y;
+  std::vector<double> rm((size_t)T * dy);
+  for (int t = 0; t < T; t++)
+    for (int j = 0; j < dy; j++) rm[(size_t)t * dy + j] = obs_host[t + (size_t)T * j];   // T x dy column-major -> row-major
+  CPIMH_CUDA_CHECK(cudaMemcpy(dst, rm.data(), sizeof(double) * rm.size(), cudaMemcpyHostToDevice));
+  return CPIMH_OK;
+}
+}  // namespace cpimh
+extern "C" {
+
+int cpimh_pf_set_observations(cpimh_pf* h, const double* obs_host) {
+  CPIMH_REQUIRE(h && obs_host, "null argument");
+  return api_upload_obs(h->cfg, obs_host, h->obs.p);
+}
+
+int cpimh_pf_set_noise(cpimh_pf* h, int64_t B, const cpimh_noise* nz) {
+  CPIMH_REQUIRE(h, "null handle");
+  memset(h->have_inj, 0, sizeof(h->have_inj));
+  if (!nz) return CPIMH_OK;
+  CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
+  const cpimh_config& c = h->cfg;
+  const size_t N = c.nparticles, T = c.nobs;
+  struct Item { const double* src; DevBuf* dst; size_t n; } items[5] = {
+      {nz->init, &h->inj_init, (size_t)B * api_n_init(c) * N},
+      {nz->trans, &h->inj_trans, (size_t)B * T * api_n_trans(c) * N},
+      {nz->resample, &h->inj_resample, (size_t)B * T * N},
+      {nz->shuffle, &h->inj_shuffle, (size_t)B * T * (N - 1)},
+      {nz->path_u, &h->inj_path, (size_t)B}};
+  for (int i = 0; i < 5; i++) {
+    if (!items[i].src || items[i].n == 0) continue;
+    int rc = items[i].dst->alloc(sizeof(double) * items[i].n, &h->bytes);
+    if (rc) return rc;
+    CPIMH_CUDA_CHECK(cudaMemcpy(items[i].dst->p, items[i].src, sizeof(double) * items[i].n, cudaMemcpyHostToDevice));
+    h->have_inj[i] = true;
+  }
+  return CPIMH_OK;
+}
+
+int cpimh_pf_record_ancestors(cpimh_pf* h, int on) {
+  CPIMH_REQUIRE(h, "null handle");
+  h->record_anc = on ? 1 : 0;
+  if (on) return h->anc_rec.alloc(sizeof(int) * (size_t)h->maxB * h->cfg.nobs * h->cfg.nparticles, &h->bytes);
+  return CPIMH_OK;
+}
+
+}  // extern "C"
+namespace cpimh {
+void api_fill_pf_params(const cpimh_config& c, const Geometry& g, int npre, PfParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->N = c.nparticles; p->T = c.nobs; p->dy = c.dim_y; p->Npad = g.Npad; p->M = g.M;
+  p->shuffle = c.shuffle; p->store_paths = c.store_paths;
+  p->npre = npre; p->integrator = c.integrator; p->substeps = c.substeps;
+  p->n_init = api_n_init(c); p->n_trans = api_n_trans(c); p->sk_M = c.sk_max_events;
+}
+}  // namespace cpimh
+extern "C" {
+
+int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, void* stream) {
+  CPIMH_REQUIRE(h, "null handle");
+  CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
+  const cpimh_config& c = h->cfg;
+  PfParams p;
+  api_fill_pf_params(c, h->geo, h->npre, &p);
+  p.B = B; p.seed = seed; p.first_filter = first_filter;
+  p.obs = h->obs.as<double>(); p.theta = h->theta.as<double>(); p.pre = h->pre.as<double>();
+  p.xbuf = h->xbuf.as<double>(); p.a_star = h->a_star.as<int>(); p.o_star = h->o_star.as<int>(); p.x_star = h->x_star.as<double>();
+  p.logz = h->logz.as<double>(); p.logz_t = h->logz_t.as<double>(); p.traj = h->traj.as<double>();
+  p.path_index = h->path_index.as<int>(); p.status = h->status.as<int>(); p.normw = h->normw.as<double>();
+  p.leaf_out = h->leaf_out.as<int>(); p.anc_rec = h->record_anc ? h->anc_rec.as<int>() : nullptr;
+  p.inj_init = h->have_inj[0] ? h->inj_init.as<double>() : nullptr;
+  p.inj_trans = h->have_inj[1] ? h->inj_trans.as<double>() : nullptr;
+  p.inj_resample = h->have_inj[2] ? h->inj_resample.as<double>() : nullptr;
+  p.inj_shuffle = h->have_inj[3] ? h->inj_shuffle.as<double>() : nullptr;
+  p.inj_path = h->have_inj[4] ? h->inj_path.as<double>() : nullptr;
+  PfLaunch L;
+  L.threads = h->geo.threads; L.smem = h->geo.smem;
+  int64_t resident = (int64_t)h->geo.blocks_per_sm * h->geo.num_sms;
+  L.grid = (int)(B < resident ? B : resident);
+  int rc = h->entry->launch_pf(p, L, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->launches += 1; h->lastB = B;
+  return CPIMH_OK;
+}
+
+static int check_status(const int* d_status, int64_t B, cudaStream_t s) {
+  std::vector<int> st((size_t)B);
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(st.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int64_t b = 0; b < B; b++)
+    if (st[(size_t)b] != 0) {
+      const int code = st[(size_t)b];
+      if (code == CPIMH_ERR_TREE_OVERFLOW) set_error("filter %lld: ancestor tree capacity exhausted (Tree::double_size needed); raise cfg.tree_capacity", (long long)b);
+      else if (code == CPIMH_ERR_NOISE_OVERFLOW) set_error("filter %lld: injected stochastic-kinetic noise exhausted; raise cfg.sk_max_events", (long long)b);
+      else set_error("filter %lld failed with status %d", (long long)b, code);
+      return code;
+    }
+  return CPIMH_OK;
+}
+
+int cpimh_pf_fetch(cpimh_pf* h, int64_t B, void* stream, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
+  CPIMH_REQUIRE(h, "null handle");
+  CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = check_status(h->status.as<int>(), B, s);
+  if (rc) return rc;
+  const cpimh_config& c = h->cfg;
+  if (logz) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz, h->logz.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  if (logz_t) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz_t, h->logz_t.p, sizeof(double) * (size_t)B * c.nobs, cudaMemcpyDeviceToHost, s));
+  if (trajectory) {
+    CPIMH_REQUIRE(c.store_paths, "trajectories need store_paths = 1");
+    CPIMH_CUDA_CHECK(cudaMemcpyAsync(trajectory, h->traj.p, sizeof(double) * (size_t)B * (c.nobs + 1) * c.dim, cudaMemcpyDeviceToHost, s));
+  }
+  if (path_index) CPIMH_CUDA_CHECK(cudaMemcpyAsync(path_index, h->path_index.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CPIMH_OK;
+}
+
+int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ancestors) {
+  CPIMH_REQUIRE(h && ancestors, "null argument");
+  CPIMH_REQUIRE(h->record_anc, "call cpimh_pf_record_ancestors(h, 1) before cpimh_pf_run");
+  CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
+  const size_t n = (size_t)h->cfg.nobs * h->cfg.nparticles;
+  cudaStream_t s = (cudaStream_t)stream;
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(ancestors, h->anc_rec.as<int>() + (size_t)b * n, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CPIMH_OK;
+}
+
+int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* exp_path, double* trajectories, double* normweights) {
+  CPIMH_REQUIRE(h, "null handle");
+  CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
+  CPIMH_REQUIRE(h->cfg.store_paths, "all-particle outputs need store_paths = 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = check_status(h->status.as<int>() + b, 1, s);
+  if (rc) return rc;
+  const size_t N = h->cfg.nparticles, D = h->cfg.dim, M = h->geo.M;
+  return api_all_particles((int)N, (int)D, (int)M, h->cfg.nobs, h->a_star.as<int>() + (size_t)b * M, h->x_star.as<double>() + (size_t)b * D * M,
+                           h->leaf_out.as<int>() + (size_t)b * N, h->normw.as<double>() + (size_t)b * N, s, exp_path, trajectories, normweights);
+}
+
+int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory) {
+  CPIMH_REQUIRE(h, "null handle");
+  if (d_logz) *d_logz = h->logz.as<double>();
+  if (d_trajectory) *d_trajectory = h->traj.as<double>();
+  return CPIMH_OK;
+}
+int64_t cpimh_pf_launch_count(const cpimh_pf* h) { return h ? h->launches : 0; }
+int64_t cpimh_pf_device_bytes(const cpimh_pf* h) { return h ? h->bytes : 0; }
+int cpimh_pf_effective_config(const cpimh_pf* h, cpimh_config* out) {
+  CPIMH_REQUIRE(h && out, "null argument");
+  *out = h->cfg;
+  out->tree_capacity = h->geo.M;
+  out->threads_per_filter = h->geo.threads;
+  out->reserved = h->geo.blocks_per_sm;
+  return CPIMH_OK;
+}
+
+int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
+                   const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
+  CPIMH_REQUIRE(cfg && obs_host, "null argument");
+  cpimh_config c = *cfg;
+  for (int attempt = 0; attempt < 4; attempt++) {
+    cpimh_pf* h = nullptr;
+    int rc = cpimh_pf_create(&c, B, &h);
+    if (rc) return rc;
+    rc = cpimh_pf_set_observations(h, obs_host);
+    if (!rc && noise_host) rc = cpimh_pf_set_noise(h, B, noise_host);
+    if (!rc) rc = cpimh_pf_run(h, B, seed, first_filter, nullptr);
+    if (!rc) rc = cpimh_pf_fetch(h, B, nullptr, logz, logz_t, trajectory, path_index);
+    int M = h->geo.M;
+    cpimh_pf_destroy(h);
+    if (rc != CPIMH_ERR_TREE_OVERFLOW) return rc;
+    c.tree_capacity = 2 * M;          // Tree::double_size (src/tree.cpp:101-116): rerun with twice the capacity (same streams => same draws)
+  }
+  return CPIMH_ERR_TREE_OVERFLOW;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// common.cuh -- shared device/host helpers for libcpimh (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/cpimh.h"
+
+namespace cpimh {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+#define CPIMH_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      ::cpimh::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                         cudaGetErrorString(_e));                                                \
+      return CPIMH_ERR_CUDA;                                                                     \
+    }                                                                                            \
+  } while (0)
+#define CPIMH_REQUIRE(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::cpimh::set_error(__VA_ARGS__);           \
+      return CPIMH_ERR_INVALID;                  \
+    }                                            \
+  } while (0)
+
+// ---------------------------------------------------------------- Philox4x32-10 (DESIGN.md "RNG")
+// counter = (c0 particle/draw index, c1 time | iteration << 20, c2 stream id, c3 purpose | draw << 8), key = seed
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// uniforms in the open interval (0,1): ((x >> 12) + 0.5) * 2^-52, exact in fp64 and identical to the oracle's
+__device__ __forceinline__ double u64_to_unit(uint32_t lo, uint32_t hi) {
+  unsigned long long x = ((unsigned long long)hi << 32) | lo;
+  return ((double)(x >> 12) + 0.5) * 0x1p-52;
+}
+struct Stream {               // identifies one filter's random streams
+  uint32_t k0, k1;            // seed
+  uint32_t c1hi;              // iteration << 20
+  uint32_t c2;                // stream id
+};
+__device__ __forceinline__ Stream make_stream(unsigned long long seed, unsigned long long filter_id) {
+  Stream s;
+  s.k0 = (uint32_t)seed; s.k1 = (uint32_t)(seed >> 32);
+  s.c1hi = ((uint32_t)(filter_id >> 32)) << 20;
+  s.c2 = (uint32_t)filter_id;
+  return s;
+}
+__device__ __forceinline__ void philox_u2(const Stream& s, uint32_t i, int t, int purpose, uint32_t draw, double& ua, double& ub) {
+  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, (uint32_t)purpose | (draw << 8)), make_uint2(s.k0, s.k1));
+  ua = u64_to_unit(r.x, r.y);
+  ub = u64_to_unit(r.z, r.w);
+}
+__device__ __forceinline__ double philox_u1(const Stream& s, uint32_t i, int t, int purpose, uint32_t draw) {
+  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, (uint32_t)purpose | (draw << 8)), make_uint2(s.k0, s.k1));
+  return u64_to_unit(r.x, r.y);
+}
+// Box-Muller pair: r = sqrt(-2 log ua), angle 2 pi ub
+__device__ __forceinline__ void normal2(double ua, double ub, double& z0, double& z1) {
+  double r = sqrt(-2.0 * log(ua));
+  double s, c;
+  sincospi(2.0 * ub, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// ---------------------------------------------------------------- warp / block primitives (fp64)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+__device__ __forceinline__ int warp_incl_scan_int(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+// Block-wide reductions through a 32-entry smem scratch.  All threads of the CTA must call; the
+// result is returned to every thread.  `scratch` must not be in use (ends with a barrier).
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double r = (lane < nw) ? scratch[lane] : 0.0;
+  r = warp_sum(r);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double r = (lane < nw) ? scratch[lane] : -INFINITY;
+  r = warp_max(r);
+  __syncthreads();
+  return r;
+}
+// exclusive prefix of one int per thread; returns the exclusive offset, *total = block total
+__device__ __forceinline__ int block_excl_scan_int(int v, int* scratch, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = warp_incl_scan_int(v, lane);
+  if (lane == 31) scratch[wid] = inc;
+  __syncthreads();
+  int w = (lane < nw) ? scratch[lane] : 0;
+  int winc = warp_incl_scan_int(w, lane);
+  int woff = __shfl_sync(0xffffffffu, winc, wid) - __shfl_sync(0xffffffffu, w, wid);
+  *total = __shfl_sync(0xffffffffu, winc, nw - 1);
+  __syncthreads();
+  return woff + inc - v;
+}
+
+// In-place inclusive scan of a[0..n) in shared memory by the whole CTA (forward: a[j] = sum_{i<=j};
+// REVERSE: a[j] = sum_{i>=j}).  Each warp owns a contiguous range of 32-wide rows, scans them with a
+// running carry (conflict-free row accesses + shuffles), warp totals are combined through `scratch`,
+// then offsets are added in a second pass.  Ends with a barrier.
+template <bool REVERSE>
+__device__ __forceinline__ void block_scan_inplace(double* a, int n, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int rows = (n + 31) >> 5;
+  const int rpw = (rows + nw - 1) / nw;
+  const int r0 = wid * rpw, r1 = min(rows, r0 + rpw);
+  double carry = 0.0;
+  for (int r = r0; r < r1; r++) {
+    int j = r * 32 + lane;
+    int idx = REVERSE ? (n - 1 - j) : j;
+    double v = (j < n) ? a[idx] : 0.0;
+    v = warp_incl_scan(v, lane) + carry;
+    if (j < n) a[idx] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) scratch[wid] = carry;
+  __syncthreads();
+  double w = (lane < nw) ? scratch[lane] : 0.0;
+  double winc = warp_incl_scan(w, lane);
+  double off = __shfl_sync(0xffffffffu, winc, wid) - __shfl_sync(0xffffffffu, w, wid);   // exclusive prefix of warp totals
+  if (wid > 0) {
+    for (int r = r0; r < r1; r++) {
+      int j = r * 32 + lane;
+      if (j < n) { int idx = REVERSE ? (n - 1 - j) : j; a[idx] += off; }
+    }
+  }
+  __syncthreads();
+}
+
+// number of entries of the (ascending) shared array c[0..n) that are <= u   (src/multinomial.cpp:25-27 rule)
+__device__ __forceinline__ int count_le(const double* c, int n, double u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (c[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// number of entries < u   (src/systematic.cpp:15-18 rule: smallest j with csw_j >= u)
+__device__ __forceinline__ int count_lt(const double* c, int n, double u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (c[mid] < u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+#define CPIMH_M_LN_SQRT_2PI 0.918938533204672741780329736406   // R's dnorm(log=TRUE) constant
+#define CPIMH_HALF_LOG_2PI_TRUNC 0.9189385                      // src/mvnorm.cpp:73,98,121 (truncated on purpose)
+
+}  // namespace cpimh

@@ -1,0 +1,26 @@
+// lorenz_wide.cu -- stand-alone wide Lorenz 96 transition kernel (see lorenz_wide.cuh)
+#include "lorenz_wide.cuh"
+
+namespace cpimh {
+
+template <int S>
+__device__ void lorenz_wide_body(const double* xin, long long n, double t0, double t1, double F, int substeps, double* xout) {
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n) return;
+  constexpr int D = 32 * S;
+  double v[S];
+#pragma unroll
+  for (int s = 0; s < S; s++) v[s] = xin[(size_t)p * D + s * 32 + lane];
+  const int ns = substeps < 1 ? 1 : substeps;
+  const double h = (t1 - t0) / ns;
+  for (int q = 0; q < ns; q++) lorenz_wide_rk4<S>(F, h, v, lane);
+#pragma unroll
+  for (int s = 0; s < S; s++) xout[(size_t)p * D + s * 32 + lane] = v[s];
+}
+__global__ void lorenz_wide_rk4_kernel(const double* xin, long long n, int d, double t0, double t1, double F, int substeps, double* xout) {
+  if (d == 64) lorenz_wide_body<2>(xin, n, t0, t1, F, substeps, xout);
+  else lorenz_wide_body<1>(xin, n, t0, t1, F, substeps, xout);
+}
+
+}  // namespace cpimh

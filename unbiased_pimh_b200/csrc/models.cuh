@@ -1,0 +1,379 @@
+// models.cuh -- device-side rinit / rtransition / dmeasurement of the five shipped models, one particle
+// per thread, state in registers.  Follows the specification the CPU oracle restates:
+//   get_gss                 reference R/model_get_gss.R:13-46
+//   get_ar(d)               R/model_get_ar.R:13-39, src/create_A_.cpp:6-13, src/mvnorm.cpp:113-132
+//   get_levy_sv             R/model_levy_sv.R:17-66, src/SVLevy_functions.cpp:40-81
+//   get_stochastic_kinetic  R/model_stochastic_kinetic.R:16-157 (exact Gillespie, 8 reactions)
+//   get_lorenz              R/model_get_lorenz.R:18-50, src/lorenz96.cpp:13-32,65-93
+// Noise comes from the filter's Philox streams (DESIGN.md "RNG") or from injected arrays.
+#pragma once
+#include "common.cuh"
+
+namespace cpimh {
+
+struct ModelCtx {
+  const double* theta;      // shared-memory copy of cfg.theta
+  const double* pre;        // shared-memory model precompute (AR: A col-major then cst; LORENZ: cst)
+  Stream stream;
+  int N;                    // particles
+  int T;
+  const double* inj_init;   // this filter's injected init noise [n_init][N] or nullptr
+  const double* inj_trans;  // this filter's injected transition noise [T][n_trans][N] or nullptr
+  int n_trans;
+  int sk_M;                 // SK injected events per particle-step
+  int integrator, substeps; // LORENZ
+};
+
+__device__ __forceinline__ double dnorm_log(double x, double mu, double sigma) {   // R nmath/dnorm.c, give_log
+  double z = (x - mu) / sigma;
+  return -(CPIMH_M_LN_SQRT_2PI + 0.5 * z * z + log(sigma));
+}
+__device__ __forceinline__ const double* trans_row(const ModelCtx& c, int t, int row) {
+  return c.inj_trans + ((size_t)(t - 1) * c.n_trans + row) * c.N;
+}
+
+// ------------------------------------------------------------------ get_gss (d = 1)
+struct GssModel {
+  static constexpr int D = 1;
+  static constexpr int NPRE = 0;
+  __device__ static double step_const(const ModelCtx&, int t) { return 8.0 * cos(1.2 * (double)(t - 1)); }
+  __device__ static void init(const ModelCtx& c, int i, double* x) {
+    double z;
+    if (c.inj_init) z = c.inj_init[i];
+    else { double ua, ub, z1; philox_u2(c.stream, i, 0, CPIMH_P_INIT, 0, ua, ub); normal2(ua, ub, z, z1); }
+    x[0] = sqrt(2.0) * z;
+  }
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double drift) {
+    double z;
+    if (c.inj_trans) z = trans_row(c, t, 0)[i];
+    else { double ua, ub, z1; philox_u2(c.stream, i, t, CPIMH_P_TRANS, 0, ua, ub); normal2(ua, ub, z, z1); }
+    double xi = x[0];
+    double means = 0.5 * xi + 25.0 * xi / (1.0 + xi * xi) + drift;
+    x[0] = means + z;
+    return 0;
+  }
+  __device__ static double logw(const ModelCtx&, const double* x, const double* y) {
+    return dnorm_log(y[0], (x[0] * x[0]) / 20.0, sqrt(10.0));
+  }
+};
+
+// ------------------------------------------------------------------ get_ar(d)
+template <int D_>
+struct ArModel {
+  static constexpr int D = D_;
+  static constexpr int NPRE = D_ * D_ + 1;     // A (column-major) + cst
+  __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
+  __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
+#pragma unroll
+    for (int j = 0; 2 * j < D; j++) {
+      double ua, ub, z0, z1;
+      philox_u2(c.stream, i, t, purpose, j, ua, ub);
+      normal2(ua, ub, z0, z1);
+      z[2 * j] = z0;
+      if (2 * j + 1 < D) z[2 * j + 1] = z1;
+    }
+  }
+  __device__ static void init(const ModelCtx& c, int i, double* x) {
+    if (c.inj_init) {
+#pragma unroll
+      for (int k = 0; k < D; k++) x[k] = c.inj_init[(size_t)k * c.N + i];
+    } else normals(c, i, 0, CPIMH_P_INIT, x);
+  }
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double) {
+    double z[D], y[D];
+    if (c.inj_trans) {
+#pragma unroll
+      for (int k = 0; k < D; k++) z[k] = trans_row(c, t, k)[i];
+    } else normals(c, i, t, CPIMH_P_TRANS, z);
+#pragma unroll
+    for (int r = 0; r < D; r++) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < D; l++) s += c.pre[r + l * D] * x[l];
+      y[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < D; r++) x[r] = y[r] + z[r];
+    return 0;
+  }
+  __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
+    const double sy = c.theta[1];
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) { double r = (x[k] - y[k]) / sy; sq += r * r; }
+    return -0.5 * sq + c.pre[D * D];
+  }
+};
+
+// ------------------------------------------------------------------ get_levy_sv (d = 2; x = (v, z))
+__device__ __forceinline__ int poisson_inv(double rate, double u) {
+  double p = exp(-rate), F = p;
+  int k = 0;
+  while (u > F && k < 1000) { k++; p = p * rate / k; F += p; }
+  return k;
+}
+struct LevySvModel {
+  static constexpr int D = 2;
+  static constexpr int NPRE = 0;
+  __device__ static double step_const(const ModelCtx& c, int) { return exp(-c.theta[4]); }
+  // compound-Poisson sums over one unit interval (src/SVLevy_functions.cpp:61-67)
+  __device__ static void jump_sums(const ModelCtx& c, int i, int t, double& swe, double& se) {
+    const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
+    double ua, ub;
+    philox_u2(c.stream, i, t, CPIMH_P_TRANS, 0, ua, ub);
+    int k = poisson_inv(lambda * xi * xi / w2, ua);
+    double a = 0.0, b = 0.0;
+    const double escale = w2 / xi;
+    for (int j = 1; j <= k; j++) {
+      philox_u2(c.stream, i, t, CPIMH_P_TRANS, j, ua, ub);
+      double e = -log(ub) * escale;
+      a += exp(-lambda * ua) * e;
+      b += e;
+    }
+    swe = a; se = b;
+  }
+  __device__ static double gamma_mt(const ModelCtx& c, int i, double shape, double scale) {
+    double a = shape < 1.0 ? shape + 1.0 : shape;
+    double d = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+    for (int m = 0; m < 64; m++) {
+      double ua, ub, z, z1, u2, ub2;
+      philox_u2(c.stream, i, 0, CPIMH_P_INIT, 2 * m, ua, ub);
+      normal2(ua, ub, z, z1);
+      double v = 1.0 + cc * z;
+      if (v <= 0) continue;
+      v = v * v * v;
+      philox_u2(c.stream, i, 0, CPIMH_P_INIT, 2 * m + 1, u2, ub2);
+      if (log(u2) < 0.5 * z * z + d - d * v + d * log(v)) {
+        double g = d * v;
+        if (shape < 1.0) g *= pow(ub2, 1.0 / shape);
+        return g * scale;
+      }
+    }
+    return shape * scale;
+  }
+  __device__ static void init(const ModelCtx& c, int i, double* x) {
+    const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
+    double z0, swe, se;
+    if (c.inj_init) { z0 = c.inj_init[i]; swe = c.inj_init[(size_t)c.N + i]; se = c.inj_init[(size_t)2 * c.N + i]; }
+    else { z0 = gamma_mt(c, i, xi * xi / w2, w2 / xi); jump_sums(c, i, 0, swe, se); }
+    double z1 = exp(-lambda) * z0 + swe;
+    x[0] = (1.0 / lambda) * (z0 - z1 + se);
+    x[1] = z1;
+  }
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double expml) {
+    const double lambda = c.theta[4];
+    double swe, se;
+    if (c.inj_trans) { swe = trans_row(c, t, 0)[i]; se = trans_row(c, t, 1)[i]; }
+    else jump_sums(c, i, t, swe, se);
+    double zold = x[1];
+    double znew = expml * zold + swe;
+    x[0] = (1.0 / lambda) * (zold - znew + se);
+    x[1] = znew;
+    return 0;
+  }
+  __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
+    return dnorm_log(y[0], c.theta[0] + c.theta[1] * x[0], sqrt(x[0]));
+  }
+};
+
+// ------------------------------------------------------------------ get_stochastic_kinetic (d = 4, d_y = 2)
+struct SkModel {
+  static constexpr int D = 4;
+  static constexpr int NPRE = 0;
+  __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
+  __device__ static void init(const ModelCtx&, int, double* x) { x[0] = 8.0; x[1] = 8.0; x[2] = 8.0; x[3] = 5.0; }
+  // returns 0, or CPIMH_ERR_NOISE_OVERFLOW when the injected event budget is exhausted; bit 8 set if an event index was clamped
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double) {
+    double tcur = 0.0;
+    int flags = 0;
+    for (int m = 0;; m++) {
+      if (c.inj_trans && m >= c.sk_M) return CPIMH_ERR_NOISE_OVERFLOW;
+      double h[8];
+      h[0] = 0.1 * x[3] * x[2];
+      h[1] = 0.7 * (5.0 - x[3]);
+      h[2] = 0.35 * x[3];
+      h[3] = 0.2 * x[0];
+      h[4] = 0.1 * x[1] * (x[1] - 1.0) / 2.0;
+      h[5] = 0.9 * x[2];
+      h[6] = 0.3 * x[0];
+      h[7] = 0.1 * x[1];
+      double h0 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) h0 += h[r];
+      double E, U;
+      if (c.inj_trans) { E = trans_row(c, t, m)[i]; U = trans_row(c, t, c.sk_M + m)[i]; }
+      else { double ua, ub; philox_u2(c.stream, i, t, CPIMH_P_TRANS, m, ua, ub); E = -log(ua); U = ub; }
+      tcur = tcur + (1.0 / h0) * E;
+      if (!(tcur < 0.1)) return flags;
+      double u_rnd = U * h0, cdf = 0.0;
+      int ev = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) { cdf += h[r]; ev += (cdf < u_rnd) ? 1 : 0; }
+      if (ev > 7) { ev = 7; flags |= 256; }
+      // stoichiometry columns r1..r8 (R/model_stochastic_kinetic.R:19-23)
+      switch (ev) {
+        case 0: x[2] -= 1.0; x[3] -= 1.0; break;
+        case 1: x[2] += 1.0; x[3] += 1.0; break;
+        case 2: x[0] += 1.0; break;
+        case 3: x[1] += 1.0; break;
+        case 4: x[1] -= 2.0; x[2] += 1.0; break;
+        case 5: x[1] += 2.0; x[2] -= 1.0; break;
+        case 6: x[0] -= 1.0; break;
+        default: x[1] -= 1.0; break;
+      }
+    }
+  }
+  __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
+    const double sd = sqrt(c.theta[0]);
+    const double* A = c.theta + 1;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      double m = 0.0;
+#pragma unroll
+      for (int l = 0; l < 4; l++) m += A[j + 2 * l] * x[l];
+      s += dnorm_log(m, y[j], sd);
+    }
+    return s;
+  }
+};
+
+// ------------------------------------------------------------------ get_lorenz, thread-per-particle (small d)
+template <int D>
+__device__ __forceinline__ void lorenz_rhs(double F, const double* x, double* dx) {
+#pragma unroll
+  for (int n = 0; n < D; n++) {
+    const int m1 = (n + D - 1) % D, p1 = (n + 1) % D, m2 = (n + D - 2) % D;
+    dx[n] = x[m1] * (x[p1] - x[m2]) - x[n] + F;
+  }
+}
+template <int D>
+__device__ __forceinline__ void lorenz_rk4(double F, double h, double* x) {
+  double k1[D], k2[D], k3[D], k4[D], tmp[D];
+  lorenz_rhs<D>(F, x, k1);
+#pragma unroll
+  for (int i = 0; i < D; i++) tmp[i] = x[i] + (0.5 * h) * k1[i];
+  lorenz_rhs<D>(F, tmp, k2);
+#pragma unroll
+  for (int i = 0; i < D; i++) tmp[i] = x[i] + (0.5 * h) * k2[i];
+  lorenz_rhs<D>(F, tmp, k3);
+#pragma unroll
+  for (int i = 0; i < D; i++) tmp[i] = x[i] + h * k3[i];
+  lorenz_rhs<D>(F, tmp, k4);
+#pragma unroll
+  for (int i = 0; i < D; i++) x[i] = x[i] + (h / 6.0) * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+}
+// Boost.odeint integrate(): controlled Dormand-Prince 5(4), eps_abs = eps_rel = 1e-6
+template <int D>
+__device__ int lorenz_dopri5(double F, double t0, double t1, double dt, double* x) {
+  const double a21 = 1.0 / 5, a31 = 3.0 / 40, a32 = 9.0 / 40, a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9,
+               a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729,
+               a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656,
+               c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+  const double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+               dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+  double k1[D], k2[D], k3[D], k4[D], k5[D], k6[D], k7[D], xt[D], xn[D];
+  double t = t0;
+  int count = 0;
+  lorenz_rhs<D>(F, x, k1);
+  while (t1 - t > 2.220446049250313e-16) {
+    if ((t + dt) - t1 > 2.220446049250313e-16) dt = t1 - t;
+    int trials = 0;
+    for (;;) {
+#pragma unroll
+      for (int i = 0; i < D; i++) xt[i] = x[i] + dt * a21 * k1[i];
+      lorenz_rhs<D>(F, xt, k2);
+#pragma unroll
+      for (int i = 0; i < D; i++) xt[i] = x[i] + dt * (a31 * k1[i] + a32 * k2[i]);
+      lorenz_rhs<D>(F, xt, k3);
+#pragma unroll
+      for (int i = 0; i < D; i++) xt[i] = x[i] + dt * (a41 * k1[i] + a42 * k2[i] + a43 * k3[i]);
+      lorenz_rhs<D>(F, xt, k4);
+#pragma unroll
+      for (int i = 0; i < D; i++) xt[i] = x[i] + dt * (a51 * k1[i] + a52 * k2[i] + a53 * k3[i] + a54 * k4[i]);
+      lorenz_rhs<D>(F, xt, k5);
+#pragma unroll
+      for (int i = 0; i < D; i++) xt[i] = x[i] + dt * (a61 * k1[i] + a62 * k2[i] + a63 * k3[i] + a64 * k4[i] + a65 * k5[i]);
+      lorenz_rhs<D>(F, xt, k6);
+#pragma unroll
+      for (int i = 0; i < D; i++) xn[i] = x[i] + dt * (c1 * k1[i] + c3 * k3[i] + c4 * k4[i] + c5 * k5[i] + c6 * k6[i]);
+      lorenz_rhs<D>(F, xn, k7);
+      double err = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        double xe = dt * (dc1 * k1[i] + dc3 * k3[i] + dc4 * k4[i] + dc5 * k5[i] + dc6 * k6[i] + dc7 * k7[i]);
+        double e = fabs(xe) / (1e-6 + 1e-6 * (fabs(x[i]) + fabs(dt) * fabs(k1[i])));
+        err = fmax(err, e);
+      }
+      if (err > 1.0) {
+        double f = 0.9 * pow(err, -1.0 / 3.0);
+        dt *= (f > 0.2 ? f : 0.2);
+        if (++trials > 500) return -1;
+        continue;
+      }
+      t += dt;
+#pragma unroll
+      for (int i = 0; i < D; i++) { x[i] = xn[i]; k1[i] = k7[i]; }
+      if (err < 0.5) {
+        double e = fmax(err, 0.00032);   // 5^-5
+        dt *= 0.9 * pow(e, -1.0 / 5.0);
+      }
+      break;
+    }
+    count++;
+  }
+  return count;
+}
+template <int D_>
+struct LorenzModel {
+  static constexpr int D = D_;
+  static constexpr int NPRE = 1;     // cst of the measurement density
+  __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
+  __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
+#pragma unroll
+    for (int j = 0; 2 * j < D; j++) {
+      double ua, ub, z0, z1;
+      philox_u2(c.stream, i, t, purpose, j, ua, ub);
+      normal2(ua, ub, z0, z1);
+      z[2 * j] = z0;
+      if (2 * j + 1 < D) z[2 * j + 1] = z1;
+    }
+  }
+  __device__ static void init(const ModelCtx& c, int i, double* x) {
+    double z[D];
+    if (c.inj_init) {
+#pragma unroll
+      for (int k = 0; k < D; k++) z[k] = c.inj_init[(size_t)k * c.N + i];
+    } else normals(c, i, 0, CPIMH_P_INIT, z);
+#pragma unroll
+    for (int k = 0; k < D; k++) x[k] = -1.0 + 4.0 * (0.5 * erfc(-z[k] / sqrt(2.0)));   // -1 + 4 pnorm(z)
+  }
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double) {
+    const double F = c.theta[0], sx = c.theta[1];
+    double z[D];
+    if (c.inj_trans) {
+#pragma unroll
+      for (int k = 0; k < D; k++) z[k] = trans_row(c, t, k)[i];
+    } else normals(c, i, t, CPIMH_P_TRANS, z);
+    const double t0 = 0.05 * (double)(t - 1), t1 = 0.05 * (double)t;
+    if (c.integrator == CPIMH_INTEGRATOR_DOPRI5) lorenz_dopri5<D>(F, t0, t1, 0.05, x);
+    else {
+      const int ns = c.substeps < 1 ? 1 : c.substeps;
+      const double h = (t1 - t0) / ns;
+      for (int s = 0; s < ns; s++) lorenz_rk4<D>(F, h, x);
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) x[k] = x[k] + sx * z[k];
+    return 0;
+  }
+  __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
+    if (isnan(y[0])) return 0.0;
+    const double sy = c.theta[2];
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) { double r = (x[k] - y[k]) / sy; sq += r * r; }
+    return -0.5 * sq + c.pre[0];
+  }
+};
+
+}  // namespace cpimh

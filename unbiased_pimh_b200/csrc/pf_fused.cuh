@@ -1,0 +1,342 @@
+// pf_fused.cuh -- the fused bootstrap-particle-filter kernel: one CTA owns one filter for all T steps.
+//
+// One iteration of the loop below is one iteration of the reference's hot loop R/CPF.R:35-67
+// (== R/particlefilter.R:22-38): multinomial resampling (src/multinomial.cpp:13-32) -> gather ->
+// rtransition -> dmeasurement -> weight normalisation + log Z increment (R/CPF.R:61-66) ->
+// Tree$update (src/tree.cpp:88-99).  Weights/CDF, sorted uniforms/log-weights, leaf slots, parent
+// slots, offspring counts and the tree's free-slot bitmap stay in shared memory for the whole filter;
+// HBM sees only the particle state (SoA, double-buffered) and the ancestor tree.
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+
+namespace cpimh {
+
+struct PfParams {
+  int N, T, dy, Npad;
+  int M;                       // tree capacity per filter (multiple of 32)
+  long long B;                 // filters in this launch
+  int shuffle, store_paths;
+  unsigned long long seed, first_filter;
+  const double* obs;           // [T][dy] row-major (device)
+  const double* theta;         // [CPIMH_MAX_THETA]
+  const double* pre;           // [npre]
+  int npre;
+  int integrator, substeps;
+  // workspaces (indexed by workspace slot)
+  double* xbuf;                // [ws][2][D][Npad]
+  int* a_star;                 // [ws][M]
+  int* o_star;                 // [ws][M]
+  double* x_star;              // [ws][D][M]
+  // outputs (indexed by filter)
+  double* logz;                // [B]
+  double* logz_t;              // [B][T] or null
+  double* traj;                // [B][T+1][D] or null
+  int* path_index;             // [B] or null
+  int* status;                 // [B]
+  double* normw;               // [B][N] or null (final normalised weights)
+  int* leaf_out;               // [B][N] or null (final leaf slots)
+  int* anc_rec;                // [B][T][N] or null
+  // injected noise (device) or null
+  const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_shuffle; const double* inj_path;
+  int n_init, n_trans, sk_M;
+};
+
+struct PfSmem {
+  double* C;        // [Npad] normalised weights, then their inclusive CDF
+  double* S;        // [Npad] log(u)/i -> suffix sums -> log-weights
+  int* leaf;        // [Npad] l_star
+  int* bpar;        // [Npad] ancestors, then parent slots b = l_star[a]
+  unsigned* off32;  // [Npad/2] 16-bit offspring counters
+  unsigned* bits;   // [M/32] free-slot bitmap (1 = free)
+  double* theta;    // [CPIMH_MAX_THETA]
+  double* pre;      // [npre]
+  double* dscr;     // [32]
+  int* iscr;        // [34]  (32 scan scratch, [32] status flag, [33] spare)
+};
+__host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre) {
+  size_t b = 0;
+  b += (size_t)Npad * 8 * 2;                 // C, S
+  b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 32) * 8;
+  b += (size_t)Npad * 4 * 2;                 // leaf, bpar
+  b += (size_t)(Npad / 2) * 4;               // off32
+  b += (size_t)(M / 32) * 4;                 // bits
+  b += 36 * 4;
+  return (b + 15) & ~(size_t)15;
+}
+__device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre) {
+  PfSmem s;
+  double* d = reinterpret_cast<double*>(raw);
+  s.C = d; d += Npad;
+  s.S = d; d += Npad;
+  s.theta = d; d += CPIMH_MAX_THETA;
+  s.pre = d; d += npre + (npre & 1);
+  s.dscr = d; d += 32;
+  int* i = reinterpret_cast<int*>(d);
+  s.leaf = i; i += Npad;
+  s.bpar = i; i += Npad;
+  s.off32 = reinterpret_cast<unsigned*>(i); i += Npad / 2;
+  s.bits = reinterpret_cast<unsigned*>(i); i += M / 32;
+  s.iscr = i;
+  return s;
+}
+
+struct FilterOut {
+  double* logz; double* logz_t; double* traj; int* path_index; int* status; double* normw; int* leaf_out; int* anc_rec;
+};
+
+__device__ __forceinline__ void set_free_bit(unsigned* bits, int slot) { atomicOr(&bits[slot >> 5], 1u << (slot & 31)); }
+
+// Runs one whole filter with the calling CTA.  `ws` selects the HBM workspace, `inj` the row of the injected
+// noise arrays (ignored when they are null).  All threads of the CTA must call.
+template <class Model>
+__device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, const Stream& stream, long long inj, const FilterOut& out) {
+  constexpr int D = Model::D;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int N = p.N, T = p.T, Npad = p.Npad, M = p.M, W = M >> 5;
+  double* xold = p.xbuf + (size_t)ws * 2 * D * Npad;
+  double* xnew = xold + (size_t)D * Npad;
+  int* a_star = p.a_star + (size_t)ws * M;
+  int* o_star = p.o_star + (size_t)ws * M;
+  double* x_star = p.x_star + (size_t)ws * D * M;
+
+  ModelCtx c;
+  c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
+  c.inj_init = p.inj_init ? p.inj_init + (size_t)inj * p.n_init * N : nullptr;
+  c.inj_trans = p.inj_trans ? p.inj_trans + (size_t)inj * T * p.n_trans * N : nullptr;
+  c.n_trans = p.n_trans; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
+  const double* inj_res = p.inj_resample ? p.inj_resample + (size_t)inj * T * N : nullptr;
+  const double* inj_shf = p.inj_shuffle ? p.inj_shuffle + (size_t)inj * T * (N - 1) : nullptr;
+  const bool tree = p.store_paths != 0;
+  int st = 0;
+
+  // ---------------- initialisation: R/CPF.R:17-28, Tree::Tree + Tree::init (src/tree.cpp:6-34)
+  if (tid == 0) sm.iscr[32] = 0;
+  if (tree) {
+    for (int j = tid; j < M; j += NT) o_star[j] = 0;
+    for (int w = tid; w < W; w += NT) {
+      int lo = w << 5;
+      sm.bits[w] = (lo + 32 <= N) ? 0u : (lo >= N ? 0xffffffffu : (0xffffffffu << (N - lo)));
+    }
+  }
+  for (int i = tid; i < N; i += NT) {
+    double x[D];
+    Model::init(c, i, x);
+#pragma unroll
+    for (int k = 0; k < D; k++) xold[(size_t)k * Npad + i] = x[k];
+    if (tree) {
+#pragma unroll
+      for (int k = 0; k < D; k++) x_star[(size_t)k * M + i] = x[k];
+      a_star[i] = -2;
+      sm.leaf[i] = i;
+    }
+    sm.C[i] = 1.0 / N;
+  }
+  double logz_sum = 0.0;
+  __syncthreads();
+
+  // ---------------- hot loop: R/CPF.R:35-67
+  for (int t = 1; t <= T; t++) {
+    const bool ident = (t == 1) || isnan(p.obs[(size_t)(t - 2) * p.dy]);     // R/CPF.R:38-40
+    const double* y = p.obs + (size_t)(t - 1) * p.dy;
+    const double sc = Model::step_const(c, t);
+    double sumw = 1.0;
+
+    // -- sorted uniforms (src/multinomial.cpp:18-24) and CDF (:17); zero the offspring counters
+    for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
+    if (!ident) {
+      if (inj_res) {
+        for (int i = tid; i < N; i += NT) sm.S[i] = inj_res[(size_t)(t - 1) * N + i];
+      } else {
+        for (int i = tid; i < N; i += NT) sm.S[i] = log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0)) / (double)(i + 1);
+      }
+      __syncthreads();
+      block_scan_inplace<false>(sm.C, N, sm.dscr);
+      if (!inj_res) block_scan_inplace<true>(sm.S, N, sm.dscr);
+      sumw = sm.C[N - 1];
+    } else {
+      __syncthreads();
+    }
+
+    // -- ancestors: count of CDF knots <= u (:25-28), clamped
+    auto ancestor_of = [&](int k) -> int {
+      if (ident) return k;
+      double e = inj_res ? sm.S[k] : exp(sm.S[k]);
+      int a = count_le(sm.C, N, sumw * e);
+      if (a >= N) { a = N - 1; st |= 512; }
+      return a;
+    };
+    // -- gather (R/CPF.R:41) -> rtransition (:44) -> dmeasurement (:60) ; tree bookkeeping part 1 (src/tree.cpp:39-42, 90-94)
+    auto propagate = [&](int k, int a) {
+      double x[D];
+#pragma unroll
+      for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
+      st |= Model::transition(c, t, k, x, sc);
+#pragma unroll
+      for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
+      sm.S[k] = Model::logw(c, x, y);
+      if (tree) {
+        sm.bpar[k] = sm.leaf[a];
+        atomicAdd(&sm.off32[a >> 1], 1u << ((a & 1) << 4));
+      }
+      if (out.anc_rec) out.anc_rec[(size_t)(t - 1) * N + k] = a;
+    };
+    if (p.shuffle && !ident) {
+      for (int k = tid; k < N; k += NT) sm.bpar[k] = ancestor_of(k);
+      __syncthreads();
+      // std::random_shuffle with randWrapper (src/multinomial.cpp:6-10,30): for i = 1..n-1 swap(a[i], a[floor(u_i (i+1))])
+      int* jidx = reinterpret_cast<int*>(sm.S);
+      for (int i = 1 + tid; i < N; i += NT) {
+        double u = inj_shf ? inj_shf[(size_t)(t - 1) * (N - 1) + (i - 1)] : philox_u1(stream, i, t, CPIMH_P_SHUFFLE, 0);
+        int j = (int)floor(u * (double)(i + 1));
+        jidx[i] = j > i ? i : j;
+      }
+      __syncthreads();
+      if (tid == 0)
+        for (int i = 1; i < N; i++) { int j = jidx[i]; int tmp = sm.bpar[i]; sm.bpar[i] = sm.bpar[j]; sm.bpar[j] = tmp; }
+      __syncthreads();
+      for (int k = tid; k < N; k += NT) propagate(k, sm.bpar[k]);
+    } else {
+      for (int k = tid; k < N; k += NT) propagate(k, ancestor_of(k));
+    }
+    __syncthreads();
+
+    // -- weights and log Z increment: R/CPF.R:61-63,66
+    double m = -INFINITY;
+    for (int k = tid; k < N; k += NT) m = fmax(m, sm.S[k]);
+    m = block_max(m, sm.dscr);
+    double s = 0.0;
+    for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; }
+    s = block_sum(s, sm.dscr);
+    for (int k = tid; k < N; k += NT) sm.C[k] = sm.C[k] / s;
+    const double lz = log(s / (double)N) + m;
+    logz_sum += lz;
+    if (tid == 0 && out.logz_t) out.logz_t[t - 1] = lz;
+
+    // -- Tree::update (src/tree.cpp:88-99)
+    if (tree) {
+      // prune (:70-86): o_star <- scatter(o, l_star); walk up from childless leaves, decrementing offspring counts
+      for (int i = tid; i < N; i += NT) {
+        int o = (sm.off32[i >> 1] >> ((i & 1) << 4)) & 0xffff;
+        int slot = sm.leaf[i];
+        o_star[slot] = o;
+        if (o == 0) {
+          set_free_bit(sm.bits, slot);
+          int j = a_star[slot];
+          while (j >= 0) {
+            int old = atomicSub(&o_star[j], 1);
+            if (old != 1) break;
+            set_free_bit(sm.bits, j);
+            j = a_star[j];
+          }
+        }
+      }
+      __syncthreads();
+      // insert (:36-68): first N free slots in index order (:45-53) from the shared-memory bitmap
+      int found = 0;
+      for (int base = 0; base < W && found < N; base += NT) {
+        int wi = base + tid;
+        unsigned w = wi < W ? sm.bits[wi] : 0u;
+        int tot;
+        int r = found + block_excl_scan_int(__popc(w), sm.iscr, &tot);
+        while (w && r < N) {
+          int b = __ffs(w) - 1;
+          sm.leaf[r] = (wi << 5) + b;
+          w &= w - 1;
+          r++;
+        }
+        if (wi < W) sm.bits[wi] = w;
+        found += tot;
+      }
+      if (found < N) {                      // Tree::double_size (:101-116) would be needed: report, host retries with 2M
+        if (tid == 0) { *out.status = CPIMH_ERR_TREE_OVERFLOW; *out.logz = nan(""); }
+        __syncthreads();
+        return;
+      }
+      __syncthreads();
+      for (int k = tid; k < N; k += NT) {   // a_star <- scatter(b, l_star); x_star <- scatter(x, l_star) (:64-67)
+        int slot = sm.leaf[k];
+        a_star[slot] = sm.bpar[k];
+#pragma unroll
+        for (int q = 0; q < D; q++) x_star[(size_t)q * M + slot] = xnew[(size_t)q * Npad + k];
+      }
+    }
+    { double* tmp = xold; xold = xnew; xnew = tmp; }
+    __syncthreads();
+  }
+
+  // ---------------- path selection: systematic_resampling_n(normweights, 1, runif(1)) + Tree$get_path (R/CPF.R:69)
+  if (st) atomicOr(&sm.iscr[32], st);
+  if (out.normw) for (int k = tid; k < N; k += NT) out.normw[k] = sm.C[k];
+  if (out.leaf_out && tree) for (int k = tid; k < N; k += NT) out.leaf_out[k] = sm.leaf[k];
+  __syncthreads();
+  block_scan_inplace<false>(sm.C, N, sm.dscr);
+  double u = p.inj_path ? p.inj_path[inj] : philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0);
+  int kidx = count_lt(sm.C, N, u);          // smallest j with csw_j >= u (src/systematic.cpp:15-18), n = 1
+  int flags = sm.iscr[32];
+  if (kidx >= N) { kidx = N - 1; flags |= 512; }
+  if (tid == 0) {
+    *out.logz = logz_sum;
+    if (out.path_index) *out.path_index = kidx;
+    int code = flags & 255;
+    *out.status = code ? code : 0;
+  }
+  if (tree && out.traj && tid < 32) {       // Tree::get_path (src/tree.cpp:118-129): one warp, lane q carries component q
+    int j = sm.leaf[kidx];
+    for (int step = T; step >= 0; step--) {
+      for (int q = tid; q < D; q += 32) out.traj[(size_t)step * D + q] = x_star[(size_t)q * M + j];
+      j = a_star[j];
+    }
+  }
+  __syncthreads();
+}
+
+template <class Model, int NT_MAX, int MIN_BLOCKS>
+__global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PfSmem sm = pf_carve(smem_raw, p.Npad, p.M, p.npre);
+  for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
+  for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
+  __syncthreads();
+  for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+    Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+    FilterOut out;
+    out.logz = p.logz + b;
+    out.logz_t = p.logz_t ? p.logz_t + (size_t)b * p.T : nullptr;
+    out.traj = p.traj ? p.traj + (size_t)b * (p.T + 1) * Model::D : nullptr;
+    out.path_index = p.path_index ? p.path_index + b : nullptr;
+    out.status = p.status + b;
+    out.normw = p.normw ? p.normw + (size_t)b * p.N : nullptr;
+    out.leaf_out = p.leaf_out ? p.leaf_out + (size_t)b * p.N : nullptr;
+    out.anc_rec = p.anc_rec ? p.anc_rec + (size_t)b * p.T * p.N : nullptr;
+    run_filter<Model>(p, sm, b, s, b, out);
+  }
+}
+
+// host-side launcher shared by the per-model translation units
+struct PfLaunch { int threads; int grid; size_t smem; };
+template <class Model>
+int launch_pf_batch(const PfParams& p, const PfLaunch& L, cudaStream_t stream) {
+  auto go = [&](auto kernel) -> int {
+    CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    kernel<<<L.grid, L.threads, L.smem, stream>>>(p);
+    CPIMH_CUDA_CHECK(cudaGetLastError());
+    return CPIMH_OK;
+  };
+  if (L.threads <= 256) return go(pf_batch_kernel<Model, 256, 2>);
+  if (L.threads <= 512) return go(pf_batch_kernel<Model, 512, 2>);
+  return go(pf_batch_kernel<Model, 1024, 1>);
+}
+template <class Model>
+int occupancy_pf_batch(int threads, size_t smem, int* blocks_per_sm) {
+  auto q = [&](auto kernel) -> int {
+    CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CPIMH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem));
+    return CPIMH_OK;
+  };
+  if (threads <= 256) return q(pf_batch_kernel<Model, 256, 2>);
+  if (threads <= 512) return q(pf_batch_kernel<Model, 512, 2>);
+  return q(pf_batch_kernel<Model, 1024, 1>);
+}
+
+}  // namespace cpimh

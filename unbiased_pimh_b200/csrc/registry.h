@@ -1,0 +1,36 @@
+// registry.h -- per-model kernel entry points (one translation unit per model keeps nvcc compile times parallel)
+#pragma once
+#include "pf_fused.cuh"
+#include "chains.cuh"
+
+namespace cpimh {
+
+struct ModelEntry {
+  int model;
+  int dim;
+  int npre;
+  int (*launch_pf)(const PfParams&, const PfLaunch&, cudaStream_t);
+  int (*occupancy_pf)(int threads, size_t smem, int* blocks_per_sm);
+  int (*launch_chains)(const ChainParams&, const PfLaunch&, cudaStream_t);
+  int (*occupancy_chains)(int threads, size_t smem, int* blocks_per_sm);
+  int (*launch_model_op)(const ModelOpParams&, cudaStream_t);
+};
+template <class Model>
+ModelEntry make_entry(int model) {
+  ModelEntry e;
+  e.model = model; e.dim = Model::D; e.npre = Model::NPRE;
+  e.launch_pf = &launch_pf_batch<Model>;
+  e.occupancy_pf = &occupancy_pf_batch<Model>;
+  e.launch_chains = &launch_chains<Model>;
+  e.occupancy_chains = &occupancy_chains<Model>;
+  e.launch_model_op = &launch_model_op<Model>;
+  return e;
+}
+const ModelEntry* entries_gss(int* n);
+const ModelEntry* entries_ar(int* n);
+const ModelEntry* entries_sv(int* n);
+const ModelEntry* entries_sk(int* n);
+const ModelEntry* entries_lorenz(int* n);
+const ModelEntry* find_entry(int model, int dim);
+
+}  // namespace cpimh

@@ -1,0 +1,179 @@
+"""The particle filters: `CPF` (ref_trajectory=NULL path) and `particlefilter`, plus their batched twins.
+
+Reference: R/CPF.R:14-78 and R/particlefilter.R:11-44.  The R functions run one filter; the CUDA library runs
+B filters per launch (one CTA each), so `cpf_batch` / `PfBatch` are the calls that use the GPU well and the
+single-filter functions are thin B = 1 wrappers with the reference's return values.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import rng
+
+
+class PfBatch:
+    """Device-resident batch of bootstrap filters (cpimh_pf handle).  Holds observations, workspaces and outputs in
+    HBM across runs; `run` is asynchronous on the given CUDA stream."""
+
+    def __init__(self, model, theta, observations, nparticles, max_filters, shuffle=0, tree_capacity=0, threads_per_filter=0,
+                 store_paths=1, sk_max_events=64, device=None):
+        obs = np.asarray(observations, dtype=np.float64)
+        self.nobs = obs.shape[0]
+        self.model = model
+        self.cfg = model.config(nparticles, theta, nobs=self.nobs, shuffle=shuffle, tree_capacity=tree_capacity,
+                                threads_per_filter=threads_per_filter, store_paths=store_paths, sk_max_events=sk_max_events)
+        if device is not None:
+            L.check(L.lib().cpimh_set_device(C.c_int(int(device))))
+        self.h = C.c_void_p()
+        L.check(L.lib().cpimh_pf_create(C.byref(self.cfg), C.c_int64(int(max_filters)), C.byref(self.h)))
+        self.max_filters = int(max_filters)
+        self.set_observations(obs)
+        self.last = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            L.lib().cpimh_pf_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_observations(self, observations):
+        ob = L.obs_matrix(observations, self.nobs)
+        L.check(L.lib().cpimh_pf_set_observations(self.h, ob.ctypes.data_as(C.c_void_p)))
+
+    def set_noise(self, nfilters, noise):
+        if noise is None:
+            L.check(L.lib().cpimh_pf_set_noise(self.h, C.c_int64(0), None))
+            return
+        nz, keep = L.make_noise(noise)
+        L.check(L.lib().cpimh_pf_set_noise(self.h, C.c_int64(int(nfilters)), C.byref(nz)))
+
+    def record_ancestors(self, on=True):
+        L.check(L.lib().cpimh_pf_record_ancestors(self.h, C.c_int(int(on))))
+
+    def run(self, nfilters, seed, first_filter=0, stream=None):
+        L.check(L.lib().cpimh_pf_run(self.h, C.c_int64(int(nfilters)), C.c_uint64(int(seed)), C.c_uint64(int(first_filter)), C.c_void_p(stream or 0)))
+        self.last = int(nfilters)
+
+    def fetch(self, nfilters=None, stream=None, logz_t=False, trajectory=True, path_index=False):
+        B = self.last if nfilters is None else int(nfilters)
+        d, T = self.cfg.dim, self.cfg.nobs
+        out = {"logz": np.empty(B)}
+        lzt = np.empty((B, T)) if logz_t else None
+        traj = np.empty((B, T + 1, d)) if (trajectory and self.cfg.store_paths) else None
+        pidx = np.empty(B, dtype=np.int32) if path_index else None
+        L.check(L.lib().cpimh_pf_fetch(self.h, C.c_int64(B), C.c_void_p(stream or 0), L.ptr(out["logz"]), L.ptr(lzt), L.ptr(traj), L.ptr(pidx)))
+        if lzt is not None:
+            out["logz_t"] = lzt
+        if traj is not None:
+            out["trajectory"] = traj.transpose(0, 2, 1)      # (B, d, T+1) like R's d x (T+1)
+        if pidx is not None:
+            out["path_index"] = pidx
+        return out
+
+    def fetch_all_particles(self, b=0, stream=None, exp_path=True, trajectories=False, normweights=True):
+        d, T, N = self.cfg.dim, self.cfg.nobs, self.cfg.nparticles
+        ep = np.empty((T + 1, d)) if exp_path else None
+        tr = np.empty((N, T + 1, d)) if trajectories else None
+        nw = np.empty(N) if normweights else None
+        L.check(L.lib().cpimh_pf_fetch_all_particles(self.h, C.c_int64(int(b)), C.c_void_p(stream or 0), L.ptr(ep), L.ptr(tr), L.ptr(nw)))
+        out = {}
+        if ep is not None:
+            out["exp_path"] = np.ascontiguousarray(ep.T)                      # d x (T+1)
+        if tr is not None:
+            out["trajectories"] = np.ascontiguousarray(tr.transpose(2, 1, 0))  # d x (T+1) x N
+        if nw is not None:
+            out["weights"] = nw
+        return out
+
+    def fetch_ancestors(self, b=0, stream=None):
+        anc = np.empty((self.cfg.nobs, self.cfg.nparticles), dtype=np.int32)
+        L.check(L.lib().cpimh_pf_fetch_ancestors(self.h, C.c_int64(int(b)), C.c_void_p(stream or 0), L.ptr(anc)))
+        return anc
+
+    def device_outputs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        L.check(L.lib().cpimh_pf_device_outputs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @property
+    def launch_count(self):
+        return int(L.lib().cpimh_pf_launch_count(self.h))
+
+    @property
+    def device_bytes(self):
+        return int(L.lib().cpimh_pf_device_bytes(self.h))
+
+    def effective_config(self):
+        c = L.Config()
+        L.check(L.lib().cpimh_pf_effective_config(self.h, C.byref(c)))
+        return {"tree_capacity": c.tree_capacity, "threads_per_filter": c.threads_per_filter, "ctas_per_sm": c.reserved}
+
+
+def cpf_batch(nparticles, model, theta, observations, nfilters, seed=None, first_filter=0, noise=None, logz_t=False, **kw):
+    """B independent CPF(nparticles, model, theta, observations) runs through the one-shot host API (cpimh_pf_batch)."""
+    obs = np.asarray(observations, dtype=np.float64)
+    T = obs.shape[0]
+    cfg = model.config(nparticles, theta, nobs=T, **kw)
+    ob = L.obs_matrix(obs, T)
+    B, d = int(nfilters), model.dimension
+    logz = np.empty(B)
+    lzt = np.empty((B, T)) if logz_t else None
+    traj = np.empty((B, T + 1, d)) if cfg.store_paths else None
+    pidx = np.empty(B, dtype=np.int32)
+    nz, keep = L.make_noise(noise)
+    seed = rng.next_seed() if seed is None else int(seed)
+    L.check(L.lib().cpimh_pf_batch(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_int64(B), C.c_uint64(seed), C.c_uint64(int(first_filter)),
+                                    C.byref(nz) if noise else None, L.ptr(logz), L.ptr(lzt), L.ptr(traj), L.ptr(pidx)))
+    out = {"logz": logz, "path_index": pidx}
+    if traj is not None:
+        out["trajectory"] = traj.transpose(0, 2, 1)
+    if lzt is not None:
+        out["logz_t"] = lzt
+    return out
+
+
+def CPF(nparticles, model, theta, observations, ref_trajectory=None, with_as=False, all_particles=False, seed=None, filter_id=0, noise=None, **kw):
+    """CPF(nparticles, model, theta, observations, ref_trajectory = NULL, with_as = FALSE, all_particles = FALSE)
+    -- R/CPF.R:14-78.  Returns {"trajectory": d x (T+1), "logz": float [, "exp_path": d x (T+1)]}."""
+    if ref_trajectory is not None or with_as:
+        raise NotImplementedError("conditional particle filtering (ref_trajectory / with_as) is outside the PIMH hot path "
+                                  "(SURVEY 8f rank 1); every PIMH kernel calls CPF with ref_trajectory = NULL")
+    seed = rng.next_seed() if seed is None else int(seed)
+    if not all_particles:
+        r = cpf_batch(nparticles, model, theta, observations, 1, seed=seed, first_filter=filter_id, noise=noise, **kw)
+        return {"trajectory": np.ascontiguousarray(r["trajectory"][0]), "logz": float(r["logz"][0])}
+    pb = PfBatch(model, theta, observations, nparticles, 1, **kw)
+    try:
+        if noise:
+            pb.set_noise(1, noise)
+        pb.run(1, seed, filter_id)
+        r = pb.fetch()
+        ap = pb.fetch_all_particles(0)
+    finally:
+        pb.close()
+    return {"trajectory": np.ascontiguousarray(r["trajectory"][0]), "exp_path": ap["exp_path"], "logz": float(r["logz"][0])}
+
+
+def particlefilter(nparticles, model, theta, observations, seed=None, filter_id=0, noise=None, **kw):
+    """particlefilter(nparticles, model, theta, observations) -- R/particlefilter.R:11-44.
+    Returns {"trajectories": d x (T+1) x N, "weights": N}."""
+    seed = rng.next_seed() if seed is None else int(seed)
+    pb = PfBatch(model, theta, observations, nparticles, 1, **kw)
+    try:
+        if noise:
+            pb.set_noise(1, noise)
+        pb.run(1, seed, filter_id)
+        pb.fetch(trajectory=False)
+        ap = pb.fetch_all_particles(0, exp_path=False, trajectories=True)
+    finally:
+        pb.close()
+    return {"trajectories": ap["trajectories"], "weights": ap["weights"]}
+
+
+def pf_get_weighted_average(arr_test, w):
+    """R/CPF.R:84-92: sum_i arr[:, :, i] * w[i].  Device version lives in cpimh_pf_fetch_all_particles; this host helper
+    only mirrors the exported R utility for arrays the user already holds."""
+    arr = np.asarray(arr_test, dtype=np.float64)
+    return np.tensordot(arr, np.asarray(w, dtype=np.float64), axes=([2], [0]))

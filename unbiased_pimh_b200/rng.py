@@ -1,0 +1,20 @@
+"""Host-side seed source.  The reference draws from R's global RNG (set.seed); the CUDA kernels use Philox streams,
+so every call that needs randomness takes one 64-bit seed from here (the R shim takes it from
+unif_rand(), so set.seed() still makes runs repeatable)."""
+import numpy as np
+
+_rng = np.random.default_rng(17)
+
+
+def set_seed(seed):
+    global _rng
+    _rng = np.random.default_rng(int(seed))
+
+
+def next_seed():
+    return int(_rng.integers(0, 2 ** 63 - 1))
+
+
+def runif(n=1):
+    u = _rng.random(n)
+    return np.where(u <= 0.0, 2.0 ** -53, u)
