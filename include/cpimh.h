@@ -75,9 +75,11 @@ typedef struct cpimh_config {
   int32_t ntheta;
   double  theta[CPIMH_MAX_THETA];
   /* ---- execution knobs (0 = automatic) ---- */
-  int32_t tree_capacity;      /* M nodes per filter; 0 => min(max(10*N*d, 3N), what fits on chip)  */
+  int32_t tree_capacity;      /* tree mode: M nodes per filter; 0 => min(max(10*N*d, 3N), 16N)     */
   int32_t threads_per_filter; /* CTA size; 0 => chosen from N                                      */
-  int32_t store_paths;        /* 1 (default when 0 passed via cpimh_config_default): ancestor tree on */
+  int32_t store_paths;        /* path storage: 0 none (log Z only), 1 auto, 2 dense particle history in
+                                 HBM, 3 Jacob-Murray-Rubenthaler tree (src/tree.cpp); auto = dense when
+                                 the histories of all resident CTAs fit in free HBM, else tree         */
   int32_t reserved;
 } cpimh_config;
 

@@ -59,8 +59,8 @@ static int poisson_inv(double rate, double u) {
 static void sv_jump_sums(const orc_config* c, uint64_t seed, uint64_t fid, uint32_t i, int t, double* swe, double* se) {
   double xi = c->theta[2], w2 = c->theta[3], lambda = c->theta[4];
   double ua, ub;
-  uni2(seed, fid, i, t, ORC_P_TRANS, 0, &ua, &ub);
-  int k = poisson_inv(lambda * xi * xi / w2, ua);
+  uni2(seed, fid, i, t, ORC_P_RESAMPLE, 0, &ua, &ub);   /* shared Philox block: ua = resampling draw of slot i, ub = Poisson uniform */
+  int k = poisson_inv(lambda * xi * xi / w2, ub);
   double a = 0, b = 0, escale = w2 / xi;
   for (int j = 1; j <= k; j++) {
     uni2(seed, fid, i, t, ORC_P_TRANS, (uint32_t)j, &ua, &ub);

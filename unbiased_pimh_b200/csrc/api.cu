@@ -57,6 +57,9 @@ std::vector<double> api_precompute(const cpimh_config& c) {
     double hl = 0;
     for (int i = 0; i < d; i++) hl += log(c.theta[1]);
     pre[(size_t)d * d] = -(hl) - (d * CPIMH_HALF_LOG_2PI_TRUNC);
+  } else if (c.model == CPIMH_MODEL_LEVY_SV) {
+    pre.push_back(exp(-c.theta[4]));                                        // src/SVLevy_functions.cpp:66 exp(-lambda)
+    pre.push_back(exp(-(c.theta[4] * c.theta[2] * c.theta[2] / c.theta[3])));  // P[k = 0] of rpois(lambda xi^2 / w2) (:61)
   } else if (c.model == CPIMH_MODEL_LORENZ) {
     double hl = 0;
     for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);
@@ -89,41 +92,66 @@ int api_validate(cpimh_config* cp) {
 
 // launch geometry shared by the filter and the chain kernels
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, Geometry* g) {
+int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, int64_t max_items, Geometry* g) {
   int dev = 0;
   CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
   cudaDeviceProp prop;
   CPIMH_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
   CPIMH_REQUIRE(prop.major >= 10, "libcpimh is built for sm_100a (Blackwell); device %d is sm_%d%d", dev, prop.major, prop.minor);
-  const int N = c.nparticles;
+  const int N = c.nparticles, T = c.nobs, D = c.dim;
   g->num_sms = prop.multiProcessorCount;
   g->Npad = (N + 31) & ~31;
-  CPIMH_REQUIRE(N <= 65535, "the CTA-per-filter kernel supports N <= 65535 particles (got %d)", N);
+  CPIMH_REQUIRE(N <= 32768, "the CTA-per-filter kernel supports N <= 32768 particles (got %d)", N);
+  // CTA size: about 8 particles per thread, snapped to a compiled variant (128/256/512/1024 threads)
   int threads = c.threads_per_filter > 0 ? c.threads_per_filter : next_pow2((N + 7) / 8);
-  threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
-  threads = (threads + 31) & ~31;
+  g->variant = pf_variant_for(threads);
+  threads = pf_variant_threads(g->variant);
+  if (c.threads_per_filter <= 0 && N <= 64) threads = 64;      // tiny filters: two warps are plenty
+  CPIMH_REQUIRE((long long)threads * CPIMH_MAX_E >= N, "N=%d needs at least %d threads per filter", N, (N + CPIMH_MAX_E - 1) / CPIMH_MAX_E);
   g->threads = threads;
   const size_t max_smem = prop.sharedMemPerBlockOptin;
-  long long Mwant;
-  if (!c.store_paths) Mwant = 32;
-  else if (c.tree_capacity > 0) Mwant = c.tree_capacity < 3LL * N ? 3LL * N : c.tree_capacity;   // src/tree.cpp:7-9
-  else { Mwant = 10LL * N * c.dim; if (Mwant < 3LL * N) Mwant = 3LL * N; if (Mwant > 12LL * N) Mwant = 12LL * N; }   // R/CPF.R:17, capped
-  Mwant = (Mwant + 31) & ~31LL;
-  if (c.tree_capacity <= 0 && c.store_paths) {
-    // prefer a capacity that lets two CTAs share an SM; never below 8N automatically
-    const size_t half = (size_t)(prop.sharedMemPerMultiprocessor / 2) - 1024;
-    while (Mwant > 8LL * N && pf_smem_bytes(g->Npad, (int)Mwant, e->npre) > half && pf_smem_bytes(g->Npad, (int)(8LL * N + 31) & ~31, e->npre) <= half) Mwant -= 32LL * ((N + 31) / 32);
-    if (Mwant < ((8LL * N + 31) & ~31LL)) Mwant = (8LL * N + 31) & ~31LL;
+  g->hist_x_elems = (size_t)(T + 1) * D * g->Npad;
+  g->hist_a_elems = (size_t)T * g->Npad;
+
+  auto tree_capacity = [&]() -> long long {
+    long long Mwant;
+    if (c.tree_capacity > 0) Mwant = c.tree_capacity < 3LL * N ? 3LL * N : c.tree_capacity;          // src/tree.cpp:7-9
+    else { Mwant = 10LL * N * D; if (Mwant < 3LL * N) Mwant = 3LL * N; if (Mwant > 16LL * N) Mwant = 16LL * N; }   // R/CPF.R:17, capped
+    return (Mwant + 31) & ~31LL;
+  };
+  auto occupancy = [&](int mode, int M, size_t* smem, int* bps) -> int {
+    *smem = pf_smem_bytes(g->Npad, M, e->npre, mode, c.shuffle);
+    if (*smem > max_smem) { *bps = 0; return CPIMH_OK; }
+    return chains ? e->occupancy_chains(g->variant, threads, *smem, bps) : e->occupancy_pf(g->variant, threads, *smem, bps);
+  };
+  // path storage: 0 none, 1 auto (dense when the histories of all resident CTAs fit in HBM, else tree), 2 dense, 3 tree
+  int mode = c.store_paths == 0 ? PATH_NONE : (c.store_paths == 3 ? PATH_TREE : PATH_DENSE);
+  int M = 32, bps = 0, rc;
+  if (mode != PATH_TREE) {
+    rc = occupancy(mode, M, &g->smem, &bps);
+    if (rc) return rc;
+    if (mode == PATH_DENSE) {
+      size_t free_b = 0, total_b = 0;
+      CPIMH_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+      long long grid = (long long)bps * g->num_sms;
+      if (max_items < grid) grid = max_items;
+      const double need = (double)grid * ((double)g->hist_x_elems * 8.0 + (double)g->hist_a_elems * 4.0);
+      if (need > 0.85 * (double)free_b) {
+        CPIMH_REQUIRE(c.store_paths != 2, "dense path history needs %.1f GB but only %.1f GB of HBM is free; use store_paths = 3 (tree)", need / 1e9, free_b / 1e9);
+        mode = PATH_TREE;
+      }
+    }
   }
-  g->M = (int)Mwant;
-  g->smem = pf_smem_bytes(g->Npad, g->M, e->npre);
-  CPIMH_REQUIRE(g->smem <= max_smem, "filter with N=%d, tree capacity %d needs %zu bytes of shared memory per CTA (limit %zu); lower tree_capacity or N",
-                N, g->M, g->smem, max_smem);
-  int bps = 0;
-  int rc = chains ? e->occupancy_chains(threads, g->smem, &bps) : e->occupancy_pf(threads, g->smem, &bps);
-  if (rc) return rc;
+  if (mode == PATH_TREE) {
+    M = (int)tree_capacity();
+    rc = occupancy(mode, M, &g->smem, &bps);
+    if (rc) return rc;
+    CPIMH_REQUIRE(g->smem <= max_smem, "filter with N=%d, tree capacity %d needs %zu bytes of shared memory per CTA (limit %zu); lower tree_capacity or N",
+                  N, M, g->smem, max_smem);
+  }
+  CPIMH_REQUIRE(g->smem <= max_smem, "filter with N=%d needs %zu bytes of shared memory per CTA (limit %zu)", N, g->smem, max_smem);
   CPIMH_REQUIRE(bps >= 1, "kernel cannot be resident with %d threads and %zu bytes of shared memory", threads, g->smem);
-  g->blocks_per_sm = bps;
+  g->M = M; g->path_mode = mode; g->blocks_per_sm = bps;
   return CPIMH_OK;
 }
 
@@ -139,6 +167,8 @@ struct cpimh_pf {
   int64_t maxB, lastB;
   int record_anc;
   int64_t launches, bytes;
+  int grid;
+  DevBuf hist_x, hist_a;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, logz, logz_t, traj, path_index, status, normw, leaf_out, anc_rec;
   DevBuf inj_init, inj_trans, inj_resample, inj_shuffle, inj_path;
   bool have_inj[5];
@@ -166,7 +196,7 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   if (rc) return rc;
   const ModelEntry* e = find_entry(cfg.model, cfg.dim);
   Geometry g;
-  rc = api_plan_geometry(cfg, e, false, &g);
+  rc = api_plan_geometry(cfg, e, false, max_filters, &g);
   if (rc) return rc;
   cpimh_pf* h = new cpimh_pf();
   h->cfg = cfg; h->entry = e; h->geo = g; h->maxB = max_filters; h->lastB = 0; h->record_anc = 0; h->launches = 0; h->bytes = 0;
@@ -179,14 +209,21 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   rc = A(h->obs, sizeof(double) * (size_t)T * cfg.dim_y);
   if (!rc) rc = A(h->theta, sizeof(double) * CPIMH_MAX_THETA);
   if (!rc) rc = A(h->pre, sizeof(double) * (pre.size() + 1));
-  if (!rc) rc = A(h->xbuf, sizeof(double) * B * 2 * D * g.Npad);
-  if (!rc && cfg.store_paths) {
-    rc = A(h->a_star, sizeof(int) * B * g.M);
-    if (!rc) rc = A(h->o_star, sizeof(int) * B * g.M);
-    if (!rc) rc = A(h->x_star, sizeof(double) * B * D * g.M);
-    if (!rc) rc = A(h->traj, sizeof(double) * B * (T + 1) * D);
-    if (!rc) rc = A(h->leaf_out, sizeof(int) * B * N);
+  const int64_t resident = (int64_t)g.blocks_per_sm * g.num_sms;
+  h->grid = (int)(max_filters < resident ? max_filters : resident);
+  const size_t G = (size_t)h->grid;          // HBM workspaces belong to resident CTAs, not to filters
+  if (!rc && g.path_mode != PATH_DENSE) rc = A(h->xbuf, sizeof(double) * G * 2 * D * g.Npad);
+  if (!rc && g.path_mode == PATH_DENSE) {
+    rc = A(h->hist_x, sizeof(double) * G * g.hist_x_elems);
+    if (!rc) rc = A(h->hist_a, sizeof(int) * G * g.hist_a_elems);
   }
+  if (!rc && g.path_mode == PATH_TREE) {
+    rc = A(h->a_star, sizeof(int) * G * g.M);
+    if (!rc) rc = A(h->o_star, sizeof(int) * G * g.M);
+    if (!rc) rc = A(h->x_star, sizeof(double) * G * D * g.M);
+    if (!rc) rc = A(h->leaf_out, sizeof(int) * G * N);
+  }
+  if (!rc && g.path_mode != PATH_NONE) rc = A(h->traj, sizeof(double) * B * (T + 1) * D);
   if (!rc) rc = A(h->logz, sizeof(double) * B);
   if (!rc) rc = A(h->logz_t, sizeof(double) * B * T);
   if (!rc) rc = A(h->path_index, sizeof(int) * B);
@@ -203,7 +240,7 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
 int cpimh_pf_destroy(cpimh_pf* h) {
   if (!h) return CPIMH_OK;
   DevBuf* all[] = {&h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->logz, &h->logz_t, &h->traj, &h->path_index,
-                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
+                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->hist_x, &h->hist_a, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
   return CPIMH_OK;
@@ -262,7 +299,7 @@ namespace cpimh {
 void api_fill_pf_params(const cpimh_config& c, const Geometry& g, int npre, PfParams* p) {
   memset(p, 0, sizeof(*p));
   p->N = c.nparticles; p->T = c.nobs; p->dy = c.dim_y; p->Npad = g.Npad; p->M = g.M;
-  p->shuffle = c.shuffle; p->store_paths = c.store_paths;
+  p->shuffle = c.shuffle; p->path_mode = g.path_mode;
   p->npre = npre; p->integrator = c.integrator; p->substeps = c.substeps;
   p->n_init = api_n_init(c); p->n_trans = api_n_trans(c); p->sk_M = c.sk_max_events;
 }
@@ -277,6 +314,7 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   api_fill_pf_params(c, h->geo, h->npre, &p);
   p.B = B; p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>(); p.theta = h->theta.as<double>(); p.pre = h->pre.as<double>();
+  p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>();
   p.xbuf = h->xbuf.as<double>(); p.a_star = h->a_star.as<int>(); p.o_star = h->o_star.as<int>(); p.x_star = h->x_star.as<double>();
   p.logz = h->logz.as<double>(); p.logz_t = h->logz_t.as<double>(); p.traj = h->traj.as<double>();
   p.path_index = h->path_index.as<int>(); p.status = h->status.as<int>(); p.normw = h->normw.as<double>();
@@ -287,9 +325,8 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   p.inj_shuffle = h->have_inj[3] ? h->inj_shuffle.as<double>() : nullptr;
   p.inj_path = h->have_inj[4] ? h->inj_path.as<double>() : nullptr;
   PfLaunch L;
-  L.threads = h->geo.threads; L.smem = h->geo.smem;
-  int64_t resident = (int64_t)h->geo.blocks_per_sm * h->geo.num_sms;
-  L.grid = (int)(B < resident ? B : resident);
+  L.threads = h->geo.threads; L.smem = h->geo.smem; L.variant = h->geo.variant;
+  L.grid = (int)(B < h->grid ? B : h->grid);
   int rc = h->entry->launch_pf(p, L, (cudaStream_t)stream);
   if (rc) return rc;
   h->launches += 1; h->lastB = B;
@@ -321,7 +358,7 @@ int cpimh_pf_fetch(cpimh_pf* h, int64_t B, void* stream, double* logz, double* l
   if (logz) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz, h->logz.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
   if (logz_t) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz_t, h->logz_t.p, sizeof(double) * (size_t)B * c.nobs, cudaMemcpyDeviceToHost, s));
   if (trajectory) {
-    CPIMH_REQUIRE(c.store_paths, "trajectories need store_paths = 1");
+    CPIMH_REQUIRE(h->geo.path_mode != PATH_NONE, "trajectories need store_paths != 0");
     CPIMH_CUDA_CHECK(cudaMemcpyAsync(trajectory, h->traj.p, sizeof(double) * (size_t)B * (c.nobs + 1) * c.dim, cudaMemcpyDeviceToHost, s));
   }
   if (path_index) CPIMH_CUDA_CHECK(cudaMemcpyAsync(path_index, h->path_index.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
@@ -343,13 +380,22 @@ int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ance
 int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* exp_path, double* trajectories, double* normweights) {
   CPIMH_REQUIRE(h, "null handle");
   CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
-  CPIMH_REQUIRE(h->cfg.store_paths, "all-particle outputs need store_paths = 1");
+  CPIMH_REQUIRE(h->geo.path_mode != PATH_NONE, "all-particle outputs need store_paths != 0");
+  CPIMH_REQUIRE(h->lastB <= h->grid, "all-particle outputs read the path store of the CTA that ran the filter: run at most %d filters per launch "
+                "(the last run had %lld)", h->grid, (long long)h->lastB);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = check_status(h->status.as<int>() + b, 1, s);
   if (rc) return rc;
   const size_t N = h->cfg.nparticles, D = h->cfg.dim, M = h->geo.M;
-  return api_all_particles((int)N, (int)D, (int)M, h->cfg.nobs, h->a_star.as<int>() + (size_t)b * M, h->x_star.as<double>() + (size_t)b * D * M,
-                           h->leaf_out.as<int>() + (size_t)b * N, h->normw.as<double>() + (size_t)b * N, s, exp_path, trajectories, normweights);
+  AllParticlesArgs a;
+  a.N = (int)N; a.D = (int)D; a.M = (int)M; a.T = h->cfg.nobs; a.Npad = h->geo.Npad; a.path_mode = h->geo.path_mode;
+  a.a_star = h->a_star.as<int>() ? h->a_star.as<int>() + (size_t)b * M : nullptr;
+  a.x_star = h->x_star.as<double>() ? h->x_star.as<double>() + (size_t)b * D * M : nullptr;
+  a.leaf = h->leaf_out.as<int>() ? h->leaf_out.as<int>() + (size_t)b * N : nullptr;
+  a.hist_x = h->hist_x.as<double>() ? h->hist_x.as<double>() + (size_t)b * h->geo.hist_x_elems : nullptr;
+  a.hist_a = h->hist_a.as<int>() ? h->hist_a.as<int>() + (size_t)b * h->geo.hist_a_elems : nullptr;
+  a.normw = h->normw.as<double>() + (size_t)b * N;
+  return api_all_particles(a, s, exp_path, trajectories, normweights);
 }
 
 int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory) {
@@ -363,8 +409,9 @@ int64_t cpimh_pf_device_bytes(const cpimh_pf* h) { return h ? h->bytes : 0; }
 int cpimh_pf_effective_config(const cpimh_pf* h, cpimh_config* out) {
   CPIMH_REQUIRE(h && out, "null argument");
   *out = h->cfg;
-  out->tree_capacity = h->geo.M;
+  out->tree_capacity = h->geo.path_mode == PATH_TREE ? h->geo.M : 0;
   out->threads_per_filter = h->geo.threads;
+  out->store_paths = h->geo.path_mode == PATH_NONE ? 0 : (h->geo.path_mode == PATH_DENSE ? 2 : 3);
   out->reserved = h->geo.blocks_per_sm;
   return CPIMH_OK;
 }
@@ -384,7 +431,8 @@ int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, u
     int M = h->geo.M;
     cpimh_pf_destroy(h);
     if (rc != CPIMH_ERR_TREE_OVERFLOW) return rc;
-    c.tree_capacity = 2 * M;          // Tree::double_size (src/tree.cpp:101-116): rerun with twice the capacity (same streams => same draws)
+    c.tree_capacity = 2 * M;
+    c.store_paths = 3;          // Tree::double_size (src/tree.cpp:101-116): rerun with twice the capacity (same streams => same draws)
   }
   return CPIMH_ERR_TREE_OVERFLOW;
 }

@@ -92,23 +92,24 @@ __global__ void tree_xgeneration_kernel(int N, int d, int lag, const int* a_star
 }
 // all-particle outputs of a finished filter (R/CPF.R:73-76, R/particlefilter.R:39-42): every leaf walks to the root
 // in lock step; per generation the weighted average (pf_get_weighted_average, R/CPF.R:84-92) is a block reduction.
-__global__ void all_paths_kernel(int N, int D, int M, int T, const int* a_star, const double* x_star /* [D][M] */, const int* leaf,
-                                 const double* normw, double* exp_path /* [T+1][D] or null */, double* paths /* [N][T+1][D] or null */, int* cur) {
+__global__ void all_paths_kernel(AllParticlesArgs a, double* exp_path /* [T+1][D] or null */, double* paths /* [N][T+1][D] or null */, int* cur) {
   __shared__ double scr[32];
-  for (int n = threadIdx.x; n < N; n += blockDim.x) cur[n] = leaf[n];
+  const int N = a.N, D = a.D, T = a.T;
+  const bool tree = a.path_mode == PATH_TREE;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) cur[n] = tree ? a.leaf[n] : n;
   __syncthreads();
   for (int step = T; step >= 0; step--) {
     for (int q = 0; q < D; q++) {
       double acc = 0;
       for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const double v = x_star[(size_t)q * M + cur[n]];
+        const double v = tree ? a.x_star[(size_t)q * a.M + cur[n]] : a.hist_x[((size_t)step * D + q) * a.Npad + cur[n]];
         if (paths) paths[((size_t)n * (T + 1) + step) * D + q] = v;
-        acc += v * normw[n];
+        acc += v * a.normw[n];
       }
       if (exp_path) { acc = block_sum(acc, scr); if (threadIdx.x == 0) exp_path[(size_t)step * D + q] = acc; }
     }
     __syncthreads();
-    if (step > 0) for (int n = threadIdx.x; n < N; n += blockDim.x) cur[n] = a_star[cur[n]];
+    if (step > 0) for (int n = threadIdx.x; n < N; n += blockDim.x) cur[n] = tree ? a.a_star[cur[n]] : a.hist_a[(size_t)(step - 1) * a.Npad + cur[n]];
     __syncthreads();
   }
 }
@@ -124,6 +125,7 @@ struct cpimh_chains {
   Geometry geo;
   int64_t maxR, lastR, launches;
   int record, max_rec, grid, npre;
+  DevBuf hist_x, hist_a;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, state, acc, scal, iscal, hbar, mt, it, status, nfilters, counter, sums;
   DevBuf samples1, samples2, log_pdf1, log_pdf2;
 };
@@ -137,7 +139,7 @@ extern "C" {
 
 int cpimh_chains_destroy(cpimh_chains* h) {
   if (!h) return CPIMH_OK;
-  DevBuf* all[] = {&h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
+  DevBuf* all[] = {&h->hist_x, &h->hist_a, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
                    &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2};
   for (auto b : all) b->release();
   delete h;
@@ -148,12 +150,12 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   CPIMH_REQUIRE(cfg_in && out, "null argument");
   CPIMH_REQUIRE(max_replicates >= 1, "max_replicates must be >= 1");
   cpimh_config cfg = *cfg_in;
-  cfg.store_paths = 1;                       // chain states are trajectories
+  if (cfg.store_paths == 0) cfg.store_paths = 1;   // chain states are trajectories
   int rc = api_validate(&cfg);
   if (rc) return rc;
   const ModelEntry* e = find_entry(cfg.model, cfg.dim);
   Geometry g;
-  rc = api_plan_geometry(cfg, e, true, &g);
+  rc = api_plan_geometry(cfg, e, true, max_replicates, &g);
   if (rc) return rc;
   cpimh_chains* h = new cpimh_chains();
   h->cfg = cfg; h->entry = e; h->geo = g; h->maxR = max_replicates; h->lastR = 0; h->launches = 0;
@@ -166,10 +168,16 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   rc = h->obs.alloc(sizeof(double) * T * cfg.dim_y);
   if (!rc) rc = h->theta.alloc(sizeof(double) * CPIMH_MAX_THETA);
   if (!rc) rc = h->pre.alloc(sizeof(double) * (pre.size() + 1));
-  if (!rc) rc = h->xbuf.alloc(sizeof(double) * G * 2 * D * g.Npad);
-  if (!rc) rc = h->a_star.alloc(sizeof(int) * G * g.M);
-  if (!rc) rc = h->o_star.alloc(sizeof(int) * G * g.M);
-  if (!rc) rc = h->x_star.alloc(sizeof(double) * G * D * g.M);
+  if (!rc && g.path_mode == PATH_DENSE) {
+    rc = h->hist_x.alloc(sizeof(double) * G * g.hist_x_elems);
+    if (!rc) rc = h->hist_a.alloc(sizeof(int) * G * g.hist_a_elems);
+  }
+  if (!rc && g.path_mode == PATH_TREE) {
+    rc = h->xbuf.alloc(sizeof(double) * G * 2 * D * g.Npad);
+    if (!rc) rc = h->a_star.alloc(sizeof(int) * G * g.M);
+    if (!rc) rc = h->o_star.alloc(sizeof(int) * G * g.M);
+    if (!rc) rc = h->x_star.alloc(sizeof(double) * G * D * g.M);
+  }
   if (!rc) rc = h->state.alloc(sizeof(double) * G * 3 * P * D);
   if (!rc) rc = h->acc.alloc(sizeof(double) * G * 2 * P * D);
   if (!rc) rc = h->scal.alloc(sizeof(double) * G * 4);
@@ -213,6 +221,7 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   api_fill_pf_params(h->cfg, h->geo, h->npre, &cp.pf);
   cp.pf.B = 0; cp.pf.seed = seed; cp.pf.first_filter = 0;
   cp.pf.obs = h->obs.as<double>(); cp.pf.theta = h->theta.as<double>(); cp.pf.pre = h->pre.as<double>();
+  cp.pf.hist_x = h->hist_x.as<double>(); cp.pf.hist_a = h->hist_a.as<int>();
   cp.pf.xbuf = h->xbuf.as<double>(); cp.pf.a_star = h->a_star.as<int>(); cp.pf.o_star = h->o_star.as<int>(); cp.pf.x_star = h->x_star.as<double>();
   cp.R = R; cp.first_replicate = first_replicate; cp.k = k; cp.K = K; cp.max_iterations = max_iterations < 0 ? 4095 : max_iterations;
   cp.state = h->state.as<double>(); cp.acc = h->acc.as<double>(); cp.scal = h->scal.as<double>(); cp.iscal = h->iscal.as<int>();
@@ -225,7 +234,7 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, sizeof(unsigned long long), s));
   CPIMH_CUDA_CHECK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), s));
   PfLaunch L;
-  L.threads = h->geo.threads; L.smem = h->geo.smem;
+  L.threads = h->geo.threads; L.smem = h->geo.smem; L.variant = h->geo.variant;
   L.grid = (int)(R < h->grid ? R : h->grid);
   int rc = h->entry->launch_chains(cp, L, s);
   if (rc) return rc;
@@ -296,6 +305,7 @@ int cpimh_coupled_pimh(const cpimh_config* cfg, const double* obs_host, int64_t 
     cpimh_chains_destroy(h);
     if (rc != CPIMH_ERR_TREE_OVERFLOW) return rc;
     c.tree_capacity = 2 * M;
+    c.store_paths = 3;
   }
   return CPIMH_ERR_TREE_OVERFLOW;
 }
@@ -484,23 +494,21 @@ int cpimh_tree_arrays(cpimh_tree* t, int32_t* a_star, int32_t* o_star, int32_t* 
 
 // ============================================================================ all-particle outputs of the filter handle
 namespace cpimh {
-int api_all_particles(int N, int D, int M, int T, const int* a_star, const double* x_star, const int* leaf, const double* normw,
-                      cudaStream_t s, double* h_exp_path, double* h_paths, double* h_normw) {
+int api_all_particles(const AllParticlesArgs& a, cudaStream_t s, double* h_exp_path, double* h_paths, double* h_normw) {
   DevBuf dexp, dpaths, dcur;
-  const size_t psz = (size_t)D * (T + 1);
-  int rc = dcur.alloc(sizeof(int) * (size_t)N);
+  const size_t psz = (size_t)a.D * (a.T + 1);
+  int rc = dcur.alloc(sizeof(int) * (size_t)a.N);
   if (!rc && h_exp_path) rc = dexp.alloc(sizeof(double) * psz);
-  if (!rc && h_paths) rc = dpaths.alloc(sizeof(double) * psz * N);
+  if (!rc && h_paths) rc = dpaths.alloc(sizeof(double) * psz * a.N);
   if (!rc && (h_exp_path || h_paths)) {
-    all_paths_kernel<<<1, 512, 0, s>>>(N, D, M, T, a_star, x_star, leaf, normw, h_exp_path ? dexp.as<double>() : nullptr,
-                                       h_paths ? dpaths.as<double>() : nullptr, dcur.as<int>());
+    all_paths_kernel<<<1, 512, 0, s>>>(a, h_exp_path ? dexp.as<double>() : nullptr, h_paths ? dpaths.as<double>() : nullptr, dcur.as<int>());
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && h_exp_path) e = cudaMemcpyAsync(h_exp_path, dexp.p, sizeof(double) * psz, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && h_paths) e = cudaMemcpyAsync(h_paths, dpaths.p, sizeof(double) * psz * N, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && h_paths) e = cudaMemcpyAsync(h_paths, dpaths.p, sizeof(double) * psz * a.N, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) { set_error("CUDA error in all_particles: %s", cudaGetErrorString(e)); rc = CPIMH_ERR_CUDA; }
   }
   if (!rc && h_normw) {
-    cudaError_t e = cudaMemcpyAsync(h_normw, normw, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaMemcpyAsync(h_normw, a.normw, sizeof(double) * (size_t)a.N, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) { set_error("CUDA error: %s", cudaGetErrorString(e)); rc = CPIMH_ERR_CUDA; }
   }
   cudaError_t e = cudaStreamSynchronize(s);

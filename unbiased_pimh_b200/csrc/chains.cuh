@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int D = Model::D;
   const PfParams& p = cp.pf;
-  PfSmem sm = pf_carve(smem_raw, p.Npad, p.M, p.npre);
+  PfSmem sm = pf_carve(smem_raw, p.Npad, p.M, p.npre, p.path_mode, p.shuffle);
   const int tid = threadIdx.x, NT = blockDim.x, P = p.T + 1;
   for (int i = tid; i < CPIMH_MAX_THETA; i += NT) sm.theta[i] = p.theta[i];
   for (int i = tid; i < p.npre; i += NT) sm.pre[i] = p.pre[i];
@@ -133,28 +133,31 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
   }
 }
 
+template <class Model, class F>
+int chains_with_kernel(int variant, F&& f) {
+  switch (variant) {
+    case PF_VARIANT_128x8: return f(chains_kernel<Model, 128, 8>);
+    case PF_VARIANT_256x3: return f(chains_kernel<Model, 256, 3>);
+    case PF_VARIANT_512x2: return f(chains_kernel<Model, 512, 2>);
+    default: return f(chains_kernel<Model, 1024, 1>);
+  }
+}
 template <class Model>
 int launch_chains(const ChainParams& cp, const PfLaunch& L, cudaStream_t stream) {
-  auto go = [&](auto kernel) -> int {
+  return chains_with_kernel<Model>(L.variant, [&](auto kernel) -> int {
     CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kernel<<<L.grid, L.threads, L.smem, stream>>>(cp);
     CPIMH_CUDA_CHECK(cudaGetLastError());
     return CPIMH_OK;
-  };
-  if (L.threads <= 256) return go(chains_kernel<Model, 256, 2>);
-  if (L.threads <= 512) return go(chains_kernel<Model, 512, 2>);
-  return go(chains_kernel<Model, 1024, 1>);
+  });
 }
 template <class Model>
-int occupancy_chains(int threads, size_t smem, int* blocks_per_sm) {
-  auto q = [&](auto kernel) -> int {
+int occupancy_chains(int variant, int threads, size_t smem, int* blocks_per_sm) {
+  return chains_with_kernel<Model>(variant, [&](auto kernel) -> int {
     CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CPIMH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem));
     return CPIMH_OK;
-  };
-  if (threads <= 256) return q(chains_kernel<Model, 256, 2>);
-  if (threads <= 512) return q(chains_kernel<Model, 512, 2>);
-  return q(chains_kernel<Model, 1024, 1>);
+  });
 }
 
 // ------------------------------------------------------------------ single model operations (primitive API)
@@ -193,7 +196,12 @@ __global__ void model_op_kernel(ModelOpParams q) {
     for (int k = 0; k < D; k++) x[k] = q.x[(size_t)i * D + k];
   }
   if (q.op == 0) Model::init(c, i, x);
-  else if (q.op == 1) { int st = Model::transition(c, q.time, i, x, Model::step_const(c, q.time)); if (st & 255) atomicOr(q.status, st & 255); }
+  else if (q.op == 1) {
+    double ua = 0.5, ub = 0.5;
+    if (Model::USES_SHARED_U && !c.inj_trans) philox_u2(c.stream, i, q.time, CPIMH_P_RESAMPLE, 0, ua, ub);
+    int st = Model::transition(c, q.time, i, x, Model::step_const(c, q.time), ub);
+    if (st & 255) atomicOr(q.status, st & 255);
+  }
   else { q.logw[i] = Model::logw(c, x, q.y); return; }
 #pragma unroll
   for (int k = 0; k < D; k++) q.x[(size_t)i * D + k] = x[k];

@@ -28,18 +28,24 @@ struct DevBuf {
 
 // launch geometry shared by the filter and the chain kernels
 struct Geometry {
-  int Npad, M, threads, blocks_per_sm, num_sms;
+  int Npad, M, threads, blocks_per_sm, num_sms, variant, path_mode;
   size_t smem;
+  size_t hist_x_elems, hist_a_elems;   // per workspace (PATH_DENSE)
 };
 
 int api_validate(cpimh_config* c);
-int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, Geometry* g);
+int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, int64_t max_items, Geometry* g);
 void api_fill_pf_params(const cpimh_config& c, const Geometry& g, int npre, PfParams* p);
 std::vector<double> api_precompute(const cpimh_config& c);
 int api_upload_obs(const cpimh_config& cfg, const double* obs_host, void* dst);
 int api_n_init(const cpimh_config& c);
 int api_n_trans(const cpimh_config& c);
-int api_all_particles(int N, int D, int M, int T, const int* a_star, const double* x_star, const int* leaf, const double* normw,
-                      cudaStream_t s, double* h_exp_path, double* h_paths, double* h_normw);
+struct AllParticlesArgs {
+  int N, D, M, T, Npad, path_mode;
+  const int* a_star; const double* x_star; const int* leaf;      // PATH_TREE
+  const double* hist_x; const int* hist_a;                       // PATH_DENSE
+  const double* normw;
+};
+int api_all_particles(const AllParticlesArgs& a, cudaStream_t s, double* h_exp_path, double* h_paths, double* h_normw);
 
 }  // namespace cpimh

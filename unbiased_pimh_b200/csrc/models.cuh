@@ -36,6 +36,7 @@ __device__ __forceinline__ const double* trans_row(const ModelCtx& c, int t, int
 struct GssModel {
   static constexpr int D = 1;
   static constexpr int NPRE = 0;
+  static constexpr bool USES_SHARED_U = false;
   __device__ static double step_const(const ModelCtx&, int t) { return 8.0 * cos(1.2 * (double)(t - 1)); }
   __device__ static void init(const ModelCtx& c, int i, double* x) {
     double z;
@@ -43,7 +44,7 @@ struct GssModel {
     else { double ua, ub, z1; philox_u2(c.stream, i, 0, CPIMH_P_INIT, 0, ua, ub); normal2(ua, ub, z, z1); }
     x[0] = sqrt(2.0) * z;
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double drift) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double drift, double /*ush*/) {
     double z;
     if (c.inj_trans) z = trans_row(c, t, 0)[i];
     else { double ua, ub, z1; philox_u2(c.stream, i, t, CPIMH_P_TRANS, 0, ua, ub); normal2(ua, ub, z, z1); }
@@ -62,6 +63,7 @@ template <int D_>
 struct ArModel {
   static constexpr int D = D_;
   static constexpr int NPRE = D_ * D_ + 1;     // A (column-major) + cst
+  static constexpr bool USES_SHARED_U = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll
@@ -79,7 +81,7 @@ struct ArModel {
       for (int k = 0; k < D; k++) x[k] = c.inj_init[(size_t)k * c.N + i];
     } else normals(c, i, 0, CPIMH_P_INIT, x);
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double /*ush*/) {
     double z[D], y[D];
     if (c.inj_trans) {
 #pragma unroll
@@ -106,25 +108,28 @@ struct ArModel {
 };
 
 // ------------------------------------------------------------------ get_levy_sv (d = 2; x = (v, z))
-__device__ __forceinline__ int poisson_inv(double rate, double u) {
-  double p = exp(-rate), F = p;
+// pre[0] = exp(-lambda), pre[1] = exp(-rate) with rate = lambda xi^2 / omega^2 (host precompute, libm like the oracle)
+__device__ __forceinline__ int poisson_inv(double rate, double exp_mrate, double u) {
+  double p = exp_mrate, F = p;
   int k = 0;
   while (u > F && k < 1000) { k++; p = p * rate / k; F += p; }
   return k;
 }
 struct LevySvModel {
   static constexpr int D = 2;
-  static constexpr int NPRE = 0;
-  __device__ static double step_const(const ModelCtx& c, int) { return exp(-c.theta[4]); }
+  static constexpr int NPRE = 2;
+  // the Poisson uniform of particle i at time t is the SECOND uniform of the Philox block whose first uniform is the
+  // resampling draw of slot i at time t (one Philox call serves both; DESIGN.md "RNG")
+  static constexpr bool USES_SHARED_U = true;
+  __device__ static double step_const(const ModelCtx& c, int) { return c.pre[0]; }
   // compound-Poisson sums over one unit interval (src/SVLevy_functions.cpp:61-67)
-  __device__ static void jump_sums(const ModelCtx& c, int i, int t, double& swe, double& se) {
+  __device__ static void jump_sums(const ModelCtx& c, int i, int t, double upois, double& swe, double& se) {
     const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
-    double ua, ub;
-    philox_u2(c.stream, i, t, CPIMH_P_TRANS, 0, ua, ub);
-    int k = poisson_inv(lambda * xi * xi / w2, ua);
+    int k = poisson_inv(lambda * xi * xi / w2, c.pre[1], upois);
     double a = 0.0, b = 0.0;
     const double escale = w2 / xi;
     for (int j = 1; j <= k; j++) {
+      double ua, ub;
       philox_u2(c.stream, i, t, CPIMH_P_TRANS, j, ua, ub);
       double e = -log(ub) * escale;
       a += exp(-lambda * ua) * e;
@@ -155,16 +160,21 @@ struct LevySvModel {
     const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
     double z0, swe, se;
     if (c.inj_init) { z0 = c.inj_init[i]; swe = c.inj_init[(size_t)c.N + i]; se = c.inj_init[(size_t)2 * c.N + i]; }
-    else { z0 = gamma_mt(c, i, xi * xi / w2, w2 / xi); jump_sums(c, i, 0, swe, se); }
-    double z1 = exp(-lambda) * z0 + swe;
+    else {
+      z0 = gamma_mt(c, i, xi * xi / w2, w2 / xi);
+      double ua, ub;
+      philox_u2(c.stream, i, 0, CPIMH_P_RESAMPLE, 0, ua, ub);
+      jump_sums(c, i, 0, ub, swe, se);
+    }
+    double z1 = c.pre[0] * z0 + swe;
     x[0] = (1.0 / lambda) * (z0 - z1 + se);
     x[1] = z1;
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double expml) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double expml, double ush) {
     const double lambda = c.theta[4];
     double swe, se;
     if (c.inj_trans) { swe = trans_row(c, t, 0)[i]; se = trans_row(c, t, 1)[i]; }
-    else jump_sums(c, i, t, swe, se);
+    else jump_sums(c, i, t, ush, swe, se);
     double zold = x[1];
     double znew = expml * zold + swe;
     x[0] = (1.0 / lambda) * (zold - znew + se);
@@ -180,10 +190,11 @@ struct LevySvModel {
 struct SkModel {
   static constexpr int D = 4;
   static constexpr int NPRE = 0;
+  static constexpr bool USES_SHARED_U = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void init(const ModelCtx&, int, double* x) { x[0] = 8.0; x[1] = 8.0; x[2] = 8.0; x[3] = 5.0; }
   // returns 0, or CPIMH_ERR_NOISE_OVERFLOW when the injected event budget is exhausted; bit 8 set if an event index was clamped
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double /*ush*/) {
     double tcur = 0.0;
     int flags = 0;
     for (int m = 0;; m++) {
@@ -328,6 +339,7 @@ template <int D_>
 struct LorenzModel {
   static constexpr int D = D_;
   static constexpr int NPRE = 1;     // cst of the measurement density
+  static constexpr bool USES_SHARED_U = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll
@@ -348,7 +360,7 @@ struct LorenzModel {
 #pragma unroll
     for (int k = 0; k < D; k++) x[k] = -1.0 + 4.0 * (0.5 * erfc(-z[k] / sqrt(2.0)));   // -1 + 4 pnorm(z)
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double /*ush*/) {
     const double F = c.theta[0], sx = c.theta[1];
     double z[D];
     if (c.inj_trans) {

@@ -3,31 +3,44 @@
 // One iteration of the loop below is one iteration of the reference's hot loop R/CPF.R:35-67
 // (== R/particlefilter.R:22-38): multinomial resampling (src/multinomial.cpp:13-32) -> gather ->
 // rtransition -> dmeasurement -> weight normalisation + log Z increment (R/CPF.R:61-66) ->
-// Tree$update (src/tree.cpp:88-99).  Weights/CDF, sorted uniforms/log-weights, leaf slots, parent
-// slots, offspring counts and the tree's free-slot bitmap stay in shared memory for the whole filter;
-// HBM sees only the particle state (SoA, double-buffered) and the ancestor tree.
+// path storage (Tree$update, src/tree.cpp:88-99).  Weights/CDF and sorted uniforms/log-weights stay in shared
+// memory for the whole filter.
+//
+// Path storage has two layouts (PfParams::path_mode):
+//   PATH_DENSE  the particle history itself: hist_x[t][q][i] (SoA) and hist_a[t][i].  Step t gathers from
+//               hist_x[t-1] and writes hist_x[t], so the state double buffer and the path store are the same
+//               bytes; nothing is pruned, get_path() is a walk over hist_a.  This is the B200 layout
+//               (180 GB of HBM; (T+1) N (8d+4) bytes per resident CTA).
+//   PATH_TREE   the reference's Jacob-Murray-Rubenthaler tree (a_star/o_star/x_star/l_star, prune + insert into
+//               the first free slots) with leaf slots, parent slots, offspring counters and the free-slot
+//               bitmap in shared memory; O(N log N) nodes, for histories that do not fit in HBM.
 #pragma once
 #include "common.cuh"
 #include "models.cuh"
 
 namespace cpimh {
 
+enum { PATH_NONE = 0, PATH_DENSE = 1, PATH_TREE = 2 };
+#define CPIMH_MAX_E 32        // particles per thread (N <= CPIMH_MAX_E * blockDim.x)
+
 struct PfParams {
   int N, T, dy, Npad;
   int M;                       // tree capacity per filter (multiple of 32)
   long long B;                 // filters in this launch
-  int shuffle, store_paths;
+  int shuffle, path_mode;
   unsigned long long seed, first_filter;
   const double* obs;           // [T][dy] row-major (device)
   const double* theta;         // [CPIMH_MAX_THETA]
   const double* pre;           // [npre]
   int npre;
   int integrator, substeps;
-  // workspaces (indexed by workspace slot)
-  double* xbuf;                // [ws][2][D][Npad]
-  int* a_star;                 // [ws][M]
-  int* o_star;                 // [ws][M]
-  double* x_star;              // [ws][D][M]
+  // workspaces (indexed by workspace slot = blockIdx.x)
+  double* xbuf;                // PATH_NONE/TREE: [ws][2][D][Npad]
+  double* hist_x;              // PATH_DENSE:     [ws][T+1][D][Npad]
+  int* hist_a;                 // PATH_DENSE:     [ws][T][Npad]
+  int* a_star;                 // PATH_TREE:      [ws][M]
+  int* o_star;                 // PATH_TREE:      [ws][M]
+  double* x_star;              // PATH_TREE:      [ws][D][M]
   // outputs (indexed by filter)
   double* logz;                // [B]
   double* logz_t;              // [B][T] or null
@@ -35,7 +48,7 @@ struct PfParams {
   int* path_index;             // [B] or null
   int* status;                 // [B]
   double* normw;               // [B][N] or null (final normalised weights)
-  int* leaf_out;               // [B][N] or null (final leaf slots)
+  int* leaf_out;               // [ws][N] or null (PATH_TREE: final leaf slots)
   int* anc_rec;                // [B][T][N] or null
   // injected noise (device) or null
   const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_shuffle; const double* inj_path;
@@ -45,26 +58,30 @@ struct PfParams {
 struct PfSmem {
   double* C;        // [Npad] normalised weights, then their inclusive CDF
   double* S;        // [Npad] log(u)/i -> suffix sums -> log-weights
-  int* leaf;        // [Npad] l_star
-  int* bpar;        // [Npad] ancestors, then parent slots b = l_star[a]
-  unsigned* off32;  // [Npad/2] 16-bit offspring counters
-  unsigned* bits;   // [M/32] free-slot bitmap (1 = free)
+  int* leaf;        // [Npad] l_star                                   (PATH_TREE, or shuffle scratch)
+  int* bpar;        // [Npad] ancestors, then parent slots b = l_star[a] (PATH_TREE, or shuffle scratch)
+  unsigned* off32;  // [Npad/2] 16-bit offspring counters              (PATH_TREE)
+  unsigned* bits;   // [M/32] free-slot bitmap (1 = free)              (PATH_TREE)
   double* theta;    // [CPIMH_MAX_THETA]
   double* pre;      // [npre]
   double* dscr;     // [32]
-  int* iscr;        // [34]  (32 scan scratch, [32] status flag, [33] spare)
+  int* iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
 };
-__host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre) {
+__host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
   size_t b = 0;
   b += (size_t)Npad * 8 * 2;                 // C, S
   b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 32) * 8;
-  b += (size_t)Npad * 4 * 2;                 // leaf, bpar
-  b += (size_t)(Npad / 2) * 4;               // off32
-  b += (size_t)(M / 32) * 4;                 // bits
+  if (path_mode == PATH_TREE) {
+    b += (size_t)Npad * 4 * 2;               // leaf, bpar
+    b += (size_t)(Npad / 2) * 4;             // off32
+    b += (size_t)(M / 32) * 4;               // bits
+  } else if (shuffle) {
+    b += (size_t)Npad * 4;                   // bpar (ancestors to permute)
+  }
   b += 36 * 4;
   return (b + 15) & ~(size_t)15;
 }
-__device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre) {
+__device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre, int path_mode, int shuffle) {
   PfSmem s;
   double* d = reinterpret_cast<double*>(raw);
   s.C = d; d += Npad;
@@ -73,10 +90,15 @@ __device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre)
   s.pre = d; d += npre + (npre & 1);
   s.dscr = d; d += 32;
   int* i = reinterpret_cast<int*>(d);
-  s.leaf = i; i += Npad;
-  s.bpar = i; i += Npad;
-  s.off32 = reinterpret_cast<unsigned*>(i); i += Npad / 2;
-  s.bits = reinterpret_cast<unsigned*>(i); i += M / 32;
+  s.leaf = nullptr; s.bpar = nullptr; s.off32 = nullptr; s.bits = nullptr;
+  if (path_mode == PATH_TREE) {
+    s.leaf = i; i += Npad;
+    s.bpar = i; i += Npad;
+    s.off32 = reinterpret_cast<unsigned*>(i); i += Npad / 2;
+    s.bits = reinterpret_cast<unsigned*>(i); i += M / 32;
+  } else if (shuffle) {
+    s.bpar = i; i += Npad;
+  }
   s.iscr = i;
   return s;
 }
@@ -94,11 +116,22 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   constexpr int D = Model::D;
   const int tid = threadIdx.x, NT = blockDim.x;
   const int N = p.N, T = p.T, Npad = p.Npad, M = p.M, W = M >> 5;
-  double* xold = p.xbuf + (size_t)ws * 2 * D * Npad;
-  double* xnew = xold + (size_t)D * Npad;
-  int* a_star = p.a_star + (size_t)ws * M;
-  int* o_star = p.o_star + (size_t)ws * M;
-  double* x_star = p.x_star + (size_t)ws * D * M;
+  const bool tree = p.path_mode == PATH_TREE, dense = p.path_mode == PATH_DENSE;
+  const size_t xstride = (size_t)D * Npad;
+  double* xold;                // state at time t-1 (SoA [D][Npad])
+  double* xnew;
+  int* hist_a = nullptr;
+  if (dense) {
+    xold = p.hist_x + (size_t)ws * (T + 1) * xstride;
+    xnew = xold + xstride;
+    hist_a = p.hist_a + (size_t)ws * T * Npad;
+  } else {
+    xold = p.xbuf + (size_t)ws * 2 * xstride;
+    xnew = xold + xstride;
+  }
+  int* a_star = tree ? p.a_star + (size_t)ws * M : nullptr;
+  int* o_star = tree ? p.o_star + (size_t)ws * M : nullptr;
+  double* x_star = tree ? p.x_star + (size_t)ws * D * M : nullptr;
 
   ModelCtx c;
   c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
@@ -107,8 +140,9 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   c.n_trans = p.n_trans; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
   const double* inj_res = p.inj_resample ? p.inj_resample + (size_t)inj * T * N : nullptr;
   const double* inj_shf = p.inj_shuffle ? p.inj_shuffle + (size_t)inj * T * (N - 1) : nullptr;
-  const bool tree = p.store_paths != 0;
+  const bool need_shared_u = Model::USES_SHARED_U && !c.inj_trans;
   int st = 0;
+  double ukeep[CPIMH_MAX_E];   // second uniform of each owned particle's resampling Philox block (local memory)
 
   // ---------------- initialisation: R/CPF.R:17-28, Tree::Tree + Tree::init (src/tree.cpp:6-34)
   if (tid == 0) sm.iscr[32] = 0;
@@ -143,18 +177,24 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     double sumw = 1.0;
 
     // -- sorted uniforms (src/multinomial.cpp:18-24) and CDF (:17); zero the offspring counters
-    for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
-    if (!ident) {
-      if (inj_res) {
-        for (int i = tid; i < N; i += NT) sm.S[i] = inj_res[(size_t)(t - 1) * N + i];
-      } else {
-        for (int i = tid; i < N; i += NT) sm.S[i] = log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0)) / (double)(i + 1);
+    if (tree) for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
+    const bool draw_res = !ident && !inj_res;
+    if (draw_res || need_shared_u) {
+      int e = 0;
+      for (int i = tid; i < N; i += NT, e++) {
+        double ua, ub;
+        philox_u2(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, ub);
+        if (draw_res) sm.S[i] = log(ua) / (double)(i + 1);
+        ukeep[e] = ub;
       }
+    }
+    if (!ident) {
+      if (inj_res) for (int i = tid; i < N; i += NT) sm.S[i] = inj_res[(size_t)(t - 1) * N + i];
       __syncthreads();
       block_scan_inplace<false>(sm.C, N, sm.dscr);
       if (!inj_res) block_scan_inplace<true>(sm.S, N, sm.dscr);
       sumw = sm.C[N - 1];
-    } else {
+    } else if (tree) {
       __syncthreads();
     }
 
@@ -166,16 +206,17 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       if (a >= N) { a = N - 1; st |= 512; }
       return a;
     };
-    // -- gather (R/CPF.R:41) -> rtransition (:44) -> dmeasurement (:60) ; tree bookkeeping part 1 (src/tree.cpp:39-42, 90-94)
-    auto propagate = [&](int k, int a) {
+    // -- gather (R/CPF.R:41) -> rtransition (:44) -> dmeasurement (:60) ; path bookkeeping
+    auto propagate = [&](int k, int a, int e) {
       double x[D];
 #pragma unroll
       for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
-      st |= Model::transition(c, t, k, x, sc);
+      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[e] : 0.5);
 #pragma unroll
       for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
       sm.S[k] = Model::logw(c, x, y);
-      if (tree) {
+      if (dense) hist_a[(size_t)(t - 1) * Npad + k] = a;
+      if (tree) {                                      // src/tree.cpp:39-42, 90-94
         sm.bpar[k] = sm.leaf[a];
         atomicAdd(&sm.off32[a >> 1], 1u << ((a & 1) << 4));
       }
@@ -195,9 +236,11 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       if (tid == 0)
         for (int i = 1; i < N; i++) { int j = jidx[i]; int tmp = sm.bpar[i]; sm.bpar[i] = sm.bpar[j]; sm.bpar[j] = tmp; }
       __syncthreads();
-      for (int k = tid; k < N; k += NT) propagate(k, sm.bpar[k]);
+      int e = 0;
+      for (int k = tid; k < N; k += NT, e++) propagate(k, sm.bpar[k], e);
     } else {
-      for (int k = tid; k < N; k += NT) propagate(k, ancestor_of(k));
+      int e = 0;
+      for (int k = tid; k < N; k += NT, e++) propagate(k, ancestor_of(k), e);
     }
     __syncthreads();
 
@@ -261,7 +304,8 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         for (int q = 0; q < D; q++) x_star[(size_t)q * M + slot] = xnew[(size_t)q * Npad + k];
       }
     }
-    { double* tmp = xold; xold = xnew; xnew = tmp; }
+    if (dense) { xold = xnew; xnew = xnew + xstride; }
+    else { double* tmp = xold; xold = xnew; xnew = tmp; }
     __syncthreads();
   }
 
@@ -278,14 +322,22 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   if (tid == 0) {
     *out.logz = logz_sum;
     if (out.path_index) *out.path_index = kidx;
-    int code = flags & 255;
-    *out.status = code ? code : 0;
+    *out.status = flags & 255;
   }
-  if (tree && out.traj && tid < 32) {       // Tree::get_path (src/tree.cpp:118-129): one warp, lane q carries component q
-    int j = sm.leaf[kidx];
-    for (int step = T; step >= 0; step--) {
-      for (int q = tid; q < D; q += 32) out.traj[(size_t)step * D + q] = x_star[(size_t)q * M + j];
-      j = a_star[j];
+  if (out.traj && tid < 32) {               // Tree::get_path (src/tree.cpp:118-129): one warp, lane q carries component q
+    if (tree) {
+      int j = sm.leaf[kidx];
+      for (int step = T; step >= 0; step--) {
+        for (int q = tid; q < D; q += 32) out.traj[(size_t)step * D + q] = x_star[(size_t)q * M + j];
+        j = a_star[j];
+      }
+    } else if (dense) {
+      const double* hx = p.hist_x + (size_t)ws * (T + 1) * xstride;
+      int j = kidx;
+      for (int step = T; step >= 0; step--) {
+        for (int q = tid; q < D; q += 32) out.traj[(size_t)step * D + q] = hx[(size_t)step * xstride + (size_t)q * Npad + j];
+        if (step > 0) j = hist_a[(size_t)(step - 1) * Npad + j];
+      }
     }
   }
   __syncthreads();
@@ -294,7 +346,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
 template <class Model, int NT_MAX, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PfSmem sm = pf_carve(smem_raw, p.Npad, p.M, p.npre);
+  PfSmem sm = pf_carve(smem_raw, p.Npad, p.M, p.npre, p.path_mode, p.shuffle);
   for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
   for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
   __syncthreads();
@@ -307,36 +359,43 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p
     out.path_index = p.path_index ? p.path_index + b : nullptr;
     out.status = p.status + b;
     out.normw = p.normw ? p.normw + (size_t)b * p.N : nullptr;
-    out.leaf_out = p.leaf_out ? p.leaf_out + (size_t)b * p.N : nullptr;
+    out.leaf_out = p.leaf_out ? p.leaf_out + (size_t)blockIdx.x * p.N : nullptr;
     out.anc_rec = p.anc_rec ? p.anc_rec + (size_t)b * p.T * p.N : nullptr;
-    run_filter<Model>(p, sm, b, s, b, out);
+    run_filter<Model>(p, sm, blockIdx.x, s, b, out);
   }
 }
 
-// host-side launcher shared by the per-model translation units
-struct PfLaunch { int threads; int grid; size_t smem; };
+// host-side launcher shared by the per-model translation units.  Kernel variants by CTA size / residency target.
+struct PfLaunch { int threads; int grid; size_t smem; int variant; };
+enum { PF_VARIANT_128x8 = 0, PF_VARIANT_256x3 = 1, PF_VARIANT_512x2 = 2, PF_VARIANT_1024x1 = 3, PF_NUM_VARIANTS = 4 };
+inline int pf_variant_threads(int v) { return v == PF_VARIANT_128x8 ? 128 : v == PF_VARIANT_256x3 ? 256 : v == PF_VARIANT_512x2 ? 512 : 1024; }
+inline int pf_variant_for(int threads) { return threads <= 128 ? PF_VARIANT_128x8 : threads <= 256 ? PF_VARIANT_256x3 : threads <= 512 ? PF_VARIANT_512x2 : PF_VARIANT_1024x1; }
+
+template <class Model, class F>
+int pf_with_kernel(int variant, F&& f) {
+  switch (variant) {
+    case PF_VARIANT_128x8: return f(pf_batch_kernel<Model, 128, 8>);
+    case PF_VARIANT_256x3: return f(pf_batch_kernel<Model, 256, 3>);
+    case PF_VARIANT_512x2: return f(pf_batch_kernel<Model, 512, 2>);
+    default: return f(pf_batch_kernel<Model, 1024, 1>);
+  }
+}
 template <class Model>
 int launch_pf_batch(const PfParams& p, const PfLaunch& L, cudaStream_t stream) {
-  auto go = [&](auto kernel) -> int {
+  return pf_with_kernel<Model>(L.variant, [&](auto kernel) -> int {
     CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kernel<<<L.grid, L.threads, L.smem, stream>>>(p);
     CPIMH_CUDA_CHECK(cudaGetLastError());
     return CPIMH_OK;
-  };
-  if (L.threads <= 256) return go(pf_batch_kernel<Model, 256, 2>);
-  if (L.threads <= 512) return go(pf_batch_kernel<Model, 512, 2>);
-  return go(pf_batch_kernel<Model, 1024, 1>);
+  });
 }
 template <class Model>
-int occupancy_pf_batch(int threads, size_t smem, int* blocks_per_sm) {
-  auto q = [&](auto kernel) -> int {
+int occupancy_pf_batch(int variant, int threads, size_t smem, int* blocks_per_sm) {
+  return pf_with_kernel<Model>(variant, [&](auto kernel) -> int {
     CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CPIMH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem));
     return CPIMH_OK;
-  };
-  if (threads <= 256) return q(pf_batch_kernel<Model, 256, 2>);
-  if (threads <= 512) return q(pf_batch_kernel<Model, 512, 2>);
-  return q(pf_batch_kernel<Model, 1024, 1>);
+  });
 }
 
 }  // namespace cpimh

@@ -10,9 +10,9 @@ struct ModelEntry {
   int dim;
   int npre;
   int (*launch_pf)(const PfParams&, const PfLaunch&, cudaStream_t);
-  int (*occupancy_pf)(int threads, size_t smem, int* blocks_per_sm);
+  int (*occupancy_pf)(int variant, int threads, size_t smem, int* blocks_per_sm);
   int (*launch_chains)(const ChainParams&, const PfLaunch&, cudaStream_t);
-  int (*occupancy_chains)(int threads, size_t smem, int* blocks_per_sm);
+  int (*occupancy_chains)(int variant, int threads, size_t smem, int* blocks_per_sm);
   int (*launch_model_op)(const ModelOpParams&, cudaStream_t);
 };
 template <class Model>

@@ -108,7 +108,8 @@ class PfBatch:
     def effective_config(self):
         c = L.Config()
         L.check(L.lib().cpimh_pf_effective_config(self.h, C.byref(c)))
-        return {"tree_capacity": c.tree_capacity, "threads_per_filter": c.threads_per_filter, "ctas_per_sm": c.reserved}
+        return {"tree_capacity": c.tree_capacity, "threads_per_filter": c.threads_per_filter, "ctas_per_sm": c.reserved,
+                "path_storage": {0: "none", 2: "dense", 3: "tree"}.get(c.store_paths, str(c.store_paths))}
 
 
 def cpf_batch(nparticles, model, theta, observations, nfilters, seed=None, first_filter=0, noise=None, logz_t=False, **kw):
