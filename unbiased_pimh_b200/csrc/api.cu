@@ -58,8 +58,24 @@ std::vector<double> api_precompute(const cpimh_config& c) {
     for (int i = 0; i < d; i++) hl += log(c.theta[1]);
     pre[(size_t)d * d] = -(hl) - (d * CPIMH_HALF_LOG_2PI_TRUNC);
   } else if (c.model == CPIMH_MODEL_LEVY_SV) {
-    pre.push_back(exp(-c.theta[4]));                                        // src/SVLevy_functions.cpp:66 exp(-lambda)
-    pre.push_back(exp(-(c.theta[4] * c.theta[2] * c.theta[2] / c.theta[3])));  // P[k = 0] of rpois(lambda xi^2 / w2) (:61)
+    const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
+    pre.push_back(exp(-lambda));                       // src/SVLevy_functions.cpp:66 exp(-lambda)
+    pre.push_back(1 / lambda);                         // :67 (1/lambda)
+    pre.push_back(w2 / xi);                            // rexp(k, xi/w2) = exp_rand() * (w2/xi) (:63)
+    // CDF of rpois(lambda xi^2 / w2) (:61) by the sequential-search recurrence, until it stops increasing
+    const double rate = lambda * xi * xi / w2;
+    std::vector<double> F;
+    double p = exp(-rate), acc = p;
+    F.push_back(acc);
+    for (int k = 1; k < 1000; k++) {
+      p = p * rate / k;
+      const double nxt = acc + p;
+      if (nxt == acc) break;
+      acc = nxt;
+      F.push_back(acc);
+    }
+    pre.push_back((double)F.size());
+    pre.insert(pre.end(), F.begin(), F.end());
   } else if (c.model == CPIMH_MODEL_LORENZ) {
     double hl = 0;
     for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);
@@ -92,7 +108,7 @@ int api_validate(cpimh_config* cp) {
 
 // launch geometry shared by the filter and the chain kernels
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, int64_t max_items, Geometry* g) {
+int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, int64_t max_items, int npre, Geometry* g) {
   int dev = 0;
   CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -120,7 +136,7 @@ int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, i
     return (Mwant + 31) & ~31LL;
   };
   auto occupancy = [&](int mode, int M, size_t* smem, int* bps) -> int {
-    *smem = pf_smem_bytes(g->Npad, M, e->npre, mode, c.shuffle);
+    *smem = pf_smem_bytes(g->Npad, M, npre, mode, c.shuffle);
     if (*smem > max_smem) { *bps = 0; return CPIMH_OK; }
     return chains ? e->occupancy_chains(g->variant, threads, *smem, bps) : e->occupancy_pf(g->variant, threads, *smem, bps);
   };
@@ -195,14 +211,14 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   int rc = api_validate(&cfg);
   if (rc) return rc;
   const ModelEntry* e = find_entry(cfg.model, cfg.dim);
+  std::vector<double> pre = api_precompute(cfg);
   Geometry g;
-  rc = api_plan_geometry(cfg, e, false, max_filters, &g);
+  rc = api_plan_geometry(cfg, e, false, max_filters, (int)pre.size(), &g);
   if (rc) return rc;
   cpimh_pf* h = new cpimh_pf();
   h->cfg = cfg; h->entry = e; h->geo = g; h->maxB = max_filters; h->lastB = 0; h->record_anc = 0; h->launches = 0; h->bytes = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
   const int D = cfg.dim, N = cfg.nparticles, T = cfg.nobs;
-  std::vector<double> pre = api_precompute(cfg);
   h->npre = (int)pre.size();
   const size_t B = (size_t)max_filters;
   auto A = [&](DevBuf& b, size_t n) { return b.alloc(n, &h->bytes); };

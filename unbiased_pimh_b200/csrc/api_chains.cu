@@ -154,8 +154,9 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   int rc = api_validate(&cfg);
   if (rc) return rc;
   const ModelEntry* e = find_entry(cfg.model, cfg.dim);
+  std::vector<double> pre = api_precompute(cfg);
   Geometry g;
-  rc = api_plan_geometry(cfg, e, true, max_replicates, &g);
+  rc = api_plan_geometry(cfg, e, true, max_replicates, (int)pre.size(), &g);
   if (rc) return rc;
   cpimh_chains* h = new cpimh_chains();
   h->cfg = cfg; h->entry = e; h->geo = g; h->maxR = max_replicates; h->lastR = 0; h->launches = 0;
@@ -163,7 +164,6 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   const int64_t resident = (int64_t)g.blocks_per_sm * g.num_sms;
   h->grid = (int)(max_replicates < resident ? max_replicates : resident);
   const size_t G = (size_t)h->grid, D = cfg.dim, T = cfg.nobs, P = T + 1, R = (size_t)max_replicates;
-  std::vector<double> pre = api_precompute(cfg);
   h->npre = (int)pre.size();
   rc = h->obs.alloc(sizeof(double) * T * cfg.dim_y);
   if (!rc) rc = h->theta.alloc(sizeof(double) * CPIMH_MAX_THETA);

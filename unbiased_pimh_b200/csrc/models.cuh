@@ -35,8 +35,8 @@ __device__ __forceinline__ const double* trans_row(const ModelCtx& c, int t, int
 // ------------------------------------------------------------------ get_gss (d = 1)
 struct GssModel {
   static constexpr int D = 1;
-  static constexpr int NPRE = 0;
   static constexpr bool USES_SHARED_U = false;
+  static constexpr bool MULTI = false;
   __device__ static double step_const(const ModelCtx&, int t) { return 8.0 * cos(1.2 * (double)(t - 1)); }
   __device__ static void init(const ModelCtx& c, int i, double* x) {
     double z;
@@ -62,8 +62,8 @@ struct GssModel {
 template <int D_>
 struct ArModel {
   static constexpr int D = D_;
-  static constexpr int NPRE = D_ * D_ + 1;     // A (column-major) + cst
-  static constexpr bool USES_SHARED_U = false;
+  static constexpr bool USES_SHARED_U = false;   // pre = A (column-major, D*D) then cst
+  static constexpr bool MULTI = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll
@@ -108,31 +108,38 @@ struct ArModel {
 };
 
 // ------------------------------------------------------------------ get_levy_sv (d = 2; x = (v, z))
-// pre[0] = exp(-lambda), pre[1] = exp(-rate) with rate = lambda xi^2 / omega^2 (host precompute, libm like the oracle)
-__device__ __forceinline__ int poisson_inv(double rate, double exp_mrate, double u) {
-  double p = exp_mrate, F = p;
+// Host precompute (api.cu, libm like the oracle): pre[0] = exp(-lambda), pre[1] = 1/lambda, pre[2] = omega^2/xi
+// (scale of the exponential jumps), pre[3] = L, pre[4..4+L) = F_0..F_{L-1}: the CDF of rpois(lambda xi^2/omega^2)
+// built by the recurrence p_k = p_{k-1} rate / k, F_k = F_{k-1} + p_k until it stops increasing.
+#define CPIMH_MULTI_MAX_E 16
+__device__ __forceinline__ int poisson_tab(const double* pre, double u) {
+  const int L = (int)pre[3];
+  const double* F = pre + 4;
   int k = 0;
-  while (u > F && k < 1000) { k++; p = p * rate / k; F += p; }
-  return k;
+  while (k < L && u > F[k]) k++;
+  return k == L ? 1000 : k;          // beyond the saturated CDF the sequential search only stops at its cap of 1000
 }
 struct LevySvModel {
   static constexpr int D = 2;
-  static constexpr int NPRE = 2;
   // the Poisson uniform of particle i at time t is the SECOND uniform of the Philox block whose first uniform is the
   // resampling draw of slot i at time t (one Philox call serves both; DESIGN.md "RNG")
   static constexpr bool USES_SHARED_U = true;
+  static constexpr bool MULTI = true;
   __device__ static double step_const(const ModelCtx& c, int) { return c.pre[0]; }
-  // compound-Poisson sums over one unit interval (src/SVLevy_functions.cpp:61-67)
+  // one jump of the compound Poisson process (src/SVLevy_functions.cpp:62-67): c' = t - c ~ U(0,1), e ~ Exp(rate xi/w2)
+  __device__ static __forceinline__ void jump(const ModelCtx& c, int i, int t, int j, double& wa, double& e) {
+    double ua, ub;
+    philox_u2(c.stream, i, t, CPIMH_P_TRANS, j, ua, ub);
+    e = -log(ub) * c.pre[2];
+    wa = exp(-c.theta[4] * ua) * e;
+  }
   __device__ static void jump_sums(const ModelCtx& c, int i, int t, double upois, double& swe, double& se) {
-    const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
-    int k = poisson_inv(lambda * xi * xi / w2, c.pre[1], upois);
+    int k = poisson_tab(c.pre, upois);
     double a = 0.0, b = 0.0;
-    const double escale = w2 / xi;
     for (int j = 1; j <= k; j++) {
-      double ua, ub;
-      philox_u2(c.stream, i, t, CPIMH_P_TRANS, j, ua, ub);
-      double e = -log(ub) * escale;
-      a += exp(-lambda * ua) * e;
+      double wa, e;
+      jump(c, i, t, j, wa, e);
+      a += wa;
       b += e;
     }
     swe = a; se = b;
@@ -157,7 +164,7 @@ struct LevySvModel {
     return shape * scale;
   }
   __device__ static void init(const ModelCtx& c, int i, double* x) {
-    const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
+    const double xi = c.theta[2], w2 = c.theta[3];
     double z0, swe, se;
     if (c.inj_init) { z0 = c.inj_init[i]; swe = c.inj_init[(size_t)c.N + i]; se = c.inj_init[(size_t)2 * c.N + i]; }
     else {
@@ -167,72 +174,132 @@ struct LevySvModel {
       jump_sums(c, i, 0, ub, swe, se);
     }
     double z1 = c.pre[0] * z0 + swe;
-    x[0] = (1.0 / lambda) * (z0 - z1 + se);
+    x[0] = c.pre[1] * (z0 - z1 + se);
     x[1] = z1;
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double expml, double ush) {
-    const double lambda = c.theta[4];
+  __device__ static __forceinline__ void finish(const ModelCtx& c, double* x, double swe, double se) {
+    double zold = x[1];
+    double znew = c.pre[0] * zold + swe;                 // src/SVLevy_functions.cpp:66
+    x[0] = c.pre[1] * (zold - znew + se);                // :67
+    x[1] = znew;
+  }
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double ush) {
     double swe, se;
     if (c.inj_trans) { swe = trans_row(c, t, 0)[i]; se = trans_row(c, t, 1)[i]; }
     else jump_sums(c, i, t, ush, swe, se);
-    double zold = x[1];
-    double znew = expml * zold + swe;
-    x[0] = (1.0 / lambda) * (zold - znew + se);
-    x[1] = znew;
+    finish(c, x, swe, se);
+    return 0;
+  }
+  // All E particles owned by one thread (particle e has index i0 + e*stride).  The jumps of the thread's particles are
+  // walked as ONE list, so a lane is busy for (its total number of jumps) iterations instead of every lane waiting for
+  // the warp-wide maximum per particle: Poisson(0.37) jump counts leave ~18 % of the lanes active otherwise.
+  __device__ static int transition_multi(const ModelCtx& c, int t, int E, int i0, int stride, double (*x)[2], const double* ush, double) {
+    if (c.inj_trans) {
+      for (int e = 0; e < E; e++) { const int i = i0 + e * stride; finish(c, x[e], trans_row(c, t, 0)[i], trans_row(c, t, 1)[i]); }
+      return 0;
+    }
+    int kk[CPIMH_MULTI_MAX_E];
+    double swe[CPIMH_MULTI_MAX_E], se[CPIMH_MULTI_MAX_E];
+    int e = E;
+    for (int q = E - 1; q >= 0; q--) { kk[q] = poisson_tab(c.pre, ush[q]); swe[q] = 0.0; se[q] = 0.0; if (kk[q] > 0) e = q; }
+    int j = 1;
+    while (e < E) {
+      double wa, ev;
+      jump(c, i0 + e * stride, t, j, wa, ev);
+      swe[e] += wa;
+      se[e] += ev;
+      if (++j > kk[e]) { j = 1; do { e++; } while (e < E && kk[e] == 0); }
+    }
+    for (int q = 0; q < E; q++) finish(c, x[q], swe[q], se[q]);
     return 0;
   }
   __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
-    return dnorm_log(y[0], c.theta[0] + c.theta[1] * x[0], sqrt(x[0]));
+    // dnorm(y, mu + beta v, sd = sqrt(v), log = TRUE) = -(M_LN_SQRT_2PI + (y - m)^2 / (2 v) + log(v) / 2)
+    const double r = y[0] - (c.theta[0] + c.theta[1] * x[0]);
+    return -(CPIMH_M_LN_SQRT_2PI + 0.5 * (r * r) / x[0] + 0.5 * log(x[0]));
   }
 };
 
 // ------------------------------------------------------------------ get_stochastic_kinetic (d = 4, d_y = 2)
 struct SkModel {
   static constexpr int D = 4;
-  static constexpr int NPRE = 0;
   static constexpr bool USES_SHARED_U = false;
+  static constexpr bool MULTI = true;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void init(const ModelCtx&, int, double* x) { x[0] = 8.0; x[1] = 8.0; x[2] = 8.0; x[3] = 5.0; }
-  // returns 0, or CPIMH_ERR_NOISE_OVERFLOW when the injected event budget is exhausted; bit 8 set if an event index was clamped
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double /*ush*/) {
+  __device__ static __forceinline__ double hazards(const double* x, double* h) {      // R/model_stochastic_kinetic.R:27-40
+    h[0] = 0.1 * x[3] * x[2];
+    h[1] = 0.7 * (5.0 - x[3]);
+    h[2] = 0.35 * x[3];
+    h[3] = 0.2 * x[0];
+    h[4] = 0.1 * x[1] * (x[1] - 1.0) / 2.0;
+    h[5] = 0.9 * x[2];
+    h[6] = 0.3 * x[0];
+    h[7] = 0.1 * x[1];
+    double h0 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) h0 += h[r];
+    return h0;
+  }
+  __device__ static __forceinline__ int fire(double* x, const double* h, double u_rnd) {     // :58-71, stoichiometry :19-23
+    double cdf = 0.0;
+    int ev = 0, clamped = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) { cdf += h[r]; ev += (cdf < u_rnd) ? 1 : 0; }
+    if (ev > 7) { ev = 7; clamped = 256; }
+    switch (ev) {
+      case 0: x[2] -= 1.0; x[3] -= 1.0; break;
+      case 1: x[2] += 1.0; x[3] += 1.0; break;
+      case 2: x[0] += 1.0; break;
+      case 3: x[1] += 1.0; break;
+      case 4: x[1] -= 2.0; x[2] += 1.0; break;
+      case 5: x[1] += 2.0; x[2] -= 1.0; break;
+      case 6: x[0] -= 1.0; break;
+      default: x[1] -= 1.0; break;
+    }
+    return clamped;
+  }
+  __device__ static __forceinline__ void draw(const ModelCtx& c, int t, int i, int m, double& E, double& U) {
+    if (c.inj_trans) { E = trans_row(c, t, m)[i]; U = trans_row(c, t, c.sk_M + m)[i]; }
+    else { double ua, ub; philox_u2(c.stream, i, t, CPIMH_P_TRANS, m, ua, ub); E = -log(ua); U = ub; }
+  }
+  // exact Gillespie over one inter-observation interval of 0.1 (:96-129).  Returns 0, or CPIMH_ERR_NOISE_OVERFLOW when
+  // the injected event budget is exhausted; bit 8 set if an event index was clamped.
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double) {
     double tcur = 0.0;
     int flags = 0;
     for (int m = 0;; m++) {
       if (c.inj_trans && m >= c.sk_M) return CPIMH_ERR_NOISE_OVERFLOW;
-      double h[8];
-      h[0] = 0.1 * x[3] * x[2];
-      h[1] = 0.7 * (5.0 - x[3]);
-      h[2] = 0.35 * x[3];
-      h[3] = 0.2 * x[0];
-      h[4] = 0.1 * x[1] * (x[1] - 1.0) / 2.0;
-      h[5] = 0.9 * x[2];
-      h[6] = 0.3 * x[0];
-      h[7] = 0.1 * x[1];
-      double h0 = 0.0;
-#pragma unroll
-      for (int r = 0; r < 8; r++) h0 += h[r];
-      double E, U;
-      if (c.inj_trans) { E = trans_row(c, t, m)[i]; U = trans_row(c, t, c.sk_M + m)[i]; }
-      else { double ua, ub; philox_u2(c.stream, i, t, CPIMH_P_TRANS, m, ua, ub); E = -log(ua); U = ub; }
-      tcur = tcur + (1.0 / h0) * E;
+      double h[8], E, U;
+      const double h0 = hazards(x, h);
+      draw(c, t, i, m, E, U);
+      tcur = tcur + (1.0 / h0) * E;            // rexp(n, rate) = exp_rand() * (1 / rate)
       if (!(tcur < 0.1)) return flags;
-      double u_rnd = U * h0, cdf = 0.0;
-      int ev = 0;
-#pragma unroll
-      for (int r = 0; r < 8; r++) { cdf += h[r]; ev += (cdf < u_rnd) ? 1 : 0; }
-      if (ev > 7) { ev = 7; flags |= 256; }
-      // stoichiometry columns r1..r8 (R/model_stochastic_kinetic.R:19-23)
-      switch (ev) {
-        case 0: x[2] -= 1.0; x[3] -= 1.0; break;
-        case 1: x[2] += 1.0; x[3] += 1.0; break;
-        case 2: x[0] += 1.0; break;
-        case 3: x[1] += 1.0; break;
-        case 4: x[1] -= 2.0; x[2] += 1.0; break;
-        case 5: x[1] += 2.0; x[2] -= 1.0; break;
-        case 6: x[0] -= 1.0; break;
-        default: x[1] -= 1.0; break;
+      flags |= fire(x, h, U * h0);
+    }
+  }
+  // All E particles of one thread as one event stream: when a particle's clock passes 0.1 the lane moves straight on to
+  // its next particle, so lanes idle only at the end (event counts per particle-step are heavy-tailed, mean ~1.7).
+  __device__ static int transition_multi(const ModelCtx& c, int t, int E, int i0, int stride, double (*xs)[4], const double*, double) {
+    int flags = 0, e = 0, m = 0;
+    double tcur = 0.0;
+    double x[4] = {xs[0][0], xs[0][1], xs[0][2], xs[0][3]};
+    while (e < E) {
+      if (c.inj_trans && m >= c.sk_M) return CPIMH_ERR_NOISE_OVERFLOW;
+      double h[8], Ex, U;
+      const double h0 = hazards(x, h);
+      draw(c, t, i0 + e * stride, m, Ex, U);
+      tcur = tcur + (1.0 / h0) * Ex;
+      if (!(tcur < 0.1)) {
+        xs[e][0] = x[0]; xs[e][1] = x[1]; xs[e][2] = x[2]; xs[e][3] = x[3];
+        e++; m = 0; tcur = 0.0;
+        if (e < E) { x[0] = xs[e][0]; x[1] = xs[e][1]; x[2] = xs[e][2]; x[3] = xs[e][3]; }
+      } else {
+        flags |= fire(x, h, U * h0);
+        m++;
       }
     }
+    return flags;
   }
   __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
     const double sd = sqrt(c.theta[0]);
@@ -338,8 +405,8 @@ __device__ int lorenz_dopri5(double F, double t0, double t1, double dt, double* 
 template <int D_>
 struct LorenzModel {
   static constexpr int D = D_;
-  static constexpr int NPRE = 1;     // cst of the measurement density
-  static constexpr bool USES_SHARED_U = false;
+  static constexpr bool USES_SHARED_U = false;   // pre[0] = cst of the measurement density
+  static constexpr bool MULTI = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll

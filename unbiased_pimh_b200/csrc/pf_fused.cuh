@@ -65,6 +65,7 @@ struct PfSmem {
   double* theta;    // [CPIMH_MAX_THETA]
   double* pre;      // [npre]
   double* dscr;     // [32]
+  int* coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
   int* iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
 };
 __host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
@@ -78,6 +79,7 @@ __host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int p
   } else if (shuffle) {
     b += (size_t)Npad * 4;                   // bpar (ancestors to permute)
   }
+  b += (size_t)(Npad / 32 + 4) * 4;          // coarse
   b += 36 * 4;
   return (b + 15) & ~(size_t)15;
 }
@@ -99,8 +101,18 @@ __device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre,
   } else if (shuffle) {
     s.bpar = i; i += Npad;
   }
+  s.coarse = i; i += Npad / 32 + 4;
   s.iscr = i;
   return s;
+}
+
+// count of c[j] <= u, known to lie in [lo, hi]
+__device__ __forceinline__ int count_le_bounded(const double* c, int lo, int hi, double u) {
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (c[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
 }
 
 struct FilterOut {
@@ -194,6 +206,14 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       block_scan_inplace<false>(sm.C, N, sm.dscr);
       if (!inj_res) block_scan_inplace<true>(sm.S, N, sm.dscr);
       sumw = sm.C[N - 1];
+      // every 32nd sorted uniform gets a full search; the others then search only between their neighbours' results
+      const int nrows = (N + 31) >> 5;
+      for (int r = tid; r <= nrows; r += NT) {
+        int a = N;
+        if (r < nrows) { double e0 = inj_res ? sm.S[r << 5] : exp(sm.S[r << 5]); a = count_le(sm.C, N, sumw * e0); }
+        sm.coarse[r] = a;
+      }
+      __syncthreads();
     } else if (tree) {
       __syncthreads();
     }
@@ -202,25 +222,31 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     auto ancestor_of = [&](int k) -> int {
       if (ident) return k;
       double e = inj_res ? sm.S[k] : exp(sm.S[k]);
-      int a = count_le(sm.C, N, sumw * e);
+      int a = count_le_bounded(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * e);
       if (a >= N) { a = N - 1; st |= 512; }
       return a;
     };
     // -- gather (R/CPF.R:41) -> rtransition (:44) -> dmeasurement (:60) ; path bookkeeping
-    auto propagate = [&](int k, int a, int e) {
-      double x[D];
-#pragma unroll
-      for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
-      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[e] : 0.5);
+    double m = -INFINITY;                                // running max of this thread's log-weights
+    auto finish_particle = [&](int k, int a, const double* x) {
 #pragma unroll
       for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
-      sm.S[k] = Model::logw(c, x, y);
+      const double lw = Model::logw(c, x, y);
+      sm.S[k] = lw;
+      m = fmax(m, lw);
       if (dense) hist_a[(size_t)(t - 1) * Npad + k] = a;
       if (tree) {                                      // src/tree.cpp:39-42, 90-94
         sm.bpar[k] = sm.leaf[a];
         atomicAdd(&sm.off32[a >> 1], 1u << ((a & 1) << 4));
       }
       if (out.anc_rec) out.anc_rec[(size_t)(t - 1) * N + k] = a;
+    };
+    auto propagate = [&](int k, int a, int e) {
+      double x[D];
+#pragma unroll
+      for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
+      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[e] : 0.5);
+      finish_particle(k, a, x);
     };
     if (p.shuffle && !ident) {
       for (int k = tid; k < N; k += NT) sm.bpar[k] = ancestor_of(k);
@@ -236,17 +262,33 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       if (tid == 0)
         for (int i = 1; i < N; i++) { int j = jidx[i]; int tmp = sm.bpar[i]; sm.bpar[i] = sm.bpar[j]; sm.bpar[j] = tmp; }
       __syncthreads();
-      int e = 0;
-      for (int k = tid; k < N; k += NT, e++) propagate(k, sm.bpar[k], e);
+    }
+    const bool shuffled = p.shuffle && !ident;
+    if constexpr (Model::MULTI) {
+      if ((N + NT - 1) / NT <= CPIMH_MULTI_MAX_E) {
+        // the thread's particles go through the transition together (see Model::transition_multi)
+        double xl[CPIMH_MULTI_MAX_E][D];
+        int al[CPIMH_MULTI_MAX_E];
+        int E = 0;
+        for (int k = tid; k < N; k += NT, E++) {
+          const int a = shuffled ? sm.bpar[k] : ancestor_of(k);
+          al[E] = a;
+#pragma unroll
+          for (int q = 0; q < D; q++) xl[E][q] = xold[(size_t)q * Npad + a];
+        }
+        if (E > 0) st |= Model::transition_multi(c, t, E, tid, NT, xl, ukeep, sc);
+        for (int e = 0; e < E; e++) finish_particle(tid + e * NT, al[e], xl[e]);
+      } else {
+        int e = 0;
+        for (int k = tid; k < N; k += NT, e++) propagate(k, shuffled ? sm.bpar[k] : ancestor_of(k), e);
+      }
     } else {
       int e = 0;
-      for (int k = tid; k < N; k += NT, e++) propagate(k, ancestor_of(k), e);
+      for (int k = tid; k < N; k += NT, e++) propagate(k, shuffled ? sm.bpar[k] : ancestor_of(k), e);
     }
     __syncthreads();
 
     // -- weights and log Z increment: R/CPF.R:61-63,66
-    double m = -INFINITY;
-    for (int k = tid; k < N; k += NT) m = fmax(m, sm.S[k]);
     m = block_max(m, sm.dscr);
     double s = 0.0;
     for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; }

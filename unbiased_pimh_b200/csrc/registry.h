@@ -8,7 +8,6 @@ namespace cpimh {
 struct ModelEntry {
   int model;
   int dim;
-  int npre;
   int (*launch_pf)(const PfParams&, const PfLaunch&, cudaStream_t);
   int (*occupancy_pf)(int variant, int threads, size_t smem, int* blocks_per_sm);
   int (*launch_chains)(const ChainParams&, const PfLaunch&, cudaStream_t);
@@ -18,7 +17,7 @@ struct ModelEntry {
 template <class Model>
 ModelEntry make_entry(int model) {
   ModelEntry e;
-  e.model = model; e.dim = Model::D; e.npre = Model::NPRE;
+  e.model = model; e.dim = Model::D;
   e.launch_pf = &launch_pf_batch<Model>;
   e.occupancy_pf = &occupancy_pf_batch<Model>;
   e.launch_chains = &launch_chains<Model>;
