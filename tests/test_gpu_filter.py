@@ -1,0 +1,208 @@
+"""GPU parity of the fused filter kernel (through the C ABI) against the CPU oracle.
+
+Tolerances (fp64): per-step log Z within 1e-10 relative given identical injected noise (north_star); ancestor
+indices identical; trajectories within 1e-9 absolute (AR/Lorenz amplify rounding along the path).
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+A_OBS = np.array([[1, 0, 0, 0], [0, 1, 2, 0]], dtype=float)
+RTOL_LOGZ = 1e-10
+
+
+@pytest.fixture(scope="module")
+def up():
+    import unbiased_pimh_b200 as m
+    return m
+
+
+def model_cases(up, oracle, golden):
+    rng = np.random.default_rng(0)
+    th_sv = golden["sv_theta_mle"]
+    return {
+        "gss": dict(model=up.get_gss(), theta=[], oid=oracle.MODEL_GSS, otheta=[], obs=golden["gss_y"], d=1, dy=1, okw={}),
+        "ar1": dict(model=up.get_ar(1), theta=[0.5, math.sqrt(10)], oid=oracle.MODEL_AR, otheta=[0.5, math.sqrt(10)], obs=golden["lgssm_y"], d=1, dy=1, okw={}),
+        "ar5": dict(model=up.get_ar(5), theta=[0.3, 1.5], oid=oracle.MODEL_AR, otheta=[0.3, 1.5], obs=rng.normal(size=(40, 5)) * 2, d=5, dy=5, okw={}),
+        "ar10": dict(model=up.get_ar(10), theta=[0.3, math.sqrt(10)], oid=oracle.MODEL_AR, otheta=[0.3, math.sqrt(10)], obs=rng.normal(size=(30, 10)) * 2, d=10, dy=10, okw={}),
+        "levy_sv": dict(model=up.get_levy_sv(), theta=th_sv, oid=oracle.MODEL_LEVY_SV, otheta=th_sv, obs=golden["sv_y"][:60], d=2, dy=1, okw={}),
+        "sk": dict(model=up.get_stochastic_kinetic(), theta={"A_obs": A_OBS, "s2_obs": 1.0}, oid=oracle.MODEL_SK, otheta=[1.0] + list(A_OBS.ravel(order="F")),
+                   obs=golden["sk_y"][:40], d=4, dy=2, okw={"sk_max_events": 48}),
+        "lorenz_rk4": dict(model=up.get_lorenz(1.0, 8, "rk4", 2), theta=[8.0, 0.5], oid=oracle.MODEL_LORENZ, otheta=[8.0, 0.5, 1.0], obs=rng.normal(size=(20, 8)) * 3 + 2,
+                           d=8, dy=8, okw={"integrator": 0, "substeps": 2}),
+        "lorenz_dopri5": dict(model=up.get_lorenz(1.0, 8, "dopri5"), theta=[8.0, 0.5], oid=oracle.MODEL_LORENZ, otheta=[8.0, 0.5, 1.0], obs=rng.normal(size=(20, 8)) * 3 + 2,
+                              d=8, dy=8, okw={"integrator": 1}),
+    }
+
+
+NAMES = ["gss", "ar1", "ar5", "ar10", "levy_sv", "sk", "lorenz_rk4", "lorenz_dopri5"]
+
+
+def injected_noise(rng, oracle, ocfg, B, N, T, shuffle):
+    ni, nt = oracle.n_init(ocfg), oracle.n_trans(ocfg)
+    nz = dict(resample=np.sort(rng.random((B, T, N)), axis=2), path_u=rng.random(B))
+    if ocfg.model == oracle.MODEL_LEVY_SV:
+        z0 = rng.gamma(7.0, 0.11, size=(B, 1, N)); sw = rng.exponential(0.02, size=(B, 1, N)) * (rng.random((B, 1, N)) < 0.3)
+        nz["init"] = np.concatenate([z0, sw, sw * 1.02], axis=1)
+        swt = rng.exponential(0.02, size=(B, T, 1, N)) * (rng.random((B, T, 1, N)) < 0.3)
+        nz["trans"] = np.concatenate([swt, swt * 1.03], axis=2)
+    elif ocfg.model == oracle.MODEL_SK:
+        M = nt // 2
+        nz["trans"] = np.concatenate([rng.exponential(size=(B, T, M, N)), rng.random((B, T, M, N))], axis=2)
+    else:
+        nz["init"] = rng.normal(size=(B, ni, N))
+        nz["trans"] = rng.normal(size=(B, T, nt, N))
+    if shuffle:
+        nz["shuffle"] = rng.random((B, T, N - 1))
+    return nz
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("shuffle", [0, 1])
+@pytest.mark.parametrize("store_paths", [2, 3])
+def test_injected_noise_parity(up, oracle, golden, name, shuffle, store_paths):
+    """Identical pre-generated noise into both implementations: ancestors identical, per-step log Z within 1e-10."""
+    c = model_cases(up, oracle, golden)[name]
+    rng = np.random.default_rng(hash((name, shuffle)) % 2 ** 31)
+    N, B = (96 if c["d"] >= 8 else 200), 3
+    T = c["obs"].shape[0]
+    ocfg = oracle.make_config(c["oid"], c["d"], c["dy"], N, T, theta=c["otheta"], shuffle=shuffle, **c["okw"])
+    nz = injected_noise(rng, oracle, ocfg, B, N, T, shuffle)
+    pb = up.PfBatch(c["model"], c["theta"], c["obs"], N, B, shuffle=shuffle, store_paths=store_paths, sk_max_events=c["okw"].get("sk_max_events", 64))
+    pb.record_ancestors(True)
+    pb.set_noise(B, nz)
+    pb.run(B, 0)
+    r = pb.fetch(logz_t=True, path_index=True)
+    for b in range(B):
+        o = oracle.cpf(ocfg, c["obs"], noise={k: v[b] for k, v in nz.items()}, all_particles=True, all_paths=(b == 0), want_ancestors=True)
+        assert np.array_equal(pb.fetch_ancestors(b), o["ancestors"]), (name, b)
+        assert np.max(np.abs(r["logz_t"][b] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ
+        assert abs(r["logz"][b] - o["logz"]) < RTOL_LOGZ * abs(o["logz"])
+        assert int(r["path_index"][b]) == o["path_index"]
+        assert np.allclose(r["trajectory"][b], o["trajectory"], rtol=1e-9, atol=1e-9)
+        ap = pb.fetch_all_particles(b, trajectories=(b == 0))
+        assert np.allclose(ap["weights"], o["normweights"], rtol=1e-9, atol=1e-300) and abs(ap["weights"].sum() - 1) < 1e-12
+        assert np.allclose(ap["exp_path"], o["exp_path"], rtol=1e-9, atol=1e-9)
+        if b == 0:
+            assert np.allclose(ap["trajectories"], o["trajectories"], rtol=1e-9, atol=1e-9)
+    pb.close()
+
+
+@pytest.mark.parametrize("name,N", [("gss", 256), ("gss", 1000), ("ar1", 150), ("ar10", 1024), ("levy_sv", 4096), ("sk", 2048), ("sk", 8192),
+                                    ("lorenz_rk4", 512), ("lorenz_dopri5", 300)])
+def test_philox_seed_for_seed_parity(up, oracle, golden, name, N):
+    """No injected arrays: both sides draw from the same Philox streams (bit-identical uniforms), so whole filters agree
+    up to libm-vs-CUDA rounding of log/exp/sincos."""
+    c = model_cases(up, oracle, golden)[name]
+    T = c["obs"].shape[0]
+    B, seed = 3, 4242
+    r = up.cpf_batch(N, c["model"], c["theta"], c["obs"], B, seed=seed, first_filter=5, logz_t=True)
+    okw = {k: v for k, v in c["okw"].items() if k != "sk_max_events"}
+    ocfg = oracle.make_config(c["oid"], c["d"], c["dy"], N, T, theta=c["otheta"], **okw)
+    for b in range(B):
+        o = oracle.cpf(ocfg, c["obs"], seed=seed, filter_id=5 + b)
+        assert np.max(np.abs(r["logz_t"][b] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ, (name, b)
+        assert int(r["path_index"][b]) == o["path_index"]
+        assert np.allclose(r["trajectory"][b], o["trajectory"], rtol=1e-8, atol=1e-8)
+
+
+def test_dense_and_tree_path_storage_agree(up, golden):
+    th = golden["sv_theta_mle"]
+    y = np.tile(golden["sv_y"], (2, 1))[:300]
+    out = {}
+    for sp in (2, 3):
+        pb = up.PfBatch(up.get_levy_sv(), th, y, 1024, 8, store_paths=sp, tree_capacity=24 * 1024)
+        assert pb.effective_config()["path_storage"] == {2: "dense", 3: "tree"}[sp]
+        pb.run(8, 99)
+        out[sp] = pb.fetch(logz_t=True, path_index=True)
+        out[sp]["ap"] = pb.fetch_all_particles(3, trajectories=True)
+        pb.close()
+    for k in ("logz", "logz_t", "trajectory", "path_index"):
+        assert np.array_equal(out[2][k], out[3][k]), k
+    assert np.array_equal(out[2]["ap"]["trajectories"], out[3]["ap"]["trajectories"])
+    assert np.allclose(out[2]["ap"]["exp_path"], out[3]["ap"]["exp_path"], rtol=1e-13)
+    pb = up.PfBatch(up.get_levy_sv(), th, y, 1024, 8, store_paths=0)          # log Z only
+    pb.run(8, 99)
+    assert np.array_equal(pb.fetch(trajectory=False)["logz"], out[2]["logz"])
+    pb.close()
+
+
+def test_tree_overflow_is_reported_and_retried(up, golden):
+    y = golden["lgssm_y"]
+    m = up.get_ar(1)
+    pb = up.PfBatch(m, [0.5, 0.05], y, 512, 4, store_paths=3, tree_capacity=3 * 512)   # uninformative weights, minimum capacity 3N
+    pb.run(4, 1)
+    with pytest.raises(up.CpimhError) as ei:
+        pb.fetch()
+    assert ei.value.code == 3 and "capacity" in str(ei.value)
+    pb.close()
+    a = up.cpf_batch(512, m, [0.5, 0.05], y, 4, seed=1, store_paths=3, tree_capacity=3 * 512)   # one-shot API doubles the capacity and reruns
+    b = up.cpf_batch(512, m, [0.5, 0.05], y, 4, seed=1, store_paths=2)
+    assert np.array_equal(a["logz"], b["logz"]) and np.array_equal(a["trajectory"], b["trajectory"])
+
+
+def test_na_observations_skip_resampling(up, oracle):
+    """R/CPF.R:38-40: no resampling after a row whose first entry is NA; get_lorenz's dmeasurement returns 0 for NA rows."""
+    rng = np.random.default_rng(3)
+    y = rng.normal(size=(12, 8)) * 2 + 2
+    y[[3, 4, 8], :] = np.nan
+    N, seed = 200, 11
+    r = up.cpf_batch(N, up.get_lorenz(1.0, 8, "rk4", 1), [8.0, 0.4], y, 2, seed=seed, logz_t=True)
+    ocfg = oracle.make_config(oracle.MODEL_LORENZ, 8, 8, N, 12, theta=[8.0, 0.4, 1.0], integrator=0, substeps=1)
+    for b in range(2):
+        o = oracle.cpf(ocfg, y, seed=seed, filter_id=b)
+        assert np.allclose(r["logz_t"][b], o["logz_t"], rtol=RTOL_LOGZ, atol=1e-300)
+        assert np.all(r["logz_t"][b][[3, 4, 8]] == 0.0)
+        assert int(r["path_index"][b]) == o["path_index"]
+
+
+def test_r_shaped_single_filter_api(up, oracle, golden):
+    y = golden["gss_y"]
+    up.set_seed(17)
+    r = up.CPF(256, up.get_gss(), [], y)
+    assert r["trajectory"].shape == (1, 101) and np.isfinite(r["logz"])
+    r2 = up.CPF(256, up.get_gss(), [], y, all_particles=True, seed=5)
+    pf = up.particlefilter(256, up.get_gss(), [], y, seed=5)
+    assert pf["trajectories"].shape == (1, 101, 256) and abs(pf["weights"].sum() - 1) < 1e-12
+    assert np.allclose(r2["exp_path"], up.pf_get_weighted_average(pf["trajectories"], pf["weights"]), rtol=1e-12)
+    ocfg = oracle.make_config(oracle.MODEL_GSS, 1, 1, 256, 100)
+    o = oracle.cpf(ocfg, y, seed=5, filter_id=0, all_particles=True, all_paths=True)
+    assert np.allclose(pf["trajectories"], o["trajectories"], rtol=1e-9, atol=1e-9) and np.allclose(r2["exp_path"], o["exp_path"], rtol=1e-9)
+
+
+def test_model_closures_match_oracle(up, oracle, golden):
+    """model$rinit / rtransition / dmeasurement one call at a time (cpimh_model_*) with injected noise."""
+    rng = np.random.default_rng(8)
+    for name, c in model_cases(up, oracle, golden).items():
+        N = 300
+        ocfg = oracle.make_config(c["oid"], c["d"], c["dy"], N, 10, theta=c["otheta"], **c["okw"])
+        ni, nt = oracle.n_init(ocfg), oracle.n_trans(ocfg)
+        if name == "levy_sv":
+            zi = np.stack([rng.gamma(7.0, 0.11, N), rng.exponential(0.02, N), rng.exponential(0.03, N)])
+            zt = np.stack([rng.exponential(0.02, N), rng.exponential(0.03, N)])
+        elif name == "sk":
+            zi = None
+            zt = np.concatenate([rng.exponential(size=(nt // 2, N)), rng.random((nt // 2, N))])
+        else:
+            zi, zt = rng.normal(size=(ni, N)), rng.normal(size=(nt, N))
+        x0g = c["model"].rinit(N, c["theta"], zi)
+        x0o = oracle.model_rinit(ocfg, zi if zi is not None else np.zeros((1, N)))
+        assert np.allclose(x0g, x0o, rtol=1e-13, atol=1e-14), name
+        x1g = c["model"].rtransition(x0o, c["theta"], 3, zt, sk_max_events=c["okw"].get("sk_max_events", 64))
+        x1o = oracle.model_rtransition(ocfg, x0o, 3, zt)
+        assert np.allclose(x1g, x1o, rtol=1e-11, atol=1e-12), name
+        yv = c["obs"][2]
+        if name == "levy_sv":
+            x1o = np.abs(x1o) + 1e-3
+        assert np.allclose(c["model"].dmeasurement(x1o, c["theta"], yv), oracle.model_dmeasurement(ocfg, x1o, yv), rtol=1e-12, atol=1e-12), name
+    x = rng.normal(size=(64, 50)) + 2
+    got = up.lorenz_transition(x, 0.0, 0.05, 0.05, [8.0], integrator="rk4", substeps=3)            # warp-per-particle path (d = 64)
+    ref = np.stack([oracle.lorenz_step(x[:, n], 8.0, 0, 3) for n in range(50)], axis=1)
+    assert np.allclose(got, ref, rtol=1e-13, atol=1e-13)
+    x8 = rng.normal(size=(8, 50)) + 2
+    got = up.lorenz_transition(x8, 0.1, 0.15, 0.05, [8.0])                                          # dopri5, the reference's integrator
+    ref = np.stack([oracle.lorenz_step(x8[:, n], 8.0, 1, 1, 0.1, 0.15, 0.05) for n in range(50)], axis=1)
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)

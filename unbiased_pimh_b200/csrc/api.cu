@@ -17,7 +17,7 @@ void set_error(const char* fmt, ...) {
 }
 
 const ModelEntry* find_entry(int model, int dim) {
-  const ModelEntry* (*tables[])(int*) = {entries_gss, entries_ar, entries_sv, entries_sk, entries_lorenz};
+  const ModelEntry* (*tables[])(int*) = {entries_gss, entries_ar, entries_ar_hi, entries_sv, entries_sk, entries_lorenz};
   for (auto tf : tables) {
     int n = 0;
     const ModelEntry* e = tf(&n);

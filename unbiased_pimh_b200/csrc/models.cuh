@@ -124,7 +124,10 @@ struct LevySvModel {
   // the Poisson uniform of particle i at time t is the SECOND uniform of the Philox block whose first uniform is the
   // resampling draw of slot i at time t (one Philox call serves both; DESIGN.md "RNG")
   static constexpr bool USES_SHARED_U = true;
-  static constexpr bool MULTI = true;
+#ifndef CPIMH_SV_MULTI
+#define CPIMH_SV_MULTI 0
+#endif
+  static constexpr bool MULTI = CPIMH_SV_MULTI != 0;
   __device__ static double step_const(const ModelCtx& c, int) { return c.pre[0]; }
   // one jump of the compound Poisson process (src/SVLevy_functions.cpp:62-67): c' = t - c ~ U(0,1), e ~ Exp(rate xi/w2)
   __device__ static __forceinline__ void jump(const ModelCtx& c, int i, int t, int j, double& wa, double& e) {

@@ -27,6 +27,7 @@ ModelEntry make_entry(int model) {
 }
 const ModelEntry* entries_gss(int* n);
 const ModelEntry* entries_ar(int* n);
+const ModelEntry* entries_ar_hi(int* n);
 const ModelEntry* entries_sv(int* n);
 const ModelEntry* entries_sk(int* n);
 const ModelEntry* entries_lorenz(int* n);
