@@ -133,14 +133,14 @@ def test_dense_and_tree_path_storage_agree(up, golden):
 def test_tree_overflow_is_reported_and_retried(up, golden):
     y = golden["lgssm_y"]
     m = up.get_ar(1)
-    pb = up.PfBatch(m, [0.5, 0.05], y, 512, 4, store_paths=3, tree_capacity=3 * 512)   # uninformative weights, minimum capacity 3N
+    pb = up.PfBatch(m, [0.5, 1e6], y, 512, 4, store_paths=3, tree_capacity=3 * 512)   # flat weights (huge sigma_y) => large genealogy; minimum capacity 3N
     pb.run(4, 1)
     with pytest.raises(up.CpimhError) as ei:
         pb.fetch()
     assert ei.value.code == 3 and "capacity" in str(ei.value)
     pb.close()
-    a = up.cpf_batch(512, m, [0.5, 0.05], y, 4, seed=1, store_paths=3, tree_capacity=3 * 512)   # one-shot API doubles the capacity and reruns
-    b = up.cpf_batch(512, m, [0.5, 0.05], y, 4, seed=1, store_paths=2)
+    a = up.cpf_batch(512, m, [0.5, 1e6], y, 4, seed=1, store_paths=3, tree_capacity=3 * 512)   # one-shot API doubles the capacity and reruns
+    b = up.cpf_batch(512, m, [0.5, 1e6], y, 4, seed=1, store_paths=2)
     assert np.array_equal(a["logz"], b["logz"]) and np.array_equal(a["trajectory"], b["trajectory"])
 
 
