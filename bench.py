@@ -99,16 +99,23 @@ def workload(name):
         A = np.array([[1, 0, 0, 0], [0, 1, 2, 0]], dtype=float)
         return dict(name="stochastic_kinetic T=100 N=8192 B=1184 (BASELINE configs[2] filter shape)", model="sk", theta={"A_obs": A, "s2_obs": 1.0},
                     obs=g["sk_y"], N=N, B=B, T=T, d=4, dy=2, bytes_per_ps=24 * 4 + 16)
+    if name == "cfg5":
+        T, N, B, d = 500, 65536, 1, 64
+        rng = np.random.default_rng(17)
+        return dict(name="lorenz96 d=64 rk4 T=500 N=65536 B=1 (BASELINE configs[4])", model="lorenz64", theta=[8.0, 0.5], obs=rng.normal(size=(T, d)) * 1.5 + 2.0,
+                    N=N, B=B, T=T, d=d, dy=d, bytes_per_ps=24 * d + 16 + 16)
     raise SystemExit("unknown workload %s" % name)
 
 
 def make_model(up, w):
-    return {"levy_sv": up.get_levy_sv, "gss": up.get_gss, "sk": up.get_stochastic_kinetic, "ar10": lambda: up.get_ar(10)}[w["model"]]()
+    return {"levy_sv": up.get_levy_sv, "gss": up.get_gss, "sk": up.get_stochastic_kinetic, "ar10": lambda: up.get_ar(10), "lorenz64": lambda: up.get_lorenz(1.0, 64, "rk4", 1)}[w["model"]]()
 
 
 def oracle_config(O, w):
-    mid = {"levy_sv": O.MODEL_LEVY_SV, "gss": O.MODEL_GSS, "sk": O.MODEL_SK, "ar10": O.MODEL_AR}[w["model"]]
+    mid = {"levy_sv": O.MODEL_LEVY_SV, "gss": O.MODEL_GSS, "sk": O.MODEL_SK, "ar10": O.MODEL_AR, "lorenz64": O.MODEL_LORENZ}[w["model"]]
     th = w["theta"]
+    if w["model"] == "lorenz64":
+        return O.make_config(mid, w["d"], w["dy"], w["N"], w["T"], theta=list(th) + [1.0], integrator=0, substeps=1)
     if w["model"] == "sk":
         th = [th["s2_obs"]] + list(np.ravel(th["A_obs"], order="F"))
     return O.make_config(mid, w["d"], w["dy"], w["N"], w["T"], theta=th)

@@ -5,6 +5,7 @@
 #include <string.h>
 #include <vector>
 #include "host_common.h"
+#include "wide.h"
 
 namespace cpimh {
 
@@ -93,7 +94,7 @@ int api_validate(cpimh_config* cp) {
   if ((c.model == CPIMH_MODEL_AR || c.model == CPIMH_MODEL_LORENZ) && c.dim_y == 0) c.dim_y = c.dim;
   CPIMH_REQUIRE(c.nparticles >= 1, "nparticles must be >= 1 (got %d)", c.nparticles);
   CPIMH_REQUIRE(c.nobs >= 1 && c.nobs < (1 << 20), "nobs must be in [1, 2^20) (got %d)", c.nobs);
-  CPIMH_REQUIRE(find_entry(c.model, c.dim) != nullptr,
+  CPIMH_REQUIRE(wide_supported(c) || find_entry(c.model, c.dim) != nullptr,
                 "model %d with dimension %d has no compiled kernel (see csrc/model_*.cu for the instantiated dimensions)", c.model, c.dim);
   if (c.model == CPIMH_MODEL_SK) CPIMH_REQUIRE(c.dim_y == 2, "stochastic kinetic model has dim_y = 2");
   if (c.model == CPIMH_MODEL_AR || c.model == CPIMH_MODEL_LORENZ) CPIMH_REQUIRE(c.dim_y == c.dim, "dim_y must equal dim for this model");
@@ -177,6 +178,7 @@ using namespace cpimh;
 
 // ============================================================================ filter handle
 struct cpimh_pf {
+  WideFilter* wide = nullptr;   // d = 32/64 Lorenz: one filter across the GPU (wide.cu); all other fields unused then
   cpimh_config cfg;
   const ModelEntry* entry;
   Geometry geo;
@@ -210,6 +212,15 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   cpimh_config cfg = *cfg_in;
   int rc = api_validate(&cfg);
   if (rc) return rc;
+  if (wide_supported(cfg)) {
+    WideFilter* w = nullptr;
+    rc = wide_create(cfg, max_filters, &w);
+    if (rc) return rc;
+    cpimh_pf* hw = new cpimh_pf();
+    hw->wide = w; hw->cfg = cfg; hw->maxB = max_filters; hw->lastB = 0;
+    *out = hw;
+    return CPIMH_OK;
+  }
   const ModelEntry* e = find_entry(cfg.model, cfg.dim);
   std::vector<double> pre = api_precompute(cfg);
   Geometry g;
@@ -255,6 +266,7 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
 
 int cpimh_pf_destroy(cpimh_pf* h) {
   if (!h) return CPIMH_OK;
+  if (h->wide) { wide_destroy(h->wide); delete h; return CPIMH_OK; }
   DevBuf* all[] = {&h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->logz, &h->logz_t, &h->traj, &h->path_index,
                    &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->hist_x, &h->hist_a, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
   for (auto b : all) b->release();
@@ -277,11 +289,13 @@ extern "C" {
 
 int cpimh_pf_set_observations(cpimh_pf* h, const double* obs_host) {
   CPIMH_REQUIRE(h && obs_host, "null argument");
+  if (h->wide) return wide_set_observations(h->wide, obs_host);
   return api_upload_obs(h->cfg, obs_host, h->obs.p);
 }
 
 int cpimh_pf_set_noise(cpimh_pf* h, int64_t B, const cpimh_noise* nz) {
   CPIMH_REQUIRE(h, "null handle");
+  if (h->wide) return wide_set_noise(h->wide, B, nz);
   memset(h->have_inj, 0, sizeof(h->have_inj));
   if (!nz) return CPIMH_OK;
   CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
@@ -305,6 +319,7 @@ int cpimh_pf_set_noise(cpimh_pf* h, int64_t B, const cpimh_noise* nz) {
 
 int cpimh_pf_record_ancestors(cpimh_pf* h, int on) {
   CPIMH_REQUIRE(h, "null handle");
+  if (h->wide) return wide_record_ancestors(h->wide, on);
   h->record_anc = on ? 1 : 0;
   if (on) return h->anc_rec.alloc(sizeof(int) * (size_t)h->maxB * h->cfg.nobs * h->cfg.nparticles, &h->bytes);
   return CPIMH_OK;
@@ -324,6 +339,7 @@ extern "C" {
 
 int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, void* stream) {
   CPIMH_REQUIRE(h, "null handle");
+  if (h->wide) { int rcw = wide_run(h->wide, B, seed, first_filter, (cudaStream_t)stream); if (!rcw) h->lastB = B; return rcw; }
   CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
   const cpimh_config& c = h->cfg;
   PfParams p;
@@ -366,6 +382,7 @@ static int check_status(const int* d_status, int64_t B, cudaStream_t s) {
 
 int cpimh_pf_fetch(cpimh_pf* h, int64_t B, void* stream, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
   CPIMH_REQUIRE(h, "null handle");
+  if (h->wide) return wide_fetch(h->wide, B, (cudaStream_t)stream, logz, logz_t, trajectory, path_index);
   CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = check_status(h->status.as<int>(), B, s);
@@ -384,6 +401,7 @@ int cpimh_pf_fetch(cpimh_pf* h, int64_t B, void* stream, double* logz, double* l
 
 int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ancestors) {
   CPIMH_REQUIRE(h && ancestors, "null argument");
+  if (h->wide) return wide_fetch_ancestors(h->wide, b, (cudaStream_t)stream, ancestors);
   CPIMH_REQUIRE(h->record_anc, "call cpimh_pf_record_ancestors(h, 1) before cpimh_pf_run");
   CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
   const size_t n = (size_t)h->cfg.nobs * h->cfg.nparticles;
@@ -395,6 +413,7 @@ int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ance
 
 int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* exp_path, double* trajectories, double* normweights) {
   CPIMH_REQUIRE(h, "null handle");
+  CPIMH_REQUIRE(!h->wide, "all-particle outputs are not available for the wide (d = 32/64) filter");
   CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
   CPIMH_REQUIRE(h->geo.path_mode != PATH_NONE, "all-particle outputs need store_paths != 0");
   CPIMH_REQUIRE(h->lastB <= h->grid, "all-particle outputs read the path store of the CTA that ran the filter: run at most %d filters per launch "
@@ -416,14 +435,16 @@ int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* e
 
 int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory) {
   CPIMH_REQUIRE(h, "null handle");
+  if (h->wide) { wide_device_outputs(h->wide, d_logz, d_trajectory); return CPIMH_OK; }
   if (d_logz) *d_logz = h->logz.as<double>();
   if (d_trajectory) *d_trajectory = h->traj.as<double>();
   return CPIMH_OK;
 }
-int64_t cpimh_pf_launch_count(const cpimh_pf* h) { return h ? h->launches : 0; }
-int64_t cpimh_pf_device_bytes(const cpimh_pf* h) { return h ? h->bytes : 0; }
+int64_t cpimh_pf_launch_count(const cpimh_pf* h) { return !h ? 0 : (h->wide ? wide_launch_count(h->wide) : h->launches); }
+int64_t cpimh_pf_device_bytes(const cpimh_pf* h) { return !h ? 0 : (h->wide ? wide_device_bytes(h->wide) : h->bytes); }
 int cpimh_pf_effective_config(const cpimh_pf* h, cpimh_config* out) {
   CPIMH_REQUIRE(h && out, "null argument");
+  if (h->wide) { wide_effective(h->wide, out); return CPIMH_OK; }
   *out = h->cfg;
   out->tree_capacity = h->geo.path_mode == PATH_TREE ? h->geo.M : 0;
   out->threads_per_filter = h->geo.threads;

@@ -3,20 +3,20 @@
 
 namespace cpimh {
 
-template <int S>
+template <int C>
 __device__ void lorenz_wide_body(const double* xin, long long n, double t0, double t1, double F, int substeps, double* xout) {
   const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (p >= n) return;
-  constexpr int D = 32 * S;
-  double v[S];
+  constexpr int D = 32 * C;
+  double v[C];
 #pragma unroll
-  for (int s = 0; s < S; s++) v[s] = xin[(size_t)p * D + s * 32 + lane];
+  for (int s = 0; s < C; s++) v[s] = xin[(size_t)p * D + lane * C + s];
   const int ns = substeps < 1 ? 1 : substeps;
   const double h = (t1 - t0) / ns;
-  for (int q = 0; q < ns; q++) lorenz_wide_rk4<S>(F, h, v, lane);
+  for (int q = 0; q < ns; q++) lorenz_wide_rk4<C>(F, h, v, lane);
 #pragma unroll
-  for (int s = 0; s < S; s++) xout[(size_t)p * D + s * 32 + lane] = v[s];
+  for (int s = 0; s < C; s++) xout[(size_t)p * D + lane * C + s] = v[s];
 }
 __global__ void lorenz_wide_rk4_kernel(const double* xin, long long n, int d, double t0, double t1, double F, int substeps, double* xout) {
   if (d == 64) lorenz_wide_body<2>(xin, n, t0, t1, F, substeps, xout);

@@ -1,0 +1,400 @@
+// wide.cu -- the bootstrap filter for WIDE states (Lorenz 96, d = 32 or 64; BASELINE config 5: d = 64, N = 65536,
+// T = 500, path storage on): one filter spans the whole GPU.  Same step as pf_fused.cuh (R/CPF.R:35-67) but split at
+// the two grid-wide dependencies:
+//   wide_propagate   warp per particle: ancestor search in the CDF, 512-byte coalesced gather of the ancestor's state,
+//                    RK4 on shuffles (lorenz_wide.cuh), process noise, measurement density, per-CTA max of log-weights
+//   wide_weights     w = exp(lw - max), per-chunk sums; next step's log(u_i)/i ladder and its per-chunk sums
+//   wide_scan        normalise, log Z increment, chunk scans with carry-in: CDF and sorted-uniform exponents
+// State and path storage are the same dense history hist_x[t][i][0..d) (array of rows: a particle's d doubles are
+// contiguous, which is also R's d x N column-major layout) + hist_a[t][i].
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "host_common.h"
+#include "lorenz_wide.cuh"
+#include "wide.h"
+
+namespace cpimh {
+
+#define WIDE_CHUNK 4096      // elements per CTA in the weight/scan kernels (1024 threads x 4)
+
+struct WideParams {
+  int N, T, D, B, NC, GX, G, substeps;
+  unsigned long long seed, first_filter;
+  const double* obs;          // [T][D]
+  double F, sx, sy, cst;
+  double* hist_x; int* hist_a;
+  double* lw; double* C; double* S;
+  double* pmax; double* psum; double* pv; double* mstep;
+  double* logz_t; double* logz; double* traj; int* path_index;
+  const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_path;
+  int* anc_rec;
+};
+
+__device__ __forceinline__ int g_count_le_w(const double* c, int n, double u) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (c[mid] <= u) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int g_count_lt_w(const double* c, int n, double u) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (c[mid] < u) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// ------------------------------------------------------------------ rinit: -1 + 4 pnorm(z)  (R/model_get_lorenz.R:18-20)
+template <int C>
+__global__ void wide_init_kernel(WideParams p) {
+  constexpr int D = 32 * C;
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= p.N) return;
+  const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+  double z[C];
+  if (p.inj_init) {
+#pragma unroll
+    for (int c = 0; c < C; c++) z[c] = p.inj_init[((size_t)b * D + lane * C + c) * p.N + i];
+  } else lorenz_wide_normals<C>(s, (unsigned)i, 0, CPIMH_P_INIT, lane, z);
+  double* x0 = p.hist_x + ((size_t)b * (p.T + 1)) * p.N * D + (size_t)i * D;
+#pragma unroll
+  for (int c = 0; c < C; c++) x0[lane * C + c] = -1.0 + 4.0 * (0.5 * erfc(-z[c] / sqrt(2.0)));
+}
+
+// ------------------------------------------------------------------ one time step for all particles of all filters
+template <int C>
+__global__ void wide_propagate_kernel(WideParams p, int t, int ident) {
+  constexpr int D = 32 * C;
+  __shared__ double smax[32];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int N = p.N, G = p.G;
+  const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+  const double* Cb = p.C + (size_t)b * N;
+  const double* Sb = p.S + (size_t)b * N;
+  const double* xold = p.hist_x + ((size_t)b * (p.T + 1) + (t - 1)) * N * D;
+  double* xnew = p.hist_x + ((size_t)b * (p.T + 1) + t) * N * D;
+  int* ha = p.hist_a + ((size_t)b * p.T + (t - 1)) * N;
+  const double* y = p.obs + (size_t)(t - 1) * D;
+  const bool na = isnan(y[0]);                                             // R/model_get_lorenz.R:39-40
+  double yv[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) yv[c] = y[lane * C + c];
+  const double h = 0.05 / (double)p.substeps;
+  double gmax = -INFINITY;
+  const long long base = ((long long)blockIdx.x * nwarp + warp) * G;
+  if (base < N) {
+    // ancestors of this warp's G particles: lanes search in parallel (src/multinomial.cpp:25-28 rule)
+    const long long k = base + lane;
+    int a = 0;
+    if (lane < G && k < N) {
+      if (ident) a = (int)k;
+      else {
+        const double sumw = Cb[N - 1];
+        const double e = p.inj_resample ? Sb[k] : exp(Sb[k]);
+        a = g_count_le_w(Cb, N, sumw * e);
+        if (a >= N) a = N - 1;
+      }
+      ha[k] = a;
+      if (p.anc_rec) p.anc_rec[((size_t)b * p.T + (t - 1)) * N + k] = a;
+    }
+    double mylw = -INFINITY;
+    for (int j = 0; j < G && base + j < N; j++) {
+      const int aj = __shfl_sync(0xffffffffu, a, j);
+      const long long kk = base + j;
+      double v[C], z[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) v[c] = xold[(size_t)aj * D + lane * C + c];
+      for (int q = 0; q < p.substeps; q++) lorenz_wide_rk4<C>(p.F, h, v, lane);      // R/model_get_lorenz.R:28
+      if (p.inj_trans) {
+#pragma unroll
+        for (int c = 0; c < C; c++) z[c] = p.inj_trans[(((size_t)b * p.T + (t - 1)) * D + lane * C + c) * N + kk];
+      } else lorenz_wide_normals<C>(s, (unsigned)kk, t, CPIMH_P_TRANS, lane, z);
+      double sq = 0.0;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        v[c] = v[c] + p.sx * z[c];                                                      // :29
+        xnew[(size_t)kk * D + lane * C + c] = v[c];
+        const double r = (v[c] - yv[c]) / p.sy;
+        sq += r * r;
+      }
+      sq = warp_sum(sq);
+      const double lw = na ? 0.0 : (-0.5 * sq + p.cst);                                // src/mvnorm.cpp:127-130
+      if (lane == j) mylw = lw;
+    }
+    if (lane < G && k < N) p.lw[(size_t)b * N + k] = mylw;
+    gmax = warp_max(mylw);
+  }
+  if (lane == 0) smax[warp] = gmax;
+  __syncthreads();
+  if (warp == 0) {
+    double m = lane < nwarp ? smax[lane] : -INFINITY;
+    m = warp_max(m);
+    if (lane == 0) p.pmax[(size_t)b * p.GX + blockIdx.x] = m;
+  }
+}
+
+// ------------------------------------------------------------------ weights of step t_done (+ uniform ladder of step t_done+1)
+__global__ void wide_weights_kernel(WideParams p, int t_done, int prep) {
+  __shared__ double scr[32];
+  const int b = blockIdx.y, N = p.N;
+  double m = -INFINITY;
+  for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[(size_t)b * p.GX + i]);
+  m = block_max(m, scr);
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.mstep[b] = m;
+  const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+  const long long lo = (long long)blockIdx.x * WIDE_CHUNK;
+  double sw = 0.0, sv = 0.0;
+  for (int q = threadIdx.x; q < WIDE_CHUNK; q += blockDim.x) {
+    const long long i = lo + q;
+    if (i >= N) break;
+    const double w = exp(p.lw[(size_t)b * N + i] - m);                               // R/CPF.R:62
+    p.C[(size_t)b * N + i] = w;
+    sw += w;
+    if (prep) {
+      double v;
+      if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t_done) * N + i];    // row of step t_done+1 (0-based t_done)
+      else { v = log(philox_u1(s, (unsigned)i, t_done + 1, CPIMH_P_RESAMPLE, 0)) / (double)(i + 1); sv += v; }   // src/multinomial.cpp:23
+      p.S[(size_t)b * N + i] = v;
+    }
+  }
+  sw = block_sum(sw, scr);
+  sv = block_sum(sv, scr);
+  if (threadIdx.x == 0) { p.psum[(size_t)b * p.NC + blockIdx.x] = sw; p.pv[(size_t)b * p.NC + blockIdx.x] = sv; }
+}
+
+// ------------------------------------------------------------------ normalise + log Z increment + scans with carry-in
+__global__ void wide_scan_kernel(WideParams p, int t_done, int prep) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  double* buf = reinterpret_cast<double*>(raw);     // [WIDE_CHUNK]
+  __shared__ double scr[32];
+  const int b = blockIdx.y, N = p.N, cta = blockIdx.x;
+  double s = 0.0, carry = 0.0, vcarry = 0.0;
+  for (int c = 0; c < p.NC; c++) {                  // NC <= 256 partial sums: every thread folds them in the same order
+    const double ps = p.psum[(size_t)b * p.NC + c];
+    if (c < cta) carry += ps;
+    s += ps;
+    if (c > cta) vcarry += p.pv[(size_t)b * p.NC + c];
+  }
+  if (cta == 0 && threadIdx.x == 0) p.logz_t[(size_t)b * p.T + (t_done - 1)] = log(s / (double)N) + p.mstep[b];   // R/CPF.R:66
+  const long long lo = (long long)cta * WIDE_CHUNK;
+  const int n = (int)min((long long)WIDE_CHUNK, (long long)N - lo);
+  if (n <= 0) return;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = p.C[(size_t)b * N + lo + q] / s;     // normweights (R/CPF.R:63)
+  __syncthreads();
+  block_scan_inplace<false>(buf, n, scr);
+  const double c0 = carry / s;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) p.C[(size_t)b * N + lo + q] = buf[q] + c0;
+  if (prep && !p.inj_resample) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = p.S[(size_t)b * N + lo + q];
+    __syncthreads();
+    block_scan_inplace<true>(buf, n, scr);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) p.S[(size_t)b * N + lo + q] = buf[q] + vcarry;
+  }
+}
+
+// ------------------------------------------------------------------ final path: systematic(normw, 1, u) + get_path (R/CPF.R:69)
+template <int C>
+__global__ void wide_path_kernel(WideParams p) {
+  constexpr int D = 32 * C;
+  const int b = blockIdx.x, lane = threadIdx.x, N = p.N, T = p.T;
+  const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+  const double u = p.inj_path ? p.inj_path[b] : philox_u1(s, 0, T + 1, CPIMH_P_PATH, 0);
+  int k = g_count_lt_w(p.C + (size_t)b * N, N, u);
+  if (k >= N) k = N - 1;
+  if (lane == 0) {
+    p.path_index[b] = k;
+    double acc = 0.0;
+    for (int t = 0; t < T; t++) acc += p.logz_t[(size_t)b * T + t];
+    p.logz[b] = acc;
+  }
+  int j = k;
+  for (int step = T; step >= 0; step--) {
+    const double* row = p.hist_x + (((size_t)b * (T + 1) + step) * N + j) * D;
+#pragma unroll
+    for (int c = 0; c < C; c++) p.traj[((size_t)b * (T + 1) + step) * D + lane * C + c] = row[lane * C + c];
+    if (step > 0) j = p.hist_a[((size_t)b * T + (step - 1)) * N + j];
+  }
+}
+
+// ================================================================== host side
+struct WideFilter {
+  cpimh_config cfg;
+  int64_t maxB, lastB, launches, bytes;
+  int NC, GX, G, record_anc;
+  std::vector<double> obs_host;
+  DevBuf obs, hist_x, hist_a, lw, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
+  DevBuf inj_init, inj_trans, inj_resample, inj_path;
+  bool have_inj[4];
+};
+
+static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* GX, int* NC) {
+  // particles per warp: enough warps to fill the machine, at most 32 so the per-group ancestor search stays one pass
+  long long target = (long long)num_sms * 48;
+  long long g = ((long long)c.nparticles * B + target - 1) / target;
+  int G_ = 1;
+  while (G_ < 32 && G_ < g) G_ <<= 1;
+  *G = G_;
+  const int warps_per_cta = 4;
+  *GX = (int)(((long long)c.nparticles + (long long)G_ * warps_per_cta - 1) / ((long long)G_ * warps_per_cta));
+  *NC = (c.nparticles + WIDE_CHUNK - 1) / WIDE_CHUNK;
+}
+
+int wide_supported(const cpimh_config& c) { return c.model == CPIMH_MODEL_LORENZ && (c.dim == 32 || c.dim == 64); }
+
+int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) {
+  CPIMH_REQUIRE(cfg.integrator == CPIMH_INTEGRATOR_RK4, "Lorenz 96 with d = %d runs the fixed-step rk4 integrator only (dopri5: d in {4, 8, 16})", cfg.dim);
+  CPIMH_REQUIRE(cfg.nparticles >= 1 && cfg.nparticles <= (1 << 20), "wide filter supports 1 <= N <= 2^20 (got %d)", cfg.nparticles);
+  CPIMH_REQUIRE(cfg.dim_y == cfg.dim, "dim_y must equal dim for the Lorenz model");
+  CPIMH_REQUIRE(!cfg.shuffle, "shuffle = 1 is not available for the wide filter");
+  int dev = 0; cudaDeviceProp prop;
+  CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
+  CPIMH_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  CPIMH_REQUIRE(prop.major >= 10, "libcpimh is built for sm_100a (Blackwell); device %d is sm_%d%d", dev, prop.major, prop.minor);
+  WideFilter* h = new WideFilter();
+  h->cfg = cfg; h->maxB = max_filters; h->lastB = 0; h->launches = 0; h->bytes = 0; h->record_anc = 0;
+  memset(h->have_inj, 0, sizeof(h->have_inj));
+  wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->GX, &h->NC);
+  CPIMH_REQUIRE(h->NC <= 256, "N too large for the chunked scan");
+  const size_t B = (size_t)max_filters, N = cfg.nparticles, T = cfg.nobs, D = cfg.dim;
+  size_t free_b = 0, total_b = 0;
+  CPIMH_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  const double need = (double)B * (T + 1) * N * D * 8.0 + (double)B * T * N * 4.0;
+  if (need > 0.9 * (double)free_b) { delete h; CPIMH_REQUIRE(false, "the particle history needs %.1f GB but %.1f GB of HBM is free; lower max_filters", need / 1e9, free_b / 1e9); }
+  auto A = [&](DevBuf& b, size_t n) { return b.alloc(n, &h->bytes); };
+  int rc = A(h->obs, sizeof(double) * T * D);
+  if (!rc) rc = A(h->hist_x, sizeof(double) * B * (T + 1) * N * D);
+  if (!rc) rc = A(h->hist_a, sizeof(int) * B * T * N);
+  if (!rc) rc = A(h->lw, sizeof(double) * B * N);
+  if (!rc) rc = A(h->C, sizeof(double) * B * N);
+  if (!rc) rc = A(h->S, sizeof(double) * B * N);
+  if (!rc) rc = A(h->pmax, sizeof(double) * B * h->GX);
+  if (!rc) rc = A(h->psum, sizeof(double) * B * h->NC);
+  if (!rc) rc = A(h->pv, sizeof(double) * B * h->NC);
+  if (!rc) rc = A(h->mstep, sizeof(double) * B);
+  if (!rc) rc = A(h->logz_t, sizeof(double) * B * T);
+  if (!rc) rc = A(h->logz, sizeof(double) * B);
+  if (!rc) rc = A(h->traj, sizeof(double) * B * (T + 1) * D);
+  if (!rc) rc = A(h->path_index, sizeof(int) * B);
+  if (rc) { wide_destroy(h); return rc; }
+  *out = h;
+  return CPIMH_OK;
+}
+
+void wide_destroy(WideFilter* h) {
+  if (!h) return;
+  DevBuf* all[] = {&h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
+                   &h->path_index, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_path};
+  for (auto b : all) b->release();
+  delete h;
+}
+
+int wide_set_observations(WideFilter* h, const double* obs_host) {
+  const int T = h->cfg.nobs, D = h->cfg.dim;
+  h->obs_host.assign((size_t)T * D, 0.0);
+  for (int t = 0; t < T; t++)
+    for (int j = 0; j < D; j++) h->obs_host[(size_t)t * D + j] = obs_host[t + (size_t)T * j];
+  CPIMH_CUDA_CHECK(cudaMemcpy(h->obs.p, h->obs_host.data(), sizeof(double) * h->obs_host.size(), cudaMemcpyHostToDevice));
+  return CPIMH_OK;
+}
+
+int wide_set_noise(WideFilter* h, int64_t B, const cpimh_noise* nz) {
+  memset(h->have_inj, 0, sizeof(h->have_inj));
+  if (!nz) return CPIMH_OK;
+  CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters out of range");
+  CPIMH_REQUIRE(!nz->shuffle, "shuffle noise is not available for the wide filter");
+  const size_t N = h->cfg.nparticles, T = h->cfg.nobs, D = h->cfg.dim;
+  struct Item { const double* src; DevBuf* dst; size_t n; } items[4] = {
+      {nz->init, &h->inj_init, (size_t)B * D * N}, {nz->trans, &h->inj_trans, (size_t)B * T * D * N},
+      {nz->resample, &h->inj_resample, (size_t)B * T * N}, {nz->path_u, &h->inj_path, (size_t)B}};
+  for (int i = 0; i < 4; i++) {
+    if (!items[i].src) continue;
+    int rc = items[i].dst->alloc(sizeof(double) * items[i].n, &h->bytes);
+    if (rc) return rc;
+    CPIMH_CUDA_CHECK(cudaMemcpy(items[i].dst->p, items[i].src, sizeof(double) * items[i].n, cudaMemcpyHostToDevice));
+    h->have_inj[i] = true;
+  }
+  return CPIMH_OK;
+}
+
+int wide_record_ancestors(WideFilter* h, int on) {
+  h->record_anc = on ? 1 : 0;
+  if (on) return h->anc_rec.alloc(sizeof(int) * (size_t)h->maxB * h->cfg.nobs * h->cfg.nparticles, &h->bytes);
+  return CPIMH_OK;
+}
+
+template <int C>
+static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
+  const int T = p.T, B = p.B;
+  const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)p.GX, (unsigned)B), gc((unsigned)p.NC, (unsigned)B);
+  wide_init_kernel<C><<<gi, 256, 0, s>>>(p);
+  h->launches++;
+  for (int t = 1; t <= T; t++) {
+    const int ident = (t == 1) || isnan(h->obs_host[(size_t)(t - 2) * p.D]);         // R/CPF.R:38-40
+    if (t >= 2) {
+      wide_weights_kernel<<<gc, 1024, 0, s>>>(p, t - 1, ident ? 0 : 1);
+      wide_scan_kernel<<<gc, 1024, WIDE_CHUNK * sizeof(double), s>>>(p, t - 1, ident ? 0 : 1);
+      h->launches += 2;
+    }
+    wide_propagate_kernel<C><<<gp, 128, 0, s>>>(p, t, ident);
+    h->launches++;
+  }
+  wide_weights_kernel<<<gc, 1024, 0, s>>>(p, T, 0);
+  wide_scan_kernel<<<gc, 1024, WIDE_CHUNK * sizeof(double), s>>>(p, T, 0);
+  wide_path_kernel<C><<<B, 32, 0, s>>>(p);
+  h->launches += 3;
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  return CPIMH_OK;
+}
+
+int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cudaStream_t s) {
+  CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
+  const cpimh_config& c = h->cfg;
+  WideParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.NC = h->NC; p.GX = h->GX; p.G = h->G; p.substeps = c.substeps < 1 ? 1 : c.substeps;
+  p.seed = seed; p.first_filter = first_filter;
+  p.obs = h->obs.as<double>();
+  p.F = c.theta[0]; p.sx = c.theta[1]; p.sy = c.theta[2];
+  double hl = 0;
+  for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);                               // src/mvnorm.cpp:120-121
+  p.cst = -(hl) - (c.dim * CPIMH_HALF_LOG_2PI_TRUNC);
+  p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.lw = h->lw.as<double>(); p.C = h->C.as<double>(); p.S = h->S.as<double>();
+  p.pmax = h->pmax.as<double>(); p.psum = h->psum.as<double>(); p.pv = h->pv.as<double>(); p.mstep = h->mstep.as<double>();
+  p.logz_t = h->logz_t.as<double>(); p.logz = h->logz.as<double>(); p.traj = h->traj.as<double>(); p.path_index = h->path_index.as<int>();
+  p.inj_init = h->have_inj[0] ? h->inj_init.as<double>() : nullptr;
+  p.inj_trans = h->have_inj[1] ? h->inj_trans.as<double>() : nullptr;
+  p.inj_resample = h->have_inj[2] ? h->inj_resample.as<double>() : nullptr;
+  p.inj_path = h->have_inj[3] ? h->inj_path.as<double>() : nullptr;
+  p.anc_rec = h->record_anc ? h->anc_rec.as<int>() : nullptr;
+  int rc = c.dim == 64 ? wide_run_t<2>(h, p, s) : wide_run_t<1>(h, p, s);
+  if (rc) return rc;
+  h->lastB = B;
+  return CPIMH_OK;
+}
+
+int wide_fetch(WideFilter* h, int64_t B, cudaStream_t s, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
+  CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
+  const cpimh_config& c = h->cfg;
+  if (logz) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz, h->logz.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  if (logz_t) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz_t, h->logz_t.p, sizeof(double) * (size_t)B * c.nobs, cudaMemcpyDeviceToHost, s));
+  if (trajectory) CPIMH_CUDA_CHECK(cudaMemcpyAsync(trajectory, h->traj.p, sizeof(double) * (size_t)B * (c.nobs + 1) * c.dim, cudaMemcpyDeviceToHost, s));
+  if (path_index) CPIMH_CUDA_CHECK(cudaMemcpyAsync(path_index, h->path_index.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CPIMH_OK;
+}
+
+int wide_fetch_ancestors(WideFilter* h, int64_t b, cudaStream_t s, int32_t* anc) {
+  CPIMH_REQUIRE(h->record_anc, "call cpimh_pf_record_ancestors(h, 1) before cpimh_pf_run");
+  CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
+  const size_t n = (size_t)h->cfg.nobs * h->cfg.nparticles;
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(anc, h->anc_rec.as<int>() + (size_t)b * n, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CPIMH_OK;
+}
+
+int64_t wide_launch_count(const WideFilter* h) { return h->launches; }
+int64_t wide_device_bytes(const WideFilter* h) { return h->bytes; }
+void wide_device_outputs(WideFilter* h, double** d_logz, double** d_traj) { if (d_logz) *d_logz = h->logz.as<double>(); if (d_traj) *d_traj = h->traj.as<double>(); }
+void wide_effective(const WideFilter* h, cpimh_config* out) { *out = h->cfg; out->tree_capacity = 0; out->threads_per_filter = h->G; out->store_paths = 2; out->reserved = h->GX; }
+
+}  // namespace cpimh
