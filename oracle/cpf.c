@@ -43,14 +43,20 @@ int orc_cpf(const orc_config* cfg, const double* obs, const orc_noise* noise, ui
     if (identity) {
       for (int i = 0; i < N; i++) anc[i] = i;
     } else {
-      const double* es;
-      if (noise && noise->resample) es = noise->resample + (size_t)(time - 1) * N;
-      else {
-        for (int i = 0; i < N; i++) { double ub; orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ubuf[i], &ub); }
-        orc_sorted_uniforms(ubuf, N, ebuf);
-        es = ebuf;
+      if (noise && noise->resample) {
+        clamp += orc_multinomial_from_sorted(normw, N, N, noise->resample + (size_t)(time - 1) * N, 1, anc);
+      } else {
+        /* Philox mode (DESIGN.md "RNG"): the sorted uniforms are the order statistics built from exponential spacings,
+         * e_i = (E_0+..+E_i) / (E_0+..+E_N), E_i = -log(u_i); same law as the recurrence of src/multinomial.cpp:20-24 */
+        double acc = 0, ua, ub;
+        for (int i = 0; i < N; i++) {
+          orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
+          acc = (i == 0) ? -log(ua) : acc + (-log(ua));
+          ebuf[i] = acc;
+        }
+        orc_philox_uniform2(seed, (uint32_t)N, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
+        clamp += orc_multinomial_from_ladder(normw, N, N, ebuf, acc - log(ua), anc);
       }
-      clamp += orc_multinomial_from_sorted(normw, N, N, es, 1, anc);
       if (cfg->shuffle) {
         const double* us;
         if (noise && noise->shuffle) us = noise->shuffle + (size_t)(time - 1) * (N - 1);

@@ -68,6 +68,7 @@ void orc_philox_uniform2(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, u
 int  orc_systematic_resampling_n(const double* w, int nparticles, int ndraws, double u, int* anc);
 void orc_sorted_uniforms(const double* u_raw, int n, double* e_sorted);
 int  orc_multinomial_from_sorted(const double* w, int nparticles, int ndraws, const double* e_sorted, int scale_by_sumw, int* anc);
+int  orc_multinomial_from_ladder(const double* w, int nparticles, int ndraws, const double* P, double total, int* anc);
 void orc_random_shuffle_int(int* a, int n, const double* u_shuffle);
 int  orc_multinomial_resampling_n(const double* w, int nparticles, int ndraws, const double* u_raw, const double* u_shuffle, int* anc);
 int  orc_coupled_multinomial_resampling_n(const double* w1, const double* w2, int nparticles, int ndraws,

@@ -53,6 +53,25 @@ int orc_multinomial_from_sorted(const double* w, int nparticles, int ndraws, con
   return clamped;
 }
 
+/* Multinomial resampling against an exponential-spacing ladder P_i (prefix sums) with grand total `total`:
+ * u_i = (sumw / total) * P_i, then the same backward merge as src/multinomial.cpp:25-28. */
+int orc_multinomial_from_ladder(const double* w, int nparticles, int ndraws, const double* P, double total, int* anc) {
+  double* cdf = (double*)malloc(sizeof(double) * (size_t)nparticles);
+  cdf[0] = w[0];
+  for (int i = 1; i < nparticles; i++) cdf[i] = cdf[i - 1] + w[i];
+  const double scale = cdf[nparticles - 1] / total;
+  int j = nparticles, clamped = 0;
+  for (int i = ndraws; i > 0; i--) {
+    double u = scale * P[i - 1];
+    while (j > 0 && u < cdf[j - 1]) j--;
+    int a = j;
+    if (a >= nparticles) { a = nparticles - 1; clamped++; }
+    anc[i - 1] = a;
+  }
+  free(cdf);
+  return clamped;
+}
+
 /* libstdc++ std::random_shuffle(first,last,rand) as called at src/multinomial.cpp:30,65 with
  * randWrapper(n) = floor(runif(1)*n) (:6-10): for i = 1..n-1: swap(a[i], a[rand(i+1)]). */
 void orc_random_shuffle_int(int* a, int n, const double* u_shuffle) {

@@ -172,6 +172,24 @@ int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, i
   return CPIMH_OK;
 }
 
+// Tail launch: when the last wave of a batch would leave most SMs with one CTA instead of two, those filters run
+// faster as one 1024-thread CTA per SM.  Returns tail->threads = 0 when no such variant applies.
+int api_plan_tail_geometry(const cpimh_config& c, const ModelEntry* e, int npre, const Geometry& main, Geometry* tail) {
+  *tail = main;
+  tail->threads = 0;
+  if (main.variant == PF_VARIANT_1024x1 || c.threads_per_filter > 0 || main.blocks_per_sm < 2 || c.nparticles < 2048) return CPIMH_OK;
+  Geometry t = main;
+  t.variant = PF_VARIANT_1024x1; t.threads = 1024;
+  t.smem = pf_smem_bytes(t.Npad, t.M, npre, t.path_mode, c.shuffle);
+  int bps = 0;
+  int rc = e->occupancy_pf(t.variant, t.threads, t.smem, &bps);
+  if (rc) return rc;
+  if (bps < 1) return CPIMH_OK;
+  t.blocks_per_sm = 1;
+  *tail = t;
+  return CPIMH_OK;
+}
+
 }  // namespace cpimh
 
 using namespace cpimh;
@@ -181,7 +199,7 @@ struct cpimh_pf {
   WideFilter* wide = nullptr;   // d = 32/64 Lorenz: one filter across the GPU (wide.cu); all other fields unused then
   cpimh_config cfg;
   const ModelEntry* entry;
-  Geometry geo;
+  Geometry geo, geo_tail;
   int64_t maxB, lastB;
   int record_anc;
   int64_t launches, bytes;
@@ -227,7 +245,9 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   rc = api_plan_geometry(cfg, e, false, max_filters, (int)pre.size(), &g);
   if (rc) return rc;
   cpimh_pf* h = new cpimh_pf();
-  h->cfg = cfg; h->entry = e; h->geo = g; h->maxB = max_filters; h->lastB = 0; h->record_anc = 0; h->launches = 0; h->bytes = 0;
+  h->cfg = cfg; h->entry = e; h->geo = g; h->maxB = max_filters;
+  rc = api_plan_tail_geometry(cfg, e, (int)pre.size(), g, &h->geo_tail);
+  if (rc) { delete h; return rc; } h->lastB = 0; h->record_anc = 0; h->launches = 0; h->bytes = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
   const int D = cfg.dim, N = cfg.nparticles, T = cfg.nobs;
   h->npre = (int)pre.size();
@@ -356,11 +376,26 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   p.inj_resample = h->have_inj[2] ? h->inj_resample.as<double>() : nullptr;
   p.inj_shuffle = h->have_inj[3] ? h->inj_shuffle.as<double>() : nullptr;
   p.inj_path = h->have_inj[4] ? h->inj_path.as<double>() : nullptr;
+  // whole waves with the main geometry; a short last wave (at most one filter per SM) as 1024-thread CTAs
+  int64_t main_B = B, tail_B = 0;
+  if (h->geo_tail.threads > 0 && B > h->grid) {
+    const int64_t rem = B % h->grid;
+    if (rem > 0 && rem <= h->geo.num_sms) { tail_B = rem; main_B = B - rem; }
+  }
   PfLaunch L;
   L.threads = h->geo.threads; L.smem = h->geo.smem; L.variant = h->geo.variant;
-  L.grid = (int)(B < h->grid ? B : h->grid);
+  L.grid = (int)(main_B < h->grid ? main_B : h->grid);
+  p.B = main_B; p.b0 = 0;
   int rc = h->entry->launch_pf(p, L, (cudaStream_t)stream);
   if (rc) return rc;
+  if (tail_B > 0) {
+    PfLaunch Lt;
+    Lt.threads = h->geo_tail.threads; Lt.smem = h->geo_tail.smem; Lt.variant = h->geo_tail.variant; Lt.grid = (int)tail_B;
+    p.B = tail_B; p.b0 = main_B;
+    rc = h->entry->launch_pf(p, Lt, (cudaStream_t)stream);
+    if (rc) return rc;
+    h->launches += 1;
+  }
   h->launches += 1; h->lastB = B;
   return CPIMH_OK;
 }

@@ -172,6 +172,38 @@ __device__ __forceinline__ void block_scan_inplace(double* a, int n, double* scr
   __syncthreads();
 }
 
+// Two forward in-place inclusive scans (a and b, same length) sharing the row loop, the barriers and the carry logic.
+// `scratch` needs 64 doubles.
+__device__ __forceinline__ void block_scan2_inplace(double* a, double* b, int n, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int rows = (n + 31) >> 5;
+  const int rpw = (rows + nw - 1) / nw;
+  const int r0 = wid * rpw, r1 = min(rows, r0 + rpw);
+  double ca = 0.0, cb = 0.0;
+  for (int r = r0; r < r1; r++) {
+    const int j = r * 32 + lane;
+    double va = (j < n) ? a[j] : 0.0, vb = (j < n) ? b[j] : 0.0;
+    va = warp_incl_scan(va, lane) + ca;
+    vb = warp_incl_scan(vb, lane) + cb;
+    if (j < n) { a[j] = va; b[j] = vb; }
+    ca = __shfl_sync(0xffffffffu, va, 31);
+    cb = __shfl_sync(0xffffffffu, vb, 31);
+  }
+  if (lane == 0) { scratch[wid] = ca; scratch[32 + wid] = cb; }
+  __syncthreads();
+  const double wa = (lane < nw) ? scratch[lane] : 0.0, wb = (lane < nw) ? scratch[32 + lane] : 0.0;
+  const double ia = warp_incl_scan(wa, lane), ib = warp_incl_scan(wb, lane);
+  const double oa = __shfl_sync(0xffffffffu, ia, wid) - __shfl_sync(0xffffffffu, wa, wid);
+  const double ob = __shfl_sync(0xffffffffu, ib, wid) - __shfl_sync(0xffffffffu, wb, wid);
+  if (wid > 0) {
+    for (int r = r0; r < r1; r++) {
+      const int j = r * 32 + lane;
+      if (j < n) { a[j] += oa; b[j] += ob; }
+    }
+  }
+  __syncthreads();
+}
+
 // number of entries of the (ascending) shared array c[0..n) that are <= u   (src/multinomial.cpp:25-27 rule)
 __device__ __forceinline__ int count_le(const double* c, int n, double u) {
   int lo = 0, hi = n;

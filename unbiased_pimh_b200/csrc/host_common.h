@@ -35,6 +35,7 @@ struct Geometry {
 
 int api_validate(cpimh_config* c);
 int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, int64_t max_items, int npre, Geometry* g);
+int api_plan_tail_geometry(const cpimh_config& c, const ModelEntry* e, int npre, const Geometry& main, Geometry* tail);
 void api_fill_pf_params(const cpimh_config& c, const Geometry& g, int npre, PfParams* p);
 std::vector<double> api_precompute(const cpimh_config& c);
 int api_upload_obs(const cpimh_config& cfg, const double* obs_host, void* dst);

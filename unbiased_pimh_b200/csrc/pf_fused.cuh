@@ -27,6 +27,7 @@ struct PfParams {
   int N, T, dy, Npad;
   int M;                       // tree capacity per filter (multiple of 32)
   long long B;                 // filters in this launch
+  long long b0;                // index of the first filter of this launch (outputs and streams are indexed b0 + ...)
   int shuffle, path_mode;
   unsigned long long seed, first_filter;
   const double* obs;           // [T][dy] row-major (device)
@@ -64,14 +65,14 @@ struct PfSmem {
   unsigned* bits;   // [M/32] free-slot bitmap (1 = free)              (PATH_TREE)
   double* theta;    // [CPIMH_MAX_THETA]
   double* pre;      // [npre]
-  double* dscr;     // [32]
+  double* dscr;     // [64]
   int* coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
   int* iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
 };
 __host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
   size_t b = 0;
   b += (size_t)Npad * 8 * 2;                 // C, S
-  b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 32) * 8;
+  b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8;
   if (path_mode == PATH_TREE) {
     b += (size_t)Npad * 4 * 2;               // leaf, bpar
     b += (size_t)(Npad / 2) * 4;             // off32
@@ -90,7 +91,7 @@ __device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre,
   s.S = d; d += Npad;
   s.theta = d; d += CPIMH_MAX_THETA;
   s.pre = d; d += npre + (npre & 1);
-  s.dscr = d; d += 32;
+  s.dscr = d; d += 64;
   int* i = reinterpret_cast<int*>(d);
   s.leaf = nullptr; s.bpar = nullptr; s.off32 = nullptr; s.bits = nullptr;
   if (path_mode == PATH_TREE) {
@@ -196,21 +197,26 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       for (int i = tid; i < N; i += NT, e++) {
         double ua, ub;
         philox_u2(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, ub);
-        if (draw_res) sm.S[i] = log(ua) / (double)(i + 1);
+        if (draw_res) sm.S[i] = -log(ua);                 // exponential spacing E_i (see the ladder comment below)
         ukeep[e] = ub;
       }
     }
     if (!ident) {
       if (inj_res) for (int i = tid; i < N; i += NT) sm.S[i] = inj_res[(size_t)(t - 1) * N + i];
       __syncthreads();
-      block_scan_inplace<false>(sm.C, N, sm.dscr);
-      if (!inj_res) block_scan_inplace<true>(sm.S, N, sm.dscr);
+      // Sorted uniforms.  Injected: S holds the ascending e_i of src/multinomial.cpp:22-24 and u_i = sumw e_i (:24).
+      // Philox: the same order statistics from exponential spacings, e_i = (E_0+..+E_i) / (E_0+..+E_N) (one log per
+      // particle instead of the recurrence's log + divide + exp; DESIGN.md "RNG"): S becomes the prefix sums P_i and
+      // u_i = (sumw / total) P_i.
+      if (inj_res) block_scan_inplace<false>(sm.C, N, sm.dscr);
+      else block_scan2_inplace(sm.C, sm.S, N, sm.dscr);
       sumw = sm.C[N - 1];
+      if (!inj_res) sumw = sumw / (sm.S[N - 1] - log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0)));
       // every 32nd sorted uniform gets a full search; the others then search only between their neighbours' results
       const int nrows = (N + 31) >> 5;
       for (int r = tid; r <= nrows; r += NT) {
         int a = N;
-        if (r < nrows) { double e0 = inj_res ? sm.S[r << 5] : exp(sm.S[r << 5]); a = count_le(sm.C, N, sumw * e0); }
+        if (r < nrows) a = count_le(sm.C, N, sumw * sm.S[r << 5]);
         sm.coarse[r] = a;
       }
       __syncthreads();
@@ -221,8 +227,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // -- ancestors: count of CDF knots <= u (:25-28), clamped
     auto ancestor_of = [&](int k) -> int {
       if (ident) return k;
-      double e = inj_res ? sm.S[k] : exp(sm.S[k]);
-      int a = count_le_bounded(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * e);
+      int a = count_le_bounded(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * sm.S[k]);
       if (a >= N) { a = N - 1; st |= 512; }
       return a;
     };
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p
   for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
   for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
   __syncthreads();
-  for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+  for (long long b = p.b0 + blockIdx.x; b < p.b0 + p.B; b += gridDim.x) {
     Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
     FilterOut out;
     out.logz = p.logz + b;

@@ -25,7 +25,7 @@ struct WideParams {
   double F, sx, sy, cst;
   double* hist_x; int* hist_a;
   double* lw; double* C; double* S;
-  double* pmax; double* psum; double* pv; double* mstep;
+  double* pmax; double* psum; double* pv; double* mstep; double* ptot;
   double* logz_t; double* logz; double* traj; int* path_index;
   const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_path;
   int* anc_rec;
@@ -88,37 +88,50 @@ __global__ void wide_propagate_kernel(WideParams p, int t, int ident) {
     if (lane < G && k < N) {
       if (ident) a = (int)k;
       else {
-        const double sumw = Cb[N - 1];
-        const double e = p.inj_resample ? Sb[k] : exp(Sb[k]);
-        a = g_count_le_w(Cb, N, sumw * e);
+        const double scale = p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b];   // u = sumw e_k  /  (sumw / total) P_k
+        a = g_count_le_w(Cb, N, scale * Sb[k]);
         if (a >= N) a = N - 1;
       }
       ha[k] = a;
       if (p.anc_rec) p.anc_rec[((size_t)b * p.T + (t - 1)) * N + k] = a;
     }
     double mylw = -INFINITY;
-    for (int j = 0; j < G && base + j < N; j++) {
-      const int aj = __shfl_sync(0xffffffffu, a, j);
-      const long long kk = base + j;
-      double v[C], z[C];
+    constexpr int PF = 4;                                   // rows in flight: the gathers of PF ancestors are issued together
+    for (int j0 = 0; j0 < G && base + j0 < N; j0 += PF) {
+      double vv[PF][C];
 #pragma unroll
-      for (int c = 0; c < C; c++) v[c] = xold[(size_t)aj * D + lane * C + c];
-      for (int q = 0; q < p.substeps; q++) lorenz_wide_rk4<C>(p.F, h, v, lane);      // R/model_get_lorenz.R:28
-      if (p.inj_trans) {
+      for (int q = 0; q < PF; q++) {
+        const int aj = __shfl_sync(0xffffffffu, a, (j0 + q) & 31);
+        if (j0 + q < G && base + j0 + q < N) {
 #pragma unroll
-        for (int c = 0; c < C; c++) z[c] = p.inj_trans[(((size_t)b * p.T + (t - 1)) * D + lane * C + c) * N + kk];
-      } else lorenz_wide_normals<C>(s, (unsigned)kk, t, CPIMH_P_TRANS, lane, z);
-      double sq = 0.0;
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        v[c] = v[c] + p.sx * z[c];                                                      // :29
-        xnew[(size_t)kk * D + lane * C + c] = v[c];
-        const double r = (v[c] - yv[c]) / p.sy;
-        sq += r * r;
+          for (int c = 0; c < C; c++) vv[q][c] = xold[(size_t)aj * D + lane * C + c];
+        }
       }
-      sq = warp_sum(sq);
-      const double lw = na ? 0.0 : (-0.5 * sq + p.cst);                                // src/mvnorm.cpp:127-130
-      if (lane == j) mylw = lw;
+#pragma unroll
+      for (int q = 0; q < PF; q++) {
+        const int j = j0 + q;
+        if (j >= G || base + j >= N) break;
+        const long long kk = base + j;
+        double v[C], z[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) v[c] = vv[q][c];
+        for (int r = 0; r < p.substeps; r++) lorenz_wide_rk4<C>(p.F, h, v, lane);      // R/model_get_lorenz.R:28
+        if (p.inj_trans) {
+#pragma unroll
+          for (int c = 0; c < C; c++) z[c] = p.inj_trans[(((size_t)b * p.T + (t - 1)) * D + lane * C + c) * N + kk];
+        } else lorenz_wide_normals<C>(s, (unsigned)kk, t, CPIMH_P_TRANS, lane, z);
+        double sq = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          v[c] = v[c] + p.sx * z[c];                                                      // :29
+          xnew[(size_t)kk * D + lane * C + c] = v[c];
+          const double r = (v[c] - yv[c]) / p.sy;
+          sq += r * r;
+        }
+        sq = warp_sum(sq);
+        const double lw = na ? 0.0 : (-0.5 * sq + p.cst);                                // src/mvnorm.cpp:127-130
+        if (lane == j) mylw = lw;
+      }
     }
     if (lane < G && k < N) p.lw[(size_t)b * N + k] = mylw;
     gmax = warp_max(mylw);
@@ -152,7 +165,7 @@ __global__ void wide_weights_kernel(WideParams p, int t_done, int prep) {
     if (prep) {
       double v;
       if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t_done) * N + i];    // row of step t_done+1 (0-based t_done)
-      else { v = log(philox_u1(s, (unsigned)i, t_done + 1, CPIMH_P_RESAMPLE, 0)) / (double)(i + 1); sv += v; }   // src/multinomial.cpp:23
+      else { v = -log(philox_u1(s, (unsigned)i, t_done + 1, CPIMH_P_RESAMPLE, 0)); sv += v; }   // exponential spacing E_i (pf_fused.cuh)
       p.S[(size_t)b * N + i] = v;
     }
   }
@@ -172,7 +185,7 @@ __global__ void wide_scan_kernel(WideParams p, int t_done, int prep) {
     const double ps = p.psum[(size_t)b * p.NC + c];
     if (c < cta) carry += ps;
     s += ps;
-    if (c > cta) vcarry += p.pv[(size_t)b * p.NC + c];
+    if (c < cta) vcarry += p.pv[(size_t)b * p.NC + c];
   }
   if (cta == 0 && threadIdx.x == 0) p.logz_t[(size_t)b * p.T + (t_done - 1)] = log(s / (double)N) + p.mstep[b];   // R/CPF.R:66
   const long long lo = (long long)cta * WIDE_CHUNK;
@@ -187,8 +200,12 @@ __global__ void wide_scan_kernel(WideParams p, int t_done, int prep) {
     __syncthreads();
     for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = p.S[(size_t)b * N + lo + q];
     __syncthreads();
-    block_scan_inplace<true>(buf, n, scr);
+    block_scan_inplace<false>(buf, n, scr);
     for (int q = threadIdx.x; q < n; q += blockDim.x) p.S[(size_t)b * N + lo + q] = buf[q] + vcarry;
+    if (cta == p.NC - 1 && threadIdx.x == 0) {
+      const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+      p.ptot[b] = (buf[n - 1] + vcarry) - log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
+    }
   }
 }
 
@@ -222,6 +239,7 @@ struct WideFilter {
   int64_t maxB, lastB, launches, bytes;
   int NC, GX, G, record_anc;
   std::vector<double> obs_host;
+  DevBuf ptot;
   DevBuf obs, hist_x, hist_a, lw, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
   DevBuf inj_init, inj_trans, inj_resample, inj_path;
   bool have_inj[4];
@@ -271,6 +289,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   if (!rc) rc = A(h->psum, sizeof(double) * B * h->NC);
   if (!rc) rc = A(h->pv, sizeof(double) * B * h->NC);
   if (!rc) rc = A(h->mstep, sizeof(double) * B);
+  if (!rc) rc = A(h->ptot, sizeof(double) * B);
   if (!rc) rc = A(h->logz_t, sizeof(double) * B * T);
   if (!rc) rc = A(h->logz, sizeof(double) * B);
   if (!rc) rc = A(h->traj, sizeof(double) * B * (T + 1) * D);
@@ -282,7 +301,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
 
 void wide_destroy(WideFilter* h) {
   if (!h) return;
-  DevBuf* all[] = {&h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
+  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
                    &h->path_index, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
@@ -359,7 +378,7 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);                               // src/mvnorm.cpp:120-121
   p.cst = -(hl) - (c.dim * CPIMH_HALF_LOG_2PI_TRUNC);
   p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.lw = h->lw.as<double>(); p.C = h->C.as<double>(); p.S = h->S.as<double>();
-  p.pmax = h->pmax.as<double>(); p.psum = h->psum.as<double>(); p.pv = h->pv.as<double>(); p.mstep = h->mstep.as<double>();
+  p.pmax = h->pmax.as<double>(); p.psum = h->psum.as<double>(); p.pv = h->pv.as<double>(); p.mstep = h->mstep.as<double>(); p.ptot = h->ptot.as<double>();
   p.logz_t = h->logz_t.as<double>(); p.logz = h->logz.as<double>(); p.traj = h->traj.as<double>(); p.path_index = h->path_index.as<int>();
   p.inj_init = h->have_inj[0] ? h->inj_init.as<double>() : nullptr;
   p.inj_trans = h->have_inj[1] ? h->inj_trans.as<double>() : nullptr;
