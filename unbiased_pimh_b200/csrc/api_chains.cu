@@ -125,7 +125,7 @@ struct cpimh_chains {
   Geometry geo;
   int64_t maxR, lastR, launches;
   int record, max_rec, grid, npre;
-  DevBuf hist_x, hist_a;
+  DevBuf hist_x, hist_a, ascr;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, state, acc, scal, iscal, hbar, mt, it, status, nfilters, counter, sums;
   DevBuf samples1, samples2, log_pdf1, log_pdf2;
 };
@@ -139,7 +139,7 @@ extern "C" {
 
 int cpimh_chains_destroy(cpimh_chains* h) {
   if (!h) return CPIMH_OK;
-  DevBuf* all[] = {&h->hist_x, &h->hist_a, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
+  DevBuf* all[] = {&h->hist_x, &h->hist_a, &h->ascr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
                    &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2};
   for (auto b : all) b->release();
   delete h;
@@ -174,6 +174,7 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   }
   if (!rc && g.path_mode == PATH_TREE) {
     rc = h->xbuf.alloc(sizeof(double) * G * 2 * D * g.Npad);
+    if (!rc) rc = h->ascr.alloc(sizeof(int) * G * g.Npad);
     if (!rc) rc = h->a_star.alloc(sizeof(int) * G * g.M);
     if (!rc) rc = h->o_star.alloc(sizeof(int) * G * g.M);
     if (!rc) rc = h->x_star.alloc(sizeof(double) * G * D * g.M);
@@ -221,7 +222,7 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   api_fill_pf_params(h->cfg, h->geo, h->npre, &cp.pf);
   cp.pf.B = 0; cp.pf.seed = seed; cp.pf.first_filter = 0;
   cp.pf.obs = h->obs.as<double>(); cp.pf.theta = h->theta.as<double>(); cp.pf.pre = h->pre.as<double>();
-  cp.pf.hist_x = h->hist_x.as<double>(); cp.pf.hist_a = h->hist_a.as<int>();
+  cp.pf.hist_x = h->hist_x.as<double>(); cp.pf.hist_a = h->hist_a.as<int>(); cp.pf.ascr = h->ascr.as<int>();
   cp.pf.xbuf = h->xbuf.as<double>(); cp.pf.a_star = h->a_star.as<int>(); cp.pf.o_star = h->o_star.as<int>(); cp.pf.x_star = h->x_star.as<double>();
   cp.R = R; cp.first_replicate = first_replicate; cp.k = k; cp.K = K; cp.max_iterations = max_iterations < 0 ? 4095 : max_iterations;
   cp.state = h->state.as<double>(); cp.acc = h->acc.as<double>(); cp.scal = h->scal.as<double>(); cp.iscal = h->iscal.as<int>();

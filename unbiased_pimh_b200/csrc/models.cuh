@@ -37,6 +37,7 @@ struct GssModel {
   static constexpr int D = 1;
   static constexpr bool USES_SHARED_U = false;
   static constexpr bool MULTI = false;
+  static constexpr bool JUMP_LIST = false;
   __device__ static double step_const(const ModelCtx&, int t) { return 8.0 * cos(1.2 * (double)(t - 1)); }
   __device__ static void init(const ModelCtx& c, int i, double* x) {
     double z;
@@ -64,6 +65,7 @@ struct ArModel {
   static constexpr int D = D_;
   static constexpr bool USES_SHARED_U = false;   // pre = A (column-major, D*D) then cst
   static constexpr bool MULTI = false;
+  static constexpr bool JUMP_LIST = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll
@@ -124,10 +126,9 @@ struct LevySvModel {
   // the Poisson uniform of particle i at time t is the SECOND uniform of the Philox block whose first uniform is the
   // resampling draw of slot i at time t (one Philox call serves both; DESIGN.md "RNG")
   static constexpr bool USES_SHARED_U = true;
-#ifndef CPIMH_SV_MULTI
-#define CPIMH_SV_MULTI 0
-#endif
-  static constexpr bool MULTI = CPIMH_SV_MULTI != 0;
+  static constexpr bool MULTI = false;
+  static constexpr bool JUMP_LIST = true;      // pf_fused.cuh walks the Poisson jumps of a thread's particles as one list
+  __device__ static __forceinline__ int token(const ModelCtx& c, double upois) { return poisson_tab(c.pre, upois); }
   __device__ static double step_const(const ModelCtx& c, int) { return c.pre[0]; }
   // one jump of the compound Poisson process (src/SVLevy_functions.cpp:62-67): c' = t - c ~ U(0,1), e ~ Exp(rate xi/w2)
   __device__ static __forceinline__ void jump(const ModelCtx& c, int i, int t, int j, double& wa, double& e) {
@@ -228,6 +229,7 @@ struct SkModel {
   static constexpr int D = 4;
   static constexpr bool USES_SHARED_U = false;
   static constexpr bool MULTI = true;
+  static constexpr bool JUMP_LIST = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void init(const ModelCtx&, int, double* x) { x[0] = 8.0; x[1] = 8.0; x[2] = 8.0; x[3] = 5.0; }
   __device__ static __forceinline__ double hazards(const double* x, double* h) {      // R/model_stochastic_kinetic.R:27-40
@@ -410,6 +412,7 @@ struct LorenzModel {
   static constexpr int D = D_;
   static constexpr bool USES_SHARED_U = false;   // pre[0] = cst of the measurement density
   static constexpr bool MULTI = false;
+  static constexpr bool JUMP_LIST = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll

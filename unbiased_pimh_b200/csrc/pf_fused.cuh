@@ -39,6 +39,7 @@ struct PfParams {
   double* xbuf;                // PATH_NONE/TREE: [ws][2][D][Npad]
   double* hist_x;              // PATH_DENSE:     [ws][T+1][D][Npad]
   int* hist_a;                 // PATH_DENSE:     [ws][T][Npad]
+  int* ascr;                   // [ws][Npad] ancestor scratch (jump-list models when the path store is not dense)
   int* a_star;                 // PATH_TREE:      [ws][M]
   int* o_star;                 // PATH_TREE:      [ws][M]
   double* x_star;              // PATH_TREE:      [ws][D][M]
@@ -155,7 +156,8 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   const double* inj_shf = p.inj_shuffle ? p.inj_shuffle + (size_t)inj * T * (N - 1) : nullptr;
   const bool need_shared_u = Model::USES_SHARED_U && !c.inj_trans;
   int st = 0;
-  double ukeep[CPIMH_MAX_E];   // second uniform of each owned particle's resampling Philox block (local memory)
+  double ukeep[Model::JUMP_LIST ? 1 : CPIMH_MAX_E];   // second uniform of each owned particle's resampling Philox block (local memory)
+  const bool jump_list = Model::JUMP_LIST && (N + NT - 1) / NT <= 16;   // tokens of <= 16 own particles fit two 64-bit registers
 
   // ---------------- initialisation: R/CPF.R:17-28, Tree::Tree + Tree::init (src/tree.cpp:6-34)
   if (tid == 0) sm.iscr[32] = 0;
@@ -192,13 +194,20 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // -- sorted uniforms (src/multinomial.cpp:18-24) and CDF (:17); zero the offspring counters
     if (tree) for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
     const bool draw_res = !ident && !inj_res;
+    unsigned long long tok0 = 0ull, tok1 = 0ull;           // 8-bit model tokens of this thread's particles (jump counts)
     if (draw_res || need_shared_u) {
       int e = 0;
       for (int i = tid; i < N; i += NT, e++) {
         double ua, ub;
         philox_u2(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, ub);
         if (draw_res) sm.S[i] = -log(ua);                 // exponential spacing E_i (see the ladder comment below)
-        ukeep[e] = ub;
+        if constexpr (Model::JUMP_LIST) {
+          if (jump_list) {                                // the model turns its uniform into a small count right away
+            int tk = Model::token(c, ub);
+            if (tk > 255) { tk = 255; st |= CPIMH_ERR_INVALID; }
+            if (e < 8) tok0 |= (unsigned long long)tk << (8 * e); else tok1 |= (unsigned long long)tk << (8 * (e - 8));
+          } else ukeep[0] = ub;
+        } else ukeep[e] = ub;
       }
     }
     if (!ident) {
@@ -250,7 +259,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       double x[D];
 #pragma unroll
       for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
-      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[e] : 0.5);
+      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[Model::JUMP_LIST ? 0 : e] : 0.5);
       finish_particle(k, a, x);
     };
     if (p.shuffle && !ident) {
@@ -269,25 +278,68 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       __syncthreads();
     }
     const bool shuffled = p.shuffle && !ident;
-    if constexpr (Model::MULTI) {
-      if ((N + NT - 1) / NT <= CPIMH_MULTI_MAX_E) {
-        // the thread's particles go through the transition together (see Model::transition_multi)
-        double xl[CPIMH_MULTI_MAX_E][D];
-        int al[CPIMH_MULTI_MAX_E];
-        int E = 0;
-        for (int k = tid; k < N; k += NT, E++) {
-          const int a = shuffled ? sm.bpar[k] : ancestor_of(k);
-          al[E] = a;
-#pragma unroll
-          for (int q = 0; q < D; q++) xl[E][q] = xold[(size_t)q * Npad + a];
+    bool done = false;
+    if constexpr (Model::JUMP_LIST) {
+      if (jump_list) {
+        // Models whose transition noise is a variable number of jumps per particle (Poisson counts: ~18 % of the lanes
+        // would be active in a per-particle loop).  (1) all ancestors first, so the CDF and the ladder are dead;
+        // (2) every thread walks the jumps of ALL its particles as one list, parking each particle's sums in that
+        // particle's own slots of S and C; (3) gather, finish the transition, weigh.
+        int* arow = dense ? hist_a + (size_t)(t - 1) * Npad : p.ascr + (size_t)ws * Npad;
+        for (int k = tid; k < N; k += NT) arow[k] = shuffled ? sm.bpar[k] : ancestor_of(k);
+        __syncthreads();
+        const int E = (N - tid + NT - 1) / NT;
+        auto tok = [&](int e) -> int { return (int)(((e < 8 ? tok0 >> (8 * e) : tok1 >> (8 * (e - 8)))) & 255ull); };
+        if (!c.inj_trans) {
+          int e = 0;
+          while (e < E && tok(e) == 0) e++;
+          double sa = 0.0, sb = 0.0;
+          int j = 1;
+          while (e < E) {
+            double wa, ev;
+            Model::jump(c, tid + e * NT, t, j, wa, ev);
+            sa += wa;
+            sb += ev;
+            if (++j > tok(e)) {
+              sm.S[tid + e * NT] = sa; sm.C[tid + e * NT] = sb;
+              sa = 0.0; sb = 0.0; j = 1;
+              do { e++; } while (e < E && tok(e) == 0);
+            }
+          }
         }
-        if (E > 0) st |= Model::transition_multi(c, t, E, tid, NT, xl, ukeep, sc);
-        for (int e = 0; e < E; e++) finish_particle(tid + e * NT, al[e], xl[e]);
-      } else {
-        int e = 0;
-        for (int k = tid; k < N; k += NT, e++) propagate(k, shuffled ? sm.bpar[k] : ancestor_of(k), e);
+        for (int e = 0; e < E; e++) {
+          const int k = tid + e * NT, a = arow[k];
+          double x[D], swe = 0.0, se = 0.0;
+#pragma unroll
+          for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
+          if (c.inj_trans) { swe = trans_row(c, t, 0)[k]; se = trans_row(c, t, 1)[k]; }
+          else if (tok(e) > 0) { swe = sm.S[k]; se = sm.C[k]; }
+          Model::finish(c, x, swe, se);
+          finish_particle(k, a, x);
+        }
+        done = true;
       }
-    } else {
+    }
+    if (!done) {
+      if constexpr (Model::MULTI) {
+        if ((N + NT - 1) / NT <= CPIMH_MULTI_MAX_E) {
+          // the thread's particles go through the transition together (see Model::transition_multi)
+          double xl[CPIMH_MULTI_MAX_E][D];
+          int al[CPIMH_MULTI_MAX_E];
+          int E = 0;
+          for (int k = tid; k < N; k += NT, E++) {
+            const int a = shuffled ? sm.bpar[k] : ancestor_of(k);
+            al[E] = a;
+#pragma unroll
+            for (int q = 0; q < D; q++) xl[E][q] = xold[(size_t)q * Npad + a];
+          }
+          if (E > 0) st |= Model::transition_multi(c, t, E, tid, NT, xl, ukeep, sc);
+          for (int e = 0; e < E; e++) finish_particle(tid + e * NT, al[e], xl[e]);
+          done = true;
+        }
+      }
+    }
+    if (!done) {
       int e = 0;
       for (int k = tid; k < N; k += NT, e++) propagate(k, shuffled ? sm.bpar[k] : ancestor_of(k), e);
     }

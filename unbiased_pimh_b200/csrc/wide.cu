@@ -13,6 +13,8 @@
 #include "host_common.h"
 #include "lorenz_wide.cuh"
 #include "wide.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace cpimh {
 
@@ -62,7 +64,7 @@ __global__ void wide_init_kernel(WideParams p) {
 
 // ------------------------------------------------------------------ one time step for all particles of all filters
 template <int C>
-__global__ void wide_propagate_kernel(WideParams p, int t, int ident) {
+__global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, int t, int ident) {
   constexpr int D = 32 * C;
   __shared__ double smax[32];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -96,7 +98,7 @@ __global__ void wide_propagate_kernel(WideParams p, int t, int ident) {
       if (p.anc_rec) p.anc_rec[((size_t)b * p.T + (t - 1)) * N + k] = a;
     }
     double mylw = -INFINITY;
-    constexpr int PF = 4;                                   // rows in flight: the gathers of PF ancestors are issued together
+    constexpr int PF = 2;                                   // rows in flight: the gathers of PF ancestors are issued together
     for (int j0 = 0; j0 < G && base + j0 < N; j0 += PF) {
       double vv[PF][C];
 #pragma unroll
@@ -207,6 +209,76 @@ __global__ void wide_scan_kernel(WideParams p, int t_done, int prep) {
       p.ptot[b] = (buf[n - 1] + vcarry) - log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
     }
   }
+}
+
+// ------------------------------------------------------------------ weights + scans of one step in ONE kernel:
+// a thread-block cluster of WIDE_CLUSTER CTAs owns one filter; the per-CTA totals are exchanged through distributed
+// shared memory and one cluster barrier replaces the kernel boundary between wide_weights and wide_scan.
+#define WIDE_CLUSTER 8
+#define WIDE_TILE 8192       // elements scanned per pass in shared memory (64 KB)
+__global__ void __cluster_dims__(WIDE_CLUSTER, 1, 1) __launch_bounds__(1024, 1)
+wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  double* buf = reinterpret_cast<double*>(raw);     // [WIDE_TILE]
+  __shared__ double scr[32];
+  __shared__ double tot[2];                         // this CTA's (sum w, sum v), read by the other CTAs of the cluster
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y, N = p.N;
+  const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+  double m = -INFINITY;
+  for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[(size_t)b * p.GX + i]);
+  m = block_max(m, scr);
+  const long long per = ((long long)N + WIDE_CLUSTER - 1) / WIDE_CLUSTER;
+  const long long lo = (long long)rank * per, hi = min((long long)N, lo + per);
+  double* Cb = p.C + (size_t)b * N;
+  double* Sb = p.S + (size_t)b * N;
+  const bool ladder = prep && !p.inj_resample;
+  double sw = 0.0, sv = 0.0;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double w = exp(p.lw[(size_t)b * N + i] - m);                               // R/CPF.R:62
+    Cb[i] = w;
+    sw += w;
+    if (prep) {
+      double v;
+      if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t_done) * N + i];
+      else { v = -log(philox_u1(st, (unsigned)i, t_done + 1, CPIMH_P_RESAMPLE, 0)); sv += v; }
+      Sb[i] = v;
+    }
+  }
+  sw = block_sum(sw, scr);
+  sv = block_sum(sv, scr);
+  if (threadIdx.x == 0) { tot[0] = sw; tot[1] = sv; }
+  cluster.sync();
+  double s = 0.0, carry = 0.0, vcarry = 0.0;
+  for (int c = 0; c < WIDE_CLUSTER; c++) {
+    const double* rt = cluster.map_shared_rank(tot, c);
+    const double a = rt[0], v = rt[1];
+    if (c < rank) { carry += a; vcarry += v; }
+    s += a;
+  }
+  cluster.sync();                                   // nobody may exit (or overwrite tot) while peers still read it
+  if (rank == 0 && threadIdx.x == 0) p.logz_t[(size_t)b * p.T + (t_done - 1)] = log(s / (double)N) + m;   // R/CPF.R:66
+  double run = carry / s, vrun = vcarry;
+  for (long long base = lo; base < hi; base += WIDE_TILE) {
+    const int n = (int)min((long long)WIDE_TILE, hi - base);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = Cb[base + q] / s;     // normweights (R/CPF.R:63)
+    __syncthreads();
+    block_scan_inplace<false>(buf, n, scr);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) Cb[base + q] = buf[q] + run;
+    run += buf[n - 1];
+    __syncthreads();
+    if (ladder) {
+      for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = Sb[base + q];
+      __syncthreads();
+      block_scan_inplace<false>(buf, n, scr);
+      for (int q = threadIdx.x; q < n; q += blockDim.x) Sb[base + q] = buf[q] + vrun;
+      vrun += buf[n - 1];
+      __syncthreads();
+    }
+  }
+  if (ladder && rank == WIDE_CLUSTER - 1 && threadIdx.x == 0)
+    p.ptot[b] = vrun - log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
 }
 
 // ------------------------------------------------------------------ final path: systematic(normw, 1, u) + get_path (R/CPF.R:69)
@@ -344,23 +416,23 @@ int wide_record_ancestors(WideFilter* h, int on) {
 template <int C>
 static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   const int T = p.T, B = p.B;
-  const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)p.GX, (unsigned)B), gc((unsigned)p.NC, (unsigned)B);
+  const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)p.GX, (unsigned)B), gc((unsigned)p.NC, (unsigned)B), gw(WIDE_CLUSTER, (unsigned)B);
+  (void)gc;
+  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_weights_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WIDE_TILE * sizeof(double))));
   wide_init_kernel<C><<<gi, 256, 0, s>>>(p);
   h->launches++;
   for (int t = 1; t <= T; t++) {
     const int ident = (t == 1) || isnan(h->obs_host[(size_t)(t - 2) * p.D]);         // R/CPF.R:38-40
     if (t >= 2) {
-      wide_weights_kernel<<<gc, 1024, 0, s>>>(p, t - 1, ident ? 0 : 1);
-      wide_scan_kernel<<<gc, 1024, WIDE_CHUNK * sizeof(double), s>>>(p, t - 1, ident ? 0 : 1);
-      h->launches += 2;
+      wide_weights_scan_kernel<<<gw, 1024, WIDE_TILE * sizeof(double), s>>>(p, t - 1, ident ? 0 : 1);
+      h->launches += 1;
     }
     wide_propagate_kernel<C><<<gp, 128, 0, s>>>(p, t, ident);
     h->launches++;
   }
-  wide_weights_kernel<<<gc, 1024, 0, s>>>(p, T, 0);
-  wide_scan_kernel<<<gc, 1024, WIDE_CHUNK * sizeof(double), s>>>(p, T, 0);
+  wide_weights_scan_kernel<<<gw, 1024, WIDE_TILE * sizeof(double), s>>>(p, T, 0);
   wide_path_kernel<C><<<B, 32, 0, s>>>(p);
-  h->launches += 3;
+  h->launches += 2;
   CPIMH_CUDA_CHECK(cudaGetLastError());
   return CPIMH_OK;
 }
