@@ -1,10 +1,12 @@
 // wide.cu -- the bootstrap filter for WIDE states (Lorenz 96, d = 32 or 64; BASELINE config 5: d = 64, N = 65536,
 // T = 500, path storage on): one filter spans the whole GPU.  Same step as pf_fused.cuh (R/CPF.R:35-67) but split at
 // the two grid-wide dependencies:
-//   wide_propagate   warp per particle: ancestor search in the CDF, 512-byte coalesced gather of the ancestor's state,
-//                    RK4 on shuffles (lorenz_wide.cuh), process noise, measurement density, per-CTA max of log-weights
-//   wide_weights     w = exp(lw - max), per-chunk sums; next step's log(u_i)/i ladder and its per-chunk sums
-//   wide_scan        normalise, log Z increment, chunk scans with carry-in: CDF and sorted-uniform exponents
+//   wide_propagate      warp per particle: ancestor search in the CDF, 512-byte coalesced gather of the ancestor's state,
+//                       RK4 on shuffles (lorenz_wide.cuh), process noise, measurement density; then block-local softmax
+//                       numerators exp(lw - m_block), block sums, and the next step's exponential spacings -log(u)
+//   wide_weights_scan   one 8-CTA thread-block cluster per filter: global max, rescale blocks by exp(m_block - m),
+//                       normalise, log Z increment, chunk scans (CDF and sorted-uniform ladder) with carries exchanged
+//                       through distributed shared memory
 // State and path storage are the same dense history hist_x[t][i][0..d) (array of rows: a particle's d doubles are
 // contiguous, which is also R's d x N column-major layout) + hist_a[t][i].
 #include <math.h>
@@ -64,9 +66,9 @@ __global__ void wide_init_kernel(WideParams p) {
 
 // ------------------------------------------------------------------ one time step for all particles of all filters
 template <int C>
-__global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, int t, int ident) {
+__global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, int t, int ident, int prep_next) {
   constexpr int D = 32 * C;
-  __shared__ double smax[32];
+  __shared__ double smax[32], ssum[32], svs[32];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int N = p.N, G = p.G;
   const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
 #pragma unroll
   for (int c = 0; c < C; c++) yv[c] = y[lane * C + c];
   const double h = 0.05 / (double)p.substeps;
-  double gmax = -INFINITY;
+  double gmax = -INFINITY, keep_lw = -INFINITY;
   const long long base = ((long long)blockIdx.x * nwarp + warp) * G;
   if (base < N) {
     // ancestors of this warp's G particles: lanes search in parallel (src/multinomial.cpp:25-28 rule)
@@ -135,116 +137,79 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
         if (lane == j) mylw = lw;
       }
     }
-    if (lane < G && k < N) p.lw[(size_t)b * N + k] = mylw;
     gmax = warp_max(mylw);
+    keep_lw = mylw;
   }
+  // Local softmax numerators: w = exp(lw - m_c) with m_c the max over THIS CTA's particles; wide_weights_scan rescales
+  // each CTA's block by exp(m_c - m) (one exp per CTA instead of a grid-wide barrier before every exp).  Also the
+  // next step's exponential spacings E_k = -log(u_k) (sorted-uniform ladder), so every SM shares the log/exp work.
   if (lane == 0) smax[warp] = gmax;
   __syncthreads();
-  if (warp == 0) {
-    double m = lane < nwarp ? smax[lane] : -INFINITY;
-    m = warp_max(m);
-    if (lane == 0) p.pmax[(size_t)b * p.GX + blockIdx.x] = m;
-  }
-}
-
-// ------------------------------------------------------------------ weights of step t_done (+ uniform ladder of step t_done+1)
-__global__ void wide_weights_kernel(WideParams p, int t_done, int prep) {
-  __shared__ double scr[32];
-  const int b = blockIdx.y, N = p.N;
-  double m = -INFINITY;
-  for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[(size_t)b * p.GX + i]);
-  m = block_max(m, scr);
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.mstep[b] = m;
-  const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
-  const long long lo = (long long)blockIdx.x * WIDE_CHUNK;
-  double sw = 0.0, sv = 0.0;
-  for (int q = threadIdx.x; q < WIDE_CHUNK; q += blockDim.x) {
-    const long long i = lo + q;
-    if (i >= N) break;
-    const double w = exp(p.lw[(size_t)b * N + i] - m);                               // R/CPF.R:62
-    p.C[(size_t)b * N + i] = w;
-    sw += w;
-    if (prep) {
-      double v;
-      if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t_done) * N + i];    // row of step t_done+1 (0-based t_done)
-      else { v = -log(philox_u1(s, (unsigned)i, t_done + 1, CPIMH_P_RESAMPLE, 0)); sv += v; }   // exponential spacing E_i (pf_fused.cuh)
-      p.S[(size_t)b * N + i] = v;
+  double mc = -INFINITY;
+  for (int w = 0; w < nwarp; w++) mc = fmax(mc, smax[w]);
+  double wsum = 0.0, vsum = 0.0;
+  {
+    const long long k = base + lane;
+    if (base < N && lane < G && k < N) {
+      const double w = (mc == -INFINITY) ? 0.0 : exp(keep_lw - mc);                 // R/CPF.R:62, block-local scaling
+      p.C[(size_t)b * N + k] = w;
+      wsum = w;
+      if (prep_next) {
+        double v;
+        if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t) * N + k];       // row of step t+1
+        else { v = -log(philox_u1(s, (unsigned)k, t + 1, CPIMH_P_RESAMPLE, 0)); vsum = v; }
+        p.S[(size_t)b * N + k] = v;
+      }
     }
   }
-  sw = block_sum(sw, scr);
-  sv = block_sum(sv, scr);
-  if (threadIdx.x == 0) { p.psum[(size_t)b * p.NC + blockIdx.x] = sw; p.pv[(size_t)b * p.NC + blockIdx.x] = sv; }
-}
-
-// ------------------------------------------------------------------ normalise + log Z increment + scans with carry-in
-__global__ void wide_scan_kernel(WideParams p, int t_done, int prep) {
-  extern __shared__ __align__(16) unsigned char raw[];
-  double* buf = reinterpret_cast<double*>(raw);     // [WIDE_CHUNK]
-  __shared__ double scr[32];
-  const int b = blockIdx.y, N = p.N, cta = blockIdx.x;
-  double s = 0.0, carry = 0.0, vcarry = 0.0;
-  for (int c = 0; c < p.NC; c++) {                  // NC <= 256 partial sums: every thread folds them in the same order
-    const double ps = p.psum[(size_t)b * p.NC + c];
-    if (c < cta) carry += ps;
-    s += ps;
-    if (c < cta) vcarry += p.pv[(size_t)b * p.NC + c];
-  }
-  if (cta == 0 && threadIdx.x == 0) p.logz_t[(size_t)b * p.T + (t_done - 1)] = log(s / (double)N) + p.mstep[b];   // R/CPF.R:66
-  const long long lo = (long long)cta * WIDE_CHUNK;
-  const int n = (int)min((long long)WIDE_CHUNK, (long long)N - lo);
-  if (n <= 0) return;
-  for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = p.C[(size_t)b * N + lo + q] / s;     // normweights (R/CPF.R:63)
+  wsum = warp_sum(wsum);
+  vsum = warp_sum(vsum);
+  if (lane == 0) { ssum[warp] = wsum; svs[warp] = vsum; }
   __syncthreads();
-  block_scan_inplace<false>(buf, n, scr);
-  const double c0 = carry / s;
-  for (int q = threadIdx.x; q < n; q += blockDim.x) p.C[(size_t)b * N + lo + q] = buf[q] + c0;
-  if (prep && !p.inj_resample) {
-    __syncthreads();
-    for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = p.S[(size_t)b * N + lo + q];
-    __syncthreads();
-    block_scan_inplace<false>(buf, n, scr);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) p.S[(size_t)b * N + lo + q] = buf[q] + vcarry;
-    if (cta == p.NC - 1 && threadIdx.x == 0) {
-      const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
-      p.ptot[b] = (buf[n - 1] + vcarry) - log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
-    }
+  if (threadIdx.x == 0) {
+    double a = 0.0, v = 0.0;
+    for (int w = 0; w < nwarp; w++) { a += ssum[w]; v += svs[w]; }
+    p.pmax[(size_t)b * p.GX + blockIdx.x] = mc;
+    p.psum[(size_t)b * p.GX + blockIdx.x] = a;
+    p.pv[(size_t)b * p.GX + blockIdx.x] = v;
   }
 }
 
-// ------------------------------------------------------------------ weights + scans of one step in ONE kernel:
-// a thread-block cluster of WIDE_CLUSTER CTAs owns one filter; the per-CTA totals are exchanged through distributed
-// shared memory and one cluster barrier replaces the kernel boundary between wide_weights and wide_scan.
+// ------------------------------------------------------------------ normalisation + scans of one step in ONE kernel:
+// a thread-block cluster of WIDE_CLUSTER CTAs owns one filter; wide_propagate left block-scaled numerators, per-block
+// maxima and sums.  The per-CTA totals are exchanged through distributed shared memory; one cluster barrier replaces a
+// kernel boundary.  Per element this kernel only multiplies, divides and scans.
 #define WIDE_CLUSTER 8
 #define WIDE_TILE 8192       // elements scanned per pass in shared memory (64 KB)
+#define WIDE_MAX_BLOCKS_PER_CTA 4096
 __global__ void __cluster_dims__(WIDE_CLUSTER, 1, 1) __launch_bounds__(1024, 1)
 wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   extern __shared__ __align__(16) unsigned char raw[];
   double* buf = reinterpret_cast<double*>(raw);     // [WIDE_TILE]
+  double* fac = buf + WIDE_TILE;                    // [blocks of this CTA] exp(m_c - m)
   __shared__ double scr[32];
   __shared__ double tot[2];                         // this CTA's (sum w, sum v), read by the other CTAs of the cluster
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y, N = p.N;
-  const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+  const int ppc = 4 * p.G;                          // particles per wide_propagate CTA
   double m = -INFINITY;
   for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[(size_t)b * p.GX + i]);
   m = block_max(m, scr);
-  const long long per = ((long long)N + WIDE_CLUSTER - 1) / WIDE_CLUSTER;
-  const long long lo = (long long)rank * per, hi = min((long long)N, lo + per);
+  // element ranges are aligned to propagate blocks
+  const int bper = (p.GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER;
+  const int c0 = rank * bper, c1 = min(p.GX, c0 + bper);
+  const long long lo = (long long)c0 * ppc, hi = min((long long)N, (long long)c1 * ppc);
   double* Cb = p.C + (size_t)b * N;
   double* Sb = p.S + (size_t)b * N;
   const bool ladder = prep && !p.inj_resample;
   double sw = 0.0, sv = 0.0;
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const double w = exp(p.lw[(size_t)b * N + i] - m);                               // R/CPF.R:62
-    Cb[i] = w;
-    sw += w;
-    if (prep) {
-      double v;
-      if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t_done) * N + i];
-      else { v = -log(philox_u1(st, (unsigned)i, t_done + 1, CPIMH_P_RESAMPLE, 0)); sv += v; }
-      Sb[i] = v;
-    }
+  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+    const double mc = p.pmax[(size_t)b * p.GX + c];
+    const double f = (mc == -INFINITY) ? 0.0 : exp(mc - m);
+    fac[c - c0] = f;
+    sw += p.psum[(size_t)b * p.GX + c] * f;
+    sv += p.pv[(size_t)b * p.GX + c];
   }
   sw = block_sum(sw, scr);
   sv = block_sum(sv, scr);
@@ -262,7 +227,7 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   double run = carry / s, vrun = vcarry;
   for (long long base = lo; base < hi; base += WIDE_TILE) {
     const int n = (int)min((long long)WIDE_TILE, hi - base);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = Cb[base + q] / s;     // normweights (R/CPF.R:63)
+    for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = (Cb[base + q] * fac[(int)((base + q - lo) / ppc)]) / s;   // normweights (R/CPF.R:63)
     __syncthreads();
     block_scan_inplace<false>(buf, n, scr);
     for (int q = threadIdx.x; q < n; q += blockDim.x) Cb[base + q] = buf[q] + run;
@@ -277,8 +242,10 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
       __syncthreads();
     }
   }
-  if (ladder && rank == WIDE_CLUSTER - 1 && threadIdx.x == 0)
+  if (ladder && rank == WIDE_CLUSTER - 1 && threadIdx.x == 0) {
+    const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
     p.ptot[b] = vrun - log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
+  }
 }
 
 // ------------------------------------------------------------------ final path: systematic(normw, 1, u) + get_path (R/CPF.R:69)
@@ -344,7 +311,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   h->cfg = cfg; h->maxB = max_filters; h->lastB = 0; h->launches = 0; h->bytes = 0; h->record_anc = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
   wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->GX, &h->NC);
-  CPIMH_REQUIRE(h->NC <= 256, "N too large for the chunked scan");
+  CPIMH_REQUIRE((h->GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER <= WIDE_MAX_BLOCKS_PER_CTA, "N too large for the cluster scan");
   const size_t B = (size_t)max_filters, N = cfg.nparticles, T = cfg.nobs, D = cfg.dim;
   size_t free_b = 0, total_b = 0;
   CPIMH_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -358,8 +325,8 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   if (!rc) rc = A(h->C, sizeof(double) * B * N);
   if (!rc) rc = A(h->S, sizeof(double) * B * N);
   if (!rc) rc = A(h->pmax, sizeof(double) * B * h->GX);
-  if (!rc) rc = A(h->psum, sizeof(double) * B * h->NC);
-  if (!rc) rc = A(h->pv, sizeof(double) * B * h->NC);
+  if (!rc) rc = A(h->psum, sizeof(double) * B * h->GX);
+  if (!rc) rc = A(h->pv, sizeof(double) * B * h->GX);
   if (!rc) rc = A(h->mstep, sizeof(double) * B);
   if (!rc) rc = A(h->ptot, sizeof(double) * B);
   if (!rc) rc = A(h->logz_t, sizeof(double) * B * T);
@@ -418,19 +385,22 @@ static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   const int T = p.T, B = p.B;
   const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)p.GX, (unsigned)B), gc((unsigned)p.NC, (unsigned)B), gw(WIDE_CLUSTER, (unsigned)B);
   (void)gc;
-  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_weights_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WIDE_TILE * sizeof(double))));
   wide_init_kernel<C><<<gi, 256, 0, s>>>(p);
   h->launches++;
+  auto is_ident = [&](int t) { return (t == 1) || isnan(h->obs_host[(size_t)(t - 2) * p.D]); };   // R/CPF.R:38-40
+  const size_t wsmem = (WIDE_TILE + WIDE_MAX_BLOCKS_PER_CTA) * sizeof(double);
+  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_weights_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
   for (int t = 1; t <= T; t++) {
-    const int ident = (t == 1) || isnan(h->obs_host[(size_t)(t - 2) * p.D]);         // R/CPF.R:38-40
+    const int ident = is_ident(t);
     if (t >= 2) {
-      wide_weights_scan_kernel<<<gw, 1024, WIDE_TILE * sizeof(double), s>>>(p, t - 1, ident ? 0 : 1);
+      wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, t - 1, ident ? 0 : 1);
       h->launches += 1;
     }
-    wide_propagate_kernel<C><<<gp, 128, 0, s>>>(p, t, ident);
+    const int prep_next = (t < T && !is_ident(t + 1)) ? 1 : 0;
+    wide_propagate_kernel<C><<<gp, 128, 0, s>>>(p, t, ident, prep_next);
     h->launches++;
   }
-  wide_weights_scan_kernel<<<gw, 1024, WIDE_TILE * sizeof(double), s>>>(p, T, 0);
+  wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, T, 0);
   wide_path_kernel<C><<<B, 32, 0, s>>>(p);
   h->launches += 2;
   CPIMH_CUDA_CHECK(cudaGetLastError());
