@@ -23,7 +23,7 @@ namespace cpimh {
 #define WIDE_CHUNK 4096      // elements per CTA in the weight/scan kernels (1024 threads x 4)
 
 struct WideParams {
-  int N, T, D, B, NC, GX, G, substeps;
+  int N, T, D, B, NC, GX, G, gshift, pgrid, substeps;   // GX = number of warp groups (softmax blocks), G = 1 << gshift particles each
   unsigned long long seed, first_filter;
   const double* obs;          // [T][D]
   double F, sx, sy, cst;
@@ -68,7 +68,6 @@ __global__ void wide_init_kernel(WideParams p) {
 template <int C>
 __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, int t, int ident, int prep_next) {
   constexpr int D = 32 * C;
-  __shared__ double smax[32], ssum[32], svs[32];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int N = p.N, G = p.G;
   const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
@@ -83,16 +82,17 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
 #pragma unroll
   for (int c = 0; c < C; c++) yv[c] = y[lane * C + c];
   const double h = 0.05 / (double)p.substeps;
-  double gmax = -INFINITY, keep_lw = -INFINITY;
-  const long long base = ((long long)blockIdx.x * nwarp + warp) * G;
-  if (base < N) {
-    // ancestors of this warp's G particles: lanes search in parallel (src/multinomial.cpp:25-28 rule)
+  const double scale = ident ? 0.0 : (p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b]);   // u = sumw e_k  /  (sumw / total) P_k
+  // persistent warps: group g = G consecutive particles; the grid covers the machine once and strides over the groups
+  for (int grp = blockIdx.x * nwarp + warp; grp < p.GX; grp += gridDim.x * nwarp) {
+    const long long base = (long long)grp << p.gshift;
+    // ancestors of this group's particles: lanes search in parallel (src/multinomial.cpp:25-28 rule)
     const long long k = base + lane;
+    const bool mine = lane < G && k < N;
     int a = 0;
-    if (lane < G && k < N) {
+    if (mine) {
       if (ident) a = (int)k;
       else {
-        const double scale = p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b];   // u = sumw e_k  /  (sumw / total) P_k
         a = g_count_le_w(Cb, N, scale * Sb[k]);
         if (a >= N) a = N - 1;
       }
@@ -100,78 +100,50 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
       if (p.anc_rec) p.anc_rec[((size_t)b * p.T + (t - 1)) * N + k] = a;
     }
     double mylw = -INFINITY;
-    constexpr int PF = 2;                                   // rows in flight: the gathers of PF ancestors are issued together
-    for (int j0 = 0; j0 < G && base + j0 < N; j0 += PF) {
-      double vv[PF][C];
+    for (int j = 0; j < G && base + j < N; j++) {
+      const int aj = __shfl_sync(0xffffffffu, a, j);
+      const long long kk = base + j;
+      double v[C], z[C];
 #pragma unroll
-      for (int q = 0; q < PF; q++) {
-        const int aj = __shfl_sync(0xffffffffu, a, (j0 + q) & 31);
-        if (j0 + q < G && base + j0 + q < N) {
+      for (int c = 0; c < C; c++) v[c] = xold[(size_t)aj * D + lane * C + c];
+      for (int r = 0; r < p.substeps; r++) lorenz_wide_rk4<C>(p.F, h, v, lane);      // R/model_get_lorenz.R:28
+      if (p.inj_trans) {
 #pragma unroll
-          for (int c = 0; c < C; c++) vv[q][c] = xold[(size_t)aj * D + lane * C + c];
-        }
+        for (int c = 0; c < C; c++) z[c] = p.inj_trans[(((size_t)b * p.T + (t - 1)) * D + lane * C + c) * N + kk];
+      } else lorenz_wide_normals<C>(s, (unsigned)kk, t, CPIMH_P_TRANS, lane, z);
+      double sq = 0.0;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        v[c] = v[c] + p.sx * z[c];                                                      // :29
+        xnew[(size_t)kk * D + lane * C + c] = v[c];
+        const double r = (v[c] - yv[c]) / p.sy;
+        sq += r * r;
       }
-#pragma unroll
-      for (int q = 0; q < PF; q++) {
-        const int j = j0 + q;
-        if (j >= G || base + j >= N) break;
-        const long long kk = base + j;
-        double v[C], z[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) v[c] = vv[q][c];
-        for (int r = 0; r < p.substeps; r++) lorenz_wide_rk4<C>(p.F, h, v, lane);      // R/model_get_lorenz.R:28
-        if (p.inj_trans) {
-#pragma unroll
-          for (int c = 0; c < C; c++) z[c] = p.inj_trans[(((size_t)b * p.T + (t - 1)) * D + lane * C + c) * N + kk];
-        } else lorenz_wide_normals<C>(s, (unsigned)kk, t, CPIMH_P_TRANS, lane, z);
-        double sq = 0.0;
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          v[c] = v[c] + p.sx * z[c];                                                      // :29
-          xnew[(size_t)kk * D + lane * C + c] = v[c];
-          const double r = (v[c] - yv[c]) / p.sy;
-          sq += r * r;
-        }
-        sq = warp_sum(sq);
-        const double lw = na ? 0.0 : (-0.5 * sq + p.cst);                                // src/mvnorm.cpp:127-130
-        if (lane == j) mylw = lw;
-      }
+      sq = warp_sum(sq);
+      const double lw = na ? 0.0 : (-0.5 * sq + p.cst);                                // src/mvnorm.cpp:127-130
+      if (lane == j) mylw = lw;
     }
-    gmax = warp_max(mylw);
-    keep_lw = mylw;
-  }
-  // Local softmax numerators: w = exp(lw - m_c) with m_c the max over THIS CTA's particles; wide_weights_scan rescales
-  // each CTA's block by exp(m_c - m) (one exp per CTA instead of a grid-wide barrier before every exp).  Also the
-  // next step's exponential spacings E_k = -log(u_k) (sorted-uniform ladder), so every SM shares the log/exp work.
-  if (lane == 0) smax[warp] = gmax;
-  __syncthreads();
-  double mc = -INFINITY;
-  for (int w = 0; w < nwarp; w++) mc = fmax(mc, smax[w]);
-  double wsum = 0.0, vsum = 0.0;
-  {
-    const long long k = base + lane;
-    if (base < N && lane < G && k < N) {
-      const double w = (mc == -INFINITY) ? 0.0 : exp(keep_lw - mc);                 // R/CPF.R:62, block-local scaling
-      p.C[(size_t)b * N + k] = w;
-      wsum = w;
+    // Group-local softmax numerators: w = exp(lw - m_g) with m_g the max over THIS group; wide_weights_scan rescales each
+    // group by exp(m_g - m) (one exp per group instead of a grid-wide barrier before every exp).  Also the next step's
+    // exponential spacings E_k = -log(u_k) (sorted-uniform ladder), so every SM shares the log/exp work.
+    const double mg = warp_max(mylw);
+    double w = 0.0, v = 0.0;
+    if (mine) {
+      w = (mg == -INFINITY) ? 0.0 : exp(mylw - mg);                                    // R/CPF.R:62, group-local scaling
+      p.lw[(size_t)b * N + k] = w;        // NOT into C: other warps of this launch are still searching the CDF
       if (prep_next) {
-        double v;
-        if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t) * N + k];       // row of step t+1
-        else { v = -log(philox_u1(s, (unsigned)k, t + 1, CPIMH_P_RESAMPLE, 0)); vsum = v; }
+        if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t) * N + k];         // row of step t+1
+        else v = -log(philox_u1(s, (unsigned)k, t + 1, CPIMH_P_RESAMPLE, 0));
         p.S[(size_t)b * N + k] = v;
+        if (p.inj_resample) v = 0.0;
       }
     }
-  }
-  wsum = warp_sum(wsum);
-  vsum = warp_sum(vsum);
-  if (lane == 0) { ssum[warp] = wsum; svs[warp] = vsum; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0.0, v = 0.0;
-    for (int w = 0; w < nwarp; w++) { a += ssum[w]; v += svs[w]; }
-    p.pmax[(size_t)b * p.GX + blockIdx.x] = mc;
-    p.psum[(size_t)b * p.GX + blockIdx.x] = a;
-    p.pv[(size_t)b * p.GX + blockIdx.x] = v;
+    const double wsum = warp_sum(w), vsum = warp_sum(v);
+    if (lane == 0) {
+      p.pmax[(size_t)b * p.GX + grp] = mg;
+      p.psum[(size_t)b * p.GX + grp] = wsum;
+      p.pv[(size_t)b * p.GX + grp] = vsum;
+    }
   }
 }
 
@@ -181,7 +153,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
 // kernel boundary.  Per element this kernel only multiplies, divides and scans.
 #define WIDE_CLUSTER 8
 #define WIDE_TILE 8192       // elements scanned per pass in shared memory (64 KB)
-#define WIDE_MAX_BLOCKS_PER_CTA 4096
+#define WIDE_MAX_BLOCKS_PER_CTA 8192
 __global__ void __cluster_dims__(WIDE_CLUSTER, 1, 1) __launch_bounds__(1024, 1)
 wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   extern __shared__ __align__(16) unsigned char raw[];
@@ -192,14 +164,14 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y, N = p.N;
-  const int ppc = 4 * p.G;                          // particles per wide_propagate CTA
+  const int gshift = p.gshift;                      // softmax block = one warp group of wide_propagate
   double m = -INFINITY;
   for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[(size_t)b * p.GX + i]);
   m = block_max(m, scr);
   // element ranges are aligned to propagate blocks
   const int bper = (p.GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER;
   const int c0 = rank * bper, c1 = min(p.GX, c0 + bper);
-  const long long lo = (long long)c0 * ppc, hi = min((long long)N, (long long)c1 * ppc);
+  const long long lo = (long long)c0 << gshift, hi = min((long long)N, (long long)c1 << gshift);
   double* Cb = p.C + (size_t)b * N;
   double* Sb = p.S + (size_t)b * N;
   const bool ladder = prep && !p.inj_resample;
@@ -225,19 +197,30 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   cluster.sync();                                   // nobody may exit (or overwrite tot) while peers still read it
   if (rank == 0 && threadIdx.x == 0) p.logz_t[(size_t)b * p.T + (t_done - 1)] = log(s / (double)N) + m;   // R/CPF.R:66
   double run = carry / s, vrun = vcarry;
+  const double* Wb = p.lw + (size_t)b * N;          // block-scaled numerators written by wide_propagate
+  constexpr int EPT = WIDE_TILE / 1024;             // elements per thread and tile: loads are issued together
   for (long long base = lo; base < hi; base += WIDE_TILE) {
     const int n = (int)min((long long)WIDE_TILE, hi - base);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = (Cb[base + q] * fac[(int)((base + q - lo) / ppc)]) / s;   // normweights (R/CPF.R:63)
+    double r[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; r[e] = q < n ? Wb[base + q] : 0.0; }
+#pragma unroll
+    for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) buf[q] = (r[e] * fac[(int)((base + q - lo) >> gshift)]) / s; }   // normweights (R/CPF.R:63)
     __syncthreads();
     block_scan_inplace<false>(buf, n, scr);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) Cb[base + q] = buf[q] + run;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) Cb[base + q] = buf[q] + run; }
     run += buf[n - 1];
     __syncthreads();
     if (ladder) {
-      for (int q = threadIdx.x; q < n; q += blockDim.x) buf[q] = Sb[base + q];
+#pragma unroll
+      for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; r[e] = q < n ? Sb[base + q] : 0.0; }
+#pragma unroll
+      for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) buf[q] = r[e]; }
       __syncthreads();
       block_scan_inplace<false>(buf, n, scr);
-      for (int q = threadIdx.x; q < n; q += blockDim.x) Sb[base + q] = buf[q] + vrun;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) Sb[base + q] = buf[q] + vrun; }
       vrun += buf[n - 1];
       __syncthreads();
     }
@@ -276,7 +259,7 @@ __global__ void wide_path_kernel(WideParams p) {
 struct WideFilter {
   cpimh_config cfg;
   int64_t maxB, lastB, launches, bytes;
-  int NC, GX, G, record_anc;
+  int NC, GX, G, gshift, pgrid, record_anc;
   std::vector<double> obs_host;
   DevBuf ptot;
   DevBuf obs, hist_x, hist_a, lw, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
@@ -284,15 +267,17 @@ struct WideFilter {
   bool have_inj[4];
 };
 
-static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* GX, int* NC) {
-  // particles per warp: enough warps to fill the machine, at most 32 so the per-group ancestor search stays one pass
+static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* gshift, int* GX, int* NC) {
+  // particles per warp group: enough groups that the persistent propagate grid balances well (>= ~4 groups per warp slot),
+  // at most 32 so the per-group ancestor search stays one pass
+  // (measured on B200, N = 65536: G = 8 beats G = 2 by 30 % -- the 16-step binary search in the global CDF is paid once
+  // per group by up to 32 lanes in parallel, so small groups are dominated by its latency)
   long long target = (long long)num_sms * 48;
   long long g = ((long long)c.nparticles * B + target - 1) / target;
-  int G_ = 1;
-  while (G_ < 32 && G_ < g) G_ <<= 1;
-  *G = G_;
-  const int warps_per_cta = 4;
-  *GX = (int)(((long long)c.nparticles + (long long)G_ * warps_per_cta - 1) / ((long long)G_ * warps_per_cta));
+  int G_ = 1, sh = 0;
+  while (G_ < 32 && G_ < g) { G_ <<= 1; sh++; }
+  *G = G_; *gshift = sh;
+  *GX = (int)(((long long)c.nparticles + G_ - 1) / G_);
   *NC = (c.nparticles + WIDE_CHUNK - 1) / WIDE_CHUNK;
 }
 
@@ -310,7 +295,8 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   WideFilter* h = new WideFilter();
   h->cfg = cfg; h->maxB = max_filters; h->lastB = 0; h->launches = 0; h->bytes = 0; h->record_anc = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
-  wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->GX, &h->NC);
+  wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->gshift, &h->GX, &h->NC);
+  h->pgrid = prop.multiProcessorCount * 8;                  // __launch_bounds__(128, 8): one resident wave
   CPIMH_REQUIRE((h->GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER <= WIDE_MAX_BLOCKS_PER_CTA, "N too large for the cluster scan");
   const size_t B = (size_t)max_filters, N = cfg.nparticles, T = cfg.nobs, D = cfg.dim;
   size_t free_b = 0, total_b = 0;
@@ -383,7 +369,7 @@ int wide_record_ancestors(WideFilter* h, int on) {
 template <int C>
 static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   const int T = p.T, B = p.B;
-  const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)p.GX, (unsigned)B), gc((unsigned)p.NC, (unsigned)B), gw(WIDE_CLUSTER, (unsigned)B);
+  const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)min((p.GX + 3) / 4, max(1, p.pgrid / B)), (unsigned)B), gc((unsigned)p.NC, (unsigned)B), gw(WIDE_CLUSTER, (unsigned)B);
   (void)gc;
   wide_init_kernel<C><<<gi, 256, 0, s>>>(p);
   h->launches++;
@@ -412,7 +398,7 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   const cpimh_config& c = h->cfg;
   WideParams p;
   memset(&p, 0, sizeof(p));
-  p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.NC = h->NC; p.GX = h->GX; p.G = h->G; p.substeps = c.substeps < 1 ? 1 : c.substeps;
+  p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.NC = h->NC; p.GX = h->GX; p.G = h->G; p.gshift = h->gshift; p.pgrid = h->pgrid; p.substeps = c.substeps < 1 ? 1 : c.substeps;
   p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>();
   p.F = c.theta[0]; p.sx = c.theta[1]; p.sy = c.theta[2];
