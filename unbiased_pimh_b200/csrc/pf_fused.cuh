@@ -291,19 +291,25 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         const int E = (N - tid + NT - 1) / NT;
         auto tok = [&](int e) -> int { return (int)(((e < 8 ? tok0 >> (8 * e) : tok1 >> (8 * (e - 8)))) & 255ull); };
         if (!c.inj_trans) {
-          int e = 0;
-          while (e < E && tok(e) == 0) e++;
+          // walk the non-zero token bytes: the position of the lowest set bit gives the next particle with jumps
+          unsigned long long rem = tok0;
+          int ebase = 0;
+          if (rem == 0ull) { rem = tok1; ebase = 8; }
           double sa = 0.0, sb = 0.0;
           int j = 1;
-          while (e < E) {
+          while (rem != 0ull) {
+            const int sh = (__ffsll((long long)rem) - 1) & ~7;            // bit offset of the current particle's byte
+            const int e = ebase + (sh >> 3);
+            const int kj = (int)((rem >> sh) & 255ull);
             double wa, ev;
             Model::jump(c, tid + e * NT, t, j, wa, ev);
             sa += wa;
             sb += ev;
-            if (++j > tok(e)) {
+            if (++j > kj) {
               sm.S[tid + e * NT] = sa; sm.C[tid + e * NT] = sb;
               sa = 0.0; sb = 0.0; j = 1;
-              do { e++; } while (e < E && tok(e) == 0);
+              rem &= ~(255ull << sh);
+              if (rem == 0ull && ebase == 0) { rem = tok1; ebase = 8; }
             }
           }
         }
@@ -350,7 +356,9 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     double s = 0.0;
     for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; }
     s = block_sum(s, sm.dscr);
-    for (int k = tid; k < N; k += NT) sm.C[k] = sm.C[k] / s;
+    // normweights = w / sum(w) (R/CPF.R:63).  Between steps only ratios matter (the ancestor search scales its
+    // uniforms by the CDF total), so the division pass is done once, for the weights the filter returns.
+    if (t == T) for (int k = tid; k < N; k += NT) sm.C[k] = sm.C[k] / s;
     const double lz = log(s / (double)N) + m;
     logz_sum += lz;
     if (tid == 0 && out.logz_t) out.logz_t[t - 1] = lz;
