@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="override threads per filter")
     ap.add_argument("--store-paths", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-chains", action="store_true", help="skip the coupled-PIMH replicates/s side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     w = workload(args.workload)
@@ -290,6 +291,28 @@ def main():
     e2e_value = units / float(te.item())
     logz_mean = float(np.mean(r["logz"]))
 
+    # ---- secondary metric of BASELINE.json: coupled-PIMH estimator replicates/s (configs[3] shape: get_ar(10), N=1024,
+    # T=100, K=1), replicates sharded over the ranks, one all-reduce of the estimator sums.  Not part of `value`.
+    cp_extra = None
+    if not args.no_chains:
+        Rrep = 20000 * world
+        arobs = simulate_ar(100, 10, 0.5, float(np.sqrt(10.0)))
+        armodel, arth = up.get_ar(10), [0.5, float(np.sqrt(10.0))]
+        lo, hi = up.shard_range(Rrep, rank, world)
+        chb = up.ChainBatch(armodel, arth, arobs, 1024, hi - lo)          # HBM workspaces allocated once, outside the timed region
+        up.unbiased_estimator_sharded(armodel, arth, arobs, 1024, Rrep, K=1, seed=3, chain_batch=chb)
+        barrier()
+        t0 = time.perf_counter()
+        est = up.unbiased_estimator_sharded(armodel, arth, arobs, 1024, Rrep, K=1, seed=4, chain_batch=chb)
+        barrier()
+        tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        chb.close()
+        cp_extra = {"metric": "coupled-PIMH estimator replicates/sec", "value": Rrep / float(tc.item()), "replicates": Rrep,
+                    "filters_run": est["nfilters"], "particle_steps_per_s": est["nfilters"] * 100.0 * 1024.0 / float(tc.item()),
+                    "workload": "get_ar(10) N=1024 T=100 K=1 (BASELINE configs[3] shape); host wall time of run + all-reduce, workspaces pre-allocated"}
+
     if rank == 0:
         peak, which = load_peaks()
         kernel_ms = ms / steps
@@ -316,6 +339,7 @@ def main():
                              "note": "dominant (only) kernel pf_batch_kernel; fp64 transcendental issue rate, not HBM, limits it (DESIGN.md)"},
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks}
+        line["coupled_pimh"] = cp_extra
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_sample(w)
             line["cpu_baseline"] = cb

@@ -207,3 +207,15 @@ def test_rdata_reader_roundtrip(golden):
     assert np.allclose(golden["sk_varlogz"], [1.0222, 0.4971, 0.3264, 0.2434, 0.1937], atol=5e-4)
     assert np.allclose(golden["sv_theta_mle"], [0.244872, -0.275641, 0.816154, 0.093333, 0.051538], atol=1e-6)
     assert golden["sk_mt_hist"].sum(axis=1).tolist() == [10000] * 5
+
+
+def test_r_shim_compiles():
+    """r-pkg/src/shim.c (the .Call binding of INTEGRATION.md) is syntactically valid C against the C ABI header and a
+    minimal stand-in for R's headers, and registers every hot-path entry of the reference's CallEntries table."""
+    shim = os.path.join(ROOT, "r-pkg", "src", "shim.c")
+    subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "r-pkg", "src", "stub"), "-I", os.path.join(ROOT, "include"), shim], check=True)
+    txt = open(shim).read()
+    for name in ("multinomial_resampling_n_", "coupled_multinomial_resampling_n_", "systematic_resampling_n_", "indexmatching_cpp", "dmvnorm",
+                 "dmvnorm_transpose", "dmvnorm_transpose_cholesky", "rmvnorm", "rmvnorm_transpose", "rmvnorm_transpose_cholesky",
+                 "rinitial_SVLevy_cpp", "rtransition_SVLevy_cpp", "dobs_SVLevy_cpp", "one_step_lorenz_vector", "create_A_"):
+        assert "ENTRY(_CoupledPIMH_%s," % name in txt, name

@@ -206,3 +206,38 @@ def test_model_closures_match_oracle(up, oracle, golden):
     got = up.lorenz_transition(x8, 0.1, 0.15, 0.05, [8.0])                                          # dopri5, the reference's integrator
     ref = np.stack([oracle.lorenz_step(x8[:, n], 8.0, 1, 1, 0.1, 0.15, 0.05) for n in range(50)], axis=1)
     assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("N", [1, 2, 10, 31, 33, 110])
+@pytest.mark.parametrize("store_paths", [2, 3])
+def test_small_and_ragged_particle_counts(up, oracle, golden, N, store_paths):
+    """N from the reference's own experiments (10..110, inst/reproduce/lgssm/lgssm_settings.R:8) down to a single particle."""
+    y = golden["lgssm_y"][:30]
+    th = [0.5, math.sqrt(10.0)]
+    r = up.cpf_batch(N, up.get_ar(1), th, y, 5, seed=77, logz_t=True, store_paths=store_paths)
+    ocfg = oracle.make_config(oracle.MODEL_AR, 1, 1, N, 30, theta=th)
+    for b in range(5):
+        o = oracle.cpf(ocfg, y, seed=77, filter_id=b)
+        assert np.allclose(r["logz_t"][b], o["logz_t"], rtol=RTOL_LOGZ, atol=0)
+        assert int(r["path_index"][b]) == o["path_index"] and np.allclose(r["trajectory"][b], o["trajectory"], rtol=1e-9, atol=1e-9)
+    one = up.cpf_batch(N, up.get_ar(1), th, y[:1], 3, seed=5, logz_t=True, store_paths=store_paths)        # T = 1
+    assert one["trajectory"].shape == (3, 1, 2) and np.all(np.isfinite(one["logz"]))
+
+
+def test_multi_wave_batches_and_tail_launch(up, golden):
+    """More filters than resident CTAs: whole waves + a 1024-thread tail launch must equal the same filters run in pieces."""
+    th = golden["sv_theta_mle"]
+    y = golden["sv_y"][:12]
+    N = 2048
+    pb = up.PfBatch(up.get_levy_sv(), th, y, N, 700)
+    eff = pb.effective_config()
+    resident = 148 * eff["ctas_per_sm"]
+    B = resident + 57 if resident + 57 <= 700 else 700
+    pb.run(B, 21)
+    a = pb.fetch(path_index=True)
+    pb.run(100, 21, first_filter=B - 100)
+    b = pb.fetch(path_index=True)
+    assert np.array_equal(a["logz"][B - 100:], b["logz"]) and np.array_equal(a["trajectory"][B - 100:], b["trajectory"])
+    assert np.array_equal(a["path_index"][B - 100:], b["path_index"])
+    assert pb.launch_count == 3 if B > resident else 2
+    pb.close()

@@ -194,29 +194,6 @@ struct LevySvModel {
     finish(c, x, swe, se);
     return 0;
   }
-  // All E particles owned by one thread (particle e has index i0 + e*stride).  The jumps of the thread's particles are
-  // walked as ONE list, so a lane is busy for (its total number of jumps) iterations instead of every lane waiting for
-  // the warp-wide maximum per particle: Poisson(0.37) jump counts leave ~18 % of the lanes active otherwise.
-  __device__ static int transition_multi(const ModelCtx& c, int t, int E, int i0, int stride, double (*x)[2], const double* ush, double) {
-    if (c.inj_trans) {
-      for (int e = 0; e < E; e++) { const int i = i0 + e * stride; finish(c, x[e], trans_row(c, t, 0)[i], trans_row(c, t, 1)[i]); }
-      return 0;
-    }
-    int kk[CPIMH_MULTI_MAX_E];
-    double swe[CPIMH_MULTI_MAX_E], se[CPIMH_MULTI_MAX_E];
-    int e = E;
-    for (int q = E - 1; q >= 0; q--) { kk[q] = poisson_tab(c.pre, ush[q]); swe[q] = 0.0; se[q] = 0.0; if (kk[q] > 0) e = q; }
-    int j = 1;
-    while (e < E) {
-      double wa, ev;
-      jump(c, i0 + e * stride, t, j, wa, ev);
-      swe[e] += wa;
-      se[e] += ev;
-      if (++j > kk[e]) { j = 1; do { e++; } while (e < E && kk[e] == 0); }
-    }
-    for (int q = 0; q < E; q++) finish(c, x[q], swe[q], se[q]);
-    return 0;
-  }
   __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
     // dnorm(y, mu + beta v, sd = sqrt(v), log = TRUE) = -(M_LN_SQRT_2PI + (y - m)^2 / (2 v) + log(v) / 2)
     const double r = y[0] - (c.theta[0] + c.theta[1] * x[0]);

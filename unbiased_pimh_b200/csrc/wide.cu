@@ -20,10 +20,9 @@ namespace cg = cooperative_groups;
 
 namespace cpimh {
 
-#define WIDE_CHUNK 4096      // elements per CTA in the weight/scan kernels (1024 threads x 4)
 
 struct WideParams {
-  int N, T, D, B, NC, GX, G, gshift, pgrid, substeps;   // GX = number of warp groups (softmax blocks), G = 1 << gshift particles each
+  int N, T, D, B, GX, G, gshift, pgrid, substeps;   // GX = number of warp groups (softmax blocks), G = 1 << gshift particles each
   unsigned long long seed, first_filter;
   const double* obs;          // [T][D]
   double F, sx, sy, cst;
@@ -259,7 +258,7 @@ __global__ void wide_path_kernel(WideParams p) {
 struct WideFilter {
   cpimh_config cfg;
   int64_t maxB, lastB, launches, bytes;
-  int NC, GX, G, gshift, pgrid, record_anc;
+  int GX, G, gshift, pgrid, record_anc;
   std::vector<double> obs_host;
   DevBuf ptot;
   DevBuf obs, hist_x, hist_a, lw, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
@@ -267,7 +266,7 @@ struct WideFilter {
   bool have_inj[4];
 };
 
-static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* gshift, int* GX, int* NC) {
+static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* gshift, int* GX) {
   // particles per warp group: enough groups that the persistent propagate grid balances well (>= ~4 groups per warp slot),
   // at most 32 so the per-group ancestor search stays one pass
   // (measured on B200, N = 65536: G = 8 beats G = 2 by 30 % -- the 16-step binary search in the global CDF is paid once
@@ -278,7 +277,6 @@ static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G,
   while (G_ < 32 && G_ < g) { G_ <<= 1; sh++; }
   *G = G_; *gshift = sh;
   *GX = (int)(((long long)c.nparticles + G_ - 1) / G_);
-  *NC = (c.nparticles + WIDE_CHUNK - 1) / WIDE_CHUNK;
 }
 
 int wide_supported(const cpimh_config& c) { return c.model == CPIMH_MODEL_LORENZ && (c.dim == 32 || c.dim == 64); }
@@ -295,7 +293,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   WideFilter* h = new WideFilter();
   h->cfg = cfg; h->maxB = max_filters; h->lastB = 0; h->launches = 0; h->bytes = 0; h->record_anc = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
-  wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->gshift, &h->GX, &h->NC);
+  wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->gshift, &h->GX);
   h->pgrid = prop.multiProcessorCount * 8;                  // __launch_bounds__(128, 8): one resident wave
   CPIMH_REQUIRE((h->GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER <= WIDE_MAX_BLOCKS_PER_CTA, "N too large for the cluster scan");
   const size_t B = (size_t)max_filters, N = cfg.nparticles, T = cfg.nobs, D = cfg.dim;
@@ -369,8 +367,7 @@ int wide_record_ancestors(WideFilter* h, int on) {
 template <int C>
 static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   const int T = p.T, B = p.B;
-  const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)min((p.GX + 3) / 4, max(1, p.pgrid / B)), (unsigned)B), gc((unsigned)p.NC, (unsigned)B), gw(WIDE_CLUSTER, (unsigned)B);
-  (void)gc;
+  const dim3 gi((unsigned)(((long long)p.N * 32 + 255) / 256), (unsigned)B), gp((unsigned)min((p.GX + 3) / 4, max(1, p.pgrid / B)), (unsigned)B), gw(WIDE_CLUSTER, (unsigned)B);
   wide_init_kernel<C><<<gi, 256, 0, s>>>(p);
   h->launches++;
   auto is_ident = [&](int t) { return (t == 1) || isnan(h->obs_host[(size_t)(t - 2) * p.D]); };   // R/CPF.R:38-40
@@ -398,7 +395,7 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   const cpimh_config& c = h->cfg;
   WideParams p;
   memset(&p, 0, sizeof(p));
-  p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.NC = h->NC; p.GX = h->GX; p.G = h->G; p.gshift = h->gshift; p.pgrid = h->pgrid; p.substeps = c.substeps < 1 ? 1 : c.substeps;
+  p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.GX = h->GX; p.G = h->G; p.gshift = h->gshift; p.pgrid = h->pgrid; p.substeps = c.substeps < 1 ? 1 : c.substeps;
   p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>();
   p.F = c.theta[0]; p.sx = c.theta[1]; p.sy = c.theta[2];

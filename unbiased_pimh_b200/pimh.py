@@ -273,7 +273,7 @@ def combine_sums(sums, dim, nobs):
 
 
 def unbiased_estimator_sharded(model, theta, observations, nparticles, nreplicates, K=1, k=0, max_iterations=math.inf, seed=17,
-                               stream=None, process_group=None):
+                               stream=None, process_group=None, chain_batch=None):
     """Coupled-PIMH unbiased smoothing estimator with replicates sharded over the ranks of a torch.distributed job
     (one process per GPU).  Each rank runs its contiguous block of replicate ids -- Philox streams are keyed by the global
     replicate id, so the per-replicate results do not depend on the number of GPUs -- and ONE all-reduce (NCCL on GPUs)
@@ -284,7 +284,7 @@ def unbiased_estimator_sharded(model, theta, observations, nparticles, nreplicat
     rank = dist.get_rank(process_group) if distributed else 0
     world = dist.get_world_size(process_group) if distributed else 1
     lo, hi = shard_range(nreplicates, rank, world)
-    cb = ChainBatch(model, theta, observations, nparticles, max(hi - lo, 1))
+    cb = chain_batch if chain_batch is not None else ChainBatch(model, theta, observations, nparticles, max(hi - lo, 1))
     try:
         sums = torch.zeros(cb.nsums, dtype=torch.float64, device="cuda")
         if hi > lo:
@@ -294,5 +294,6 @@ def unbiased_estimator_sharded(model, theta, observations, nparticles, nreplicat
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=process_group)
         res = combine_sums(sums.cpu().numpy(), model.dimension, cb.nobs)
     finally:
-        cb.close()
+        if chain_batch is None:
+            cb.close()
     return res
