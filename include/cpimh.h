@@ -171,6 +171,11 @@ int cpimh_chains_fetch(cpimh_chains* h, int64_t nreplicates, void* stream, cpimh
 int cpimh_chains_fetch_samples(cpimh_chains* h, int64_t r, void* stream, int max_rows, double* samples1, double* samples2,
                                double* log_pdf1, double* log_pdf2);
 int64_t cpimh_chains_launch_count(const cpimh_chains* h);
+/* execution strategy: 0 auto, 1 one persistent CTA per replicate, 2 iteration-synchronous rounds of batched (and, once few
+ * replicates remain, speculative) proposals -- PIMH proposals do not depend on the chain state, so a long replicate's
+ * proposals run in parallel.  Results are identical; auto = rounds unless samples are recorded. */
+int cpimh_chains_set_mode(cpimh_chains* h, int mode);
+int64_t cpimh_chains_filters_launched(const cpimh_chains* h);   /* including discarded speculative proposals */
 
 /* ============================== primitives (batched over B independent problems) ==============================
  * Bit-exact with the reference natives given identical weights and uniforms.  All pointers are HOST pointers. */

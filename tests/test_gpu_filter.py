@@ -225,7 +225,9 @@ def test_small_and_ragged_particle_counts(up, oracle, golden, N, store_paths):
 
 
 def test_multi_wave_batches_and_tail_launch(up, golden):
-    """More filters than resident CTAs: whole waves + a 1024-thread tail launch must equal the same filters run in pieces."""
+    """More filters than resident CTAs: whole waves + a 1024-thread tail launch must agree with the same filters run in
+    pieces.  The block scans/reductions associate differently for different CTA sizes, so filters that move between the
+    512- and 1024-thread variants agree to rounding (1e-12 relative), not bit for bit; same geometry => same bits."""
     th = golden["sv_theta_mle"]
     y = golden["sv_y"][:12]
     N = 2048
@@ -237,7 +239,10 @@ def test_multi_wave_batches_and_tail_launch(up, golden):
     a = pb.fetch(path_index=True)
     pb.run(100, 21, first_filter=B - 100)
     b = pb.fetch(path_index=True)
-    assert np.array_equal(a["logz"][B - 100:], b["logz"]) and np.array_equal(a["trajectory"][B - 100:], b["trajectory"])
+    assert np.allclose(a["logz"][B - 100:], b["logz"], rtol=1e-12, atol=0) and np.allclose(a["trajectory"][B - 100:], b["trajectory"], rtol=1e-9, atol=1e-12)
     assert np.array_equal(a["path_index"][B - 100:], b["path_index"])
-    assert pb.launch_count == 3 if B > resident else 2
+    assert pb.launch_count == (3 if B > resident else 2)
+    pb.run(B, 21)
+    c = pb.fetch(path_index=True)
+    assert np.array_equal(a["logz"], c["logz"]) and np.array_equal(a["trajectory"], c["trajectory"])
     pb.close()

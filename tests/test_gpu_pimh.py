@@ -183,3 +183,29 @@ def test_full_size_config3_ancestors_sorted_and_in_range(up, golden):
     assert np.all(tr == np.round(tr)) and np.all(tr[:, 3, :] >= 0) and np.all(tr[:, 3, :] <= 5)
     assert np.array_equal(tr[:, :, 0], np.tile([8.0, 8.0, 8.0, 5.0], (2, 1)))
     pb.close()
+
+
+def test_round_based_driver_equals_persistent_kernel(up, oracle, golden):
+    """The two execution strategies of the chain driver (persistent CTA per replicate / rounds of batched, speculative
+    proposals) consume the same Philox streams in the same order: identical meeting times, iterations, H_bar, filters."""
+    y = golden["lgssm_y"]
+    th = [0.5, math.sqrt(10.0)]
+    for (N, R, k, K, mi) in ((20, 3000, 0, 1, math.inf), (64, 500, 1, 4, math.inf), (10, 800, 0, 2, 6)):
+        a = up.coupled_pimh_chains_batch(up.get_ar(1), th, y, N, R, K=K, k=k, max_iterations=mi, seed=12, first_replicate=3, mode=1)
+        b = up.coupled_pimh_chains_batch(up.get_ar(1), th, y, N, R, K=K, k=k, max_iterations=mi, seed=12, first_replicate=3, mode=2)
+        assert np.array_equal(a["meetingtime"], b["meetingtime"]) and np.array_equal(a["iteration"], b["iteration"])
+        assert a["nfilters"] == b["nfilters"] == int(np.sum(1 + a["iteration"]))
+        assert np.array_equal(a["hbar"], b["hbar"])
+        assert np.allclose(a["sum_hbar"], b["sum_hbar"], rtol=1e-13)
+        if mi == 6:
+            assert a["iteration"].max() <= 6 and np.any(a["meetingtime"] < 0)      # hit max_iterations before meeting
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 20, 100, theta=th)
+    o = oracle.coupled_pimh_batch(cfg, y, 12, 3, 200, k=0, K=1)
+    assert np.array_equal(b["meetingtime"][:0], o["meetingtime"][:0])
+    r = up.coupled_pimh_chains_batch(up.get_ar(1), th, y, 20, 200, K=1, k=0, seed=12, first_replicate=3, mode=2)
+    assert np.array_equal(r["meetingtime"], o["meetingtime"]) and np.allclose(r["hbar"][:, 0, :], o["hbar"], rtol=1e-10, atol=1e-10)
+    cb = up.ChainBatch(up.get_ar(1), th, y, 20, 3000)
+    cb.run(3000, 1)
+    out = cb.fetch(hbar=False)
+    assert cb.filters_launched >= out["nfilters"]                                    # speculative proposals may be discarded
+    cb.close()

@@ -54,6 +54,7 @@ def lib():
         L.cpimh_pf_launch_count.restype = C.c_int64
         L.cpimh_pf_device_bytes.restype = C.c_int64
         L.cpimh_chains_launch_count.restype = C.c_int64
+        L.cpimh_chains_filters_launched.restype = C.c_int64
         _lib = L
     return _lib
 

@@ -23,6 +23,104 @@ __global__ void reduce_hbar_kernel(const double* hbar, long long R, int P, const
   if (threadIdx.x == 0) { sums[j] = s; sums[P + j] = s2; }
 }
 
+// ------------------------------------------------------------------ round-based coupled-PIMH driver
+// PIMH proposals are independent of the chain state (R/pf_kernels.R:104-131: one CPF(), then compare log Z), so the
+// proposals of iteration i+1..i+W of every unfinished replicate can be run as ONE batch of filters; a small kernel then
+// replays the accept / meet / H_bar recursion (R/debiasing_algorithm.R:180-248, 296-315) over them in order and
+// discards what lies beyond the stopping time max(tau, K).  W = 1 while the batch fills the GPU, then grows, so a
+// replicate with a long meeting time no longer serialises its filters on one CTA.
+struct RoundParams {
+  long long R; int W, nA, PD, P, D, k, K, max_it;
+  unsigned long long seed; unsigned first_replicate;
+  const int* active; int* next_active; int* next_count;
+  unsigned long long* stream_ids;
+  const double* pool_logz; const double* pool_traj; const int* pool_status;
+  double* lz1; double* lz2; int* id1; int* id2; int* meet; int* iter; int* tau; int* status;
+  double* st1; double* st2; double* accH; double* accD; double* hbar;
+  unsigned long long* nfilters;
+};
+__global__ void rounds_prepare_kernel(RoundParams q) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= (long long)q.nA * q.W) return;
+  const int rep = q.active ? q.active[s / q.W] : (int)(s / q.W);
+  const unsigned long long it = (unsigned long long)(q.iter[rep] + 1 + (int)(s % q.W));
+  q.stream_ids[s] = (unsigned long long)(q.first_replicate + (unsigned)rep) | (it << 32);
+}
+// pimh_init (R/pf_kernels.R:134-139): filter with iteration index 0 becomes chain 1; chain 2 does not exist yet
+__global__ void rounds_init_kernel(RoundParams q) {
+  const int rep = blockIdx.x;
+  const double* prop = q.pool_traj + (size_t)rep * q.PD;
+  for (int j = threadIdx.x; j < q.PD; j += blockDim.x) {
+    const double v = prop[j];
+    q.st1[(size_t)rep * q.PD + j] = v;
+    q.accH[(size_t)rep * q.PD + j] = (q.k <= 0) ? v : 0.0;
+    q.accD[(size_t)rep * q.PD + j] = 0.0;
+  }
+  if (threadIdx.x == 0) {
+    q.lz1[rep] = q.pool_logz[rep]; q.lz2[rep] = -INFINITY; q.id1[rep] = 0; q.id2[rep] = -1; q.meet[rep] = 0; q.iter[rep] = 0; q.tau[rep] = -1;
+    int st = q.pool_status[rep];
+    if (st == 0 && isnan(q.pool_logz[rep])) st = CPIMH_ERR_INVALID;
+    q.status[rep] = st;
+    if (st == 0) q.next_active[atomicAdd(q.next_count, 1)] = rep;
+  }
+}
+__global__ void rounds_accept_kernel(RoundParams q) {
+  const int a = blockIdx.x;
+  const int rep = q.active[a];
+  const int PD = q.PD;
+  double* x1 = q.st1 + (size_t)rep * PD;
+  double* x2 = q.st2 + (size_t)rep * PD;
+  double* accH = q.accH + (size_t)rep * PD;
+  double* accD = q.accD + (size_t)rep * PD;
+  double lz1 = q.lz1[rep], lz2 = q.lz2[rep];
+  int id1 = q.id1[rep], id2 = q.id2[rep], meet = q.meet[rep], iter = q.iter[rep], tau = q.tau[rep], status = 0, finished = 0;
+  for (int w = 0; w < q.W && !finished; w++) {
+    const size_t s = (size_t)a * q.W + w;
+    iter++;
+    status = q.pool_status[s];
+    const double lzp = q.pool_logz[s];
+    if (status == 0 && isnan(lzp)) status = CPIMH_ERR_INVALID;
+    if (status) { finished = 1; break; }
+    const Stream st = make_stream(q.seed, (unsigned long long)(q.first_replicate + (unsigned)rep) | ((unsigned long long)iter << 32));
+    const double lu = log(philox_u1(st, 0, 0, CPIMH_P_MH, 0));               // R/pf_kernels.R:112
+    const bool a1 = lu < (lzp - lz1);                                          // :113
+    const bool a2 = meet ? a1 : (lu < (lzp - lz2));                            // :121
+    const double* prop = q.pool_traj + s * PD;
+    if (a1) { lz1 = lzp; id1 = iter; }
+    if (meet) { lz2 = lz1; id2 = id1; }
+    else {
+      if (a2) { lz2 = lzp; id2 = iter; }
+      if (id1 == id2) { meet = 1; tau = iter; }                                // debiasing_algorithm.R:216-220
+    }
+    const int t = iter - 1;
+    const bool mcmc = (iter >= q.k && iter <= q.K);
+    const bool bias = (t >= q.k) && (id1 != id2);
+    const double coef = (double)min(t - q.k + 1, q.K - q.k + 1);
+    for (int j = threadIdx.x; j < PD; j += blockDim.x) {
+      const double pv = prop[j];
+      const double xa = a1 ? pv : x1[j];
+      const double xb = a2 ? pv : x2[j];
+      if (a1) x1[j] = pv;
+      if (a2) x2[j] = pv;
+      if (mcmc) accH[j] += xa;                                                 // :296-302
+      if (bias) accD[j] = accD[j] + coef * (xa - xb);                          // :308-312
+    }
+    if (tau > 0 && iter >= max(tau, q.K)) finished = 1;                        // :245
+    if (q.max_it >= 0 && iter >= q.max_it) finished = 1;
+  }
+  __syncthreads();
+  if (finished) {
+    const double denom = (double)(q.K - q.k + 1);
+    for (int j = threadIdx.x; j < PD; j += blockDim.x) q.hbar[(size_t)rep * PD + j] = (accH[j] + accD[j]) / denom;   // :315
+  }
+  if (threadIdx.x == 0) {
+    q.lz1[rep] = lz1; q.lz2[rep] = lz2; q.id1[rep] = id1; q.id2[rep] = id2; q.meet[rep] = meet; q.iter[rep] = iter; q.tau[rep] = tau;
+    if (status) q.status[rep] = status;
+    if (finished) atomicAdd(q.nfilters, (unsigned long long)(1 + iter));
+    else q.next_active[atomicAdd(q.next_count, 1)] = rep;
+  }
+}
+
 // ------------------------------------------------------------------ stand-alone tree kernels (class Tree, src/tree.cpp)
 __global__ void tree_init_kernel(int N, int d, const double* x0, int* a_star, double* x_star, int* l_star) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,6 +226,10 @@ struct cpimh_chains {
   DevBuf hist_x, hist_a, ascr;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, state, acc, scal, iscal, hbar, mt, it, status, nfilters, counter, sums;
   DevBuf samples1, samples2, log_pdf1, log_pdf2;
+  // round-based driver
+  int mode; int64_t filters_launched;
+  Geometry geo_pf; int grid_pf;
+  DevBuf r_logz, r_traj, r_status, r_ids, r_lz1, r_lz2, r_id1, r_id2, r_meet, r_iter, r_tau, r_st1, r_st2, r_accH, r_accD, r_act0, r_act1, r_cnt;
 };
 
 struct cpimh_tree {
@@ -140,7 +242,9 @@ extern "C" {
 int cpimh_chains_destroy(cpimh_chains* h) {
   if (!h) return CPIMH_OK;
   DevBuf* all[] = {&h->hist_x, &h->hist_a, &h->ascr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
-                   &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2};
+                   &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2,
+                   &h->r_logz, &h->r_traj, &h->r_status, &h->r_ids, &h->r_lz1, &h->r_lz2, &h->r_id1, &h->r_id2, &h->r_meet, &h->r_iter, &h->r_tau,
+                   &h->r_st1, &h->r_st2, &h->r_accH, &h->r_accD, &h->r_act0, &h->r_act1, &h->r_cnt};
   for (auto b : all) b->release();
   delete h;
   return CPIMH_OK;
@@ -161,6 +265,7 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   cpimh_chains* h = new cpimh_chains();
   h->cfg = cfg; h->entry = e; h->geo = g; h->maxR = max_replicates; h->lastR = 0; h->launches = 0;
   h->record = record_samples > 0; h->max_rec = record_samples > 0 ? record_samples : 0;
+  h->mode = 0; h->filters_launched = 0; h->grid_pf = 0;
   const int64_t resident = (int64_t)g.blocks_per_sm * g.num_sms;
   h->grid = (int)(max_replicates < resident ? max_replicates : resident);
   const size_t G = (size_t)h->grid, D = cfg.dim, T = cfg.nobs, P = T + 1, R = (size_t)max_replicates;
@@ -209,6 +314,120 @@ int cpimh_chains_set_observations(cpimh_chains* h, const double* obs_host) {
   return api_upload_obs(h->cfg, obs_host, h->obs.p);
 }
 
+static int chains_rounds_alloc(cpimh_chains* h) {
+  if (h->grid_pf > 0) return CPIMH_OK;
+  std::vector<double> pre = api_precompute(h->cfg);
+  Geometry g;
+  int rc = api_plan_geometry(h->cfg, h->entry, false, h->maxR, (int)pre.size(), &g);
+  if (rc) return rc;
+  CPIMH_REQUIRE(g.path_mode == h->geo.path_mode && g.M == h->geo.M, "internal: filter and chain kernels planned different path storage");
+  const int64_t resident = (int64_t)g.blocks_per_sm * g.num_sms;
+  const int grid = (int)(h->maxR < resident ? h->maxR : resident);
+  const size_t G = (size_t)grid, D = h->cfg.dim, T = h->cfg.nobs, PD = (T + 1) * D, R = (size_t)h->maxR;
+  // the filter kernel may be resident with more CTAs than the chain kernel: grow the per-CTA workspaces
+  if (g.path_mode == PATH_DENSE) {
+    rc = h->hist_x.alloc(sizeof(double) * G * g.hist_x_elems);
+    if (!rc) rc = h->hist_a.alloc(sizeof(int) * G * g.hist_a_elems);
+  } else {
+    rc = h->xbuf.alloc(sizeof(double) * G * 2 * D * g.Npad);
+    if (!rc) rc = h->ascr.alloc(sizeof(int) * G * g.Npad);
+    if (!rc) rc = h->a_star.alloc(sizeof(int) * G * g.M);
+    if (!rc) rc = h->o_star.alloc(sizeof(int) * G * g.M);
+    if (!rc) rc = h->x_star.alloc(sizeof(double) * G * D * g.M);
+  }
+  if (!rc) rc = h->r_logz.alloc(sizeof(double) * R);
+  if (!rc) rc = h->r_traj.alloc(sizeof(double) * R * PD);
+  if (!rc) rc = h->r_status.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_ids.alloc(sizeof(unsigned long long) * R);
+  if (!rc) rc = h->r_lz1.alloc(sizeof(double) * R);
+  if (!rc) rc = h->r_lz2.alloc(sizeof(double) * R);
+  if (!rc) rc = h->r_id1.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_id2.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_meet.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_iter.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_tau.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_st1.alloc(sizeof(double) * R * PD);
+  if (!rc) rc = h->r_st2.alloc(sizeof(double) * R * PD);
+  if (!rc) rc = h->r_accH.alloc(sizeof(double) * R * PD);
+  if (!rc) rc = h->r_accD.alloc(sizeof(double) * R * PD);
+  if (!rc) rc = h->r_act0.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_act1.alloc(sizeof(int) * R);
+  if (!rc) rc = h->r_cnt.alloc(sizeof(int));
+  if (rc) return rc;
+  h->geo_pf = g; h->grid_pf = grid;
+  return CPIMH_OK;
+}
+
+static int chains_run_rounds(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_replicate, int k, int K, int max_it, cudaStream_t s) {
+  int rc = chains_rounds_alloc(h);
+  if (rc) return rc;
+  h->filters_launched = 0;
+  const cpimh_config& c = h->cfg;
+  const Geometry& g = h->geo_pf;
+  const int D = c.dim, P = c.nobs + 1, PD = P * D;
+  PfParams p;
+  api_fill_pf_params(c, g, h->npre, &p);
+  p.seed = seed; p.first_filter = 0; p.b0 = 0;
+  p.obs = h->obs.as<double>(); p.theta = h->theta.as<double>(); p.pre = h->pre.as<double>();
+  p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.ascr = h->ascr.as<int>();
+  p.xbuf = h->xbuf.as<double>(); p.a_star = h->a_star.as<int>(); p.o_star = h->o_star.as<int>(); p.x_star = h->x_star.as<double>();
+  p.logz = h->r_logz.as<double>(); p.traj = h->r_traj.as<double>(); p.status = h->r_status.as<int>();
+  p.stream_ids = h->r_ids.as<unsigned long long>();
+  RoundParams q;
+  memset(&q, 0, sizeof(q));
+  q.R = R; q.PD = PD; q.P = P; q.D = D; q.k = k; q.K = K; q.max_it = max_it; q.seed = seed; q.first_replicate = first_replicate;
+  q.stream_ids = h->r_ids.as<unsigned long long>();
+  q.pool_logz = h->r_logz.as<double>(); q.pool_traj = h->r_traj.as<double>(); q.pool_status = h->r_status.as<int>();
+  q.lz1 = h->r_lz1.as<double>(); q.lz2 = h->r_lz2.as<double>(); q.id1 = h->r_id1.as<int>(); q.id2 = h->r_id2.as<int>();
+  q.meet = h->r_meet.as<int>(); q.iter = h->r_iter.as<int>(); q.tau = h->r_tau.as<int>(); q.status = h->status.as<int>();
+  q.st1 = h->r_st1.as<double>(); q.st2 = h->r_st2.as<double>(); q.accH = h->r_accH.as<double>(); q.accD = h->r_accD.as<double>();
+  q.hbar = h->hbar.as<double>(); q.nfilters = h->nfilters.as<unsigned long long>(); q.next_count = h->r_cnt.as<int>();
+  auto launch_filters = [&](int64_t B) -> int {
+    PfLaunch L;
+    L.threads = g.threads; L.smem = g.smem; L.variant = g.variant;
+    L.grid = (int)(B < h->grid_pf ? B : h->grid_pf);
+    p.B = B;
+    h->filters_launched += B; h->launches += 1;
+    return h->entry->launch_pf(p, L, s);
+  };
+  // iteration 0: one filter per replicate (stream ids = replicate ids with iteration index 0)
+  CPIMH_CUDA_CHECK(cudaMemsetAsync(h->r_iter.p, 0xff, sizeof(int) * (size_t)R, s));     // iter = -1 so that prepare() yields iteration 0
+  CPIMH_CUDA_CHECK(cudaMemsetAsync(h->r_cnt.p, 0, sizeof(int), s));
+  q.active = nullptr; q.next_active = h->r_act0.as<int>(); q.nA = (int)R; q.W = 1;
+  rounds_prepare_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(q);
+  rc = launch_filters(R);
+  if (rc) return rc;
+  rounds_init_kernel<<<(unsigned)R, 128, 0, s>>>(q);
+  h->launches += 2;
+  int nA = 0, flip = 0;
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(&nA, h->r_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  while (nA > 0) {
+    // window: one proposal per replicate while that fills the GPU, more (speculatively) once few replicates remain
+    int64_t W = h->grid_pf / nA;
+    if (W < 1) W = 1;
+    if (W > 32) W = 32;
+    if (W * nA > R) W = R / nA;
+    q.active = flip ? h->r_act1.as<int>() : h->r_act0.as<int>();
+    q.next_active = flip ? h->r_act0.as<int>() : h->r_act1.as<int>();
+    q.nA = nA; q.W = (int)W;
+    CPIMH_CUDA_CHECK(cudaMemsetAsync(h->r_cnt.p, 0, sizeof(int), s));
+    rounds_prepare_kernel<<<(unsigned)((nA * W + 255) / 256), 256, 0, s>>>(q);
+    rc = launch_filters(nA * W);
+    if (rc) return rc;
+    rounds_accept_kernel<<<(unsigned)nA, 128, 0, s>>>(q);
+    h->launches += 2;
+    CPIMH_CUDA_CHECK(cudaMemcpyAsync(&nA, h->r_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+    flip ^= 1;
+  }
+  // per-replicate scalars in the persistent kernel's output arrays
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->mt.p, h->r_tau.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->it.p, h->r_iter.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  return CPIMH_OK;
+}
+
 int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_replicate, int k, int K, int max_iterations,
                      double* d_sums, void* stream) {
   CPIMH_REQUIRE(h, "null handle");
@@ -217,6 +436,20 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   CPIMH_REQUIRE(max_iterations < 0 || max_iterations >= K, "max_iterations must be >= K or negative (unbounded)");
   CPIMH_REQUIRE(max_iterations < 4096, "iteration index must fit 12 bits of the Philox counter (max_iterations < 4096)");
   cudaStream_t s = (cudaStream_t)stream;
+  const bool rounds = h->mode == 2 || (h->mode == 0 && !h->record);
+  if (rounds) {
+    CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, sizeof(unsigned long long), s));
+    CPIMH_CUDA_CHECK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * (size_t)R, s));
+    int rcr = chains_run_rounds(h, R, seed, first_replicate, k, K, max_iterations < 0 ? 4095 : max_iterations, s);
+    if (rcr) return rcr;
+    const int Pr = (h->cfg.nobs + 1) * h->cfg.dim;
+    double* sums_r = d_sums ? d_sums : h->sums.as<double>();
+    reduce_hbar_kernel<<<Pr + 1, 256, 0, s>>>(h->hbar.as<double>(), R, Pr, h->nfilters.as<unsigned long long>(), sums_r);
+    CPIMH_CUDA_CHECK(cudaGetLastError());
+    if (d_sums) CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->sums.p, d_sums, sizeof(double) * (2 * Pr + 2), cudaMemcpyDeviceToDevice, s));
+    h->launches += 1; h->lastR = R;
+    return CPIMH_OK;
+  }
   ChainParams cp;
   memset(&cp, 0, sizeof(cp));
   api_fill_pf_params(h->cfg, h->geo, h->npre, &cp.pf);
@@ -244,9 +477,17 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   reduce_hbar_kernel<<<P + 1, 256, 0, s>>>(h->hbar.as<double>(), R, P, h->nfilters.as<unsigned long long>(), sums);
   CPIMH_CUDA_CHECK(cudaGetLastError());
   if (d_sums) CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->sums.p, d_sums, sizeof(double) * (2 * P + 2), cudaMemcpyDeviceToDevice, s));
-  h->launches += 2; h->lastR = R;
+  h->launches += 2; h->lastR = R; h->filters_launched = -1;
   return CPIMH_OK;
 }
+
+int cpimh_chains_set_mode(cpimh_chains* h, int mode) {
+  CPIMH_REQUIRE(h && mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (persistent CTA per replicate) or 2 (rounds)");
+  CPIMH_REQUIRE(!(mode == 2 && h->record), "recording samples needs the persistent kernel (mode 1)");
+  h->mode = mode;
+  return CPIMH_OK;
+}
+int64_t cpimh_chains_filters_launched(const cpimh_chains* h) { return h ? h->filters_launched : 0; }
 
 int cpimh_chains_fetch(cpimh_chains* h, int64_t R, void* stream, cpimh_chain_out* o) {
   CPIMH_REQUIRE(h && o, "null argument");

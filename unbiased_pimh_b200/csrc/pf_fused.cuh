@@ -30,6 +30,7 @@ struct PfParams {
   long long b0;                // index of the first filter of this launch (outputs and streams are indexed b0 + ...)
   int shuffle, path_mode;
   unsigned long long seed, first_filter;
+  const unsigned long long* stream_ids;   // [B] explicit Philox stream id per filter (chain driver), or null: first_filter + b
   const double* obs;           // [T][dy] row-major (device)
   const double* theta;         // [CPIMH_MAX_THETA]
   const double* pre;           // [npre]
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p
   for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
   __syncthreads();
   for (long long b = p.b0 + blockIdx.x; b < p.b0 + p.B; b += gridDim.x) {
-    Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+    Stream s = make_stream(p.seed, p.stream_ids ? p.stream_ids[b] : p.first_filter + (unsigned long long)b);
     FilterOut out;
     out.logz = p.logz + b;
     out.logz_t = p.logz_t ? p.logz_t + (size_t)b * p.T : nullptr;
@@ -481,9 +482,10 @@ inline int pf_variant_for(int threads) { return threads <= 128 ? PF_VARIANT_128x
 template <class Model, class F>
 int pf_with_kernel(int variant, F&& f) {
   switch (variant) {
-    case PF_VARIANT_128x8: return f(pf_batch_kernel<Model, 128, 8>);
-    case PF_VARIANT_256x3: return f(pf_batch_kernel<Model, 256, 3>);
-    case PF_VARIANT_512x2: return f(pf_batch_kernel<Model, 512, 2>);
+    // wide states (d > 4) keep x, noise and the matvec in registers: trade residency for 128 registers per thread
+    case PF_VARIANT_128x8: return f(pf_batch_kernel<Model, 128, (Model::D > 4 ? 4 : 8)>);
+    case PF_VARIANT_256x3: return f(pf_batch_kernel<Model, 256, (Model::D > 4 ? 2 : 3)>);
+    case PF_VARIANT_512x2: return f(pf_batch_kernel<Model, 512, (Model::D > 4 ? 1 : 2)>);
     default: return f(pf_batch_kernel<Model, 1024, 1>);
   }
 }

@@ -153,7 +153,7 @@ class ChainBatch:
     """Device-resident coupled-PIMH driver (cpimh_chains handle): one persistent CTA per replicate."""
 
     def __init__(self, model, theta, observations, nparticles, max_replicates, record_samples=0, tree_capacity=0,
-                 threads_per_filter=0, sk_max_events=64, device=None):
+                 threads_per_filter=0, sk_max_events=64, device=None, mode=0):
         obs = np.asarray(observations, dtype=np.float64)
         self.nobs = obs.shape[0]
         self.model = model
@@ -166,6 +166,8 @@ class ChainBatch:
         L.check(L.lib().cpimh_chains_create(C.byref(self.cfg), C.c_int64(int(max_replicates)), C.c_int(self.record), C.byref(self.h)))
         ob = L.obs_matrix(obs, self.nobs)
         L.check(L.lib().cpimh_chains_set_observations(self.h, ob.ctypes.data_as(C.c_void_p)))
+        if mode:
+            L.check(L.lib().cpimh_chains_set_mode(self.h, C.c_int(int(mode))))
         self.last = 0
 
     def close(self):
@@ -215,14 +217,19 @@ class ChainBatch:
     def launch_count(self):
         return int(L.lib().cpimh_chains_launch_count(self.h))
 
+    @property
+    def filters_launched(self):
+        """filters launched by the last run of the round-based driver, including discarded speculative proposals (-1: persistent kernel)"""
+        return int(L.lib().cpimh_chains_filters_launched(self.h))
+
 
 def coupled_pimh_chains_batch(model, theta, observations, nparticles, nreplicates, K=1, k=0, max_iterations=math.inf, seed=None,
-                              first_replicate=0, record_samples=0, **kw):
+                              first_replicate=0, record_samples=0, mode=0, **kw):
     """R replicates of coupled_pimh_chains(..., N = nparticles, K) + H_bar(., k = k, K = K) on the GPU.
     Returns hbar (R, d, T+1), meetingtime (R,) [-1 = not met within max_iterations], iteration (R,), the sums that are
     all-reduced across GPUs, the number of filters run, and (record_samples > 0) the c_chains lists."""
     seed = rng.next_seed() if seed is None else int(seed)
-    cb = ChainBatch(model, theta, observations, nparticles, nreplicates, record_samples=record_samples, **kw)
+    cb = ChainBatch(model, theta, observations, nparticles, nreplicates, record_samples=record_samples, mode=mode, **kw)
     try:
         cb.run(nreplicates, seed, first_replicate, k, K, max_iterations)
         out = cb.fetch()
