@@ -209,3 +209,13 @@ def test_round_based_driver_equals_persistent_kernel(up, oracle, golden):
     out = cb.fetch(hbar=False)
     assert cb.filters_launched >= out["nfilters"]                                    # speculative proposals may be discarded
     cb.close()
+
+
+def test_chains_with_tree_path_storage(up, golden):
+    """Both chain strategies on top of the Jacob-Murray-Rubenthaler tree instead of the dense history."""
+    y = golden["lgssm_y"]
+    th = [0.5, math.sqrt(10.0)]
+    ref = up.coupled_pimh_chains_batch(up.get_ar(1), th, y, 100, 300, K=2, seed=4)
+    for mode in (1, 2):
+        r = up.coupled_pimh_chains_batch(up.get_ar(1), th, y, 100, 300, K=2, seed=4, mode=mode, store_paths=3)
+        assert np.array_equal(r["meetingtime"], ref["meetingtime"]) and np.array_equal(r["hbar"], ref["hbar"])

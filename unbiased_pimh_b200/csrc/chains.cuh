@@ -1,4 +1,5 @@
-// chains.cuh -- coupled PIMH chains + unbiased (H_bar) estimator, one persistent CTA per replicate.
+// chains.cuh -- coupled PIMH chains + unbiased (H_bar) estimator, one persistent CTA per replicate (strategy 1 of the
+// chain driver; the default round-based strategy with batched speculative proposals lives in api_chains.cu).
 //
 // Restates, batched on the GPU, the reference's R-level drivers:
 //   pimh_init / single_kernel / coupled_kernel   R/pf_kernels.R:86-145   (one CPF proposal, one uniform,

@@ -153,12 +153,12 @@ class ChainBatch:
     """Device-resident coupled-PIMH driver (cpimh_chains handle): one persistent CTA per replicate."""
 
     def __init__(self, model, theta, observations, nparticles, max_replicates, record_samples=0, tree_capacity=0,
-                 threads_per_filter=0, sk_max_events=64, device=None, mode=0):
+                 threads_per_filter=0, sk_max_events=64, device=None, mode=0, store_paths=1):
         obs = np.asarray(observations, dtype=np.float64)
         self.nobs = obs.shape[0]
         self.model = model
         self.cfg = model.config(nparticles, theta, nobs=self.nobs, tree_capacity=tree_capacity, threads_per_filter=threads_per_filter,
-                                sk_max_events=sk_max_events)
+                                sk_max_events=sk_max_events, store_paths=store_paths)
         if device is not None:
             L.check(L.lib().cpimh_set_device(C.c_int(int(device))))
         self.h = C.c_void_p()
