@@ -122,8 +122,8 @@ int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, i
   // CTA size: about 8 particles per thread, snapped to a compiled variant (128/256/512/1024 threads)
   int threads = c.threads_per_filter > 0 ? c.threads_per_filter : next_pow2((N + 7) / 8);
   g->variant = pf_variant_for(threads);
-  threads = pf_variant_threads(g->variant);
-  if (c.threads_per_filter <= 0 && N <= 64) threads = 64;      // tiny filters: two warps are plenty
+  if (threads >= 128) threads = pf_variant_threads(g->variant);
+  else threads = threads <= 32 ? 32 : 64;                      // small filters: one or two warps (no cross-warp barriers to pay for)
   CPIMH_REQUIRE((long long)threads * CPIMH_MAX_E >= N, "N=%d needs at least %d threads per filter", N, (N + CPIMH_MAX_E - 1) / CPIMH_MAX_E);
   g->threads = threads;
   const size_t max_smem = prop.sharedMemPerBlockOptin;
