@@ -154,6 +154,8 @@ typedef struct cpimh_chain_out {
   double*  sum_hbar;     /* [d x (T+1)] sum over replicates (nullable)                             */
   double*  sum_hbar_sq;  /* [d x (T+1)] sum of squares (nullable)                                  */
   int64_t* nfilters;     /* [1]       particle filters actually run (nullable)                     */
+  double*  bc;           /* [R] x (d x (T+1))  bias-correction term BC(c_chains, k, K) alone,
+                            R/debiasing_algorithm.R:330-363 (nullable)                              */
 } cpimh_chain_out;
 int cpimh_coupled_pimh(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, cpimh_chain_out* out_host);

@@ -163,7 +163,7 @@ SEXP cpimh_R_coupled_pimh(SEXP cfg_raw, SEXP obs, SEXP R_, SEXP k_, SEXP K_, SEX
   int R = Rf_asInteger(R_), P = cfg->dim * (cfg->nobs + 1);
   SEXP hbar = PROTECT(Rf_allocMatrix(REALSXP, P, R));
   SEXP tau = PROTECT(Rf_allocVector(INTSXP, R)), it = PROTECT(Rf_allocVector(INTSXP, R));
-  cpimh_chain_out o = {REAL(hbar), INTEGER(tau), INTEGER(it), NULL, NULL, NULL};
+  cpimh_chain_out o = {REAL(hbar), INTEGER(tau), INTEGER(it), NULL, NULL, NULL, NULL};
   check(cpimh_coupled_pimh(cfg, REAL(obs), R, seed_from_R(), 0, Rf_asInteger(k_), Rf_asInteger(K_), Rf_asInteger(maxit), &o));
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)); SET_VECTOR_ELT(out, 0, hbar); SET_VECTOR_ELT(out, 1, tau); SET_VECTOR_ELT(out, 2, it);
   UNPROTECT(4); return out;

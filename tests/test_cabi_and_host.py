@@ -138,6 +138,10 @@ def test_coupled_pimh_chains_and_hbar_host_logic():
                 ref = ref + min(t - k + 1, K - k + 1) * (c["samples1"][t + 1] - c["samples2"][t])
         assert np.allclose(hb, ref / (K - k + 1), rtol=1e-14)
     assert up.H_bar(c, k=9, K=10) is None                 # k beyond the horizon (R prints an error and returns NULL)
+    for k, K in ((0, 1), (1, 3), (0, 5)):                  # H_bar = MCMC average + BC (R/debiasing_algorithm.R:330-363)
+        mcmc = sum(c["samples1"][t] for t in range(k, K + 1)) / (K - k + 1)
+        assert np.allclose(up.H_bar(c, k=k, K=K), mcmc + up.BC(c, k=k, K=K), rtol=1e-14)
+    assert np.allclose(up.BC(c, k=0, K=math.inf), sum(min(t + 1, math.inf) * (c["samples1"][t + 1] - c["samples2"][t]) for t in range(0, 3)))
 
 
 def test_python_hbar_equals_oracle_hbar(oracle, golden):

@@ -39,6 +39,7 @@ def test_coupled_chains_match_oracle_replicate_for_replicate(up, oracle, golden)
             assert np.allclose(g["log_pdf1"][:, 0], c["log_pdf1"][:n + 1], rtol=1e-10)
             if c["iteration"] <= 16:
                 assert np.allclose(up.H_bar(g, k=k, K=K), r["hbar"][rep, 0], rtol=1e-10, atol=1e-10)
+                assert np.allclose(up.BC(g, k=k, K=K), r["bc"][rep, 0], rtol=1e-10, atol=1e-10)
 
 
 def test_multi_component_models_in_chains(up, oracle, golden):

@@ -11,7 +11,7 @@ from .resampling import (multinomial_resampling_n, multinomial_resampling_n_, sy
                          coupled_multinomial_resampling_n_, indexmatching_cpp, CR_multinomial, CR_systematic, CR_indexmatching,
                          normalize_weight, sorted_uniforms)
 from .filters import CPF, particlefilter, cpf_batch, PfBatch, pf_get_weighted_average  # noqa: F401
-from .pimh import (get_pimh_kernels, coupled_pimh_chains, H_bar, rheeglynn_estimator, coupled_pimh_chains_batch, ChainBatch,  # noqa: F401
+from .pimh import (get_pimh_kernels, coupled_pimh_chains, H_bar, BC, rheeglynn_estimator, coupled_pimh_chains_batch, ChainBatch,  # noqa: F401
                    unbiased_estimator_sharded, shard_range, combine_sums)
 from .tree import Tree  # noqa: F401
 from .mvnorm import (fast_dmvnorm, fast_dmvnorm_transpose, fast_dmvnorm_transpose_cholesky, fast_rmvnorm, fast_rmvnorm_transpose,  # noqa: F401

@@ -36,7 +36,7 @@ struct RoundParams {
   unsigned long long* stream_ids;
   const double* pool_logz; const double* pool_traj; const int* pool_status;
   double* lz1; double* lz2; int* id1; int* id2; int* meet; int* iter; int* tau; int* status;
-  double* st1; double* st2; double* accH; double* accD; double* hbar;
+  double* st1; double* st2; double* accH; double* accD; double* hbar; double* bc;
   unsigned long long* nfilters;
 };
 __global__ void rounds_prepare_kernel(RoundParams q) {
@@ -111,7 +111,10 @@ __global__ void rounds_accept_kernel(RoundParams q) {
   __syncthreads();
   if (finished) {
     const double denom = (double)(q.K - q.k + 1);
-    for (int j = threadIdx.x; j < PD; j += blockDim.x) q.hbar[(size_t)rep * PD + j] = (accH[j] + accD[j]) / denom;   // :315
+    for (int j = threadIdx.x; j < PD; j += blockDim.x) {
+      q.hbar[(size_t)rep * PD + j] = (accH[j] + accD[j]) / denom;   // :315
+      q.bc[(size_t)rep * PD + j] = accD[j] / denom;                 // BC(), :330-363
+    }
   }
   if (threadIdx.x == 0) {
     q.lz1[rep] = lz1; q.lz2[rep] = lz2; q.id1[rep] = id1; q.id2[rep] = id2; q.meet[rep] = meet; q.iter[rep] = iter; q.tau[rep] = tau;
@@ -224,6 +227,7 @@ struct cpimh_chains {
   int64_t maxR, lastR, launches;
   int record, max_rec, grid, npre;
   DevBuf hist_x, hist_a, ascr;
+  DevBuf bc;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, state, acc, scal, iscal, hbar, mt, it, status, nfilters, counter, sums;
   DevBuf samples1, samples2, log_pdf1, log_pdf2;
   // round-based driver
@@ -241,7 +245,7 @@ extern "C" {
 
 int cpimh_chains_destroy(cpimh_chains* h) {
   if (!h) return CPIMH_OK;
-  DevBuf* all[] = {&h->hist_x, &h->hist_a, &h->ascr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
+  DevBuf* all[] = {&h->bc, &h->hist_x, &h->hist_a, &h->ascr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
                    &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2,
                    &h->r_logz, &h->r_traj, &h->r_status, &h->r_ids, &h->r_lz1, &h->r_lz2, &h->r_id1, &h->r_id2, &h->r_meet, &h->r_iter, &h->r_tau,
                    &h->r_st1, &h->r_st2, &h->r_accH, &h->r_accD, &h->r_act0, &h->r_act1, &h->r_cnt};
@@ -289,6 +293,7 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   if (!rc) rc = h->scal.alloc(sizeof(double) * G * 4);
   if (!rc) rc = h->iscal.alloc(sizeof(int) * G * 4);
   if (!rc) rc = h->hbar.alloc(sizeof(double) * R * P * D);
+  if (!rc) rc = h->bc.alloc(sizeof(double) * R * P * D);
   if (!rc) rc = h->mt.alloc(sizeof(int) * R);
   if (!rc) rc = h->it.alloc(sizeof(int) * R);
   if (!rc) rc = h->status.alloc(sizeof(int) * R);
@@ -381,7 +386,7 @@ static int chains_run_rounds(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t
   q.lz1 = h->r_lz1.as<double>(); q.lz2 = h->r_lz2.as<double>(); q.id1 = h->r_id1.as<int>(); q.id2 = h->r_id2.as<int>();
   q.meet = h->r_meet.as<int>(); q.iter = h->r_iter.as<int>(); q.tau = h->r_tau.as<int>(); q.status = h->status.as<int>();
   q.st1 = h->r_st1.as<double>(); q.st2 = h->r_st2.as<double>(); q.accH = h->r_accH.as<double>(); q.accD = h->r_accD.as<double>();
-  q.hbar = h->hbar.as<double>(); q.nfilters = h->nfilters.as<unsigned long long>(); q.next_count = h->r_cnt.as<int>();
+  q.hbar = h->hbar.as<double>(); q.bc = h->bc.as<double>(); q.nfilters = h->nfilters.as<unsigned long long>(); q.next_count = h->r_cnt.as<int>();
   auto launch_filters = [&](int64_t B) -> int {
     PfLaunch L;
     L.threads = g.threads; L.smem = g.smem; L.variant = g.variant;
@@ -459,7 +464,7 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   cp.pf.xbuf = h->xbuf.as<double>(); cp.pf.a_star = h->a_star.as<int>(); cp.pf.o_star = h->o_star.as<int>(); cp.pf.x_star = h->x_star.as<double>();
   cp.R = R; cp.first_replicate = first_replicate; cp.k = k; cp.K = K; cp.max_iterations = max_iterations < 0 ? 4095 : max_iterations;
   cp.state = h->state.as<double>(); cp.acc = h->acc.as<double>(); cp.scal = h->scal.as<double>(); cp.iscal = h->iscal.as<int>();
-  cp.hbar = h->hbar.as<double>(); cp.meetingtime = h->mt.as<int>(); cp.iteration = h->it.as<int>(); cp.status = h->status.as<int>();
+  cp.hbar = h->hbar.as<double>(); cp.bc = h->bc.as<double>(); cp.meetingtime = h->mt.as<int>(); cp.iteration = h->it.as<int>(); cp.status = h->status.as<int>();
   cp.nfilters = h->nfilters.as<unsigned long long>(); cp.work_counter = h->counter.as<int>();
   if (h->record) {
     cp.samples1 = h->samples1.as<double>(); cp.samples2 = h->samples2.as<double>();
@@ -506,6 +511,7 @@ int cpimh_chains_fetch(cpimh_chains* h, int64_t R, void* stream, cpimh_chain_out
   std::vector<double> sums(2 * P + 2);
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(sums.data(), h->sums.p, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost, s));
   if (o->hbar) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->hbar, h->hbar.p, sizeof(double) * (size_t)R * P, cudaMemcpyDeviceToHost, s));
+  if (o->bc) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->bc, h->bc.p, sizeof(double) * (size_t)R * P, cudaMemcpyDeviceToHost, s));
   if (o->meetingtime) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->meetingtime, h->mt.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
   if (o->iteration) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->iteration, h->it.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));

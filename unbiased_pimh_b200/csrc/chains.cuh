@@ -26,6 +26,7 @@ struct ChainParams {
   double* scal;                // [grid][4]           scratch scalars written by run_filter (logz)
   int* iscal;                  // [grid][4]
   double* hbar;                // [R][T+1][D] or null (R layout d x (T+1) column-major per replicate)
+  double* bc;                  // [R][T+1][D] or null: bias-correction term alone (BC(), R/debiasing_algorithm.R:330-363)
   int* meetingtime;            // [R]
   int* iteration;              // [R]
   int* status;                 // [R]
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
     __syncthreads();
     const double denom = (double)(cp.K - cp.k + 1);
     if (cp.hbar) for (int j = tid; j < PD; j += NT) cp.hbar[(size_t)r * PD + j] = (accH[j] + accD[j]) / denom;
+    if (cp.bc) for (int j = tid; j < PD; j += NT) cp.bc[(size_t)r * PD + j] = accD[j] / denom;
     if (tid == 0) {
       cp.meetingtime[r] = tau;
       cp.iteration[r] = iter;

@@ -148,6 +148,26 @@ def H_bar(c_chains, h=lambda x: x, k=0, K=1):
     return hb / (K - k + 1)
 
 
+def BC(c_chains, h=lambda x: x, k=0, K=1):
+    """BC(c_chains, h = function(x) x, k = 0, K = 1) -- the bias-correction term of H_bar alone
+    (R/debiasing_algorithm.R:330-363); K = Inf gives the un-normalised almost-sure limit."""
+    maxiter = c_chains["iteration"]
+    if k > maxiter:
+        print("error: k has to be less than the horizon of the coupled chains")
+        return None
+    if K > maxiter and math.isfinite(K):
+        print("error: K has to be less than the horizon of the coupled chains")
+        return None
+    s1, s2 = c_chains["samples1"], c_chains["samples2"]
+    dterm = np.zeros_like(np.atleast_1d(h(s1[0])), dtype=np.float64)
+    tau = c_chains["meetingtime"]
+    if not (tau <= k + 1):
+        for t in range(k, int(min(maxiter - 1, tau - 1)) + 1):
+            coef = min(t - k + 1, K - k + 1)
+            dterm = dterm + coef * (np.atleast_1d(h(s1[t + 1])) - np.atleast_1d(h(s2[t])))
+    return dterm if not math.isfinite(K) else dterm / (K - k + 1)
+
+
 # ---------------------------------------------------------------------------------------------- batched GPU twins
 class ChainBatch:
     """Device-resident coupled-PIMH driver (cpimh_chains handle): one persistent CTA per replicate."""
@@ -187,7 +207,7 @@ class ChainBatch:
                                          C.c_int(int(k)), C.c_int(int(K)), C.c_int(mi), C.c_void_p(d_sums or 0), C.c_void_p(stream or 0)))
         self.last = int(nreplicates)
 
-    def fetch(self, nreplicates=None, stream=None, hbar=True):
+    def fetch(self, nreplicates=None, stream=None, hbar=True, bc=False):
         R = self.last if nreplicates is None else int(nreplicates)
         d, P = self.cfg.dim, self.cfg.nobs + 1
         hb = np.empty((R, P, d)) if hbar else None
@@ -198,12 +218,16 @@ class ChainBatch:
         nf = np.zeros(1, dtype=np.int64)
         o = L.ChainOut()
         o.hbar = hb.ctypes.data if hbar else None
+        bcv = np.empty((R, P, d)) if bc else None
+        o.bc = bcv.ctypes.data if bc else None
         o.meetingtime, o.iteration = mt.ctypes.data, it.ctypes.data
         o.sum_hbar, o.sum_hbar_sq, o.nfilters = s.ctypes.data, s2.ctypes.data, nf.ctypes.data
         L.check(L.lib().cpimh_chains_fetch(self.h, C.c_int64(R), C.c_void_p(stream or 0), C.byref(o)))
         out = {"meetingtime": mt, "iteration": it, "sum_hbar": s.T.copy(), "sum_hbar_sq": s2.T.copy(), "nfilters": int(nf[0])}
         if hbar:
             out["hbar"] = hb.transpose(0, 2, 1)       # (R, d, T+1)
+        if bc:
+            out["bc"] = bcv.transpose(0, 2, 1)
         return out
 
     def fetch_chains(self, r, stream=None):
@@ -232,7 +256,7 @@ def coupled_pimh_chains_batch(model, theta, observations, nparticles, nreplicate
     cb = ChainBatch(model, theta, observations, nparticles, nreplicates, record_samples=record_samples, mode=mode, **kw)
     try:
         cb.run(nreplicates, seed, first_replicate, k, K, max_iterations)
-        out = cb.fetch()
+        out = cb.fetch(bc=True)
         if record_samples:
             chains = []
             for r in range(int(nreplicates)):
