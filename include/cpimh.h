@@ -127,6 +127,10 @@ int cpimh_pf_fetch(cpimh_pf* h, int64_t nfilters, void* stream, double* logz, do
 /* all_particles=TRUE outputs (R/CPF.R:73-76, R/particlefilter.R:39-43) for filter b of the last run:
  *   exp_path d x (T+1); trajectories d x (T+1) x N; normweights [N]   (any may be NULL) */
 int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* exp_path, double* trajectories, double* normweights);
+/* the same exp_path for EVERY filter of a batch, computed inside the filter kernel (what coupled_pimh_chains_all_particles
+ * consumes, R/pf_kernels.R:205-230): switch on before cpimh_pf_run, then fetch [B] x (d x (T+1) col-major) */
+int cpimh_pf_all_particles(cpimh_pf* h, int on);
+int cpimh_pf_fetch_exp_paths(cpimh_pf* h, int64_t nfilters, void* stream, double* exp_path);
 /* per-step ancestors [T][N] (0-based, as passed to Tree$update) of filter b; requires cpimh_pf_record_ancestors(h,1) before run */
 int cpimh_pf_record_ancestors(cpimh_pf* h, int on);
 int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ancestors);
@@ -156,6 +160,11 @@ typedef struct cpimh_chain_out {
   int64_t* nfilters;     /* [1]       particle filters actually run (nullable)                     */
   double*  bc;           /* [R] x (d x (T+1))  bias-correction term BC(c_chains, k, K) alone,
                             R/debiasing_algorithm.R:330-363 (nullable)                              */
+  /* all_particles = TRUE chains (cpimh_chains_set_all_particles): H_bar over exp_samples1/2, the weighted average of
+   * all N paths instead of the one drawn path (R/debiasing_algorithm.R:164-171,239-242; R/pf_kernels.R:147-215) */
+  double*  hbar_rb;        /* [R] x (d x (T+1))  (nullable) */
+  double*  sum_hbar_rb;    /* [d x (T+1)]        (nullable) */
+  double*  sum_hbar_rb_sq; /* [d x (T+1)]        (nullable) */
 } cpimh_chain_out;
 int cpimh_coupled_pimh(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, cpimh_chain_out* out_host);
@@ -177,6 +186,9 @@ int64_t cpimh_chains_launch_count(const cpimh_chains* h);
  * replicates remain, speculative) proposals -- PIMH proposals do not depend on the chain state, so a long replicate's
  * proposals run in parallel.  Results are identical; auto = rounds unless samples are recorded. */
 int cpimh_chains_set_mode(cpimh_chains* h, int mode);
+/* get_pimh_kernels(with_as, all_particles = TRUE): every proposal also carries exp_path; fills the *_rb outputs.
+ * Round-based driver only (no recorded samples). */
+int cpimh_chains_set_all_particles(cpimh_chains* h, int on);
 int64_t cpimh_chains_filters_launched(const cpimh_chains* h);   /* including discarded speculative proposals */
 
 /* ============================== primitives (batched over B independent problems) ==============================

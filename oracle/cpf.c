@@ -141,10 +141,10 @@ int orc_cpf_batch(const orc_config* cfg, const double* obs, uint64_t seed, uint6
 
 /* ---- coupled PIMH chains ---- */
 static int run_filter(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate, uint32_t iter_index,
-                      double* traj, double* logz) {
+                      double* traj, double* logz, double* exp_path) {
   orc_pf_out o; memset(&o, 0, sizeof(o));
   double* lzt = (double*)malloc(sizeof(double) * (size_t)cfg->nobs);
-  o.trajectory = traj; o.logz = logz; o.logz_t = lzt;
+  o.trajectory = traj; o.logz = logz; o.logz_t = lzt; o.exp_path = exp_path;
   int rc = orc_cpf(cfg, obs, NULL, seed, (uint64_t)replicate | ((uint64_t)iter_index << 32), &o);
   free(lzt);
   return rc;
@@ -152,9 +152,17 @@ static int run_filter(const orc_config* cfg, const double* obs, uint64_t seed, u
 
 int orc_coupled_pimh_chains(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
                             int K, int max_iterations, int run_discarded_init, orc_chains* out) {
+  return orc_coupled_pimh_chains_ap(cfg, obs, seed, replicate, K, max_iterations, run_discarded_init, 0, out);
+}
+
+/* all_particles != 0: the *_all_particles kernels (R/pf_kernels.R:147-215): exp_path is accepted together with the state */
+int orc_coupled_pimh_chains_ap(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
+                               int K, int max_iterations, int run_discarded_init, int all_particles, orc_chains* out) {
   const int d = cfg->dim, p = cfg->nobs + 1;
   size_t psz = (size_t)d * p;
   double *s1 = (double*)malloc(sizeof(double) * psz), *s2 = (double*)malloc(sizeof(double) * psz), *prop = (double*)malloc(sizeof(double) * psz);
+  double *e1 = NULL, *e2 = NULL, *eprop = NULL;
+  if (all_particles) { e1 = (double*)calloc(psz, sizeof(double)); e2 = (double*)calloc(psz, sizeof(double)); eprop = (double*)calloc(psz, sizeof(double)); }
   int have2 = 0, cap = K + 10 + 1, nf = 0;
   double lz1, lz2 = -INFINITY, lzp;
   memset(out, 0, sizeof(*out));
@@ -163,25 +171,31 @@ int orc_coupled_pimh_chains(const orc_config* cfg, const double* obs, uint64_t s
   out->samples2 = (double*)malloc(sizeof(double) * (size_t)cap * p);
   out->log_pdf1 = (double*)malloc(sizeof(double) * (size_t)cap);
   out->log_pdf2 = (double*)malloc(sizeof(double) * (size_t)cap);
-  int rc = run_filter(cfg, obs, seed, replicate, 0, s1, &lz1); nf++;     /* pimh_init, R/pf_kernels.R:134-139 */
+  if (all_particles) {                                                   /* debiasing_algorithm.R:164-171 */
+    out->exp_samples1 = (double*)malloc(sizeof(double) * (size_t)cap * p);
+    out->exp_samples2 = (double*)malloc(sizeof(double) * (size_t)cap * p);
+  }
+  int rc = run_filter(cfg, obs, seed, replicate, 0, s1, &lz1, e1); nf++;     /* pimh_init, R/pf_kernels.R:134-139 (:200-206) */
   if (rc) return rc;
-  if (run_discarded_init) { double lzd; run_filter(cfg, obs, seed, replicate, 0xFFF, prop, &lzd); nf++; }  /* :140-142, discarded at debiasing_algorithm.R:160-161 */
+  if (run_discarded_init) { double lzd; run_filter(cfg, obs, seed, replicate, 0xFFF, prop, &lzd, NULL); nf++; }  /* :140-142, discarded at debiasing_algorithm.R:160-161 */
   for (int t = 0; t < p; t++) out->samples1[t] = s1[(size_t)t * d];      /* :156 chain_state1[1,] */
+  if (all_particles) for (int t = 0; t < p; t++) out->exp_samples1[t] = e1[(size_t)t * d];   /* :169 */
   out->log_pdf1[0] = lz1;
   int iter = 0, meet = 0, finished = 0, meetingtime = -1;
   while (!finished && (max_iterations < 0 || iter < max_iterations)) {   /* :180 */
     iter++;
-    rc = run_filter(cfg, obs, seed, replicate, (uint32_t)iter, prop, &lzp); nf++;
+    rc = run_filter(cfg, obs, seed, replicate, (uint32_t)iter, prop, &lzp, eprop); nf++;
     if (rc) return rc;
     double u, ub;
     orc_philox_uniform2(seed, 0, (uint32_t)iter << 20, replicate, ORC_P_MH, &u, &ub);
     double lu = log(u);
-    if (meet) {                                                          /* single_kernel R/pf_kernels.R:88-101 */
-      if (lu < (lzp - lz1)) { memcpy(s1, prop, sizeof(double) * psz); lz1 = lzp; }
+    if (meet) {                                                          /* single_kernel R/pf_kernels.R:88-101 (:147-162) */
+      if (lu < (lzp - lz1)) { memcpy(s1, prop, sizeof(double) * psz); lz1 = lzp; if (all_particles) memcpy(e1, eprop, sizeof(double) * psz); }
       memcpy(s2, s1, sizeof(double) * psz); lz2 = lz1;
-    } else {                                                             /* coupled_kernel :104-131 */
-      if (lu < (lzp - lz1)) { memcpy(s1, prop, sizeof(double) * psz); lz1 = lzp; }
-      if (lu < (lzp - lz2)) { memcpy(s2, prop, sizeof(double) * psz); lz2 = lzp; have2 = 1; }
+      if (all_particles) memcpy(e2, e1, sizeof(double) * psz);
+    } else {                                                             /* coupled_kernel :104-131 (:165-197) */
+      if (lu < (lzp - lz1)) { memcpy(s1, prop, sizeof(double) * psz); lz1 = lzp; if (all_particles) memcpy(e1, eprop, sizeof(double) * psz); }
+      if (lu < (lzp - lz2)) { memcpy(s2, prop, sizeof(double) * psz); lz2 = lzp; have2 = 1; if (all_particles) memcpy(e2, eprop, sizeof(double) * psz); }
       if (have2 && lz1 == lz2 && memcmp(s1, s2, sizeof(double) * psz) == 0) { meet = 1; meetingtime = iter; }  /* debiasing_algorithm.R:216-220 */
     }
     if (iter + 1 > cap) {                                                /* :222-233 */
@@ -190,6 +204,14 @@ int orc_coupled_pimh_chains(const orc_config* cfg, const double* obs, uint64_t s
       out->samples2 = (double*)realloc(out->samples2, sizeof(double) * (size_t)cap * p);
       out->log_pdf1 = (double*)realloc(out->log_pdf1, sizeof(double) * (size_t)cap);
       out->log_pdf2 = (double*)realloc(out->log_pdf2, sizeof(double) * (size_t)cap);
+      if (all_particles) {
+        out->exp_samples1 = (double*)realloc(out->exp_samples1, sizeof(double) * (size_t)cap * p);
+        out->exp_samples2 = (double*)realloc(out->exp_samples2, sizeof(double) * (size_t)cap * p);
+      }
+    }
+    if (all_particles) for (int t = 0; t < p; t++) {                     /* :239-242 */
+      out->exp_samples1[(size_t)iter * p + t] = e1[(size_t)t * d];
+      out->exp_samples2[(size_t)(iter - 1) * p + t] = e2[(size_t)t * d];
     }
     for (int t = 0; t < p; t++) {                                        /* :235-236 */
       out->samples1[(size_t)iter * p + t] = s1[(size_t)t * d];
@@ -200,24 +222,34 @@ int orc_coupled_pimh_chains(const orc_config* cfg, const double* obs, uint64_t s
     if (stop_at >= 0 && iter >= stop_at) finished = 1;                   /* :245 iter >= max(meetingtime, K) */
   }
   out->iteration = iter; out->meetingtime = meetingtime; out->finished = finished; out->nrows1 = iter + 1; out->nfilters = nf;
-  free(s1); free(s2); free(prop);
+  free(s1); free(s2); free(prop); free(e1); free(e2); free(eprop);
   return 0;
 }
-void orc_chains_free(orc_chains* c) { free(c->samples1); free(c->samples2); free(c->log_pdf1); free(c->log_pdf2); memset(c, 0, sizeof(*c)); }
+void orc_chains_free(orc_chains* c) {
+  free(c->samples1); free(c->samples2); free(c->log_pdf1); free(c->log_pdf2); free(c->exp_samples1); free(c->exp_samples2);
+  memset(c, 0, sizeof(*c));
+}
 
+static int hbar_impl(const orc_chains* c, const double* samples1, const double* samples2, int k, int K, double* hbar);
 /* R/debiasing_algorithm.R:284-316 with h = identity */
-int orc_H_bar(const orc_chains* c, int k, int K, double* hbar) {
+int orc_H_bar(const orc_chains* c, int k, int K, double* hbar) { return hbar_impl(c, c->samples1, c->samples2, k, K, hbar); }
+/* the same estimator over exp_samples1/2 (what the all_particles experiments feed H_bar) */
+int orc_H_bar_exp(const orc_chains* c, int k, int K, double* hbar) {
+  if (!c->exp_samples1) return 2;
+  return hbar_impl(c, c->exp_samples1, c->exp_samples2, k, K, hbar);
+}
+static int hbar_impl(const orc_chains* c, const double* samples1, const double* samples2, int k, int K, double* hbar) {
   int maxiter = c->iteration, p = c->p;
   if (k > maxiter || K > maxiter) return 1;                              /* :286-293 */
   for (int j = 0; j < p; j++) hbar[j] = 0;
-  for (int t = k; t <= K; t++) for (int j = 0; j < p; j++) hbar[j] += c->samples1[(size_t)t * p + j];   /* :296-302 */
+  for (int t = k; t <= K; t++) for (int j = 0; j < p; j++) hbar[j] += samples1[(size_t)t * p + j];   /* :296-302 */
   int tau = c->meetingtime < 0 ? 2147483647 : c->meetingtime;
   if (!(tau <= k + 1)) {                                                 /* :303 */
     int tmax = maxiter - 1 < tau - 1 ? maxiter - 1 : tau - 1;
     double* dt = (double*)calloc((size_t)p, sizeof(double));
     for (int t = k; t <= tmax; t++) {                                    /* :308-312 */
       int coef = (t - k + 1) < (K - k + 1) ? (t - k + 1) : (K - k + 1);
-      for (int j = 0; j < p; j++) dt[j] = dt[j] + coef * (c->samples1[(size_t)(t + 1) * p + j] - c->samples2[(size_t)t * p + j]);
+      for (int j = 0; j < p; j++) dt[j] = dt[j] + coef * (samples1[(size_t)(t + 1) * p + j] - samples2[(size_t)t * p + j]);
     }
     for (int j = 0; j < p; j++) hbar[j] = hbar[j] + dt[j];
     free(dt);

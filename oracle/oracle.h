@@ -147,11 +147,16 @@ typedef struct orc_chains {
   double* log_pdf1; /* [nrows1] */
   double* log_pdf2; /* [iteration] */
   int nfilters;     /* filters actually run */
+  double* exp_samples1; /* [nrows1][p]   all_particles only, else NULL (debiasing_algorithm.R:168-171) */
+  double* exp_samples2; /* [iteration][p] */
 } orc_chains;
 int  orc_coupled_pimh_chains(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
                              int K, int max_iterations, int run_discarded_init, orc_chains* out);
+int  orc_coupled_pimh_chains_ap(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
+                                int K, int max_iterations, int run_discarded_init, int all_particles, orc_chains* out);
 void orc_chains_free(orc_chains*);
 int  orc_H_bar(const orc_chains* c, int k, int K, double* hbar /* [p] */);
+int  orc_H_bar_exp(const orc_chains* c, int k, int K, double* hbar /* [p] */);
 int  orc_coupled_pimh_batch(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t first_replicate, int nrep,
                             int k, int K, int max_iterations, int nthreads,
                             double* hbar /* [nrep][p] */, int* meetingtime /* [nrep] */, int* iterations /* [nrep] */,

@@ -51,7 +51,8 @@ class PfOut(C.Structure):
 class Chains(C.Structure):
     _fields_ = [("iteration", C.c_int), ("meetingtime", C.c_int), ("finished", C.c_int), ("p", C.c_int), ("nrows1", C.c_int),
                 ("samples1", C.POINTER(C.c_double)), ("samples2", C.POINTER(C.c_double)),
-                ("log_pdf1", C.POINTER(C.c_double)), ("log_pdf2", C.POINTER(C.c_double)), ("nfilters", C.c_int)]
+                ("log_pdf1", C.POINTER(C.c_double)), ("log_pdf2", C.POINTER(C.c_double)), ("nfilters", C.c_int),
+                ("exp_samples1", C.POINTER(C.c_double)), ("exp_samples2", C.POINTER(C.c_double))]
 
 
 _lib = None
@@ -366,12 +367,12 @@ def cpf_batch(cfg, obs, seed, first_filter, nfilters, nthreads=0, want_traj=True
     return logz, (traj.transpose(0, 2, 1) if want_traj else None)   # (B, d, T+1)
 
 
-def coupled_pimh_chains(cfg, obs, seed, replicate, K=1, max_iterations=-1, run_discarded_init=False):
+def coupled_pimh_chains(cfg, obs, seed, replicate, K=1, max_iterations=-1, run_discarded_init=False, all_particles=False, hbar_k=None):
     T = cfg.nobs
     ob = np.asfortranarray(np.asarray(obs, dtype=np.float64).reshape(T, -1))
     c = Chains()
-    rc = lib().orc_coupled_pimh_chains(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_uint64(seed), C.c_uint32(replicate), C.c_int(K),
-                                       C.c_int(max_iterations), C.c_int(int(run_discarded_init)), C.byref(c))
+    rc = lib().orc_coupled_pimh_chains_ap(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_uint64(seed), C.c_uint32(replicate), C.c_int(K),
+                                          C.c_int(max_iterations), C.c_int(int(run_discarded_init)), C.c_int(int(all_particles)), C.byref(c))
     if rc:
         raise RuntimeError("oracle coupled_pimh_chains failed (%d)" % rc)
     p, it = c.p, c.iteration
@@ -380,6 +381,15 @@ def coupled_pimh_chains(cfg, obs, seed, replicate, K=1, max_iterations=-1, run_d
                log_pdf1=np.ctypeslib.as_array(c.log_pdf1, shape=(it + 1,)).copy(),
                log_pdf2=np.ctypeslib.as_array(c.log_pdf2, shape=(max(it, 1),))[:it].copy(),
                meetingtime=(np.inf if c.meetingtime < 0 else c.meetingtime), iteration=it, finished=bool(c.finished), nfilters=c.nfilters)
+    if all_particles:
+        out["exp_samples1"] = np.ctypeslib.as_array(c.exp_samples1, shape=(it + 1, p)).copy()
+        out["exp_samples2"] = np.ctypeslib.as_array(c.exp_samples2, shape=(max(it, 1), p))[:it].copy()
+    if hbar_k is not None:                                 # H_bar / H_bar over exp_samples by the C restatement
+        hb = np.empty(p)
+        if lib().orc_H_bar(C.byref(c), C.c_int(int(hbar_k)), C.c_int(int(K)), _p(hb)) == 0:
+            out["hbar"] = hb.copy()
+        if all_particles and lib().orc_H_bar_exp(C.byref(c), C.c_int(int(hbar_k)), C.c_int(int(K)), _p(hb)) == 0:
+            out["hbar_exp"] = hb.copy()
     lib().orc_chains_free(C.byref(c))
     return out
 

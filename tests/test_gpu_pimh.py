@@ -220,3 +220,43 @@ def test_chains_with_tree_path_storage(up, golden):
     for mode in (1, 2):
         r = up.coupled_pimh_chains_batch(up.get_ar(1), th, y, 100, 300, K=2, seed=4, mode=mode, store_paths=3)
         assert np.array_equal(r["meetingtime"], ref["meetingtime"]) and np.array_equal(r["hbar"], ref["hbar"])
+
+
+def test_all_particles_batch_and_chains_match_oracle(up, oracle, golden):
+    """all_particles = TRUE end to end: the in-kernel weighted-average path of every filter of a batch equals the oracle's
+    pf_get_weighted_average, for both path stores, and the chain driver's H_bar over exp_samples equals the oracle's."""
+    from unbiased_pimh_b200.filters import PfBatch
+    y = golden["sv_y"][:40]
+    th = golden["sv_theta_mle"]
+    ocfg = oracle.make_config(oracle.MODEL_LEVY_SV, 2, 1, 300, 40, theta=th)
+    for sp in (2, 3):
+        pf = PfBatch(up.get_levy_sv(), th, y, 300, 20, store_paths=sp)
+        pf.all_particles(True)
+        pf.run(20, 77, first_filter=3)
+        ep = pf.fetch_exp_paths()
+        one = pf.fetch_all_particles(b=11)
+        pf.close()
+        assert ep.shape == (20, 2, 41)
+        assert np.allclose(ep[11], one["exp_path"], rtol=1e-12, atol=1e-13)
+        for b in (0, 11, 19):
+            o = oracle.cpf(ocfg, y, seed=77, filter_id=3 + b, all_particles=True)
+            assert np.allclose(ep[b], o["exp_path"], rtol=1e-9, atol=1e-10)
+    yl = golden["lgssm_y"]
+    tha = [0.5, math.sqrt(10.0)]
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 64, 100, theta=tha)
+    for (k, K) in ((0, 1), (1, 4)):
+        r = up.coupled_pimh_chains_batch(up.get_ar(1), tha, yl, 64, 48, K=K, k=k, seed=31, first_replicate=7, all_particles=True)
+        plain = up.coupled_pimh_chains_batch(up.get_ar(1), tha, yl, 64, 48, K=K, k=k, seed=31, first_replicate=7)
+        assert np.array_equal(r["meetingtime"], plain["meetingtime"]) and np.allclose(r["hbar"], plain["hbar"], rtol=0, atol=0)
+        for rep in range(48):
+            c = oracle.coupled_pimh_chains(cfg, yl, 31, 7 + rep, K=K, all_particles=True, hbar_k=k)
+            assert c["meetingtime"] == r["meetingtime"][rep]
+            assert np.allclose(r["hbar_rb"][rep, 0], c["hbar_exp"], rtol=1e-10, atol=1e-10)
+        assert np.allclose(r["sum_hbar_rb"], r["hbar_rb"].sum(axis=0), rtol=1e-12, atol=1e-10)
+        assert np.allclose(r["sum_hbar_rb_sq"], (r["hbar_rb"] ** 2).sum(axis=0), rtol=1e-12, atol=1e-10)
+    # a multi-component model through the tree store
+    r = up.coupled_pimh_chains_batch(up.get_levy_sv(), th, y, 256, 12, K=2, seed=8, all_particles=True, store_paths=3)
+    cfg = oracle.make_config(oracle.MODEL_LEVY_SV, 2, 1, 256, 40, theta=th)
+    for rep in range(12):
+        c = oracle.coupled_pimh_chains(cfg, y, 8, rep, K=2, all_particles=True, hbar_k=0)
+        assert np.allclose(r["hbar_rb"][rep, 0], c["hbar_exp"], rtol=1e-9, atol=1e-10)

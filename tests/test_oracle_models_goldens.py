@@ -259,3 +259,33 @@ def test_hbar_matches_formula_and_smoothing_mean(oracle, golden):
         ms[t] = mf[t] + G * (ms[t + 1] - mp[t + 1])
     zscores = (est - ms) / se
     assert np.max(np.abs(zscores)) < 4.5 and np.mean(np.abs(zscores) > 2) < 0.15
+
+
+def test_all_particles_chains_rao_blackwellised_estimator(oracle, golden):
+    """coupled_pimh_chains with the *_all_particles kernels (R/pf_kernels.R:147-215): exp_samples follow the same accept
+    decisions as samples, lag-one coincidence after meeting, and H_bar over them is unbiased with a smaller variance."""
+    y = golden["lgssm_y"]
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 64, 100, theta=[0.5, math.sqrt(10.0)])
+    plain = oracle.coupled_pimh_chains(cfg, y, 3, 5, K=4, hbar_k=1)
+    c = oracle.coupled_pimh_chains(cfg, y, 3, 5, K=4, all_particles=True, hbar_k=1)
+    assert c["iteration"] == plain["iteration"] and c["meetingtime"] == plain["meetingtime"]
+    assert np.array_equal(c["samples1"], plain["samples1"]) and np.array_equal(c["hbar"], plain["hbar"])
+    assert c["exp_samples1"].shape == c["samples1"].shape and c["exp_samples2"].shape == c["samples2"].shape
+    for t in range(int(c["meetingtime"]), c["iteration"] + 1):
+        assert np.array_equal(c["exp_samples1"][t], c["exp_samples2"][t - 1])
+    # rows of exp_samples1 change exactly when rows of samples1 change (accepted together)
+    ch_s = np.any(np.diff(c["samples1"], axis=0) != 0, axis=1)
+    ch_e = np.any(np.diff(c["exp_samples1"], axis=0) != 0, axis=1)
+    assert np.array_equal(ch_s, ch_e)
+    # first row = exp_path of the init filter = weighted average of its N paths
+    f = oracle.cpf(cfg, y, seed=3, filter_id=5, all_particles=True, all_paths=True)
+    assert np.allclose(c["exp_samples1"][0], f["exp_path"][0], rtol=0, atol=0)
+    # variance reduction: over replicates the RB estimator has smaller spread at most time points, same mean within error
+    hb, hbe = [], []
+    for rep in range(150):
+        r = oracle.coupled_pimh_chains(cfg, y, 13, rep, K=3, all_particles=True, hbar_k=1)
+        hb.append(r["hbar"]); hbe.append(r["hbar_exp"])
+    hb, hbe = np.array(hb), np.array(hbe)
+    assert np.mean(hbe.var(axis=0) < hb.var(axis=0)) > 0.8
+    z = (hb.mean(0) - hbe.mean(0)) / np.sqrt((hb.var(0) + hbe.var(0)) / 150)
+    assert np.max(np.abs(z)) < 4.5

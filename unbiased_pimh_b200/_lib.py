@@ -36,7 +36,8 @@ class Noise(C.Structure):
 
 class ChainOut(C.Structure):
     _fields_ = [("hbar", C.c_void_p), ("meetingtime", C.c_void_p), ("iteration", C.c_void_p), ("sum_hbar", C.c_void_p),
-                ("sum_hbar_sq", C.c_void_p), ("nfilters", C.c_void_p), ("bc", C.c_void_p)]
+                ("sum_hbar_sq", C.c_void_p), ("nfilters", C.c_void_p), ("bc", C.c_void_p),
+                ("hbar_rb", C.c_void_p), ("sum_hbar_rb", C.c_void_p), ("sum_hbar_rb_sq", C.c_void_p)]
 
 
 _lib = None

@@ -201,11 +201,11 @@ struct cpimh_pf {
   const ModelEntry* entry;
   Geometry geo, geo_tail;
   int64_t maxB, lastB;
-  int record_anc;
+  int record_anc, all_particles;
   int64_t launches, bytes;
   int grid;
   DevBuf hist_x, hist_a, ascr;
-  DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, logz, logz_t, traj, path_index, status, normw, leaf_out, anc_rec;
+  DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, logz, logz_t, traj, path_index, status, normw, leaf_out, anc_rec, exp_path;
   DevBuf inj_init, inj_trans, inj_resample, inj_shuffle, inj_path;
   bool have_inj[5];
   int npre;
@@ -247,7 +247,7 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   cpimh_pf* h = new cpimh_pf();
   h->cfg = cfg; h->entry = e; h->geo = g; h->maxB = max_filters;
   rc = api_plan_tail_geometry(cfg, e, (int)pre.size(), g, &h->geo_tail);
-  if (rc) { delete h; return rc; } h->lastB = 0; h->record_anc = 0; h->launches = 0; h->bytes = 0;
+  if (rc) { delete h; return rc; } h->lastB = 0; h->record_anc = 0; h->all_particles = 0; h->launches = 0; h->bytes = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
   const int D = cfg.dim, N = cfg.nparticles, T = cfg.nobs;
   h->npre = (int)pre.size();
@@ -289,11 +289,21 @@ int cpimh_pf_destroy(cpimh_pf* h) {
   if (!h) return CPIMH_OK;
   if (h->wide) { wide_destroy(h->wide); delete h; return CPIMH_OK; }
   DevBuf* all[] = {&h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->logz, &h->logz_t, &h->traj, &h->path_index,
-                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->hist_x, &h->hist_a, &h->ascr, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
+                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->exp_path, &h->hist_x, &h->hist_a, &h->ascr, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
   return CPIMH_OK;
 }
+
+int cpimh_pf_all_particles(cpimh_pf* h, int on) {
+  CPIMH_REQUIRE(h, "null handle");
+  CPIMH_REQUIRE(!h->wide, "all-particle outputs are not available for the wide (d = 32/64) filter");
+  CPIMH_REQUIRE(!on || h->geo.path_mode != PATH_NONE, "all-particle outputs need store_paths != 0");
+  h->all_particles = on ? 1 : 0;
+  if (on) return h->exp_path.alloc(sizeof(double) * (size_t)h->maxB * (h->cfg.nobs + 1) * h->cfg.dim, &h->bytes);
+  return CPIMH_OK;
+}
+
 
 }  // extern "C"
 namespace cpimh {
@@ -372,6 +382,7 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   p.logz = h->logz.as<double>(); p.logz_t = h->logz_t.as<double>(); p.traj = h->traj.as<double>();
   p.path_index = h->path_index.as<int>(); p.status = h->status.as<int>(); p.normw = h->normw.as<double>();
   p.leaf_out = h->leaf_out.as<int>(); p.anc_rec = h->record_anc ? h->anc_rec.as<int>() : nullptr;
+  p.exp_path = h->all_particles ? h->exp_path.as<double>() : nullptr;
   p.inj_init = h->have_inj[0] ? h->inj_init.as<double>() : nullptr;
   p.inj_trans = h->have_inj[1] ? h->inj_trans.as<double>() : nullptr;
   p.inj_resample = h->have_inj[2] ? h->inj_resample.as<double>() : nullptr;
@@ -443,6 +454,18 @@ int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ance
   const size_t n = (size_t)h->cfg.nobs * h->cfg.nparticles;
   cudaStream_t s = (cudaStream_t)stream;
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(ancestors, h->anc_rec.as<int>() + (size_t)b * n, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CPIMH_OK;
+}
+
+int cpimh_pf_fetch_exp_paths(cpimh_pf* h, int64_t B, void* stream, double* exp_path) {
+  CPIMH_REQUIRE(h && exp_path, "null argument");
+  CPIMH_REQUIRE(!h->wide && h->all_particles, "call cpimh_pf_all_particles(h, 1) before cpimh_pf_run");
+  CPIMH_REQUIRE(B >= 0 && B <= h->lastB, "filter count out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = check_status(h->status.as<int>(), B, s);
+  if (rc) return rc;
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(exp_path, h->exp_path.p, sizeof(double) * (size_t)B * (h->cfg.nobs + 1) * h->cfg.dim, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
   return CPIMH_OK;
 }

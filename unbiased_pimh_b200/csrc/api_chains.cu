@@ -38,6 +38,8 @@ struct RoundParams {
   double* lz1; double* lz2; int* id1; int* id2; int* meet; int* iter; int* tau; int* status;
   double* st1; double* st2; double* accH; double* accD; double* hbar; double* bc;
   unsigned long long* nfilters;
+  // all_particles = TRUE (R/pf_kernels.R:147-215): the weighted-average path travels with the chain state; null when off
+  const double* pool_exp; double* e1; double* e2; double* accHe; double* accDe; double* hbar_rb;
 };
 __global__ void rounds_prepare_kernel(RoundParams q) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,6 +57,12 @@ __global__ void rounds_init_kernel(RoundParams q) {
     q.st1[(size_t)rep * q.PD + j] = v;
     q.accH[(size_t)rep * q.PD + j] = (q.k <= 0) ? v : 0.0;
     q.accD[(size_t)rep * q.PD + j] = 0.0;
+    if (q.pool_exp) {                                                          // exp_samples1[1,] (debiasing_algorithm.R:166-170)
+      const double e = q.pool_exp[(size_t)rep * q.PD + j];
+      q.e1[(size_t)rep * q.PD + j] = e;
+      q.accHe[(size_t)rep * q.PD + j] = (q.k <= 0) ? e : 0.0;
+      q.accDe[(size_t)rep * q.PD + j] = 0.0;
+    }
   }
   if (threadIdx.x == 0) {
     q.lz1[rep] = q.pool_logz[rep]; q.lz2[rep] = -INFINITY; q.id1[rep] = 0; q.id2[rep] = -1; q.meet[rep] = 0; q.iter[rep] = 0; q.tau[rep] = -1;
@@ -105,6 +113,20 @@ __global__ void rounds_accept_kernel(RoundParams q) {
       if (mcmc) accH[j] += xa;                                                 // :296-302
       if (bias) accD[j] = accD[j] + coef * (xa - xb);                          // :308-312
     }
+    if (q.pool_exp) {                                                          // exp_path follows the same accept decisions (pf_kernels.R:176-190)
+      const double* pe = q.pool_exp + s * PD;
+      double* e1 = q.e1 + (size_t)rep * PD; double* e2 = q.e2 + (size_t)rep * PD;
+      double* aHe = q.accHe + (size_t)rep * PD; double* aDe = q.accDe + (size_t)rep * PD;
+      for (int j = threadIdx.x; j < PD; j += blockDim.x) {
+        const double pv = pe[j];
+        const double xa = a1 ? pv : e1[j];
+        const double xb = a2 ? pv : e2[j];
+        if (a1) e1[j] = pv;
+        if (a2) e2[j] = pv;
+        if (mcmc) aHe[j] += xa;
+        if (bias) aDe[j] = aDe[j] + coef * (xa - xb);
+      }
+    }
     if (tau > 0 && iter >= max(tau, q.K)) finished = 1;                        // :245
     if (q.max_it >= 0 && iter >= q.max_it) finished = 1;
   }
@@ -114,6 +136,7 @@ __global__ void rounds_accept_kernel(RoundParams q) {
     for (int j = threadIdx.x; j < PD; j += blockDim.x) {
       q.hbar[(size_t)rep * PD + j] = (accH[j] + accD[j]) / denom;   // :315
       q.bc[(size_t)rep * PD + j] = accD[j] / denom;                 // BC(), :330-363
+      if (q.pool_exp) q.hbar_rb[(size_t)rep * PD + j] = (q.accHe[(size_t)rep * PD + j] + q.accDe[(size_t)rep * PD + j]) / denom;
     }
   }
   if (threadIdx.x == 0) {
@@ -228,6 +251,8 @@ struct cpimh_chains {
   int record, max_rec, grid, npre;
   DevBuf hist_x, hist_a, ascr;
   DevBuf bc;
+  int all_particles;
+  DevBuf r_exp, r_e1, r_e2, r_accHe, r_accDe, hbar_rb, sums_rb;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, state, acc, scal, iscal, hbar, mt, it, status, nfilters, counter, sums;
   DevBuf samples1, samples2, log_pdf1, log_pdf2;
   // round-based driver
@@ -245,7 +270,7 @@ extern "C" {
 
 int cpimh_chains_destroy(cpimh_chains* h) {
   if (!h) return CPIMH_OK;
-  DevBuf* all[] = {&h->bc, &h->hist_x, &h->hist_a, &h->ascr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
+  DevBuf* all[] = {&h->bc, &h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe, &h->hbar_rb, &h->sums_rb, &h->hist_x, &h->hist_a, &h->ascr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
                    &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2,
                    &h->r_logz, &h->r_traj, &h->r_status, &h->r_ids, &h->r_lz1, &h->r_lz2, &h->r_id1, &h->r_id2, &h->r_meet, &h->r_iter, &h->r_tau,
                    &h->r_st1, &h->r_st2, &h->r_accH, &h->r_accD, &h->r_act0, &h->r_act1, &h->r_cnt};
@@ -269,7 +294,7 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
   cpimh_chains* h = new cpimh_chains();
   h->cfg = cfg; h->entry = e; h->geo = g; h->maxR = max_replicates; h->lastR = 0; h->launches = 0;
   h->record = record_samples > 0; h->max_rec = record_samples > 0 ? record_samples : 0;
-  h->mode = 0; h->filters_launched = 0; h->grid_pf = 0;
+  h->mode = 0; h->filters_launched = 0; h->grid_pf = 0; h->all_particles = 0;
   const int64_t resident = (int64_t)g.blocks_per_sm * g.num_sms;
   h->grid = (int)(max_replicates < resident ? max_replicates : resident);
   const size_t G = (size_t)h->grid, D = cfg.dim, T = cfg.nobs, P = T + 1, R = (size_t)max_replicates;
@@ -378,6 +403,7 @@ static int chains_run_rounds(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t
   p.xbuf = h->xbuf.as<double>(); p.a_star = h->a_star.as<int>(); p.o_star = h->o_star.as<int>(); p.x_star = h->x_star.as<double>();
   p.logz = h->r_logz.as<double>(); p.traj = h->r_traj.as<double>(); p.status = h->r_status.as<int>();
   p.stream_ids = h->r_ids.as<unsigned long long>();
+  p.exp_path = h->all_particles ? h->r_exp.as<double>() : nullptr;
   RoundParams q;
   memset(&q, 0, sizeof(q));
   q.R = R; q.PD = PD; q.P = P; q.D = D; q.k = k; q.K = K; q.max_it = max_it; q.seed = seed; q.first_replicate = first_replicate;
@@ -387,6 +413,10 @@ static int chains_run_rounds(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t
   q.meet = h->r_meet.as<int>(); q.iter = h->r_iter.as<int>(); q.tau = h->r_tau.as<int>(); q.status = h->status.as<int>();
   q.st1 = h->r_st1.as<double>(); q.st2 = h->r_st2.as<double>(); q.accH = h->r_accH.as<double>(); q.accD = h->r_accD.as<double>();
   q.hbar = h->hbar.as<double>(); q.bc = h->bc.as<double>(); q.nfilters = h->nfilters.as<unsigned long long>(); q.next_count = h->r_cnt.as<int>();
+  if (h->all_particles) {
+    q.pool_exp = h->r_exp.as<double>(); q.e1 = h->r_e1.as<double>(); q.e2 = h->r_e2.as<double>();
+    q.accHe = h->r_accHe.as<double>(); q.accDe = h->r_accDe.as<double>(); q.hbar_rb = h->hbar_rb.as<double>();
+  }
   auto launch_filters = [&](int64_t B) -> int {
     PfLaunch L;
     L.threads = g.threads; L.smem = g.smem; L.variant = g.variant;
@@ -441,7 +471,7 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   CPIMH_REQUIRE(max_iterations < 0 || max_iterations >= K, "max_iterations must be >= K or negative (unbounded)");
   CPIMH_REQUIRE(max_iterations < 4096, "iteration index must fit 12 bits of the Philox counter (max_iterations < 4096)");
   cudaStream_t s = (cudaStream_t)stream;
-  const bool rounds = h->mode == 2 || (h->mode == 0 && !h->record);
+  const bool rounds = h->all_particles || h->mode == 2 || (h->mode == 0 && !h->record);
   if (rounds) {
     CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, sizeof(unsigned long long), s));
     CPIMH_CUDA_CHECK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * (size_t)R, s));
@@ -452,6 +482,11 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
     reduce_hbar_kernel<<<Pr + 1, 256, 0, s>>>(h->hbar.as<double>(), R, Pr, h->nfilters.as<unsigned long long>(), sums_r);
     CPIMH_CUDA_CHECK(cudaGetLastError());
     if (d_sums) CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->sums.p, d_sums, sizeof(double) * (2 * Pr + 2), cudaMemcpyDeviceToDevice, s));
+    if (h->all_particles) {
+      reduce_hbar_kernel<<<Pr + 1, 256, 0, s>>>(h->hbar_rb.as<double>(), R, Pr, h->nfilters.as<unsigned long long>(), h->sums_rb.as<double>());
+      CPIMH_CUDA_CHECK(cudaGetLastError());
+      h->launches += 1;
+    }
     h->launches += 1; h->lastR = R;
     return CPIMH_OK;
   }
@@ -486,9 +521,21 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   return CPIMH_OK;
 }
 
+int cpimh_chains_set_all_particles(cpimh_chains* h, int on) {
+  CPIMH_REQUIRE(h, "null handle");
+  CPIMH_REQUIRE(!on || (!h->record && h->mode != 1), "all_particles runs on the round-based driver: no recorded samples, mode 0 or 2");
+  h->all_particles = on ? 1 : 0;
+  if (!on) return CPIMH_OK;
+  const size_t n = sizeof(double) * (size_t)h->maxR * (h->cfg.nobs + 1) * h->cfg.dim;
+  DevBuf* bufs[] = {&h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe, &h->hbar_rb};
+  for (auto b : bufs) { int rc = b->alloc(n); if (rc) return rc; }
+  return h->sums_rb.alloc(sizeof(double) * (2 * (size_t)(h->cfg.nobs + 1) * h->cfg.dim + 2));
+}
+
 int cpimh_chains_set_mode(cpimh_chains* h, int mode) {
   CPIMH_REQUIRE(h && mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (persistent CTA per replicate) or 2 (rounds)");
   CPIMH_REQUIRE(!(mode == 2 && h->record), "recording samples needs the persistent kernel (mode 1)");
+  CPIMH_REQUIRE(!(mode == 1 && h->all_particles), "all_particles runs on the round-based driver (mode 0 or 2)");
   h->mode = mode;
   return CPIMH_OK;
 }
@@ -512,12 +559,18 @@ int cpimh_chains_fetch(cpimh_chains* h, int64_t R, void* stream, cpimh_chain_out
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(sums.data(), h->sums.p, sizeof(double) * sums.size(), cudaMemcpyDeviceToHost, s));
   if (o->hbar) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->hbar, h->hbar.p, sizeof(double) * (size_t)R * P, cudaMemcpyDeviceToHost, s));
   if (o->bc) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->bc, h->bc.p, sizeof(double) * (size_t)R * P, cudaMemcpyDeviceToHost, s));
+  CPIMH_REQUIRE(h->all_particles || !(o->hbar_rb || o->sum_hbar_rb || o->sum_hbar_rb_sq), "the *_rb outputs need cpimh_chains_set_all_particles(h, 1) before the run");
+  std::vector<double> sums_rb(2 * P + 2);
+  if (h->all_particles) CPIMH_CUDA_CHECK(cudaMemcpyAsync(sums_rb.data(), h->sums_rb.p, sizeof(double) * sums_rb.size(), cudaMemcpyDeviceToHost, s));
+  if (o->hbar_rb) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->hbar_rb, h->hbar_rb.p, sizeof(double) * (size_t)R * P, cudaMemcpyDeviceToHost, s));
   if (o->meetingtime) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->meetingtime, h->mt.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
   if (o->iteration) CPIMH_CUDA_CHECK(cudaMemcpyAsync(o->iteration, h->it.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
   if (o->sum_hbar) memcpy(o->sum_hbar, sums.data(), sizeof(double) * P);
   if (o->sum_hbar_sq) memcpy(o->sum_hbar_sq, sums.data() + P, sizeof(double) * P);
   if (o->nfilters) *o->nfilters = (int64_t)sums[2 * P];
+  if (o->sum_hbar_rb) memcpy(o->sum_hbar_rb, sums_rb.data(), sizeof(double) * P);
+  if (o->sum_hbar_rb_sq) memcpy(o->sum_hbar_rb_sq, sums_rb.data() + P, sizeof(double) * P);
   return CPIMH_OK;
 }
 

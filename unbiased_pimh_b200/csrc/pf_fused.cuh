@@ -53,6 +53,7 @@ struct PfParams {
   double* normw;               // [B][N] or null (final normalised weights)
   int* leaf_out;               // [ws][N] or null (PATH_TREE: final leaf slots)
   int* anc_rec;                // [B][T][N] or null
+  double* exp_path;            // [B][T+1][D] or null: weighted average of all N paths (all_particles = TRUE, R/CPF.R:73-76)
   // injected noise (device) or null
   const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_shuffle; const double* inj_path;
   int n_init, n_trans, sk_M;
@@ -119,7 +120,7 @@ __device__ __forceinline__ int count_le_bounded(const double* c, int lo, int hi,
 }
 
 struct FilterOut {
-  double* logz; double* logz_t; double* traj; int* path_index; int* status; double* normw; int* leaf_out; int* anc_rec;
+  double* logz; double* logz_t; double* traj; int* path_index; int* status; double* normw; int* leaf_out; int* anc_rec; double* exp_path;
 };
 
 __device__ __forceinline__ void set_free_bit(unsigned* bits, int slot) { atomicOr(&bits[slot >> 5], 1u << (slot & 31)); }
@@ -421,6 +422,24 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   if (st) atomicOr(&sm.iscr[32], st);
   if (out.normw) for (int k = tid; k < N; k += NT) out.normw[k] = sm.C[k];
   if (out.leaf_out && tree) for (int k = tid; k < N; k += NT) out.leaf_out[k] = sm.leaf[k];
+  if (out.exp_path && (tree || dense)) {
+    // pf_get_weighted_average (R/CPF.R:84-92) over sapply(0:(N-1), Tree$get_path) (:73-74): all N leaves walk to the root
+    // in lock step; per generation and component one block reduction of w_n x.  S is free and holds the walkers.
+    int* cur = reinterpret_cast<int*>(sm.S);
+    const double* hx = dense ? p.hist_x + (size_t)ws * (T + 1) * xstride : nullptr;
+    for (int n = tid; n < N; n += NT) cur[n] = tree ? sm.leaf[n] : n;
+    for (int step = T; step >= 0; step--) {
+#pragma unroll
+      for (int q = 0; q < D; q++) {
+        double acc = 0.0;
+        for (int n = tid; n < N; n += NT)
+          acc += (tree ? x_star[(size_t)q * M + cur[n]] : hx[(size_t)step * xstride + (size_t)q * Npad + cur[n]]) * sm.C[n];
+        acc = block_sum(acc, sm.dscr);
+        if (tid == 0) out.exp_path[(size_t)step * D + q] = acc;
+      }
+      if (step > 0) for (int n = tid; n < N; n += NT) cur[n] = tree ? a_star[cur[n]] : hist_a[(size_t)(step - 1) * Npad + cur[n]];
+    }
+  }
   __syncthreads();
   block_scan_inplace<false>(sm.C, N, sm.dscr);
   double u = p.inj_path ? p.inj_path[inj] : philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0);
@@ -469,6 +488,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p
     out.normw = p.normw ? p.normw + (size_t)b * p.N : nullptr;
     out.leaf_out = p.leaf_out ? p.leaf_out + (size_t)blockIdx.x * p.N : nullptr;
     out.anc_rec = p.anc_rec ? p.anc_rec + (size_t)b * p.T * p.N : nullptr;
+    out.exp_path = p.exp_path ? p.exp_path + (size_t)b * (p.T + 1) * Model::D : nullptr;
     run_filter<Model>(p, sm, blockIdx.x, s, b, out);
   }
 }

@@ -52,6 +52,16 @@ class PfBatch:
     def record_ancestors(self, on=True):
         L.check(L.lib().cpimh_pf_record_ancestors(self.h, C.c_int(int(on))))
 
+    def all_particles(self, on=True):
+        """CPF(..., all_particles = TRUE) for the whole batch: the kernel also reduces the weighted average of the N paths."""
+        L.check(L.lib().cpimh_pf_all_particles(self.h, C.c_int(int(on))))
+
+    def fetch_exp_paths(self, nfilters=None, stream=None):
+        B = self.last if nfilters is None else int(nfilters)
+        ep = np.empty((B, self.cfg.nobs + 1, self.cfg.dim))
+        L.check(L.lib().cpimh_pf_fetch_exp_paths(self.h, C.c_int64(B), C.c_void_p(stream or 0), L.ptr(ep)))
+        return ep.transpose(0, 2, 1)                         # (B, d, T+1)
+
     def run(self, nfilters, seed, first_filter=0, stream=None):
         L.check(L.lib().cpimh_pf_run(self.h, C.c_int64(int(nfilters)), C.c_uint64(int(seed)), C.c_uint64(int(first_filter)), C.c_void_p(stream or 0)))
         self.last = int(nfilters)

@@ -173,10 +173,11 @@ class ChainBatch:
     """Device-resident coupled-PIMH driver (cpimh_chains handle): one persistent CTA per replicate."""
 
     def __init__(self, model, theta, observations, nparticles, max_replicates, record_samples=0, tree_capacity=0,
-                 threads_per_filter=0, sk_max_events=64, device=None, mode=0, store_paths=1):
+                 threads_per_filter=0, sk_max_events=64, device=None, mode=0, store_paths=1, all_particles=False):
         obs = np.asarray(observations, dtype=np.float64)
         self.nobs = obs.shape[0]
         self.model = model
+        self.all_particles = bool(all_particles)
         self.cfg = model.config(nparticles, theta, nobs=self.nobs, tree_capacity=tree_capacity, threads_per_filter=threads_per_filter,
                                 sk_max_events=sk_max_events, store_paths=store_paths)
         if device is not None:
@@ -188,6 +189,8 @@ class ChainBatch:
         L.check(L.lib().cpimh_chains_set_observations(self.h, ob.ctypes.data_as(C.c_void_p)))
         if mode:
             L.check(L.lib().cpimh_chains_set_mode(self.h, C.c_int(int(mode))))
+        if self.all_particles:
+            L.check(L.lib().cpimh_chains_set_all_particles(self.h, C.c_int(1)))
         self.last = 0
 
     def close(self):
@@ -222,12 +225,22 @@ class ChainBatch:
         o.bc = bcv.ctypes.data if bc else None
         o.meetingtime, o.iteration = mt.ctypes.data, it.ctypes.data
         o.sum_hbar, o.sum_hbar_sq, o.nfilters = s.ctypes.data, s2.ctypes.data, nf.ctypes.data
+        rb = self.all_particles
+        hrb = np.empty((R, P, d)) if (rb and hbar) else None
+        srb, srb2 = (np.empty((P, d)), np.empty((P, d))) if rb else (None, None)
+        if rb:
+            o.hbar_rb = hrb.ctypes.data if hbar else None
+            o.sum_hbar_rb, o.sum_hbar_rb_sq = srb.ctypes.data, srb2.ctypes.data
         L.check(L.lib().cpimh_chains_fetch(self.h, C.c_int64(R), C.c_void_p(stream or 0), C.byref(o)))
         out = {"meetingtime": mt, "iteration": it, "sum_hbar": s.T.copy(), "sum_hbar_sq": s2.T.copy(), "nfilters": int(nf[0])}
         if hbar:
             out["hbar"] = hb.transpose(0, 2, 1)       # (R, d, T+1)
         if bc:
             out["bc"] = bcv.transpose(0, 2, 1)
+        if rb:
+            out["sum_hbar_rb"], out["sum_hbar_rb_sq"] = srb.T.copy(), srb2.T.copy()
+            if hbar:
+                out["hbar_rb"] = hrb.transpose(0, 2, 1)
         return out
 
     def fetch_chains(self, r, stream=None):
@@ -251,7 +264,9 @@ def coupled_pimh_chains_batch(model, theta, observations, nparticles, nreplicate
                               first_replicate=0, record_samples=0, mode=0, **kw):
     """R replicates of coupled_pimh_chains(..., N = nparticles, K) + H_bar(., k = k, K = K) on the GPU.
     Returns hbar (R, d, T+1), meetingtime (R,) [-1 = not met within max_iterations], iteration (R,), the sums that are
-    all-reduced across GPUs, the number of filters run, and (record_samples > 0) the c_chains lists."""
+    all-reduced across GPUs, the number of filters run, and (record_samples > 0) the c_chains lists.
+    all_particles=True (get_pimh_kernels(with_as, all_particles = TRUE), R/pf_kernels.R:147-222) adds hbar_rb: H_bar over
+    exp_samples1/2, the weighted average of all N paths of each accepted filter."""
     seed = rng.next_seed() if seed is None else int(seed)
     cb = ChainBatch(model, theta, observations, nparticles, nreplicates, record_samples=record_samples, mode=mode, **kw)
     try:
