@@ -51,7 +51,7 @@ enum {
 enum { CPIMH_MODEL_GSS = 0, CPIMH_MODEL_AR = 1, CPIMH_MODEL_LEVY_SV = 2, CPIMH_MODEL_SK = 3, CPIMH_MODEL_LORENZ = 4 };
 enum { CPIMH_INTEGRATOR_RK4 = 0, CPIMH_INTEGRATOR_DOPRI5 = 1 };
 /* Philox stream purposes (counter word 3, low byte) */
-enum { CPIMH_P_RESAMPLE = 1, CPIMH_P_INIT = 2, CPIMH_P_TRANS = 3, CPIMH_P_PATH = 4, CPIMH_P_MH = 5, CPIMH_P_SHUFFLE = 6 };
+enum { CPIMH_P_RESAMPLE = 1, CPIMH_P_INIT = 2, CPIMH_P_TRANS = 3, CPIMH_P_PATH = 4, CPIMH_P_MH = 5, CPIMH_P_SHUFFLE = 6, CPIMH_P_COUPLE = 7, CPIMH_P_AS = 8 };
 
 #define CPIMH_MAX_THETA 32
 
@@ -136,6 +136,7 @@ int cpimh_pf_record_ancestors(cpimh_pf* h, int on);
 int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ancestors);
 /* device pointers of the resident outputs (valid until destroy): logz [B], trajectory [B][T+1][d] */
 int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory);
+int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status);   /* [B] per-filter status of the last run (0 = ok) */
 /* kernels launched by this handle so far (bench.py's gpu_launches) and bytes of HBM it holds */
 int64_t cpimh_pf_launch_count(const cpimh_pf* h);
 int64_t cpimh_pf_device_bytes(const cpimh_pf* h);
@@ -190,6 +191,24 @@ int cpimh_chains_set_mode(cpimh_chains* h, int mode);
  * Round-based driver only (no recorded samples). */
 int cpimh_chains_set_all_particles(cpimh_chains* h, int on);
 int64_t cpimh_chains_filters_launched(const cpimh_chains* h);   /* including discarded speculative proposals */
+
+/* ============================== conditional particle filters ==============================
+ * nsys = 1: CPF(nparticles, model, theta, observations, ref_trajectory = ref1, with_as)   -- R/CPF.R:14-78 (:22-24, :45-58)
+ * nsys = 2: CPF_coupled(nparticles, model, theta, observations, ref1, ref2, CR_indexmatching, with_as) -- R/CPF_coupled.R:14-112
+ * One CTA per filter; filter b uses Philox stream id first_filter + b for BOTH systems (common random numbers).  The last
+ * particle follows the reference path, the other N-1 get sorted multinomial (nsys = 1) or index-matching (nsys = 2,
+ * src/coupledresamplingindexmatching.cpp:8-57) ancestors; cfg.shuffle must be 0.  with_as (ancestor sampling) needs
+ * model$dtransition: get_gss and get_ar.  ref*, traj*: [B] x (d x (T+1) col-major); logz [B] (system 1, R/CPF.R:71);
+ * path_index [B][2]; ancestors [B][2][T][N] 0-based (nullable).  noise: init / trans arrays only (nullable). */
+int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nfilters, uint64_t seed, uint64_t first_filter,
+                     int nsys, int with_as, const double* ref1_host, const double* ref2_host, const cpimh_noise* noise,
+                     double* traj1, double* traj2, double* logz, int32_t* path_index, int32_t* ancestors);
+/* coupled_ccpf_chains(single_kernel, coupled_kernel, pimh_init, N, K, max_iterations) with get_cpf_kernels(with_as) and
+ * pimh_init of get_pimh_kernels, + H_bar(c_chains, k, K) and BC -- R/debiasing_algorithm.R:23-111, R/pf_kernels.R:236-265,134-145.
+ * R replicates advance together, one launch of conditional filters per iteration; replicate r uses stream id
+ * first_replicate + r with the iteration index in counter word 1 (0 and 0xFFF: the two initial bootstrap filters). */
+int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
+                       int k, int K, int max_iterations, int with_as, cpimh_chain_out* out_host);
 
 /* ============================== primitives (batched over B independent problems) ==============================
  * Bit-exact with the reference natives given identical weights and uniforms.  All pointers are HOST pointers. */

@@ -32,7 +32,7 @@ extern "C" {
 /* ---- model ids / flags: numerically identical to include/cpimh.h (checked by tests) ---- */
 enum { ORC_MODEL_GSS = 0, ORC_MODEL_AR = 1, ORC_MODEL_LEVY_SV = 2, ORC_MODEL_SK = 3, ORC_MODEL_LORENZ = 4 };
 enum { ORC_INTEGRATOR_RK4 = 0, ORC_INTEGRATOR_DOPRI5 = 1 };
-enum { ORC_P_RESAMPLE = 1, ORC_P_INIT = 2, ORC_P_TRANS = 3, ORC_P_PATH = 4, ORC_P_MH = 5, ORC_P_SHUFFLE = 6 };
+enum { ORC_P_RESAMPLE = 1, ORC_P_INIT = 2, ORC_P_TRANS = 3, ORC_P_PATH = 4, ORC_P_MH = 5, ORC_P_SHUFFLE = 6, ORC_P_COUPLE = 7, ORC_P_AS = 8 };
 
 #define ORC_MAX_THETA 32
 #define ORC_SK_MAX_EVENTS_DEFAULT 64
@@ -161,6 +161,25 @@ int  orc_coupled_pimh_batch(const orc_config* cfg, const double* obs, uint64_t s
                             int k, int K, int max_iterations, int nthreads,
                             double* hbar /* [nrep][p] */, int* meetingtime /* [nrep] */, int* iterations /* [nrep] */,
                             long long* nfilters_total);
+
+/* ---- conditional filters: CPF(ref_trajectory, with_as) R/CPF.R:22-24,45-58 ; CPF_coupled R/CPF_coupled.R:14-112 ;
+ *      get_cpf_kernels R/pf_kernels.R:236-265 ; coupled_ccpf_chains R/debiasing_algorithm.R:23-111 ---- */
+typedef struct orc_ccpf_out {
+  double* trajectory[2];  /* d x (T+1) each; [1] used when nsys == 2            */
+  int*    ancestors[2];   /* [T][N] 0-based (nullable)                          */
+  int     path_index[2];
+  double  logz;           /* system 1's sum of log Z increments                 */
+  int     clamp_count;
+} orc_ccpf_out;
+int  orc_model_has_dtransition(const orc_config*);
+void orc_model_dtransition(const orc_config*, const double* next_x /* d */, const double* x /* d x N */, int time, double* out /* N */);
+int  orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise /* init/trans only */, uint64_t seed, uint64_t filter_id,
+              int nsys, const double* ref1, const double* ref2 /* d x (T+1) */, int with_as, orc_ccpf_out* out);
+int  orc_coupled_ccpf_chains(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
+                             int K, int max_iterations, int with_as, orc_chains* out);
+int  orc_coupled_ccpf_batch(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t first_replicate, int nrep,
+                            int k, int K, int max_iterations, int with_as, int nthreads,
+                            double* hbar /* [nrep][p] */, int* meetingtime, int* iterations, long long* nfilters_total);
 
 const char* orc_version(void);
 

@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "build", "liboracle.so")
-SOURCES = ["philox.c", "resampling.c", "tree.c", "mvnorm.c", "models.c", "cpf.c"]
+SOURCES = ["philox.c", "resampling.c", "tree.c", "mvnorm.c", "models.c", "cpf.c", "ccpf.c"]
 
 MODEL_GSS, MODEL_AR, MODEL_LEVY_SV, MODEL_SK, MODEL_LORENZ = range(5)
 INTEGRATOR_RK4, INTEGRATOR_DOPRI5 = 0, 1
@@ -402,4 +402,87 @@ def coupled_pimh_batch(cfg, obs, seed, first_replicate, nrep, k=0, K=1, max_iter
                                       C.c_int(k), C.c_int(K), C.c_int(max_iterations), C.c_int(nthreads), _p(hbar), _p(mt), _p(it), C.byref(nf))
     if rc:
         raise RuntimeError("oracle coupled_pimh_batch failed (%d)" % rc)
+    return dict(hbar=hbar, meetingtime=mt, iteration=it, nfilters=nf.value)
+
+
+# ---------------------------------------------------------------- conditional filters
+class CcpfOut(C.Structure):
+    _fields_ = [("trajectory", C.c_void_p * 2), ("ancestors", C.c_void_p * 2), ("path_index", C.c_int * 2), ("logz", C.c_double),
+                ("clamp_count", C.c_int)]
+
+
+def ccpf(cfg, obs, ref1, ref2=None, with_as=False, seed=0, filter_id=0, noise=None, want_ancestors=False):
+    """CPF(..., ref_trajectory = ref1, with_as) when ref2 is None, else CPF_coupled(..., ref1, ref2, CR_indexmatching, with_as).
+    refs and returned trajectories are d x (T+1)."""
+    T, d, N = cfg.nobs, cfg.dim, cfg.nparticles
+    ob = np.asfortranarray(np.asarray(obs, dtype=np.float64).reshape(T, -1))
+    nsys = 1 if ref2 is None else 2
+    refs = [np.asfortranarray(np.asarray(r, dtype=np.float64).reshape(d, T + 1)) for r in ([ref1] if nsys == 1 else [ref1, ref2])]
+    tr = [np.empty((d, T + 1), order="F") for _ in range(2)]
+    anc = [np.empty((T, N), dtype=np.int32) for _ in range(2)] if want_ancestors else None
+    nz = Noise(); keep = []
+    if noise:
+        for k in ("init", "trans"):
+            if noise.get(k) is not None:
+                a = _f64(noise[k]); keep.append(a); setattr(nz, k, a.ctypes.data)
+    o = CcpfOut()
+    for s_ in range(2):
+        o.trajectory[s_] = tr[s_].ctypes.data
+        o.ancestors[s_] = anc[s_].ctypes.data if want_ancestors else None
+    lib().orc_ccpf.restype = C.c_int
+    rc = lib().orc_ccpf(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.byref(nz) if noise else None, C.c_uint64(seed), C.c_uint64(filter_id),
+                        C.c_int(nsys), refs[0].ctypes.data_as(C.c_void_p), refs[1].ctypes.data_as(C.c_void_p) if nsys == 2 else None,
+                        C.c_int(int(with_as)), C.byref(o))
+    if rc:
+        raise RuntimeError("oracle ccpf failed (%d)" % rc)
+    res = dict(trajectory1=np.ascontiguousarray(tr[0]), logz=float(o.logz), path_index=[int(o.path_index[0]), int(o.path_index[1])],
+               clamp_count=int(o.clamp_count))
+    if nsys == 2:
+        res["trajectory2"] = np.ascontiguousarray(tr[1])
+    if want_ancestors:
+        res["ancestors1"] = anc[0]
+        if nsys == 2:
+            res["ancestors2"] = anc[1]
+    return res
+
+
+def model_dtransition(cfg, next_x, x, time):
+    """model$dtransition(next_x, xparticles (d x N), theta, time): gss and ar only."""
+    xx = np.asfortranarray(np.asarray(x, dtype=np.float64).reshape(cfg.dim, cfg.nparticles))
+    out = np.empty(cfg.nparticles)
+    lib().orc_model_dtransition(C.byref(cfg), _p(_f64(next_x)), xx.ctypes.data_as(C.c_void_p), C.c_int(int(time)), _p(out))
+    return out
+
+
+def coupled_ccpf_chains(cfg, obs, seed, replicate, K=1, max_iterations=-1, with_as=False, hbar_k=None):
+    T = cfg.nobs
+    ob = np.asfortranarray(np.asarray(obs, dtype=np.float64).reshape(T, -1))
+    c = Chains()
+    rc = lib().orc_coupled_ccpf_chains(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_uint64(seed), C.c_uint32(replicate), C.c_int(K),
+                                       C.c_int(max_iterations), C.c_int(int(with_as)), C.byref(c))
+    if rc:
+        raise RuntimeError("oracle coupled_ccpf_chains failed (%d)" % rc)
+    p, it = c.p, c.iteration
+    out = dict(samples1=np.ctypeslib.as_array(c.samples1, shape=(it + 1, p)).copy(),
+               samples2=np.ctypeslib.as_array(c.samples2, shape=(it, p)).copy(),
+               log_pdf1=np.ctypeslib.as_array(c.log_pdf1, shape=(it + 1,)).copy(),
+               log_pdf2=np.ctypeslib.as_array(c.log_pdf2, shape=(it,)).copy(),
+               meetingtime=(np.inf if c.meetingtime < 0 else c.meetingtime), iteration=it, finished=bool(c.finished), nfilters=c.nfilters)
+    if hbar_k is not None:
+        hb = np.empty(p)
+        if lib().orc_H_bar(C.byref(c), C.c_int(int(hbar_k)), C.c_int(int(K)), _p(hb)) == 0:
+            out["hbar"] = hb.copy()
+    lib().orc_chains_free(C.byref(c))
+    return out
+
+
+def coupled_ccpf_batch(cfg, obs, seed, first_replicate, nrep, k=0, K=1, max_iterations=-1, with_as=False, nthreads=0):
+    T = cfg.nobs; p = T + 1
+    ob = np.asfortranarray(np.asarray(obs, dtype=np.float64).reshape(T, -1))
+    hbar = np.empty((nrep, p)); mt = np.empty(nrep, dtype=np.int32); it = np.empty(nrep, dtype=np.int32); nf = C.c_longlong(0)
+    rc = lib().orc_coupled_ccpf_batch(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_uint64(seed), C.c_uint32(first_replicate), C.c_int(nrep),
+                                      C.c_int(k), C.c_int(K), C.c_int(max_iterations), C.c_int(int(with_as)), C.c_int(nthreads),
+                                      _p(hbar), _p(mt), _p(it), C.byref(nf))
+    if rc:
+        raise RuntimeError("oracle coupled_ccpf_batch failed (%d)" % rc)
     return dict(hbar=hbar, meetingtime=mt, iteration=it, nfilters=nf.value)

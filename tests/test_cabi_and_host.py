@@ -64,8 +64,12 @@ def test_no_cpu_fallback_and_argument_checks():
     with pytest.raises(up.CpimhError) as ei:
         up.cpf_batch(16, up.get_ar(7), [0.5, 1.0], np.zeros((5, 7)), 1, seed=1)   # no compiled kernel for d = 7
     assert "dimension" in str(ei.value)
-    with pytest.raises(NotImplementedError):
-        up.CPF(16, up.get_gss(), [], y, ref_trajectory=np.zeros((1, 6)))
+    with pytest.raises(up.CpimhError) as ei:          # conditional filters: argument checks come before any CUDA call
+        up.CPF(16, up.get_gss(), [], y, ref_trajectory=np.zeros((1, 6)), shuffle=1)
+    assert ei.value.code == 1 and "shuffle" in str(ei.value)
+    with pytest.raises(up.CpimhError) as ei:
+        up.coupled_ccpf_chains_batch(up.get_gss(), [], y, 16, 4, K=3, k=5)
+    assert ei.value.code == 1
 
 
 def test_product_does_not_import_the_oracle():

@@ -1,0 +1,157 @@
+"""GPU tests of the conditional particle filters: CPF(ref_trajectory, with_as), CPF_coupled with index-matching
+resampling, and coupled_ccpf_chains -- compared with the oracle (oracle/ccpf.c) on the same Philox streams."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+A_OBS = np.array([[1, 0, 0, 0], [0, 1, 2, 0]], dtype=float)
+SK_THETA = {"A_obs": A_OBS, "s2_obs": 1.0}
+TH_AR = [0.5, math.sqrt(10.0)]
+
+
+@pytest.fixture(scope="module")
+def up():
+    import unbiased_pimh_b200 as m
+    return m
+
+
+def _refs(oracle, cfg, y, seed, n):
+    return [oracle.cpf(cfg, y, seed=seed, filter_id=100 + i)["trajectory"] for i in range(n)]
+
+
+@pytest.mark.parametrize("name,with_as", [("ar1", False), ("ar1", True), ("gss", False), ("gss", True), ("ar3", True), ("sv", False), ("sk", False)])
+def test_conditional_filter_matches_oracle(up, oracle, golden, name, with_as):
+    """One system: same streams => same ancestors (the last one pinned to N-1 or ancestor-sampled), same trajectory and log Z."""
+    if name == "ar1":
+        m, th, y, N, oc = up.get_ar(1), TH_AR, golden["lgssm_y"], 64, (oracle.MODEL_AR, 1, 1)
+    elif name == "ar3":
+        m, th, y, N, oc = up.get_ar(3), TH_AR, np.random.default_rng(4).normal(size=(30, 3)), 100, (oracle.MODEL_AR, 3, 3)
+    elif name == "gss":
+        m, th, y, N, oc = up.get_gss(), [], golden["gss_y"][:60], 128, (oracle.MODEL_GSS, 1, 1)
+    elif name == "sv":
+        m, th, y, N, oc = up.get_levy_sv(), golden["sv_theta_mle"], golden["sv_y"][:40], 96, (oracle.MODEL_LEVY_SV, 2, 1)
+    else:
+        m, th, y, N, oc = up.get_stochastic_kinetic(), SK_THETA, golden["sk_y"][:20], 64, (oracle.MODEL_SK, 4, 2)
+    T = y.shape[0]
+    oth = th if name != "sk" else [1.0] + list(A_OBS.flatten(order="F"))
+    cfg = oracle.make_config(oc[0], oc[1], oc[2], N, T, theta=oth)
+    refs = _refs(oracle, cfg, y, 9, 3)
+    g = up.ccpf_batch(N, m, th, y, refs, with_as=with_as, seed=21, first_filter=4, ancestors=True)
+    for b in range(3):
+        o = oracle.ccpf(cfg, y, refs[b], with_as=with_as, seed=21, filter_id=4 + b, want_ancestors=True)
+        assert np.array_equal(g["ancestors"][b, 0], o["ancestors1"])
+        assert g["path_index"][b, 0] == o["path_index"][0]
+        assert np.allclose(g["trajectory1"][b], o["trajectory1"], rtol=1e-9, atol=1e-9)
+        assert abs(g["logz"][b] - o["logz"]) <= 1e-9 * abs(o["logz"])
+        if not with_as:
+            assert np.all(g["ancestors"][b, 0][:, -1] == N - 1)
+
+
+@pytest.mark.parametrize("name,with_as", [("ar1", False), ("ar1", True), ("gss", True), ("ar3", False), ("sv", False), ("sk", False)])
+def test_coupled_conditional_filter_matches_oracle(up, oracle, golden, name, with_as):
+    """Two systems, index-matching resampling, common random numbers: both ancestor tables and both trajectories equal the oracle's."""
+    if name == "ar1":
+        m, th, y, N, oc = up.get_ar(1), TH_AR, golden["lgssm_y"], 64, (oracle.MODEL_AR, 1, 1)
+    elif name == "ar3":
+        m, th, y, N, oc = up.get_ar(3), TH_AR, np.random.default_rng(4).normal(size=(30, 3)), 100, (oracle.MODEL_AR, 3, 3)
+    elif name == "gss":
+        m, th, y, N, oc = up.get_gss(), [], golden["gss_y"][:60], 128, (oracle.MODEL_GSS, 1, 1)
+    elif name == "sv":
+        m, th, y, N, oc = up.get_levy_sv(), golden["sv_theta_mle"], golden["sv_y"][:40], 96, (oracle.MODEL_LEVY_SV, 2, 1)
+    else:
+        m, th, y, N, oc = up.get_stochastic_kinetic(), SK_THETA, golden["sk_y"][:20], 64, (oracle.MODEL_SK, 4, 2)
+    T = y.shape[0]
+    oth = th if name != "sk" else [1.0] + list(A_OBS.flatten(order="F"))
+    cfg = oracle.make_config(oc[0], oc[1], oc[2], N, T, theta=oth)
+    refs = _refs(oracle, cfg, y, 9, 6)
+    g = up.ccpf_batch(N, m, th, y, refs[:3], refs[3:], with_as=with_as, seed=22, first_filter=1, ancestors=True)
+    for b in range(3):
+        o = oracle.ccpf(cfg, y, refs[b], refs[3 + b], with_as=with_as, seed=22, filter_id=1 + b, want_ancestors=True)
+        assert np.array_equal(g["ancestors"][b, 0], o["ancestors1"]) and np.array_equal(g["ancestors"][b, 1], o["ancestors2"])
+        assert list(g["path_index"][b]) == o["path_index"]
+        assert np.allclose(g["trajectory1"][b], o["trajectory1"], rtol=1e-9, atol=1e-9)
+        assert np.allclose(g["trajectory2"][b], o["trajectory2"], rtol=1e-9, atol=1e-9)
+
+
+def test_injected_noise_and_faithful_coupling(up, oracle, golden):
+    """Injected init/transition noise (the reference's rinit_rand / rtransition_rand arrays) gives the oracle's result, and two
+    systems started from the SAME reference return bitwise identical trajectories (the chains stay together once met)."""
+    y = golden["lgssm_y"][:50]
+    N, T, B = 80, 50, 2
+    rng = np.random.default_rng(3)
+    noise = {"init": rng.normal(size=(B, 1, N)), "trans": rng.normal(size=(B, T, 1, N))}
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, N, T, theta=TH_AR)
+    refs = _refs(oracle, cfg, y, 5, 4)
+    g = up.ccpf_batch(N, up.get_ar(1), TH_AR, y, refs[:2], refs[2:], with_as=True, seed=6, noise=noise, ancestors=True)
+    for b in range(B):
+        o = oracle.ccpf(cfg, y, refs[b], refs[2 + b], with_as=True, seed=6, filter_id=b, noise={"init": noise["init"][b], "trans": noise["trans"][b]},
+                        want_ancestors=True)
+        assert np.array_equal(g["ancestors"][b, 0], o["ancestors1"]) and np.array_equal(g["ancestors"][b, 1], o["ancestors2"])
+        assert np.allclose(g["trajectory1"][b], o["trajectory1"], rtol=1e-10, atol=1e-10)
+        assert np.allclose(g["trajectory2"][b], o["trajectory2"], rtol=1e-10, atol=1e-10)
+    same = up.ccpf_batch(N, up.get_ar(1), TH_AR, y, refs[:2], refs[:2], with_as=False, seed=8)
+    assert np.array_equal(same["trajectory1"], same["trajectory2"])
+
+
+def test_r_shaped_conditional_api_and_errors(up, golden):
+    y = golden["lgssm_y"][:30]
+    m = up.get_ar(1)
+    up.set_seed(5)
+    x0 = up.CPF(50, m, TH_AR, y)["trajectory"]
+    r = up.CPF(50, m, TH_AR, y, ref_trajectory=x0, with_as=True)
+    assert r["trajectory"].shape == (1, 31) and np.isfinite(r["logz"])
+    c = up.CPF_coupled(50, m, TH_AR, y, x0, r["trajectory"], up.CR_indexmatching, with_as=False)
+    assert c["new_trajectory1"].shape == (1, 31) and c["new_trajectory2"].shape == (1, 31)
+    ker = up.get_cpf_kernels(True, model=m, theta=TH_AR, observations=y)
+    init = up.get_pimh_kernels(False, model=m, theta=TH_AR, observations=y)["pimh_init"]
+    ch = up.coupled_ccpf_chains(ker["single_kernel"], ker["coupled_kernel"], init, 50, K=3, max_iterations=200)
+    assert ch["finished"] and ch["samples1"].shape == (ch["iteration"] + 1, 31) and ch["samples2"].shape == (ch["iteration"], 31)
+    tau = ch["meetingtime"]
+    for t in range(int(tau), ch["iteration"] + 1):
+        assert np.array_equal(ch["samples1"][t], ch["samples2"][t - 1])
+    assert up.H_bar(ch, k=1, K=3).shape == (31,)
+    with pytest.raises(up.CpimhError):
+        up.ccpf_batch(50, m, TH_AR, y, [x0], shuffle=1)
+    with pytest.raises(up.CpimhError):
+        ysv = golden["sv_y"][:10]
+        xs = up.CPF(64, up.get_levy_sv(), golden["sv_theta_mle"], ysv)["trajectory"]
+        up.CPF(64, up.get_levy_sv(), golden["sv_theta_mle"], ysv, ref_trajectory=xs, with_as=True)
+
+
+@pytest.mark.parametrize("with_as", [False, True])
+def test_ccpf_chains_match_oracle(up, oracle, golden, with_as):
+    y = golden["lgssm_y"]
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 64, 100, theta=TH_AR)
+    for (k, K) in ((0, 1), (2, 5)):
+        g = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 64, 40, K=K, k=k, with_as=with_as, seed=12, first_replicate=3, max_iterations=400)
+        o = oracle.coupled_ccpf_batch(cfg, y, 12, 3, 40, k=k, K=K, with_as=with_as, max_iterations=400)
+        assert np.array_equal(g["meetingtime"], o["meetingtime"]) and np.array_equal(g["iteration"], o["iteration"])
+        assert g["nfilters"] == o["nfilters"]
+        assert np.allclose(g["hbar"][:, 0, :], o["hbar"], rtol=1e-9, atol=1e-9)
+        assert np.allclose(g["sum_hbar"][0], o["hbar"].sum(axis=0), rtol=1e-9, atol=1e-8)
+
+
+def test_ccpf_estimator_is_unbiased_for_the_smoothing_mean(up, golden):
+    """H_bar averaged over replicates matches the Kalman/RTS smoothing mean of the LGSSM (x0 ~ N(0,1), a = 0.5, R = 10)."""
+    y = golden["lgssm_y"]
+    T, a, Rv = 100, 0.5, 10.0
+    mp, Pp, mf, Pf = np.zeros(T + 1), np.zeros(T + 1), np.zeros(T + 1), np.zeros(T + 1)
+    mf[0], Pf[0] = 0.0, 1.0
+    for t in range(1, T + 1):
+        mp[t], Pp[t] = a * mf[t - 1], a * a * Pf[t - 1] + 1
+        Kg = Pp[t] / (Pp[t] + Rv)
+        mf[t], Pf[t] = mp[t] + Kg * (y[t - 1, 0] - mp[t]), (1 - Kg) * Pp[t]
+    ms = mf.copy()
+    for t in range(T - 1, -1, -1):
+        ms[t] = mf[t] + Pf[t] * a / Pp[t + 1] * (ms[t + 1] - mp[t + 1])
+    R = 3000
+    g = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 128, R, K=8, k=3, with_as=True, seed=77)
+    assert g["meetingtime"].min() >= 2 and g["meetingtime"].max() < 60
+    est = g["hbar"][:, 0, :].mean(axis=0)
+    se = g["hbar"][:, 0, :].std(axis=0, ddof=1) / math.sqrt(R)
+    z = (est - ms) / se
+    assert np.max(np.abs(z)) < 4.5 and np.mean(np.abs(z) > 2) < 0.15
+    assert np.allclose(g["sum_hbar"][0] / R, est, rtol=1e-10, atol=1e-12)

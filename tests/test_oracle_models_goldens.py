@@ -289,3 +289,55 @@ def test_all_particles_chains_rao_blackwellised_estimator(oracle, golden):
     assert np.mean(hbe.var(axis=0) < hb.var(axis=0)) > 0.8
     z = (hb.mean(0) - hbe.mean(0)) / np.sqrt((hb.var(0) + hbe.var(0)) / 150)
     assert np.max(np.abs(z)) < 4.5
+
+
+def test_conditional_filters_oracle_properties(oracle, golden):
+    """oracle/ccpf.c: the reference particle is pinned, identical references give identical systems, dtransition equals
+    scipy's normal log-density, and the coupled-CCPF estimator is unbiased for the Kalman smoothing mean."""
+    from scipy.stats import norm
+    y = golden["lgssm_y"]
+    th = [0.5, math.sqrt(10.0)]
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 64, 100, theta=th)
+    ref = oracle.cpf(cfg, y, seed=1, filter_id=0)["trajectory"]
+    ref2 = oracle.cpf(cfg, y, seed=1, filter_id=1)["trajectory"]
+    r = oracle.ccpf(cfg, y, ref, seed=2, filter_id=5, want_ancestors=True)
+    assert np.all(r["ancestors1"][:, -1] == 63) and r["clamp_count"] == 0
+    assert np.all(np.diff(r["ancestors1"][1:, :-1], axis=1) >= 0)          # N-1 sorted multinomial draws
+    # if the pinned particle is selected at the end, the reference path is returned unchanged
+    hits = 0
+    for f in range(40):
+        rr = oracle.ccpf(cfg, y, ref, seed=4, filter_id=f)
+        if rr["path_index"][0] == 63:
+            hits += 1
+            assert rr["trajectory1"][0, -1] == ref[0, -1]
+    same = oracle.ccpf(cfg, y, ref, ref, seed=2, filter_id=5)
+    assert np.array_equal(same["trajectory1"], same["trajectory2"])
+    two = oracle.ccpf(cfg, y, ref, ref2, seed=2, filter_id=5, with_as=True, want_ancestors=True)
+    assert two["trajectory1"].shape == (1, 101) and np.all(two["ancestors1"] >= 0) and np.all(two["ancestors2"] < 64)
+    # dtransition: gss and ar(1)
+    x = np.linspace(-3, 3, 64)
+    lt = oracle.model_dtransition(cfg, [0.7], x, 3)
+    assert np.allclose(lt, norm.logpdf(0.7, loc=0.5 * x, scale=1.0), atol=2e-7)     # the reference truncates log(sqrt(2 pi)) to 0.9189385
+    gcfg = oracle.make_config(oracle.MODEL_GSS, 1, 1, 64, 100)
+    lg = oracle.model_dtransition(gcfg, [1.3], x, 4)
+    mean = 0.5 * x + 25 * x / (1 + x * x) + 8 * math.cos(1.2 * 3)
+    assert np.allclose(lg, norm.logpdf(1.3, loc=mean, scale=1.0), rtol=1e-12, atol=1e-12)
+    # unbiasedness (ancestor sampling on: short meeting times)
+    T, a, Rv = 100, 0.5, 10.0
+    mp, Pp, mf, Pf = np.zeros(T + 1), np.zeros(T + 1), np.zeros(T + 1), np.zeros(T + 1)
+    mf[0], Pf[0] = 0.0, 1.0
+    for t in range(1, T + 1):
+        mp[t], Pp[t] = a * mf[t - 1], a * a * Pf[t - 1] + 1
+        Kg = Pp[t] / (Pp[t] + Rv)
+        mf[t], Pf[t] = mp[t] + Kg * (y[t - 1, 0] - mp[t]), (1 - Kg) * Pp[t]
+    ms = mf.copy()
+    for t in range(T - 1, -1, -1):
+        ms[t] = mf[t] + Pf[t] * a / Pp[t + 1] * (ms[t + 1] - mp[t + 1])
+    b = oracle.coupled_ccpf_batch(cfg, y, 11, 0, 400, k=3, K=8, with_as=True)
+    est = b["hbar"].mean(axis=0); se = b["hbar"].std(axis=0, ddof=1) / math.sqrt(400)
+    z = (est - ms) / se
+    assert np.max(np.abs(z)) < 4.5 and np.mean(np.abs(z) > 2) < 0.15
+    c = oracle.coupled_ccpf_chains(cfg, y, 11, 7, K=4, with_as=True, hbar_k=1)
+    assert c["finished"] and c["samples1"].shape == (c["iteration"] + 1, 101) and c["samples2"].shape == (c["iteration"], 101)
+    for t in range(int(c["meetingtime"]), c["iteration"] + 1):
+        assert np.array_equal(c["samples1"][t], c["samples2"][t - 1])

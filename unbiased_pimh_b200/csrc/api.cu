@@ -492,6 +492,13 @@ int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* e
   return api_all_particles(a, s, exp_path, trajectories, normweights);
 }
 
+int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status) {
+  CPIMH_REQUIRE(h && d_status, "null argument");
+  CPIMH_REQUIRE(!h->wide, "not available for the wide (d = 32/64) filter");
+  *d_status = h->status.as<int>();
+  return CPIMH_OK;
+}
+
 int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory) {
   CPIMH_REQUIRE(h, "null handle");
   if (h->wide) { wide_device_outputs(h->wide, d_logz, d_trajectory); return CPIMH_OK; }

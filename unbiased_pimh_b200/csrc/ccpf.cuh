@@ -1,0 +1,338 @@
+// ccpf.cuh -- conditional particle filters, one CTA per filter:
+//   CPF(N, model, theta, obs, ref_trajectory = x, with_as)                  R/CPF.R:14-78 (branches :22-24, :45-58)
+//   CPF_coupled(N, model, theta, obs, ref1, ref2, CR_indexmatching, with_as) R/CPF_coupled.R:14-112
+// The last particle of each system is pinned to its reference path; the other N-1 are resampled -- by sorted
+// multinomial draws (one system, src/multinomial.cpp:13-32) or by index-matching coupled resampling (two systems,
+// src/coupledresamplingindexmatching.cpp:8-57) -- and both systems are driven by the SAME Philox streams (common random
+// numbers, R/CPF_coupled.R:24,29,57-59), so that particles that coincide stay bitwise identical and the two returned
+// trajectories can meet exactly.  The sorted-uniform ladder, the coupling flags and the one-draw index matching used
+// for ancestor sampling and the final path are specified in oracle/ccpf.c (header) and DESIGN.md "RNG".
+//
+// Layout: the particle history is the path store, as in the bootstrap filter's PATH_DENSE mode, once per system:
+// hist_x[ws][sys][t][q][i] and hist_a[ws][sys][t][i].  Shared memory holds, per CTA, the two weight vectors (which become
+// the residual CDFs), nu = min(w1, w2) (its CDF), the ladder of exponential-spacing prefix sums and the per-index
+// coupled/residual ranks; the log-weights of a step reuse the nu / ladder arrays once all ancestors are known.
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+
+namespace cpimh {
+
+struct CcpfParams {
+  int N, T, dy, Npad;
+  long long B;                 // filters in this launch
+  int nsys;                    // 1 or 2 (when `single` is null)
+  int with_as;
+  unsigned long long seed, first_filter;
+  const unsigned long long* stream_ids;   // [B] explicit Philox stream id per filter, or null: first_filter + b
+  const int* slot;             // [B] slot of refs / outputs used by filter b (chain driver: replicate), or null: b
+  const int* single;           // [slot] != 0: run system 1 only (chain driver: the replicate's chains have met), or null
+  const double* obs; const double* theta; const double* pre;
+  int npre, integrator, substeps;
+  const double* ref1; const double* ref2;   // [slot][T+1][D]
+  double* hist_x;              // [ws][2][T+1][D][Npad]
+  int* hist_a;                 // [ws][2][T][Npad]
+  double* traj1; double* traj2;             // [slot][T+1][D]
+  double* logz;                // [slot]   system 1's log Z (R/CPF.R:71)
+  int* path_index;             // [slot][2] or null
+  int* status;                 // [slot]
+  int* anc_rec;                // [slot][2][T][N] or null
+  const double* inj_init; const double* inj_trans;
+  int n_init, n_trans, sk_M;
+};
+
+struct CcpfSmem {
+  double* C1; double* C2;      // [Npad] weights of system 1 / 2 -> residual CDFs
+  double* V;                   // [Npad + 32] nu -> its CDF ; log-weights of system 1 ; ancestor-sampling weights
+  double* P;                   // [Npad + 32] ladder prefix sums ; log-weights of system 2
+  int* R;                      // [Npad] rank among the coupled (>= 0) or the residual (~rank < 0) indices
+  double* theta; double* pre; double* dscr; int* iscr;
+};
+__host__ __device__ inline size_t ccpf_smem_bytes(int Npad, int npre) {
+  size_t b = (size_t)(4 * Npad + 64) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + (size_t)Npad * 4 + 36 * 4;
+  return (b + 15) & ~(size_t)15;
+}
+__device__ inline CcpfSmem ccpf_carve(unsigned char* raw, int Npad, int npre) {
+  CcpfSmem s;
+  double* d = reinterpret_cast<double*>(raw);
+  s.C1 = d; d += Npad;
+  s.C2 = d; d += Npad;
+  s.V = d; d += Npad + 32;
+  s.P = d; d += Npad + 32;
+  s.theta = d; d += CPIMH_MAX_THETA;
+  s.pre = d; d += npre + (npre & 1);
+  s.dscr = d; d += 64;
+  int* i = reinterpret_cast<int*>(d);
+  s.R = i; i += Npad;
+  s.iscr = i;
+  return s;
+}
+
+__device__ __forceinline__ int clampN(int a, int N) { return a >= N ? N - 1 : a; }
+
+// indexmatching_cpp(w1, w2, ndraws = 1) with the uniforms (uc, ud): coupled with probability alpha = sum min(w1, w2),
+// then one draw from mu, else one common-uniform draw from the two residuals.  Destroys A and Bv.  All threads call.
+__device__ inline void im_single_draw(double* A, double* Bv, int N, double uc, double ud, double* dscr, int& a1, int& a2) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  double al = 0.0;
+  for (int k = tid; k < N; k += NT) al += fmin(A[k], Bv[k]);
+  al = block_sum(al, dscr);
+  if (uc < al) {
+    for (int k = tid; k < N; k += NT) A[k] = fmin(A[k], Bv[k]);
+    __syncthreads();
+    block_scan_inplace<false>(A, N, dscr);
+    a1 = a2 = clampN(count_le(A, N, ud * A[N - 1]), N);
+  } else {
+    for (int k = tid; k < N; k += NT) { const double nu = fmin(A[k], Bv[k]); A[k] -= nu; Bv[k] -= nu; }
+    __syncthreads();
+    block_scan2_inplace(A, Bv, N, dscr);
+    a1 = clampN(count_le(A, N, ud * A[N - 1]), N);
+    a2 = clampN(count_le(Bv, N, ud * Bv[N - 1]), N);
+  }
+  __syncthreads();
+}
+
+template <class Model>
+__device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, const Stream& stream, long long inj, int nsys, long long slot) {
+  constexpr int D = Model::D;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int N = p.N, T = p.T, Npad = p.Npad, nd = N - 1;
+  const size_t xstride = (size_t)D * Npad;
+  double* hx[2];
+  int* ha[2];
+  const double* ref[2] = {p.ref1 + (size_t)slot * (T + 1) * D, p.ref2 ? p.ref2 + (size_t)slot * (T + 1) * D : nullptr};
+  for (int s = 0; s < 2; s++) {
+    hx[s] = p.hist_x + ((size_t)ws * 2 + s) * (T + 1) * xstride;
+    ha[s] = p.hist_a + ((size_t)ws * 2 + s) * T * Npad;
+  }
+  double* Wk[2] = {sm.C1, sm.C2};
+  double* Lk[2] = {sm.V, sm.P};
+  ModelCtx c;
+  c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
+  c.inj_init = p.inj_init ? p.inj_init + (size_t)inj * p.n_init * N : nullptr;
+  c.inj_trans = p.inj_trans ? p.inj_trans + (size_t)inj * T * p.n_trans * N : nullptr;
+  c.n_trans = p.n_trans; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
+  int st = 0;
+  if (tid == 0) sm.iscr[32] = 0;
+
+  // ---------------- initialisation (R/CPF.R:19-28, R/CPF_coupled.R:22-33): common init noise, last particle = ref[, 1]
+  for (int i = tid; i < N; i += NT) {
+    double x[D];
+    Model::init(c, i, x);
+    for (int s = 0; s < nsys; s++) {
+#pragma unroll
+      for (int q = 0; q < D; q++) hx[s][(size_t)q * Npad + i] = (i == N - 1) ? ref[s][q] : x[q];
+      Wk[s][i] = 1.0;
+    }
+  }
+  double ssum[2] = {(double)N, (double)N};
+  double logz_sum = 0.0;
+  __syncthreads();
+
+  for (int t = 1; t <= T; t++) {
+    const bool ident = (t == 1) || isnan(p.obs[(size_t)(t - 2) * p.dy]);     // R/CPF.R:38-40, R/CPF_coupled.R:45-48
+    const double* y = p.obs + (size_t)(t - 1) * p.dy;
+    const double sc = Model::step_const(c, t);
+    const double* xprev[2] = {hx[0] + (size_t)(t - 1) * xstride, hx[1] + (size_t)(t - 1) * xstride};
+    double* xcur[2] = {hx[0] + (size_t)t * xstride, hx[1] + (size_t)t * xstride};
+    int* arow[2] = {ha[0] + (size_t)(t - 1) * Npad, ha[1] + (size_t)(t - 1) * Npad};
+
+    // normweights = w / sum(w)  (R/CPF.R:63; index matching compares the two systems' NORMALISED weights)
+    for (int s = 0; s < nsys; s++)
+      for (int k = tid; k < N; k += NT) Wk[s][k] = Wk[s][k] / ssum[s];
+    __syncthreads();
+
+    // ---- ancestor of the reference particle: R/CPF.R:47-57, R/CPF_coupled.R:64-84
+    int aref[2] = {N - 1, N - 1};
+    if constexpr (Model::HAS_DTRANS) {
+      if (p.with_as) {
+        for (int s = 0; s < nsys; s++) {
+          double next[D];
+#pragma unroll
+          for (int q = 0; q < D; q++) next[q] = ref[s][(size_t)t * D + q];
+          double m = -INFINITY;
+          for (int k = tid; k < N; k += NT) {
+            double x[D];
+#pragma unroll
+            for (int q = 0; q < D; q++) x[q] = xprev[s][(size_t)q * Npad + k];
+            const double lm = log(Wk[s][k]) + Model::dtrans(c, next, x, t, sc);
+            Lk[s][k] = lm;
+            m = fmax(m, lm);
+          }
+          m = block_max(m, sm.dscr);
+          double sum = 0.0;
+          for (int k = tid; k < N; k += NT) { const double w = exp(Lk[s][k] - m); Lk[s][k] = w; sum += w; }
+          sum = block_sum(sum, sm.dscr);
+          for (int k = tid; k < N; k += NT) Lk[s][k] = Lk[s][k] / sum;
+        }
+        __syncthreads();
+        double ua, ub;
+        philox_u2(stream, 0, t, CPIMH_P_AS, 0, ua, ub);
+        if (nsys == 1) {
+          block_scan_inplace<false>(Lk[0], N, sm.dscr);
+          aref[0] = clampN(count_lt(Lk[0], N, ua), N);                       // systematic_resampling_n(w_as, 1, u)
+          __syncthreads();
+        } else {
+          im_single_draw(Lk[0], Lk[1], N, ua, ub, sm.dscr, aref[0], aref[1]);  // CR_indexmatching(w_as1, w_as2, ntrials = 1)
+        }
+      }
+    }
+
+    // ---- ancestors of the N-1 free particles
+    if (!ident) {
+      for (int i = tid; i <= nd + 1; i += NT) sm.P[i] = -log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
+      if (nsys == 1) {
+        __syncthreads();
+        block_scan_inplace<false>(sm.C1, N, sm.dscr);
+        block_scan_inplace<false>(sm.P, nd + 1, sm.dscr);
+        const double scale = sm.C1[N - 1] / sm.P[nd];
+        for (int k = tid; k < nd; k += NT) {
+          int a = count_le(sm.C1, N, scale * sm.P[k]);
+          if (a >= N) { a = N - 1; st |= 512; }
+          arow[0][k] = a;
+        }
+      } else {
+        double al = 0.0;                                                     // coupledresamplingindexmatching.cpp:13-21
+        for (int k = tid; k < N; k += NT) {
+          const double nu = fmin(sm.C1[k], sm.C2[k]);
+          sm.V[k] = nu; sm.C1[k] -= nu; sm.C2[k] -= nu;
+          al += nu;
+        }
+        al = block_sum(al, sm.dscr);
+        // coupled flags (:26-33) and each index's rank inside its group: thread `tid` owns a contiguous chunk of indices
+        const int chunk = (nd + NT - 1) / NT, i0 = min(nd, tid * chunk), i1 = min(nd, i0 + chunk);
+        int cnt = 0;
+        for (int i = i0; i < i1; i++) { const int f = philox_u1(stream, i, t, CPIMH_P_COUPLE, 0) < al; sm.R[i] = f; cnt += f; }
+        int nc;
+        int jc = block_excl_scan_int(cnt, sm.iscr, &nc);
+        int jr = i0 - jc;
+        for (int i = i0; i < i1; i++) { if (sm.R[i]) sm.R[i] = jc++; else sm.R[i] = ~(jr++); }
+        block_scan2_inplace(sm.C1, sm.C2, N, sm.dscr);
+        block_scan_inplace<false>(sm.V, N, sm.dscr);
+        block_scan_inplace<false>(sm.P, nd + 2, sm.dscr);
+        const double Pnc = sm.P[nc], den = sm.P[nd + 1] - Pnc;
+        const double totV = sm.V[N - 1], tot1 = sm.C1[N - 1], tot2 = sm.C2[N - 1];
+        for (int k = tid; k < nd; k += NT) {
+          const int r = sm.R[k];
+          int a1, a2;
+          if (r >= 0) {                                                      // :36-38 common draw from mu = nu / alpha
+            a1 = a2 = clampN(count_le(sm.V, N, (sm.P[r] / Pnc) * totV), N);
+          } else {                                                           // :40-42 residuals with a common uniform
+            const double u = (sm.P[nc + 1 + (~r)] - Pnc) / den;
+            a1 = clampN(count_le(sm.C1, N, u * tot1), N);
+            a2 = clampN(count_le(sm.C2, N, u * tot2), N);
+          }
+          arow[0][k] = a1; arow[1][k] = a2;
+        }
+      }
+    } else {
+      for (int s = 0; s < nsys; s++)
+        for (int k = tid; k < nd; k += NT) arow[s][k] = k;
+    }
+    if (tid == 0) for (int s = 0; s < nsys; s++) arow[s][N - 1] = aref[s];
+    __syncthreads();                                                         // ancestors complete: CDFs, ladder and ranks are dead
+
+    // ---- gather -> common-noise transition -> pin the reference -> weigh  (R/CPF_coupled.R:50-62, 87-88)
+    double m[2] = {-INFINITY, -INFINITY};
+    for (int k = tid; k < N; k += NT) {
+      double ush = 0.5;
+      if (Model::USES_SHARED_U && !c.inj_trans) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
+      for (int s = 0; s < nsys; s++) {
+        double x[D];
+        if (k == N - 1) {
+#pragma unroll
+          for (int q = 0; q < D; q++) x[q] = ref[s][(size_t)t * D + q];
+        } else {
+          const int a = arow[s][k];
+#pragma unroll
+          for (int q = 0; q < D; q++) x[q] = xprev[s][(size_t)q * Npad + a];
+          st |= Model::transition(c, t, k, x, sc, ush);
+        }
+#pragma unroll
+        for (int q = 0; q < D; q++) xcur[s][(size_t)q * Npad + k] = x[q];
+        const double lw = Model::logw(c, x, y);
+        Lk[s][k] = lw;
+        m[s] = fmax(m[s], lw);
+      }
+    }
+    __syncthreads();
+    // ---- weights and log Z increment (R/CPF.R:61-63,66)
+    for (int s = 0; s < nsys; s++) {
+      const double ms = block_max(m[s], sm.dscr);
+      double sum = 0.0;
+      for (int k = tid; k < N; k += NT) { const double w = exp(Lk[s][k] - ms); Wk[s][k] = w; sum += w; }
+      ssum[s] = block_sum(sum, sm.dscr);
+      if (s == 0) logz_sum += log(ssum[0] / (double)N) + ms;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- path selection: R/CPF.R:69 (one system) / R/CPF_coupled.R:101-106 (one index-matching draw)
+  if (st) atomicOr(&sm.iscr[32], st);
+  for (int s = 0; s < nsys; s++)
+    for (int k = tid; k < N; k += NT) Wk[s][k] = Wk[s][k] / ssum[s];
+  __syncthreads();
+  double ua, ub;
+  philox_u2(stream, 0, T + 1, CPIMH_P_PATH, 0, ua, ub);
+  int kidx[2] = {0, 0};
+  if (nsys == 1) {
+    block_scan_inplace<false>(sm.C1, N, sm.dscr);
+    kidx[0] = clampN(count_lt(sm.C1, N, ua), N);
+  } else {
+    im_single_draw(sm.C1, sm.C2, N, ua, ub, sm.dscr, kidx[0], kidx[1]);
+  }
+  const int flags = sm.iscr[32];
+  if (tid == 0) {
+    p.logz[slot] = logz_sum;
+    if (p.path_index) { p.path_index[2 * slot] = kidx[0]; p.path_index[2 * slot + 1] = nsys == 2 ? kidx[1] : -1; }
+    p.status[slot] = flags & 255;
+  }
+  if (tid < 32) {                                      // Tree$get_path: one warp walks the ancestor rows, lane q carries component q
+    for (int s = 0; s < nsys; s++) {
+      double* tr = (s == 0 ? p.traj1 : p.traj2) + (size_t)slot * (T + 1) * D;
+      int j = kidx[s];
+      for (int step = T; step >= 0; step--) {
+        for (int q = tid; q < D; q += 32) tr[(size_t)step * D + q] = hx[s][(size_t)step * xstride + (size_t)q * Npad + j];
+        if (step > 0) j = ha[s][(size_t)(step - 1) * Npad + j];
+      }
+    }
+  }
+  if (p.anc_rec)
+    for (int s = 0; s < nsys; s++)
+      for (int t = 0; t < T; t++)
+        for (int k = tid; k < N; k += NT) p.anc_rec[(((size_t)slot * 2 + s) * T + t) * N + k] = ha[s][(size_t)t * Npad + k];
+  __syncthreads();
+}
+
+template <class Model>
+__global__ void __launch_bounds__(512, 1) ccpf_kernel(CcpfParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CcpfSmem sm = ccpf_carve(smem_raw, p.Npad, p.npre);
+  for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
+  for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
+  __syncthreads();
+  for (long long b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const long long slot = p.slot ? p.slot[b] : b;
+    const int nsys = p.single ? (p.single[slot] ? 1 : 2) : p.nsys;
+    const Stream s = make_stream(p.seed, p.stream_ids ? p.stream_ids[b] : p.first_filter + (unsigned long long)b);
+    run_ccpf<Model>(p, sm, blockIdx.x, s, b, nsys, slot);
+  }
+}
+
+struct CcpfLaunch { int grid, threads; size_t smem; };
+template <class Model>
+int launch_ccpf(const CcpfParams& p, const CcpfLaunch& L, cudaStream_t stream) {
+  if (p.with_as && !Model::HAS_DTRANS) { set_error("ancestor sampling needs model$dtransition: defined for get_gss and get_ar only"); return CPIMH_ERR_INVALID; }
+  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(ccpf_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  ccpf_kernel<Model><<<L.grid, L.threads, L.smem, stream>>>(p);
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  return CPIMH_OK;
+}
+template <class Model>
+int occupancy_ccpf(int threads, size_t smem, int* blocks_per_sm) {
+  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(ccpf_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CPIMH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ccpf_kernel<Model>, threads, smem));
+  return CPIMH_OK;
+}
+
+}  // namespace cpimh

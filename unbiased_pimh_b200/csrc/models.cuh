@@ -38,6 +38,13 @@ struct GssModel {
   static constexpr bool USES_SHARED_U = false;
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = false;
+  static constexpr bool HAS_DTRANS = true;
+  // dtransition(next_x, xparticles, theta, time): R/model_get_gss.R:30-33
+  __device__ static double dtrans(const ModelCtx&, const double* next, const double* x, int, double drift) {
+    const double xi = x[0];
+    const double means = 0.5 * xi + 25.0 * xi / (1.0 + xi * xi) + drift;
+    return dnorm_log(next[0], means, 1.0);
+  }
   __device__ static double step_const(const ModelCtx&, int t) { return 8.0 * cos(1.2 * (double)(t - 1)); }
   __device__ static void init(const ModelCtx& c, int i, double* x) {
     double z;
@@ -66,6 +73,20 @@ struct ArModel {
   static constexpr bool USES_SHARED_U = false;   // pre = A (column-major, D*D) then cst
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = false;
+  static constexpr bool HAS_DTRANS = true;
+  // dtransition = dmvnorm_transpose_cholesky(A x, next_x, I): R/model_get_ar.R:28-30, src/mvnorm.cpp:113-132
+  __device__ static double dtrans(const ModelCtx& c, const double* next, const double* x, int, double) {
+    double sq = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; r++) {
+      double s = 0.0;
+#pragma unroll
+      for (int l = 0; l < D; l++) s += c.pre[r + l * D] * x[l];
+      const double e = s - next[r];
+      sq += e * e;
+    }
+    return -0.5 * sq + (-0.0 - (double)D * 0.9189385);
+  }
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll
@@ -128,6 +149,7 @@ struct LevySvModel {
   static constexpr bool USES_SHARED_U = true;
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = true;      // pf_fused.cuh walks the Poisson jumps of a thread's particles as one list
+  static constexpr bool HAS_DTRANS = false;
   __device__ static __forceinline__ int token(const ModelCtx& c, double upois) { return poisson_tab(c.pre, upois); }
   __device__ static double step_const(const ModelCtx& c, int) { return c.pre[0]; }
   // one jump of the compound Poisson process (src/SVLevy_functions.cpp:62-67): c' = t - c ~ U(0,1), e ~ Exp(rate xi/w2)
@@ -207,6 +229,7 @@ struct SkModel {
   static constexpr bool USES_SHARED_U = false;
   static constexpr bool MULTI = true;
   static constexpr bool JUMP_LIST = false;
+  static constexpr bool HAS_DTRANS = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void init(const ModelCtx&, int, double* x) { x[0] = 8.0; x[1] = 8.0; x[2] = 8.0; x[3] = 5.0; }
   __device__ static __forceinline__ double hazards(const double* x, double* h) {      // R/model_stochastic_kinetic.R:27-40
@@ -390,6 +413,7 @@ struct LorenzModel {
   static constexpr bool USES_SHARED_U = false;   // pre[0] = cst of the measurement density
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = false;
+  static constexpr bool HAS_DTRANS = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll

@@ -2,6 +2,7 @@
 #pragma once
 #include "pf_fused.cuh"
 #include "chains.cuh"
+#include "ccpf.cuh"
 
 namespace cpimh {
 
@@ -13,6 +14,8 @@ struct ModelEntry {
   int (*launch_chains)(const ChainParams&, const PfLaunch&, cudaStream_t);
   int (*occupancy_chains)(int variant, int threads, size_t smem, int* blocks_per_sm);
   int (*launch_model_op)(const ModelOpParams&, cudaStream_t);
+  int (*launch_ccpf)(const CcpfParams&, const CcpfLaunch&, cudaStream_t);
+  int (*occupancy_ccpf)(int threads, size_t smem, int* blocks_per_sm);
 };
 template <class Model>
 ModelEntry make_entry(int model) {
@@ -23,6 +26,8 @@ ModelEntry make_entry(int model) {
   e.launch_chains = &launch_chains<Model>;
   e.occupancy_chains = &occupancy_chains<Model>;
   e.launch_model_op = &launch_model_op<Model>;
+  e.launch_ccpf = &launch_ccpf<Model>;
+  e.occupancy_ccpf = &occupancy_ccpf<Model>;
   return e;
 }
 const ModelEntry* entries_gss(int* n);

@@ -148,10 +148,13 @@ def cpf_batch(nparticles, model, theta, observations, nfilters, seed=None, first
 def CPF(nparticles, model, theta, observations, ref_trajectory=None, with_as=False, all_particles=False, seed=None, filter_id=0, noise=None, **kw):
     """CPF(nparticles, model, theta, observations, ref_trajectory = NULL, with_as = FALSE, all_particles = FALSE)
     -- R/CPF.R:14-78.  Returns {"trajectory": d x (T+1), "logz": float [, "exp_path": d x (T+1)]}."""
-    if ref_trajectory is not None or with_as:
-        raise NotImplementedError("conditional particle filtering (ref_trajectory / with_as) is outside the PIMH hot path "
-                                  "(SURVEY 8f rank 1); every PIMH kernel calls CPF with ref_trajectory = NULL")
     seed = rng.next_seed() if seed is None else int(seed)
+    if ref_trajectory is not None:
+        if all_particles:
+            raise NotImplementedError("all_particles = TRUE is wired for the bootstrap filter (ref_trajectory = NULL) only")
+        r = ccpf_batch(nparticles, model, theta, observations, [ref_trajectory], with_as=with_as, seed=seed, first_filter=filter_id, noise=noise, **kw)
+        return {"trajectory": np.ascontiguousarray(r["trajectory1"][0]), "logz": float(r["logz"][0])}
+    # with_as without a reference trajectory has no effect in the reference either (R/CPF.R:45)
     if not all_particles:
         r = cpf_batch(nparticles, model, theta, observations, 1, seed=seed, first_filter=filter_id, noise=noise, **kw)
         return {"trajectory": np.ascontiguousarray(r["trajectory"][0]), "logz": float(r["logz"][0])}
@@ -165,6 +168,49 @@ def CPF(nparticles, model, theta, observations, ref_trajectory=None, with_as=Fal
     finally:
         pb.close()
     return {"trajectory": np.ascontiguousarray(r["trajectory"][0]), "exp_path": ap["exp_path"], "logz": float(r["logz"][0])}
+
+
+def ccpf_batch(nparticles, model, theta, observations, ref1, ref2=None, with_as=False, seed=None, first_filter=0, noise=None,
+               ancestors=False, **kw):
+    """B conditional particle filters (cpimh_ccpf_batch).  ref1 / ref2: (B, d, T+1) reference trajectories; ref2 = None runs
+    CPF(ref_trajectory = ref1[b], with_as) (R/CPF.R:14-78), otherwise CPF_coupled(ref1[b], ref2[b], CR_indexmatching, with_as)
+    (R/CPF_coupled.R:14-112).  Filter b uses Philox stream first_filter + b for both systems."""
+    obs = np.asarray(observations, dtype=np.float64)
+    T = obs.shape[0]
+    cfg = model.config(nparticles, theta, nobs=T, **kw)
+    ob = L.obs_matrix(obs, T)
+    d, N = model.dimension, int(nparticles)
+    r1 = np.ascontiguousarray(np.asarray(ref1, dtype=np.float64).reshape(-1, d, T + 1).transpose(0, 2, 1))     # (B, T+1, d) = d x (T+1) col-major
+    B = r1.shape[0]
+    nsys = 1 if ref2 is None else 2
+    r2 = np.ascontiguousarray(np.asarray(ref2, dtype=np.float64).reshape(-1, d, T + 1).transpose(0, 2, 1)) if nsys == 2 else None
+    if nsys == 2 and r2.shape != r1.shape:
+        raise ValueError("ref1 and ref2 must have the same shape")
+    t1 = np.empty((B, T + 1, d)); t2 = np.empty((B, T + 1, d)) if nsys == 2 else None
+    logz = np.empty(B); pidx = np.empty((B, 2), dtype=np.int32)
+    anc = np.empty((B, 2, T, N), dtype=np.int32) if ancestors else None
+    nz, keep = L.make_noise(noise)
+    seed = rng.next_seed() if seed is None else int(seed)
+    L.check(L.lib().cpimh_ccpf_batch(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_int64(B), C.c_uint64(seed), C.c_uint64(int(first_filter)),
+                                      C.c_int(nsys), C.c_int(int(bool(with_as))), L.ptr(r1), L.ptr(r2), C.byref(nz) if noise else None,
+                                      L.ptr(t1), L.ptr(t2), L.ptr(logz), L.ptr(pidx), L.ptr(anc)))
+    out = {"trajectory1": t1.transpose(0, 2, 1), "logz": logz, "path_index": pidx}
+    if nsys == 2:
+        out["trajectory2"] = t2.transpose(0, 2, 1)
+    if ancestors:
+        out["ancestors"] = anc
+    return out
+
+
+def CPF_coupled(nparticles, model, theta, observations, ref_trajectory1, ref_trajectory2, coupled_resampling=None, with_as=False,
+                seed=None, filter_id=0, noise=None, **kw):
+    """CPF_coupled(nparticles, model, theta, observations, ref_trajectory1, ref_trajectory2, coupled_resampling, with_as)
+    -- R/CPF_coupled.R:14-112.  The coupled resampling scheme is index matching (what get_cpf_kernels passes,
+    R/pf_kernels.R:238), fused into the kernel; `coupled_resampling` is accepted for signature compatibility.
+    Returns {"new_trajectory1", "new_trajectory2"}: d x (T+1) each."""
+    r = ccpf_batch(nparticles, model, theta, observations, [ref_trajectory1], [ref_trajectory2], with_as=with_as, seed=seed,
+                   first_filter=filter_id, noise=noise, **kw)
+    return {"new_trajectory1": np.ascontiguousarray(r["trajectory1"][0]), "new_trajectory2": np.ascontiguousarray(r["trajectory2"][0])}
 
 
 def particlefilter(nparticles, model, theta, observations, seed=None, filter_id=0, noise=None, **kw):

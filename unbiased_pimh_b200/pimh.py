@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib as L
 from . import rng
-from .filters import CPF
+from .filters import CPF, CPF_coupled
 
 
 # ---------------------------------------------------------------------------------------------- R-shaped API
@@ -166,6 +166,80 @@ def BC(c_chains, h=lambda x: x, k=0, K=1):
             coef = min(t - k + 1, K - k + 1)
             dterm = dterm + coef * (np.atleast_1d(h(s1[t + 1])) - np.atleast_1d(h(s2[t])))
     return dterm if not math.isfinite(K) else dterm / (K - k + 1)
+
+
+# ---------------------------------------------------------------------------------------------- conditional-filter chains
+def get_cpf_kernels(with_as=False, model=None, theta=None, observations=None):
+    """get_cpf_kernels(with_as) -- R/pf_kernels.R:236-265.  As for get_pimh_kernels, the R closures capture `model`, `theta`
+    and `observations` from the calling environment; here they are passed.  Returns single_kernel / coupled_kernel."""
+    def single_kernel(chain_state, log_pdf_state, iter, nparticles):
+        r = CPF(nparticles, model, theta, observations, ref_trajectory=chain_state, with_as=with_as)
+        return {"chain_state": r["trajectory"], "log_pdf_state": r["logz"]}
+
+    def coupled_kernel(chain_state1, chain_state2, log_pdf_state1, log_pdf_state2, iter, nparticles):
+        r = CPF_coupled(nparticles, model, theta, observations, chain_state1, chain_state2, with_as=with_as)
+        return {"chain_state1": r["new_trajectory1"], "chain_state2": r["new_trajectory2"],
+                "log_pdf_state1": log_pdf_state1, "log_pdf_state2": log_pdf_state2}
+
+    return {"single_kernel": single_kernel, "coupled_kernel": coupled_kernel}
+
+
+def coupled_ccpf_chains(single_kernel, coupled_kernel, pimh_init, N, K=1, max_iterations=math.inf, preallocate=10, verbose=False):
+    """coupled_ccpf_chains(single_kernel, coupled_kernel, pimh_init, N, K, max_iterations) -- R/debiasing_algorithm.R:23-111.
+    Chain 1 is moved once by the single kernel, then both chains by the coupled kernel until they meet (X_t == Y_{t-1})."""
+    init = pimh_init(N)
+    chain_state1, chain_state2 = init["chain_state1"], init["chain_state2"]
+    log_pdf_state1, log_pdf_state2 = init["log_pdf_state1"], init["log_pdf_state2"]
+    samples1, samples2 = [np.array(chain_state1[0, :])], [np.array(chain_state2[0, :])]
+    log_pdf1, log_pdf2 = [log_pdf_state1], [log_pdf_state2]
+    it = 1
+    mh = single_kernel(chain_state1, log_pdf_state1, it, N)
+    chain_state1, log_pdf_state1 = mh["chain_state"], mh["log_pdf_state"]
+    samples1.append(np.array(chain_state1[0, :])); log_pdf1.append(log_pdf_state1)
+    meet, finished, meetingtime = False, False, math.inf
+    while not finished and it < max_iterations:
+        it += 1
+        if meet:
+            mh = single_kernel(chain_state1, log_pdf_state1, it, N)
+            chain_state1 = chain_state2 = mh["chain_state"]
+            log_pdf_state1 = log_pdf_state2 = mh["log_pdf_state"]
+        else:
+            mh = coupled_kernel(chain_state1, chain_state2, log_pdf_state1, log_pdf_state2, it, N)
+            chain_state1, chain_state2 = mh["chain_state1"], mh["chain_state2"]
+            log_pdf_state1, log_pdf_state2 = mh["log_pdf_state1"], mh["log_pdf_state2"]
+            if np.array_equal(chain_state1, chain_state2) and not meet:
+                meet, meetingtime = True, it
+        samples1.append(np.array(chain_state1[0, :])); samples2.append(np.array(chain_state2[0, :]))
+        log_pdf1.append(log_pdf_state1); log_pdf2.append(log_pdf_state2)
+        if it >= max(meetingtime, K):
+            finished = True
+    # samples2 holds iteration rows: the initial state and one row per loop iteration but the last is aligned as in R
+    return {"samples1": np.array(samples1), "samples2": np.array(samples2[:it]), "log_pdf1": np.array(log_pdf1).reshape(-1, 1),
+            "log_pdf2": np.array(log_pdf2[:it]).reshape(-1, 1), "meetingtime": meetingtime, "iteration": it, "finished": finished}
+
+
+def coupled_ccpf_chains_batch(model, theta, observations, nparticles, nreplicates, K=1, k=0, max_iterations=math.inf, with_as=False,
+                              seed=None, first_replicate=0, **kw):
+    """R replicates of coupled_ccpf_chains(get_cpf_kernels(with_as), pimh_init, N = nparticles, K) + H_bar(., k, K) + BC on the
+    GPU (cpimh_coupled_ccpf): all replicates advance together, one launch of conditional filters per iteration.
+    Returns hbar / bc (R, d, T+1), meetingtime (R,) [-1: not met within max_iterations], iteration (R,), sums, nfilters."""
+    obs = np.asarray(observations, dtype=np.float64)
+    T = obs.shape[0]
+    cfg = model.config(nparticles, theta, nobs=T, **kw)
+    ob = L.obs_matrix(obs, T)
+    R, d, P = int(nreplicates), model.dimension, T + 1
+    seed = rng.next_seed() if seed is None else int(seed)
+    mi = -1 if (max_iterations is None or max_iterations == math.inf or max_iterations < 0) else int(max_iterations)
+    hb, bcv = np.empty((R, P, d)), np.empty((R, P, d))
+    mt, it = np.empty(R, dtype=np.int32), np.empty(R, dtype=np.int32)
+    s, s2, nf = np.empty((P, d)), np.empty((P, d)), np.zeros(1, dtype=np.int64)
+    o = L.ChainOut()
+    o.hbar, o.bc, o.meetingtime, o.iteration = hb.ctypes.data, bcv.ctypes.data, mt.ctypes.data, it.ctypes.data
+    o.sum_hbar, o.sum_hbar_sq, o.nfilters = s.ctypes.data, s2.ctypes.data, nf.ctypes.data
+    L.check(L.lib().cpimh_coupled_ccpf(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_int64(R), C.c_uint64(seed), C.c_uint32(int(first_replicate)),
+                                        C.c_int(int(k)), C.c_int(int(K)), C.c_int(mi), C.c_int(int(bool(with_as))), C.byref(o)))
+    return {"hbar": hb.transpose(0, 2, 1), "bc": bcv.transpose(0, 2, 1), "meetingtime": mt, "iteration": it,
+            "sum_hbar": s.T.copy(), "sum_hbar_sq": s2.T.copy(), "nfilters": int(nf[0])}
 
 
 # ---------------------------------------------------------------------------------------------- batched GPU twins
