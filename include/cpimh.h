@@ -136,6 +136,7 @@ int cpimh_pf_record_ancestors(cpimh_pf* h, int on);
 int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ancestors);
 /* device pointers of the resident outputs (valid until destroy): logz [B], trajectory [B][T+1][d] */
 int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory);
+int cpimh_pf_device_exp_paths(cpimh_pf* h, double** d_exp_path);   /* [B][T+1][d]; after cpimh_pf_all_particles(h, 1) */
 int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status);   /* [B] per-filter status of the last run (0 = ok) */
 /* kernels launched by this handle so far (bench.py's gpu_launches) and bytes of HBM it holds */
 int64_t cpimh_pf_launch_count(const cpimh_pf* h);
@@ -202,11 +203,16 @@ int64_t cpimh_chains_filters_launched(const cpimh_chains* h);   /* including dis
  * path_index [B][2]; ancestors [B][2][T][N] 0-based (nullable).  noise: init / trans arrays only (nullable). */
 int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nfilters, uint64_t seed, uint64_t first_filter,
                      int nsys, int with_as, const double* ref1_host, const double* ref2_host, const cpimh_noise* noise,
-                     double* traj1, double* traj2, double* logz, int32_t* path_index, int32_t* ancestors);
+                     double* traj1, double* traj2, double* logz, int32_t* path_index, int32_t* ancestors,
+                     double* exp_path1, double* exp_path2 /* CPF_RB / CPF_RB_coupled estimates with test_function = identity
+                                                             (R/rheeglynn_estimator_RB.R:2-167): [B] x (d x (T+1)), nullable */);
 /* coupled_ccpf_chains(single_kernel, coupled_kernel, pimh_init, N, K, max_iterations) with get_cpf_kernels(with_as) and
  * pimh_init of get_pimh_kernels, + H_bar(c_chains, k, K) and BC -- R/debiasing_algorithm.R:23-111, R/pf_kernels.R:236-265,134-145.
  * R replicates advance together, one launch of conditional filters per iteration; replicate r uses stream id
- * first_replicate + r with the iteration index in counter word 1 (0 and 0xFFF: the two initial bootstrap filters). */
+ * first_replicate + r with the iteration index in counter word 1 (0 and 0xFFF: the two initial bootstrap filters).
+ * Requesting hbar_rb / sum_hbar_rb* also carries every filter's weighted average of all N paths through the chains:
+ * with k = K = 0 that is rheeglynn_estimator_RB, with k = K = m rheeglynn_estimator_RB2 (R/rheeglynn_estimator_RB.R:170-265);
+ * k = K = 0 without it is rheeglynn_estimator with lambda = 0 (R/rheeglynn_estimator.R:14-66). */
 int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, int with_as, cpimh_chain_out* out_host);
 

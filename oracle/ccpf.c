@@ -203,6 +203,17 @@ int orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise, u
     for (int s = 0; s < nsys; s++) {
       orc_tree_get_path(tree[s], k[s], out->trajectory[s]);
       out->path_index[s] = k[s];
+      if (out->exp_path[s]) {                        /* CPF_RB / CPF_RB_coupled with test_function = identity (R/rheeglynn_estimator_RB.R:50-56) */
+        size_t psz = (size_t)d * (T + 1);
+        double* path = (double*)malloc(sizeof(double) * psz);
+        long double* acc = (long double*)calloc(psz, sizeof(long double));
+        for (int n = 0; n < N; n++) {
+          orc_tree_get_path(tree[s], n, path);
+          for (size_t e = 0; e < psz; e++) acc[e] += normw[s][n] * path[e];
+        }
+        for (size_t e = 0; e < psz; e++) out->exp_path[s][e] = (double)acc[e];
+        free(path); free(acc);
+      }
     }
     long double sum = 0;
     for (int t = 0; t < T; t++) sum += lzt[t];
@@ -222,11 +233,19 @@ done:
  * and the initial states of pimh_init (R/pf_kernels.R:134-145: two independent bootstrap filters) ---- */
 int orc_coupled_ccpf_chains(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
                             int K, int max_iterations, int with_as, orc_chains* out) {
+  return orc_coupled_ccpf_chains_rb(cfg, obs, seed, replicate, K, max_iterations, with_as, 0, out);
+}
+/* rb != 0: also record the weighted average of all N paths of every filter (exp_samples1/2): the Rao-Blackwellised
+ * chains of rheeglynn_estimator_RB / RB2 (R/rheeglynn_estimator_RB.R:170-265) with test_function = identity */
+int orc_coupled_ccpf_chains_rb(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
+                               int K, int max_iterations, int with_as, int rb, orc_chains* out) {
   const int d = cfg->dim, p = cfg->nobs + 1;
   const size_t psz = (size_t)d * p;
   double *s1 = (double*)malloc(sizeof(double) * psz), *s2 = (double*)malloc(sizeof(double) * psz);
   double *n1 = (double*)malloc(sizeof(double) * psz), *n2 = (double*)malloc(sizeof(double) * psz);
   double* lzt = (double*)malloc(sizeof(double) * (size_t)cfg->nobs);
+  double *e1 = (double*)calloc(psz, sizeof(double)), *e2 = (double*)calloc(psz, sizeof(double));
+  double *ne1 = (double*)calloc(psz, sizeof(double)), *ne2 = (double*)calloc(psz, sizeof(double));
   int cap = K + 10 + 1, nf = 0, rc = 0;
   double lz1 = 0, lz2 = 0;
   memset(out, 0, sizeof(*out));
@@ -235,21 +254,29 @@ int orc_coupled_ccpf_chains(const orc_config* cfg, const double* obs, uint64_t s
   out->samples2 = (double*)malloc(sizeof(double) * (size_t)cap * p);
   out->log_pdf1 = (double*)malloc(sizeof(double) * (size_t)cap);
   out->log_pdf2 = (double*)malloc(sizeof(double) * (size_t)cap);
+  if (rb) {
+    out->exp_samples1 = (double*)malloc(sizeof(double) * (size_t)cap * p);
+    out->exp_samples2 = (double*)malloc(sizeof(double) * (size_t)cap * p);
+  }
   orc_pf_out o; memset(&o, 0, sizeof(o));
   o.logz_t = lzt;
-  o.trajectory = s1; o.logz = &lz1;
+  o.trajectory = s1; o.logz = &lz1; o.exp_path = rb ? e1 : NULL;
   rc = orc_cpf(cfg, obs, NULL, seed, (uint64_t)replicate, &o); nf++;                               /* pimh_init: chain_state1 */
-  o.trajectory = s2; o.logz = &lz2;
+  o.trajectory = s2; o.logz = &lz2; o.exp_path = rb ? e2 : NULL;
   if (!rc) { rc = orc_cpf(cfg, obs, NULL, seed, (uint64_t)replicate | ((uint64_t)0xFFF << 32), &o); nf++; }   /* chain_state2 */
   if (rc) goto fail;
   for (int t = 0; t < p; t++) { out->samples1[t] = s1[(size_t)t * d]; out->samples2[t] = s2[(size_t)t * d]; }   /* :42-43 */
   out->log_pdf1[0] = lz1; out->log_pdf2[0] = lz2;
+  if (rb) for (int t = 0; t < p; t++) { out->exp_samples1[t] = e1[(size_t)t * d]; out->exp_samples2[t] = e2[(size_t)t * d]; }
   orc_ccpf_out co;
   int iter = 1, meet = 0, finished = 0, meetingtime = -1;
   memset(&co, 0, sizeof(co)); co.trajectory[0] = n1; co.trajectory[1] = n2;
+  if (rb) { co.exp_path[0] = ne1; co.exp_path[1] = ne2; }
   rc = orc_ccpf(cfg, obs, NULL, seed, (uint64_t)replicate | ((uint64_t)iter << 32), 1, s1, NULL, with_as, &co); nf++;   /* :50-52 */
   if (rc) goto fail;
   memcpy(s1, n1, sizeof(double) * psz); lz1 = co.logz;
+  memcpy(e1, ne1, sizeof(double) * psz);
+  if (rb) for (int t = 0; t < p; t++) out->exp_samples1[(size_t)p + t] = e1[(size_t)t * d];
   for (int t = 0; t < p; t++) out->samples1[(size_t)p + t] = s1[(size_t)t * d];                    /* :56-58 */
   out->log_pdf1[1] = lz1;
   while (!finished && (max_iterations < 0 || iter < max_iterations)) {                             /* :63 */
@@ -258,11 +285,13 @@ int orc_coupled_ccpf_chains(const orc_config* cfg, const double* obs, uint64_t s
       rc = orc_ccpf(cfg, obs, NULL, seed, (uint64_t)replicate | ((uint64_t)iter << 32), 1, s1, NULL, with_as, &co); nf++;
       if (rc) goto fail;
       memcpy(s1, n1, sizeof(double) * psz); memcpy(s2, n1, sizeof(double) * psz);
+      memcpy(e1, ne1, sizeof(double) * psz); memcpy(e2, ne1, sizeof(double) * psz);
       lz1 = lz2 = co.logz;
     } else {                                                                                       /* :75-87 */
       rc = orc_ccpf(cfg, obs, NULL, seed, (uint64_t)replicate | ((uint64_t)iter << 32), 2, s1, s2, with_as, &co); nf++;
       if (rc) goto fail;
       memcpy(s1, n1, sizeof(double) * psz); memcpy(s2, n2, sizeof(double) * psz);                  /* log_pdf states unchanged */
+      memcpy(e1, ne1, sizeof(double) * psz); memcpy(e2, ne2, sizeof(double) * psz);
       if (memcmp(s1, s2, sizeof(double) * psz) == 0) { meet = 1; meetingtime = iter; }
     }
     if (iter + 1 > cap) {
@@ -271,6 +300,14 @@ int orc_coupled_ccpf_chains(const orc_config* cfg, const double* obs, uint64_t s
       out->samples2 = (double*)realloc(out->samples2, sizeof(double) * (size_t)cap * p);
       out->log_pdf1 = (double*)realloc(out->log_pdf1, sizeof(double) * (size_t)cap);
       out->log_pdf2 = (double*)realloc(out->log_pdf2, sizeof(double) * (size_t)cap);
+      if (rb) {
+        out->exp_samples1 = (double*)realloc(out->exp_samples1, sizeof(double) * (size_t)cap * p);
+        out->exp_samples2 = (double*)realloc(out->exp_samples2, sizeof(double) * (size_t)cap * p);
+      }
+    }
+    if (rb) for (int t = 0; t < p; t++) {
+      out->exp_samples1[(size_t)iter * p + t] = e1[(size_t)t * d];
+      out->exp_samples2[(size_t)(iter - 1) * p + t] = e2[(size_t)t * d];
     }
     for (int t = 0; t < p; t++) {                                                                  /* :98-99 */
       out->samples1[(size_t)iter * p + t] = s1[(size_t)t * d];
@@ -282,13 +319,13 @@ int orc_coupled_ccpf_chains(const orc_config* cfg, const double* obs, uint64_t s
   }
   out->iteration = iter; out->meetingtime = meetingtime; out->finished = finished; out->nrows1 = iter + 1; out->nfilters = nf;
 fail:
-  free(s1); free(s2); free(n1); free(n2); free(lzt);
+  free(s1); free(s2); free(n1); free(n2); free(lzt); free(e1); free(e2); free(ne1); free(ne2);
   return rc;
 }
 
 int orc_coupled_ccpf_batch(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t first_replicate, int nrep,
                            int k, int K, int max_iterations, int with_as, int nthreads,
-                           double* hbar, int* meetingtime, int* iterations, long long* nfilters_total) {
+                           double* hbar, double* hbar_rb, int* meetingtime, int* iterations, long long* nfilters_total) {
   int rc = 0; long long nf = 0; int p = cfg->nobs + 1;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -296,9 +333,10 @@ int orc_coupled_ccpf_batch(const orc_config* cfg, const double* obs, uint64_t se
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nf)
   for (int r = 0; r < nrep; r++) {
     orc_chains c;
-    int e = orc_coupled_ccpf_chains(cfg, obs, seed, first_replicate + (uint32_t)r, K, max_iterations, with_as, &c);
+    int e = orc_coupled_ccpf_chains_rb(cfg, obs, seed, first_replicate + (uint32_t)r, K, max_iterations, with_as, hbar_rb != NULL, &c);
     if (!e) {
       if (hbar) orc_H_bar(&c, k, K, hbar + (size_t)r * p);
+      if (hbar_rb) orc_H_bar_exp(&c, k, K, hbar_rb + (size_t)r * p);
       if (meetingtime) meetingtime[r] = c.meetingtime;
       if (iterations) iterations[r] = c.iteration;
       nf += c.nfilters;

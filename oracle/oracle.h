@@ -166,6 +166,7 @@ int  orc_coupled_pimh_batch(const orc_config* cfg, const double* obs, uint64_t s
  *      get_cpf_kernels R/pf_kernels.R:236-265 ; coupled_ccpf_chains R/debiasing_algorithm.R:23-111 ---- */
 typedef struct orc_ccpf_out {
   double* trajectory[2];  /* d x (T+1) each; [1] used when nsys == 2            */
+  double* exp_path[2];    /* d x (T+1) weighted average of all N paths (nullable) */
   int*    ancestors[2];   /* [T][N] 0-based (nullable)                          */
   int     path_index[2];
   double  logz;           /* system 1's sum of log Z increments                 */
@@ -177,9 +178,12 @@ int  orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise /
               int nsys, const double* ref1, const double* ref2 /* d x (T+1) */, int with_as, orc_ccpf_out* out);
 int  orc_coupled_ccpf_chains(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
                              int K, int max_iterations, int with_as, orc_chains* out);
+int  orc_coupled_ccpf_chains_rb(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t replicate,
+                                int K, int max_iterations, int with_as, int rb, orc_chains* out);
 int  orc_coupled_ccpf_batch(const orc_config* cfg, const double* obs, uint64_t seed, uint32_t first_replicate, int nrep,
                             int k, int K, int max_iterations, int with_as, int nthreads,
-                            double* hbar /* [nrep][p] */, int* meetingtime, int* iterations, long long* nfilters_total);
+                            double* hbar /* [nrep][p] */, double* hbar_rb /* [nrep][p], nullable */, int* meetingtime, int* iterations,
+                            long long* nfilters_total);
 
 const char* orc_version(void);
 

@@ -407,11 +407,11 @@ def coupled_pimh_batch(cfg, obs, seed, first_replicate, nrep, k=0, K=1, max_iter
 
 # ---------------------------------------------------------------- conditional filters
 class CcpfOut(C.Structure):
-    _fields_ = [("trajectory", C.c_void_p * 2), ("ancestors", C.c_void_p * 2), ("path_index", C.c_int * 2), ("logz", C.c_double),
+    _fields_ = [("trajectory", C.c_void_p * 2), ("exp_path", C.c_void_p * 2), ("ancestors", C.c_void_p * 2), ("path_index", C.c_int * 2), ("logz", C.c_double),
                 ("clamp_count", C.c_int)]
 
 
-def ccpf(cfg, obs, ref1, ref2=None, with_as=False, seed=0, filter_id=0, noise=None, want_ancestors=False):
+def ccpf(cfg, obs, ref1, ref2=None, with_as=False, seed=0, filter_id=0, noise=None, want_ancestors=False, exp_path=False):
     """CPF(..., ref_trajectory = ref1, with_as) when ref2 is None, else CPF_coupled(..., ref1, ref2, CR_indexmatching, with_as).
     refs and returned trajectories are d x (T+1)."""
     T, d, N = cfg.nobs, cfg.dim, cfg.nparticles
@@ -419,6 +419,7 @@ def ccpf(cfg, obs, ref1, ref2=None, with_as=False, seed=0, filter_id=0, noise=No
     nsys = 1 if ref2 is None else 2
     refs = [np.asfortranarray(np.asarray(r, dtype=np.float64).reshape(d, T + 1)) for r in ([ref1] if nsys == 1 else [ref1, ref2])]
     tr = [np.empty((d, T + 1), order="F") for _ in range(2)]
+    ep = [np.empty((d, T + 1), order="F") for _ in range(2)]
     anc = [np.empty((T, N), dtype=np.int32) for _ in range(2)] if want_ancestors else None
     nz = Noise(); keep = []
     if noise:
@@ -428,6 +429,7 @@ def ccpf(cfg, obs, ref1, ref2=None, with_as=False, seed=0, filter_id=0, noise=No
     o = CcpfOut()
     for s_ in range(2):
         o.trajectory[s_] = tr[s_].ctypes.data
+        o.exp_path[s_] = ep[s_].ctypes.data if exp_path else None
         o.ancestors[s_] = anc[s_].ctypes.data if want_ancestors else None
     lib().orc_ccpf.restype = C.c_int
     rc = lib().orc_ccpf(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.byref(nz) if noise else None, C.c_uint64(seed), C.c_uint64(filter_id),
@@ -439,6 +441,10 @@ def ccpf(cfg, obs, ref1, ref2=None, with_as=False, seed=0, filter_id=0, noise=No
                clamp_count=int(o.clamp_count))
     if nsys == 2:
         res["trajectory2"] = np.ascontiguousarray(tr[1])
+    if exp_path:
+        res["exp_path1"] = np.ascontiguousarray(ep[0])
+        if nsys == 2:
+            res["exp_path2"] = np.ascontiguousarray(ep[1])
     if want_ancestors:
         res["ancestors1"] = anc[0]
         if nsys == 2:
@@ -476,13 +482,17 @@ def coupled_ccpf_chains(cfg, obs, seed, replicate, K=1, max_iterations=-1, with_
     return out
 
 
-def coupled_ccpf_batch(cfg, obs, seed, first_replicate, nrep, k=0, K=1, max_iterations=-1, with_as=False, nthreads=0):
+def coupled_ccpf_batch(cfg, obs, seed, first_replicate, nrep, k=0, K=1, max_iterations=-1, with_as=False, nthreads=0, rb=False):
     T = cfg.nobs; p = T + 1
     ob = np.asfortranarray(np.asarray(obs, dtype=np.float64).reshape(T, -1))
     hbar = np.empty((nrep, p)); mt = np.empty(nrep, dtype=np.int32); it = np.empty(nrep, dtype=np.int32); nf = C.c_longlong(0)
+    hrb = np.empty((nrep, p)) if rb else None
     rc = lib().orc_coupled_ccpf_batch(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_uint64(seed), C.c_uint32(first_replicate), C.c_int(nrep),
                                       C.c_int(k), C.c_int(K), C.c_int(max_iterations), C.c_int(int(with_as)), C.c_int(nthreads),
-                                      _p(hbar), _p(mt), _p(it), C.byref(nf))
+                                      _p(hbar), _p(hrb), _p(mt), _p(it), C.byref(nf))
     if rc:
         raise RuntimeError("oracle coupled_ccpf_batch failed (%d)" % rc)
-    return dict(hbar=hbar, meetingtime=mt, iteration=it, nfilters=nf.value)
+    out = dict(hbar=hbar, meetingtime=mt, iteration=it, nfilters=nf.value)
+    if rb:
+        out["hbar_rb"] = hrb
+    return out

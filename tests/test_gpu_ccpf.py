@@ -155,3 +155,39 @@ def test_ccpf_estimator_is_unbiased_for_the_smoothing_mean(up, golden):
     z = (est - ms) / se
     assert np.max(np.abs(z)) < 4.5 and np.mean(np.abs(z) > 2) < 0.15
     assert np.allclose(g["sum_hbar"][0] / R, est, rtol=1e-10, atol=1e-12)
+
+
+def test_rao_blackwellised_conditional_filters_and_rheeglynn(up, oracle, golden):
+    """CPF_RB / CPF_RB_coupled estimates (identity test function) equal the oracle's weighted average over all N paths; the chain
+    driver's hbar_rb equals H_bar over the oracle's exp_samples; rheeglynn_estimator(_RB) are the k = K = 0 instances."""
+    y = golden["lgssm_y"]
+    N = 64
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, N, 100, theta=TH_AR)
+    refs = _refs(oracle, cfg, y, 9, 4)
+    g = up.ccpf_batch(N, up.get_ar(1), TH_AR, y, refs[:2], refs[2:], with_as=True, seed=30, exp_path=True)
+    g1 = up.ccpf_batch(N, up.get_ar(1), TH_AR, y, refs[:2], with_as=False, seed=31, exp_path=True)
+    for b in range(2):
+        o = oracle.ccpf(cfg, y, refs[b], refs[2 + b], with_as=True, seed=30, filter_id=b, exp_path=True)
+        assert np.allclose(g["exp_path1"][b], o["exp_path1"], rtol=1e-9, atol=1e-10)
+        assert np.allclose(g["exp_path2"][b], o["exp_path2"], rtol=1e-9, atol=1e-10)
+        o1 = oracle.ccpf(cfg, y, refs[b], with_as=False, seed=31, filter_id=b, exp_path=True)
+        assert np.allclose(g1["exp_path1"][b], o1["exp_path1"], rtol=1e-9, atol=1e-10)
+    for (k, K) in ((0, 0), (2, 2), (1, 4)):
+        gg = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, N, 30, K=K, k=k, with_as=True, seed=12, first_replicate=3, rb=True)
+        oo = oracle.coupled_ccpf_batch(cfg, y, 12, 3, 30, k=k, K=K, with_as=True, rb=True)
+        assert np.array_equal(gg["meetingtime"], oo["meetingtime"])
+        assert np.allclose(gg["hbar"][:, 0, :], oo["hbar"], rtol=1e-9, atol=1e-9)
+        assert np.allclose(gg["hbar_rb"][:, 0, :], oo["hbar_rb"], rtol=1e-9, atol=1e-9)
+        assert np.allclose(gg["sum_hbar_rb"][0], oo["hbar_rb"].sum(axis=0), rtol=1e-9, atol=1e-8)
+    ap = {"nparticles": N, "with_as": True, "lambda": 0, "coupled_resampling": up.CR_indexmatching}
+    e = up.rheeglynn_estimator(y, up.get_ar(1), TH_AR, ap, seed=12, replicate=3)
+    erb = up.rheeglynn_estimator_RB(y, up.get_ar(1), TH_AR, ap, seed=12, replicate=3)
+    o0 = oracle.coupled_ccpf_batch(cfg, y, 12, 3, 1, k=0, K=0, with_as=True, rb=True)
+    assert np.allclose(e["estimate"][0], o0["hbar"][0], rtol=1e-9, atol=1e-9) and e["iteration"] == o0["iteration"][0]
+    assert np.allclose(erb["estimate"][0], o0["hbar_rb"][0], rtol=1e-9, atol=1e-9)
+    r = up.CPF_RB(N, up.get_ar(1), TH_AR, y, ref_trajectory=refs[0], with_as=True, seed=5)
+    assert r["estimate"].shape == (1, 101) and r["new_trajectory"].shape == (1, 101)
+    r0 = up.CPF_RB(N, up.get_ar(1), TH_AR, y, seed=5)
+    assert r0["estimate"].shape == (1, 101)
+    rc = up.CPF_RB_coupled(N, up.get_ar(1), TH_AR, y, refs[0], refs[1], with_as=False, seed=5)
+    assert rc["estimate1"].shape == (1, 101) and not np.array_equal(rc["estimate1"], rc["estimate2"])

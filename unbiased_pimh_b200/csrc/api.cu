@@ -499,6 +499,13 @@ int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status) {
   return CPIMH_OK;
 }
 
+int cpimh_pf_device_exp_paths(cpimh_pf* h, double** d_exp_path) {
+  CPIMH_REQUIRE(h && d_exp_path, "null argument");
+  CPIMH_REQUIRE(!h->wide && h->all_particles, "call cpimh_pf_all_particles(h, 1) first");
+  *d_exp_path = h->exp_path.as<double>();
+  return CPIMH_OK;
+}
+
 int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory) {
   CPIMH_REQUIRE(h, "null handle");
   if (h->wide) { wide_device_outputs(h->wide, d_logz, d_trajectory); return CPIMH_OK; }

@@ -86,6 +86,8 @@ struct CcRound {
   int* single; int* iter; int* tau; int* status;
   double* accH; double* accD; double* hbar; double* bc;
   unsigned long long* nfilters;
+  // Rao-Blackwellised twin (null when off): exp paths of the new filters / of the current states, accumulators, output
+  const double* newe1; const double* newe2; double* e1; double* e2; double* accHe; double* accDe; double* hbar_rb;
 };
 __global__ void cc_prepare_kernel(CcRound q) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,6 +101,7 @@ __global__ void cc_init_kernel(CcRound q, const int* pf_status1, const int* pf_s
   for (int j = threadIdx.x; j < q.PD; j += blockDim.x) {
     q.accH[(size_t)rep * q.PD + j] = (q.k <= 0) ? q.st1[(size_t)rep * q.PD + j] : 0.0;       // samples1[1,] (debiasing_algorithm.R:42)
     q.accD[(size_t)rep * q.PD + j] = 0.0;
+    if (q.e1) { q.accHe[(size_t)rep * q.PD + j] = (q.k <= 0) ? q.e1[(size_t)rep * q.PD + j] : 0.0; q.accDe[(size_t)rep * q.PD + j] = 0.0; }
   }
   if (threadIdx.x == 0) {
     q.single[rep] = 1;                                   // iteration 1 is a single-kernel move of chain 1 (:50-52)
@@ -124,7 +127,6 @@ __global__ void cc_accept_kernel(CcRound q) {
   if (status == 0 && isnan(q.new_logz[rep])) status = CPIMH_ERR_INVALID;
   const int t = it - 1;
   const bool mcmc = (it >= q.k && it <= q.K);
-  const bool bias = (t >= q.k);
   const double coef = (double)min(t - q.k + 1, q.K - q.k + 1);
   int same = 1;
   for (int j = threadIdx.x; j < PD; j += blockDim.x) {
@@ -133,8 +135,6 @@ __global__ void cc_accept_kernel(CcRound q) {
     const double xb = (it == 1) ? x2[j] : (single ? xa : n2[j]);
     x1[j] = xa; x2[j] = xb;
     if (xa != xb) same = 0;
-    if (mcmc) accH[j] += xa;                                                   // H_bar, debiasing_algorithm.R:296-302
-    if (bias) accD[j] = accD[j] + coef * (xa - xb);                            // :308-312 (zero once the chains have met)
   }
   same = __syncthreads_and(same);
   int finished = 0;
@@ -142,11 +142,28 @@ __global__ void cc_accept_kernel(CcRound q) {
   if (it >= 2 && !single && same && tau < 0) tau = it;                         // :82-86 all(chain_state1 == chain_state2)
   if (tau > 0 && it >= max(tau, q.K)) finished = 1;                            // :104-106
   if (q.max_it >= 0 && it >= q.max_it) finished = 1;
+  // H_bar (debiasing_algorithm.R:296-312): MCMC sum over k..K plus coef_t (X_{t+1} - Y_t) for k <= t <= tau - 1, skipped
+  // altogether when tau <= k + 1 (:303).  For the states the skipped term is zero; for the weighted-average paths it is not.
+  const bool bias = (t >= q.k) && !(tau > 0 && tau <= q.k + 1);
+  for (int j = threadIdx.x; j < PD; j += blockDim.x) {
+    const double xa = x1[j], xb = x2[j];
+    if (mcmc) accH[j] += xa;
+    if (bias) accD[j] = accD[j] + coef * (xa - xb);
+    if (q.e1) {                                                                // the same recursion over the filters' weighted-average paths
+      const size_t o = (size_t)rep * PD + j;
+      const double ea = q.newe1[o];
+      const double eb = (it == 1) ? q.e2[o] : (single ? ea : q.newe2[o]);
+      q.e1[o] = ea; q.e2[o] = eb;
+      if (mcmc) q.accHe[o] += ea;
+      if (bias) q.accDe[o] = q.accDe[o] + coef * (ea - eb);
+    }
+  }
   if (finished) {
     const double denom = (double)(q.K - q.k + 1);
     for (int j = threadIdx.x; j < PD; j += blockDim.x) {
       q.hbar[(size_t)rep * PD + j] = (accH[j] + accD[j]) / denom;
       q.bc[(size_t)rep * PD + j] = accD[j] / denom;
+      if (q.e1) q.hbar_rb[(size_t)rep * PD + j] = (q.accHe[(size_t)rep * PD + j] + q.accDe[(size_t)rep * PD + j]) / denom;
     }
   }
   if (threadIdx.x == 0) {
@@ -176,7 +193,8 @@ extern "C" {
 
 int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
                      int nsys, int with_as, const double* ref1_host, const double* ref2_host, const cpimh_noise* noise,
-                     double* traj1, double* traj2, double* logz, int32_t* path_index, int32_t* ancestors) {
+                     double* traj1, double* traj2, double* logz, int32_t* path_index, int32_t* ancestors,
+                     double* exp_path1, double* exp_path2) {
   CPIMH_REQUIRE(cfg && obs_host && ref1_host && traj1, "null argument");
   CPIMH_REQUIRE(B >= 1, "nfilters must be >= 1");
   CPIMH_REQUIRE(nsys == 1 || nsys == 2, "nsys must be 1 (CPF with a reference trajectory) or 2 (CPF_coupled)");
@@ -187,8 +205,10 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B,
   if (rc) return rc;
   const cpimh_config& c = w.cfg;
   const size_t N = c.nparticles, T = c.nobs, PD = (size_t)(c.nobs + 1) * c.dim;
-  DevBuf ref1, ref2, t1, t2, lz, pidx, status, anc, ninit, ntrans;
-  struct Rel { DevBuf* b[10]; ~Rel() { for (auto x : b) x->release(); } } rel{{&ref1, &ref2, &t1, &t2, &lz, &pidx, &status, &anc, &ninit, &ntrans}};
+  DevBuf ref1, ref2, t1, t2, lz, pidx, status, anc, ninit, ntrans, ex1, ex2;
+  struct Rel { DevBuf* b[12]; ~Rel() { for (auto x : b) x->release(); } } rel{{&ref1, &ref2, &t1, &t2, &lz, &pidx, &status, &anc, &ninit, &ntrans, &ex1, &ex2}};
+  const bool want_exp = exp_path1 != nullptr || exp_path2 != nullptr;
+  if (want_exp) { rc = ex1.alloc(sizeof(double) * B * PD); if (!rc) rc = ex2.alloc(sizeof(double) * B * PD); if (rc) return rc; }
   rc = ref1.alloc(sizeof(double) * B * PD);
   if (!rc) rc = t1.alloc(sizeof(double) * B * PD);
   if (!rc && nsys == 2) rc = ref2.alloc(sizeof(double) * B * PD);
@@ -221,6 +241,7 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B,
   p.ref1 = ref1.as<double>(); p.ref2 = nsys == 2 ? ref2.as<double>() : nullptr;
   p.traj1 = t1.as<double>(); p.traj2 = t2.as<double>(); p.logz = lz.as<double>(); p.path_index = pidx.as<int>();
   p.status = status.as<int>(); p.anc_rec = ancestors ? anc.as<int>() : nullptr;
+  if (want_exp) { p.exp1 = ex1.as<double>(); p.exp2 = ex2.as<double>(); }
   rc = ccpf_launch(w, p, nullptr);
   if (rc) return rc;
   CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
@@ -233,6 +254,8 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B,
   if (logz) CPIMH_CUDA_CHECK(cudaMemcpy(logz, lz.p, sizeof(double) * B, cudaMemcpyDeviceToHost));
   if (path_index) CPIMH_CUDA_CHECK(cudaMemcpy(path_index, pidx.p, sizeof(int) * 2 * B, cudaMemcpyDeviceToHost));
   if (ancestors) CPIMH_CUDA_CHECK(cudaMemcpy(ancestors, anc.p, anc.bytes, cudaMemcpyDeviceToHost));
+  if (exp_path1) CPIMH_CUDA_CHECK(cudaMemcpy(exp_path1, ex1.p, sizeof(double) * B * PD, cudaMemcpyDeviceToHost));
+  if (exp_path2 && nsys == 2) CPIMH_CUDA_CHECK(cudaMemcpy(exp_path2, ex2.p, sizeof(double) * B * PD, cudaMemcpyDeviceToHost));
   return CPIMH_OK;
 }
 
@@ -243,7 +266,7 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   CPIMH_REQUIRE(k >= 0 && K >= k, "need 0 <= k <= K (got k=%d K=%d)", k, K);
   CPIMH_REQUIRE(max_iterations < 0 || max_iterations >= (K > 1 ? K : 1), "max_iterations must be >= max(K, 1) or negative (unbounded)");
   CPIMH_REQUIRE(max_iterations < 4096, "iteration index must fit 12 bits of the Philox counter (max_iterations < 4096)");
-  CPIMH_REQUIRE(!(o->hbar_rb || o->sum_hbar_rb || o->sum_hbar_rb_sq), "the *_rb outputs belong to the all_particles PIMH chains");
+  const bool rb = o->hbar_rb || o->sum_hbar_rb || o->sum_hbar_rb_sq;
   const int max_it = max_iterations < 0 ? 4094 : max_iterations;
   CcpfWork w;
   int rc = ccpf_work_init(&w, cfg, obs_host, R);
@@ -258,11 +281,19 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   rc = cpimh_pf_create(&cpf, R, &pf);
   if (rc) return rc;
   DevBuf st1, st2, n1, n2, lz1, lz2, nlz, nst, single, iter, tau, status, accH, accD, hbar, bc, act0, act1, cnt, ids, nf, sums, pst1, pst2;
-  DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &act0, &act1, &cnt, &ids, &nf, &sums, &pst1, &pst2};
+  DevBuf e1, e2, ne1, ne2, accHe, accDe, hbar_rb, sums_rb;
+  DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &act0, &act1, &cnt, &ids, &nf, &sums, &pst1, &pst2,
+                   &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb};
   struct Rel { DevBuf** b; size_t n; cpimh_pf** pf; ~Rel() { for (size_t i = 0; i < n; i++) b[i]->release(); if (*pf) cpimh_pf_destroy(*pf); } } rel{all, sizeof(all) / sizeof(all[0]), &pf};
   const size_t RPD = sizeof(double) * (size_t)R * PD;
   DevBuf* dbl[] = {&st1, &st2, &n1, &n2, &accH, &accD, &hbar, &bc};
   for (auto b : dbl) { rc = b->alloc(RPD); if (rc) return rc; }
+  if (rb) {
+    DevBuf* dre[] = {&e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb};
+    for (auto b : dre) { rc = b->alloc(RPD); if (rc) return rc; }
+    rc = sums_rb.alloc(sizeof(double) * (2 * (size_t)PD)); if (rc) return rc;
+    rc = cpimh_pf_all_particles(pf, 1); if (rc) return rc;
+  }
   DevBuf* dR[] = {&lz1, &lz2, &nlz};
   for (auto b : dR) { rc = b->alloc(sizeof(double) * (size_t)R); if (rc) return rc; }
   DevBuf* iR[] = {&nst, &single, &iter, &tau, &status, &act0, &act1, &pst1, &pst2};
@@ -279,6 +310,8 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   if (rc) return rc;
   rc = cpimh_pf_device_status(pf, &d_st);
   if (rc) return rc;
+  double* d_ex = nullptr;
+  if (rb) { rc = cpimh_pf_device_exp_paths(pf, &d_ex); if (rc) return rc; }
   for (int which = 0; which < 2; which++) {
     const uint64_t first = (uint64_t)first_replicate | (which ? ((uint64_t)0xFFF << 32) : 0ull);
     rc = cpimh_pf_run(pf, R, seed, first, s);
@@ -286,6 +319,7 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
     CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? st2.p : st1.p, d_tr, RPD, cudaMemcpyDeviceToDevice, s));
     CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? lz2.p : lz1.p, d_lz, sizeof(double) * (size_t)R, cudaMemcpyDeviceToDevice, s));
     CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? pst2.p : pst1.p, d_st, sizeof(int) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+    if (rb) CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? e2.p : e1.p, d_ex, RPD, cudaMemcpyDeviceToDevice, s));
   }
   CcRound q;
   memset(&q, 0, sizeof(q));
@@ -296,6 +330,10 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   q.single = single.as<int>(); q.iter = iter.as<int>(); q.tau = tau.as<int>(); q.status = status.as<int>();
   q.accH = accH.as<double>(); q.accD = accD.as<double>(); q.hbar = hbar.as<double>(); q.bc = bc.as<double>();
   q.nfilters = nf.as<unsigned long long>(); q.next_count = cnt.as<int>();
+  if (rb) {
+    q.newe1 = ne1.as<double>(); q.newe2 = ne2.as<double>(); q.e1 = e1.as<double>(); q.e2 = e2.as<double>();
+    q.accHe = accHe.as<double>(); q.accDe = accDe.as<double>(); q.hbar_rb = hbar_rb.as<double>();
+  }
   CPIMH_CUDA_CHECK(cudaMemsetAsync(nf.p, 0, sizeof(unsigned long long), s));
   CPIMH_CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(int), s));
   q.next_active = act0.as<int>();
@@ -309,6 +347,7 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   p.single = single.as<int>();
   p.ref1 = st1.as<double>(); p.ref2 = st2.as<double>();
   p.traj1 = n1.as<double>(); p.traj2 = n2.as<double>(); p.logz = nlz.as<double>(); p.status = nst.as<int>();
+  if (rb) { p.exp1 = ne1.as<double>(); p.exp2 = ne2.as<double>(); }
   int64_t filters = 2 * R;
   for (int it = 1; nA > 0; it++) {
     q.it = it;
@@ -327,6 +366,7 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
     flip ^= 1;
   }
   cc_reduce_kernel<<<PD, 256, 0, s>>>(hbar.as<double>(), R, PD, sums.as<double>());
+  if (rb) cc_reduce_kernel<<<PD, 256, 0, s>>>(hbar_rb.as<double>(), R, PD, sums_rb.as<double>());
   CPIMH_CUDA_CHECK(cudaGetLastError());
   std::vector<int> stv((size_t)R);
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(stv.data(), status.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
@@ -342,6 +382,12 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   if (o->sum_hbar) memcpy(o->sum_hbar, hs.data(), sizeof(double) * PD);
   if (o->sum_hbar_sq) memcpy(o->sum_hbar_sq, hs.data() + PD, sizeof(double) * PD);
   if (o->nfilters) *o->nfilters = filters;
+  if (rb) {
+    CPIMH_CUDA_CHECK(cudaMemcpy(hs.data(), sums_rb.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost));
+    if (o->hbar_rb) CPIMH_CUDA_CHECK(cudaMemcpy(o->hbar_rb, hbar_rb.p, RPD, cudaMemcpyDeviceToHost));
+    if (o->sum_hbar_rb) memcpy(o->sum_hbar_rb, hs.data(), sizeof(double) * PD);
+    if (o->sum_hbar_rb_sq) memcpy(o->sum_hbar_rb_sq, hs.data() + PD, sizeof(double) * PD);
+  }
   return CPIMH_OK;
 }
 

@@ -37,6 +37,7 @@ struct CcpfParams {
   int* path_index;             // [slot][2] or null
   int* status;                 // [slot]
   int* anc_rec;                // [slot][2][T][N] or null
+  double* exp1; double* exp2;  // [slot][T+1][D] or null: weighted average of all N paths (CPF_RB, R/rheeglynn_estimator_RB.R:50-56)
   const double* inj_init; const double* inj_trans;
   int n_init, n_trans, sk_M;
 };
@@ -92,15 +93,17 @@ __device__ inline void im_single_draw(double* A, double* Bv, int N, double uc, d
   __syncthreads();
 }
 
-template <class Model>
-__device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, const Stream& stream, long long inj, int nsys, long long slot) {
+template <class Model, int NSYS>
+__device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, const Stream& stream, long long inj, long long slot) {
   constexpr int D = Model::D;
+  constexpr int nsys = NSYS;
   const int tid = threadIdx.x, NT = blockDim.x;
   const int N = p.N, T = p.T, Npad = p.Npad, nd = N - 1;
   const size_t xstride = (size_t)D * Npad;
   double* hx[2];
   int* ha[2];
   const double* ref[2] = {p.ref1 + (size_t)slot * (T + 1) * D, p.ref2 ? p.ref2 + (size_t)slot * (T + 1) * D : nullptr};
+#pragma unroll
   for (int s = 0; s < 2; s++) {
     hx[s] = p.hist_x + ((size_t)ws * 2 + s) * (T + 1) * xstride;
     ha[s] = p.hist_a + ((size_t)ws * 2 + s) * T * Npad;
@@ -119,6 +122,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   for (int i = tid; i < N; i += NT) {
     double x[D];
     Model::init(c, i, x);
+#pragma unroll
     for (int s = 0; s < nsys; s++) {
 #pragma unroll
       for (int q = 0; q < D; q++) hx[s][(size_t)q * Npad + i] = (i == N - 1) ? ref[s][q] : x[q];
@@ -138,6 +142,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     int* arow[2] = {ha[0] + (size_t)(t - 1) * Npad, ha[1] + (size_t)(t - 1) * Npad};
 
     // normweights = w / sum(w)  (R/CPF.R:63; index matching compares the two systems' NORMALISED weights)
+#pragma unroll
     for (int s = 0; s < nsys; s++)
       for (int k = tid; k < N; k += NT) Wk[s][k] = Wk[s][k] / ssum[s];
     __syncthreads();
@@ -146,6 +151,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     int aref[2] = {N - 1, N - 1};
     if constexpr (Model::HAS_DTRANS) {
       if (p.with_as) {
+#pragma unroll
         for (int s = 0; s < nsys; s++) {
           double next[D];
 #pragma unroll
@@ -226,10 +232,14 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
         }
       }
     } else {
+#pragma unroll
       for (int s = 0; s < nsys; s++)
         for (int k = tid; k < nd; k += NT) arow[s][k] = k;
     }
-    if (tid == 0) for (int s = 0; s < nsys; s++) arow[s][N - 1] = aref[s];
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < nsys; s++) arow[s][N - 1] = aref[s];
+    }
     __syncthreads();                                                         // ancestors complete: CDFs, ladder and ranks are dead
 
     // ---- gather -> common-noise transition -> pin the reference -> weigh  (R/CPF_coupled.R:50-62, 87-88)
@@ -237,6 +247,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     for (int k = tid; k < N; k += NT) {
       double ush = 0.5;
       if (Model::USES_SHARED_U && !c.inj_trans) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
+#pragma unroll
       for (int s = 0; s < nsys; s++) {
         double x[D];
         if (k == N - 1) {
@@ -257,6 +268,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     }
     __syncthreads();
     // ---- weights and log Z increment (R/CPF.R:61-63,66)
+#pragma unroll
     for (int s = 0; s < nsys; s++) {
       const double ms = block_max(m[s], sm.dscr);
       double sum = 0.0;
@@ -269,9 +281,30 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
 
   // ---------------- path selection: R/CPF.R:69 (one system) / R/CPF_coupled.R:101-106 (one index-matching draw)
   if (st) atomicOr(&sm.iscr[32], st);
+#pragma unroll
   for (int s = 0; s < nsys; s++)
     for (int k = tid; k < N; k += NT) Wk[s][k] = Wk[s][k] / ssum[s];
   __syncthreads();
+  if (p.exp1) {
+    // estimate = sum_k normweights[k] * Tree$get_path(k) (R/rheeglynn_estimator_RB.R:50-56, test_function = identity): all N
+    // leaves walk to the root in lock step, one block reduction per generation and component; R holds the walkers
+#pragma unroll
+    for (int s = 0; s < nsys; s++) {
+      double* ex = (s == 0 ? p.exp1 : p.exp2) + (size_t)slot * (T + 1) * D;
+      for (int n = tid; n < N; n += NT) sm.R[n] = n;
+      for (int step = T; step >= 0; step--) {
+#pragma unroll
+        for (int q = 0; q < D; q++) {
+          double acc = 0.0;
+          for (int n = tid; n < N; n += NT) acc += hx[s][(size_t)step * xstride + (size_t)q * Npad + sm.R[n]] * Wk[s][n];
+          acc = block_sum(acc, sm.dscr);
+          if (tid == 0) ex[(size_t)step * D + q] = acc;
+        }
+        if (step > 0) for (int n = tid; n < N; n += NT) sm.R[n] = ha[s][(size_t)(step - 1) * Npad + sm.R[n]];
+      }
+    }
+    __syncthreads();
+  }
   double ua, ub;
   philox_u2(stream, 0, T + 1, CPIMH_P_PATH, 0, ua, ub);
   int kidx[2] = {0, 0};
@@ -288,6 +321,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     p.status[slot] = flags & 255;
   }
   if (tid < 32) {                                      // Tree$get_path: one warp walks the ancestor rows, lane q carries component q
+#pragma unroll
     for (int s = 0; s < nsys; s++) {
       double* tr = (s == 0 ? p.traj1 : p.traj2) + (size_t)slot * (T + 1) * D;
       int j = kidx[s];
@@ -298,6 +332,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     }
   }
   if (p.anc_rec)
+#pragma unroll
     for (int s = 0; s < nsys; s++)
       for (int t = 0; t < T; t++)
         for (int k = tid; k < N; k += NT) p.anc_rec[(((size_t)slot * 2 + s) * T + t) * N + k] = ha[s][(size_t)t * Npad + k];
@@ -315,7 +350,8 @@ __global__ void __launch_bounds__(512, 1) ccpf_kernel(CcpfParams p) {
     const long long slot = p.slot ? p.slot[b] : b;
     const int nsys = p.single ? (p.single[slot] ? 1 : 2) : p.nsys;
     const Stream s = make_stream(p.seed, p.stream_ids ? p.stream_ids[b] : p.first_filter + (unsigned long long)b);
-    run_ccpf<Model>(p, sm, blockIdx.x, s, b, nsys, slot);
+    if (nsys == 1) run_ccpf<Model, 1>(p, sm, blockIdx.x, s, b, slot);
+    else run_ccpf<Model, 2>(p, sm, blockIdx.x, s, b, slot);
   }
 }
 

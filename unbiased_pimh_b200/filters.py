@@ -171,7 +171,7 @@ def CPF(nparticles, model, theta, observations, ref_trajectory=None, with_as=Fal
 
 
 def ccpf_batch(nparticles, model, theta, observations, ref1, ref2=None, with_as=False, seed=None, first_filter=0, noise=None,
-               ancestors=False, **kw):
+               ancestors=False, exp_path=False, **kw):
     """B conditional particle filters (cpimh_ccpf_batch).  ref1 / ref2: (B, d, T+1) reference trajectories; ref2 = None runs
     CPF(ref_trajectory = ref1[b], with_as) (R/CPF.R:14-78), otherwise CPF_coupled(ref1[b], ref2[b], CR_indexmatching, with_as)
     (R/CPF_coupled.R:14-112).  Filter b uses Philox stream first_filter + b for both systems."""
@@ -189,12 +189,18 @@ def ccpf_batch(nparticles, model, theta, observations, ref1, ref2=None, with_as=
     t1 = np.empty((B, T + 1, d)); t2 = np.empty((B, T + 1, d)) if nsys == 2 else None
     logz = np.empty(B); pidx = np.empty((B, 2), dtype=np.int32)
     anc = np.empty((B, 2, T, N), dtype=np.int32) if ancestors else None
+    e1 = np.empty((B, T + 1, d)) if exp_path else None
+    e2 = np.empty((B, T + 1, d)) if (exp_path and nsys == 2) else None
     nz, keep = L.make_noise(noise)
     seed = rng.next_seed() if seed is None else int(seed)
     L.check(L.lib().cpimh_ccpf_batch(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_int64(B), C.c_uint64(seed), C.c_uint64(int(first_filter)),
                                       C.c_int(nsys), C.c_int(int(bool(with_as))), L.ptr(r1), L.ptr(r2), C.byref(nz) if noise else None,
-                                      L.ptr(t1), L.ptr(t2), L.ptr(logz), L.ptr(pidx), L.ptr(anc)))
+                                      L.ptr(t1), L.ptr(t2), L.ptr(logz), L.ptr(pidx), L.ptr(anc), L.ptr(e1), L.ptr(e2)))
     out = {"trajectory1": t1.transpose(0, 2, 1), "logz": logz, "path_index": pidx}
+    if exp_path:
+        out["exp_path1"] = e1.transpose(0, 2, 1)
+        if nsys == 2:
+            out["exp_path2"] = e2.transpose(0, 2, 1)
     if nsys == 2:
         out["trajectory2"] = t2.transpose(0, 2, 1)
     if ancestors:
@@ -211,6 +217,31 @@ def CPF_coupled(nparticles, model, theta, observations, ref_trajectory1, ref_tra
     r = ccpf_batch(nparticles, model, theta, observations, [ref_trajectory1], [ref_trajectory2], with_as=with_as, seed=seed,
                    first_filter=filter_id, noise=noise, **kw)
     return {"new_trajectory1": np.ascontiguousarray(r["trajectory1"][0]), "new_trajectory2": np.ascontiguousarray(r["trajectory2"][0])}
+
+
+def CPF_RB(nparticles, model, theta, observations, ref_trajectory=None, with_as=False, test_function=None, seed=None, filter_id=0, **kw):
+    """CPF_RB(nparticles, model, theta, observations, ref_trajectory, with_as, test_function) -- R/rheeglynn_estimator_RB.R:2-60.
+    `estimate` is the weighted average of test_function over all N paths, reduced inside the filter kernel; only the default
+    test_function (identity) is fused.  Returns {"new_trajectory", "estimate"}: d x (T+1) each."""
+    if test_function is not None:
+        raise NotImplementedError("the fused Rao-Blackwellised estimate is the identity test function (the reference's default)")
+    if ref_trajectory is None:
+        r = CPF(nparticles, model, theta, observations, all_particles=True, seed=seed, filter_id=filter_id, **kw)
+        return {"new_trajectory": r["trajectory"], "estimate": r["exp_path"]}
+    r = ccpf_batch(nparticles, model, theta, observations, [ref_trajectory], with_as=with_as, seed=seed, first_filter=filter_id, exp_path=True, **kw)
+    return {"new_trajectory": np.ascontiguousarray(r["trajectory1"][0]), "estimate": np.ascontiguousarray(r["exp_path1"][0])}
+
+
+def CPF_RB_coupled(nparticles, model, theta, observations, ref_trajectory1, ref_trajectory2, coupled_resampling=None, with_as=False,
+                   test_function=None, seed=None, filter_id=0, **kw):
+    """CPF_RB_coupled(...) -- R/rheeglynn_estimator_RB.R:62-167 (identity test function).
+    Returns {"new_trajectory1", "new_trajectory2", "estimate1", "estimate2"}."""
+    if test_function is not None:
+        raise NotImplementedError("the fused Rao-Blackwellised estimate is the identity test function (the reference's default)")
+    r = ccpf_batch(nparticles, model, theta, observations, [ref_trajectory1], [ref_trajectory2], with_as=with_as, seed=seed,
+                   first_filter=filter_id, exp_path=True, **kw)
+    return {"new_trajectory1": np.ascontiguousarray(r["trajectory1"][0]), "new_trajectory2": np.ascontiguousarray(r["trajectory2"][0]),
+            "estimate1": np.ascontiguousarray(r["exp_path1"][0]), "estimate2": np.ascontiguousarray(r["exp_path2"][0])}
 
 
 def particlefilter(nparticles, model, theta, observations, seed=None, filter_id=0, noise=None, **kw):

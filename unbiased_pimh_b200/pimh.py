@@ -219,10 +219,12 @@ def coupled_ccpf_chains(single_kernel, coupled_kernel, pimh_init, N, K=1, max_it
 
 
 def coupled_ccpf_chains_batch(model, theta, observations, nparticles, nreplicates, K=1, k=0, max_iterations=math.inf, with_as=False,
-                              seed=None, first_replicate=0, **kw):
+                              seed=None, first_replicate=0, rb=False, **kw):
     """R replicates of coupled_ccpf_chains(get_cpf_kernels(with_as), pimh_init, N = nparticles, K) + H_bar(., k, K) + BC on the
     GPU (cpimh_coupled_ccpf): all replicates advance together, one launch of conditional filters per iteration.
-    Returns hbar / bc (R, d, T+1), meetingtime (R,) [-1: not met within max_iterations], iteration (R,), sums, nfilters."""
+    Returns hbar / bc (R, d, T+1), meetingtime (R,) [-1: not met within max_iterations], iteration (R,), sums, nfilters.
+    rb=True adds hbar_rb: the same estimator over every filter's weighted average of all N paths (Rao-Blackwellised,
+    R/rheeglynn_estimator_RB.R:170-265: k = K = 0 is rheeglynn_estimator_RB, k = K = m is rheeglynn_estimator_RB2)."""
     obs = np.asarray(observations, dtype=np.float64)
     T = obs.shape[0]
     cfg = model.config(nparticles, theta, nobs=T, **kw)
@@ -236,10 +238,16 @@ def coupled_ccpf_chains_batch(model, theta, observations, nparticles, nreplicate
     o = L.ChainOut()
     o.hbar, o.bc, o.meetingtime, o.iteration = hb.ctypes.data, bcv.ctypes.data, mt.ctypes.data, it.ctypes.data
     o.sum_hbar, o.sum_hbar_sq, o.nfilters = s.ctypes.data, s2.ctypes.data, nf.ctypes.data
+    hrb, srb, srb2 = (np.empty((R, P, d)), np.empty((P, d)), np.empty((P, d))) if rb else (None, None, None)
+    if rb:
+        o.hbar_rb, o.sum_hbar_rb, o.sum_hbar_rb_sq = hrb.ctypes.data, srb.ctypes.data, srb2.ctypes.data
     L.check(L.lib().cpimh_coupled_ccpf(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_int64(R), C.c_uint64(seed), C.c_uint32(int(first_replicate)),
                                         C.c_int(int(k)), C.c_int(int(K)), C.c_int(mi), C.c_int(int(bool(with_as))), C.byref(o)))
-    return {"hbar": hb.transpose(0, 2, 1), "bc": bcv.transpose(0, 2, 1), "meetingtime": mt, "iteration": it,
-            "sum_hbar": s.T.copy(), "sum_hbar_sq": s2.T.copy(), "nfilters": int(nf[0])}
+    out = {"hbar": hb.transpose(0, 2, 1), "bc": bcv.transpose(0, 2, 1), "meetingtime": mt, "iteration": it,
+           "sum_hbar": s.T.copy(), "sum_hbar_sq": s2.T.copy(), "nfilters": int(nf[0])}
+    if rb:
+        out.update({"hbar_rb": hrb.transpose(0, 2, 1), "sum_hbar_rb": srb.T.copy(), "sum_hbar_rb_sq": srb2.T.copy()})
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- batched GPU twins
@@ -361,18 +369,31 @@ def coupled_pimh_chains_batch(model, theta, observations, nparticles, nreplicate
     return out
 
 
-def rheeglynn_estimator(observations, model, theta, algoparameters, force_niterations=0, max_niterations=0, seed=None):
+def rheeglynn_estimator(observations, model, theta, algoparameters, force_niterations=0, max_niterations=0, seed=None, replicate=0):
     """rheeglynn_estimator(observations, model, theta, algoparameters, force_niterations = 0, max_niterations = 0)
-    -- R/rheeglynn_estimator.R:14-66.  The shipped R function is not runnable (it adds the list returned by CPF(),
-    SURVEY D6) and its coupled step needs the conditional filter; this is the PIMH instance of the same estimator,
-    X_0 + sum_{n>=1} (X_n - Y_{n-1}) up to the meeting time, i.e. H_bar with k = K = 0, for all state components.
-    `lambda` (geometric truncation) must be 0."""
+    -- R/rheeglynn_estimator.R:14-66: X_0 + sum_{n >= 1} (X_n - X~_{n-1}) over coupled conditional particle filters until the two
+    reference trajectories meet, i.e. H_bar with k = K = 0 over coupled_ccpf_chains.  algoparameters: nparticles, with_as,
+    coupled_resampling (index matching is what is fused), lambda (geometric truncation; must be 0).  The shipped R function
+    adds the lists returned by CPF(); this is the estimator it intends, for all state components."""
     if algoparameters.get("lambda", 0) and algoparameters["lambda"] > 0:
-        raise NotImplementedError("geometric truncation (lambda > 0) is not part of the PIMH hot path; use lambda = 0")
-    K = int(force_niterations) if force_niterations else 0
-    mi = int(max_niterations) if max_niterations else math.inf
-    r = coupled_pimh_chains_batch(model, theta, observations, int(algoparameters["nparticles"]), 1, K=K, k=0, max_iterations=mi, seed=seed)
-    return {"estimate": r["hbar"][0], "iteration": int(r["iteration"][0]), "truncation": math.inf}
+        raise NotImplementedError("geometric truncation (lambda > 0) is not fused; use lambda = 0")
+    mi = int(force_niterations) if force_niterations else (int(max_niterations) if max_niterations else math.inf)
+    r = coupled_ccpf_chains_batch(model, theta, observations, int(algoparameters["nparticles"]), 1, K=0, k=0, max_iterations=mi,
+                                  with_as=bool(algoparameters.get("with_as", False)), seed=seed, first_replicate=replicate)
+    it = int(force_niterations) if force_niterations else int(r["iteration"][0])
+    return {"estimate": r["hbar"][0], "iteration": it, "truncation": math.inf}
+
+
+def rheeglynn_estimator_RB(observations, model, theta, algoparameters, test_function=None, seed=None, replicate=0):
+    """rheeglynn_estimator_RB / rheeglynn_estimator_RB2 (algoparameters["m"]) -- R/rheeglynn_estimator_RB.R:170-265, identity
+    test function: the Rhee-Glynn sum over the filters' weighted averages of all N paths instead of the one drawn path."""
+    if test_function is not None:
+        raise NotImplementedError("the fused Rao-Blackwellised estimate is the identity test function (the reference's default)")
+    m = int(algoparameters.get("m", 0) or 0)
+    r = coupled_ccpf_chains_batch(model, theta, observations, int(algoparameters["nparticles"]), 1, K=m, k=m,
+                                  with_as=bool(algoparameters.get("with_as", False)), seed=seed, first_replicate=replicate, rb=True)
+    tau = int(r["meetingtime"][0])
+    return {"estimate": r["hbar_rb"][0], "iteration": int(r["iteration"][0]), "meetingtime": math.inf if tau < 0 else tau}
 
 
 def shard_range(nreplicates, rank, world_size):
