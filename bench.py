@@ -313,6 +313,30 @@ def main():
                     "filters_run": est["nfilters"], "particle_steps_per_s": est["nfilters"] * 100.0 * 1024.0 / float(tc.item()),
                     "workload": "get_ar(10) N=1024 T=100 K=1 (BASELINE configs[3] shape); host wall time of run + all-reduce, workspaces pre-allocated"}
 
+    # ---- coupled conditional-particle-filter chains (coupled_ccpf_chains + H_bar, ancestor sampling), the
+    # LGSSM shape of inst/reproduce/lgssm (get_ar(1), T=100), N=128, k=3, K=10; replicates sharded, sums all-reduced.
+    cc_extra = None
+    if not args.no_chains:
+        Rcc = 10000 * world
+        obs1 = simulate_ar(100, 1, 0.5, float(np.sqrt(10.0)))
+        m1, th1 = up.get_ar(1), [0.5, float(np.sqrt(10.0))]
+        lo, hi = up.shard_range(Rcc, rank, world)
+        up.coupled_ccpf_chains_batch(m1, th1, obs1, 128, min(hi - lo, 2000), K=10, k=3, with_as=True, seed=5, first_replicate=lo)   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        g = up.coupled_ccpf_chains_batch(m1, th1, obs1, 128, hi - lo, K=10, k=3, with_as=True, seed=6, first_replicate=lo)
+        sums = torch.tensor(np.concatenate([g["sum_hbar"].ravel(), g["sum_hbar_sq"].ravel(), [g["nfilters"], hi - lo]]), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sums)
+        barrier()
+        tcc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tcc, op=dist.ReduceOp.MAX)
+        nf = float(sums[-2].item())
+        cc_extra = {"metric": "coupled-CCPF estimator replicates/sec", "value": Rcc / float(tcc.item()), "replicates": Rcc, "filters_run": int(nf),
+                    "mean_meeting_time": float(np.mean(g["meetingtime"])),
+                    "workload": "get_ar(1) N=128 T=100 k=3 K=10 ancestor sampling; host wall time incl. allocation, H2D/D2H and the all-reduce"}
+
     if rank == 0:
         peak, which = load_peaks()
         kernel_ms = ms / steps
@@ -340,6 +364,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks}
         line["coupled_pimh"] = cp_extra
+        line["coupled_ccpf"] = cc_extra
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_sample(w)
             line["cpu_baseline"] = cb
