@@ -75,6 +75,11 @@ __device__ __forceinline__ void normal2(double ua, double ub, double& z0, double
   z1 = r * s;
 }
 
+// first normal of the pair only (models that consume one normal per draw): the same value as normal2's z0
+__device__ __forceinline__ double normal1(double ua, double ub) {
+  return sqrt(-2.0 * log(ua)) * cospi(2.0 * ub);
+}
+
 // ---------------------------------------------------------------- warp / block primitives (fp64)
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -224,6 +229,7 @@ __device__ __forceinline__ int count_lt(const double* c, int n, double u) {
 }
 
 #define CPIMH_M_LN_SQRT_2PI 0.918938533204672741780329736406   // R's dnorm(log=TRUE) constant
+#define CPIMH_LOG_SQRT_10 0x1.26bb1bbb55516p+0                 // log(sqrt(10.0)) as libm rounds it (gss measurement sd)
 #define CPIMH_HALF_LOG_2PI_TRUNC 0.9189385                      // src/mvnorm.cpp:73,98,121 (truncated on purpose)
 
 }  // namespace cpimh

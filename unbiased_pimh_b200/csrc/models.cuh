@@ -39,6 +39,7 @@ struct GssModel {
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = false;
   static constexpr bool HAS_DTRANS = true;
+  static constexpr bool SPLIT_W = false;
   // dtransition(next_x, xparticles, theta, time): R/model_get_gss.R:30-33
   __device__ static double dtrans(const ModelCtx&, const double* next, const double* x, int, double drift) {
     const double xi = x[0];
@@ -49,20 +50,22 @@ struct GssModel {
   __device__ static void init(const ModelCtx& c, int i, double* x) {
     double z;
     if (c.inj_init) z = c.inj_init[i];
-    else { double ua, ub, z1; philox_u2(c.stream, i, 0, CPIMH_P_INIT, 0, ua, ub); normal2(ua, ub, z, z1); }
+    else { double ua, ub; philox_u2(c.stream, i, 0, CPIMH_P_INIT, 0, ua, ub); z = normal1(ua, ub); }
     x[0] = sqrt(2.0) * z;
   }
   __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double drift, double /*ush*/) {
     double z;
     if (c.inj_trans) z = trans_row(c, t, 0)[i];
-    else { double ua, ub, z1; philox_u2(c.stream, i, t, CPIMH_P_TRANS, 0, ua, ub); normal2(ua, ub, z, z1); }
+    else { double ua, ub; philox_u2(c.stream, i, t, CPIMH_P_TRANS, 0, ua, ub); z = normal1(ua, ub); }
     double xi = x[0];
     double means = 0.5 * xi + 25.0 * xi / (1.0 + xi * xi) + drift;
     x[0] = means + z;
     return 0;
   }
   __device__ static double logw(const ModelCtx&, const double* x, const double* y) {
-    return dnorm_log(y[0], (x[0] * x[0]) / 20.0, sqrt(10.0));
+    // dnorm(y, x^2 / 20, sd = sqrt(10), log = TRUE) (R/model_get_gss.R:36) with log(sd) folded into a constant
+    const double z = (y[0] - (x[0] * x[0]) / 20.0) / sqrt(10.0);
+    return -(CPIMH_M_LN_SQRT_2PI + 0.5 * z * z + CPIMH_LOG_SQRT_10);
   }
 };
 
@@ -74,6 +77,7 @@ struct ArModel {
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = false;
   static constexpr bool HAS_DTRANS = true;
+  static constexpr bool SPLIT_W = false;
   // dtransition = dmvnorm_transpose_cholesky(A x, next_x, I): R/model_get_ar.R:28-30, src/mvnorm.cpp:113-132
   __device__ static double dtrans(const ModelCtx& c, const double* next, const double* x, int, double) {
     double sq = 0.0;
@@ -150,6 +154,7 @@ struct LevySvModel {
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = true;      // pf_fused.cuh walks the Poisson jumps of a thread's particles as one list
   static constexpr bool HAS_DTRANS = false;
+  static constexpr bool SPLIT_W = true;       // the weight factorises as exp(a) * f without a log (see weight_parts)
   __device__ static __forceinline__ int token(const ModelCtx& c, double upois) { return poisson_tab(c.pre, upois); }
   __device__ static double step_const(const ModelCtx& c, int) { return c.pre[0]; }
   // one jump of the compound Poisson process (src/SVLevy_functions.cpp:62-67): c' = t - c ~ U(0,1), e ~ Exp(rate xi/w2)
@@ -221,6 +226,14 @@ struct LevySvModel {
     const double r = y[0] - (c.theta[0] + c.theta[1] * x[0]);
     return -(CPIMH_M_LN_SQRT_2PI + 0.5 * (r * r) / x[0] + 0.5 * log(x[0]));
   }
+  // the same density as weight = exp(a) * f * exp(W_CONST): a = -(y - m)^2 / (2 v), f = v^(-1/2).  The filter only needs
+  // w / sum(w) and log(mean(w)), so the per-particle log(v) (and the exp that undoes it) is replaced by one rsqrt.
+  __device__ static __forceinline__ void weight_parts(const ModelCtx& c, const double* x, const double* y, double& a, double& f) {
+    const double r = y[0] - (c.theta[0] + c.theta[1] * x[0]);
+    a = -(0.5 * (r * r) / x[0]);
+    f = rsqrt(x[0]);
+  }
+  __device__ static __forceinline__ double w_const() { return -CPIMH_M_LN_SQRT_2PI; }
 };
 
 // ------------------------------------------------------------------ get_stochastic_kinetic (d = 4, d_y = 2)
@@ -230,6 +243,7 @@ struct SkModel {
   static constexpr bool MULTI = true;
   static constexpr bool JUMP_LIST = false;
   static constexpr bool HAS_DTRANS = false;
+  static constexpr bool SPLIT_W = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void init(const ModelCtx&, int, double* x) { x[0] = 8.0; x[1] = 8.0; x[2] = 8.0; x[3] = 5.0; }
   __device__ static __forceinline__ double hazards(const double* x, double* h) {      // R/model_stochastic_kinetic.R:27-40
@@ -414,6 +428,7 @@ struct LorenzModel {
   static constexpr bool MULTI = false;
   static constexpr bool JUMP_LIST = false;
   static constexpr bool HAS_DTRANS = false;
+  static constexpr bool SPLIT_W = false;
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
   __device__ static void normals(const ModelCtx& c, int i, int t, int purpose, double* z) {
 #pragma unroll

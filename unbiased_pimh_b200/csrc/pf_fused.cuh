@@ -244,10 +244,17 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     };
     // -- gather (R/CPF.R:41) -> rtransition (:44) -> dmeasurement (:60) ; path bookkeeping
     double m = -INFINITY;                                // running max of this thread's log-weights
+    // models whose weight factorises as exp(a) f (Model::SPLIT_W) park f in C next to a in S: both arrays are dead once
+    // all ancestors are known, which the jump-list path guarantees
+    const bool split_w = Model::SPLIT_W && jump_list;
     auto finish_particle = [&](int k, int a, const double* x) {
 #pragma unroll
       for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
-      const double lw = Model::logw(c, x, y);
+      double lw;
+      if constexpr (Model::SPLIT_W) {
+        if (split_w) { double f; Model::weight_parts(c, x, y, lw, f); sm.C[k] = f; }
+        else lw = Model::logw(c, x, y);
+      } else lw = Model::logw(c, x, y);
       sm.S[k] = lw;
       m = fmax(m, lw);
       if (dense) hist_a[(size_t)(t - 1) * Npad + k] = a;
@@ -356,12 +363,14 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // -- weights and log Z increment: R/CPF.R:61-63,66
     m = block_max(m, sm.dscr);
     double s = 0.0;
-    for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; }
+    if (split_w) { for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m) * sm.C[k]; sm.C[k] = w; s += w; } }
+    else { for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; } }
     s = block_sum(s, sm.dscr);
     // normweights = w / sum(w) (R/CPF.R:63).  Between steps only ratios matter (the ancestor search scales its
     // uniforms by the CDF total), so the division pass is done once, for the weights the filter returns.
     if (t == T) for (int k = tid; k < N; k += NT) sm.C[k] = sm.C[k] / s;
-    const double lz = log(s / (double)N) + m;
+    double lz = log(s / (double)N) + m;
+    if constexpr (Model::SPLIT_W) { if (split_w) lz += Model::w_const(); }
     logz_sum += lz;
     if (tid == 0 && out.logz_t) out.logz_t[t - 1] = lz;
 
