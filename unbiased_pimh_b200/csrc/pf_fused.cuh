@@ -69,13 +69,14 @@ struct PfSmem {
   double* theta;    // [CPIMH_MAX_THETA]
   double* pre;      // [npre]
   double* dscr;     // [64]
+  double* dscr2;    // [2]   E_N of the ladder (written by thread 0 before the scans)
   int* coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
   int* iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
 };
 __host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
   size_t b = 0;
   b += (size_t)Npad * 8 * 2;                 // C, S
-  b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8;
+  b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64 + 2) * 8;
   if (path_mode == PATH_TREE) {
     b += (size_t)Npad * 4 * 2;               // leaf, bpar
     b += (size_t)(Npad / 2) * 4;             // off32
@@ -95,6 +96,7 @@ __device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre,
   s.theta = d; d += CPIMH_MAX_THETA;
   s.pre = d; d += npre + (npre & 1);
   s.dscr = d; d += 64;
+  s.dscr2 = d; d += 2;
   int* i = reinterpret_cast<int*>(d);
   s.leaf = nullptr; s.bpar = nullptr; s.off32 = nullptr; s.bits = nullptr;
   if (path_mode == PATH_TREE) {
@@ -197,6 +199,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     if (tree) for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
     const bool draw_res = !ident && !inj_res;
     unsigned long long tok0 = 0ull, tok1 = 0ull;           // 8-bit model tokens of this thread's particles (jump counts)
+    if (draw_res && tid == 0) sm.dscr2[0] = -log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0));   // E_N, read after the scan's barriers
     if (draw_res || need_shared_u) {
       int e = 0;
       for (int i = tid; i < N; i += NT, e++) {
@@ -222,7 +225,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       if (inj_res) block_scan_inplace<false>(sm.C, N, sm.dscr);
       else block_scan2_inplace(sm.C, sm.S, N, sm.dscr);
       sumw = sm.C[N - 1];
-      if (!inj_res) sumw = sumw / (sm.S[N - 1] - log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0)));
+      if (!inj_res) sumw = sumw / (sm.S[N - 1] + sm.dscr2[0]);   // total = P_{N-1} + E_N
       // every 32nd sorted uniform gets a full search; the others then search only between their neighbours' results
       const int nrows = (N + 31) >> 5;
       for (int r = tid; r <= nrows; r += NT) {
@@ -369,10 +372,12 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // normweights = w / sum(w) (R/CPF.R:63).  Between steps only ratios matter (the ancestor search scales its
     // uniforms by the CDF total), so the division pass is done once, for the weights the filter returns.
     if (t == T) for (int k = tid; k < N; k += NT) sm.C[k] = sm.C[k] / s;
-    double lz = log(s / (double)N) + m;
-    if constexpr (Model::SPLIT_W) { if (split_w) lz += Model::w_const(); }
-    logz_sum += lz;
-    if (tid == 0 && out.logz_t) out.logz_t[t - 1] = lz;
+    if (tid == 0) {                                      // only thread 0 reports log Z
+      double lz = log(s / (double)N) + m;
+      if constexpr (Model::SPLIT_W) { if (split_w) lz += Model::w_const(); }
+      logz_sum += lz;
+      if (out.logz_t) out.logz_t[t - 1] = lz;
+    }
 
     // -- Tree::update (src/tree.cpp:88-99)
     if (tree) {
