@@ -30,8 +30,12 @@ cpimh_config <- function(model, theta, nparticles, nobs, shuffle = 0L, store_pat
 
 # CPF(nparticles, model, theta, observations, ref_trajectory = NULL, with_as = FALSE, all_particles = FALSE)
 CPF_gpu <- function(nparticles, model, theta, observations, ref_trajectory = NULL, with_as = FALSE, all_particles = FALSE) {
-  if (!is.null(ref_trajectory) || with_as || all_particles || is.null(model$name))
+  if (all_particles || is.null(model$name))
     return(CPF(nparticles, model, theta, observations, ref_trajectory, with_as, all_particles))   # outside the GPU path
+  if (!is.null(ref_trajectory)) {                                                                 # conditional filter (R/CPF.R:22-24,45-58)
+    res <- .Call("cpimh_R_ccpf", cpimh_config(model, theta, nparticles, nrow(observations)), observations, ref_trajectory, NULL, with_as)
+    return(list(trajectory = res[[1]], logz = res[[3]][1]))
+  }
   res <- .Call("cpimh_R_pf_batch", cpimh_config(model, theta, nparticles, nrow(observations)), observations, 1L)
   list(trajectory = matrix(res[[2]][, , 1], nrow = model$dimension), logz = res[[1]][1])
 }
@@ -48,6 +52,22 @@ coupled_pimh_chains_batch <- function(model, theta, observations, nparticles, R,
                as.integer(R), as.integer(k), as.integer(K), as.integer(max_iterations))
   P <- nrow(observations) + 1
   list(hbar = array(res[[1]], dim = c(model$dimension, P, R)), meetingtime = ifelse(res[[2]] < 0, Inf, res[[2]]), iteration = res[[3]])
+}
+
+# CPF_coupled(nparticles, model, theta, observations, ref_trajectory1, ref_trajectory2, coupled_resampling, with_as): index matching is fused
+CPF_coupled_gpu <- function(nparticles, model, theta, observations, ref_trajectory1, ref_trajectory2, coupled_resampling = NULL, with_as = FALSE) {
+  res <- .Call("cpimh_R_ccpf", cpimh_config(model, theta, nparticles, nrow(observations)), observations, ref_trajectory1, ref_trajectory2, with_as)
+  list(new_trajectory1 = res[[1]], new_trajectory2 = res[[2]])
+}
+# foreach(r = 1:R) { coupled_ccpf_chains(get_cpf_kernels(with_as), pimh_init, N, K); H_bar(., k, K) }  in ONE call;
+# k = K = 0 is rheeglynn_estimator (lambda = 0), and with rb = TRUE rheeglynn_estimator_RB
+coupled_ccpf_chains_batch <- function(model, theta, observations, nparticles, R, k = 0, K = 1, max_iterations = -1L, with_as = FALSE, rb = FALSE) {
+  res <- .Call("cpimh_R_coupled_ccpf", cpimh_config(model, theta, nparticles, nrow(observations)), observations,
+               as.integer(R), as.integer(k), as.integer(K), as.integer(max_iterations), with_as, rb)
+  P <- nrow(observations) + 1
+  out <- list(hbar = array(res[[1]], dim = c(model$dimension, P, R)), meetingtime = ifelse(res[[2]] < 0, Inf, res[[2]]), iteration = res[[3]])
+  if (rb) out$hbar_rb <- array(res[[4]], dim = c(model$dimension, P, R))
+  out
 }
 
 # TreeClass <- module_tree$Tree  becomes:

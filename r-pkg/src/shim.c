@@ -169,6 +169,30 @@ SEXP cpimh_R_coupled_pimh(SEXP cfg_raw, SEXP obs, SEXP R_, SEXP k_, SEXP K_, SEX
   UNPROTECT(4); return out;
 }
 
+/* CPF(ref_trajectory = x, with_as) / CPF_coupled(ref1, ref2, CR_indexmatching, with_as): R/CPF.R:22-24,45-58, R/CPF_coupled.R:14-112 */
+SEXP cpimh_R_ccpf(SEXP cfg_raw, SEXP obs, SEXP ref1, SEXP ref2, SEXP with_as) {
+  const cpimh_config* cfg = (const cpimh_config*)RAW(cfg_raw);
+  int d = cfg->dim, T = cfg->nobs, nsys = Rf_isNull(ref2) ? 1 : 2;
+  SEXP t1 = PROTECT(Rf_allocMatrix(REALSXP, d, T + 1)), t2 = PROTECT(Rf_allocMatrix(REALSXP, d, T + 1));
+  SEXP lz = PROTECT(Rf_allocVector(REALSXP, 1));
+  check(cpimh_ccpf_batch(cfg, REAL(obs), 1, seed_from_R(), 0, nsys, Rf_asLogical(with_as), REAL(ref1), nsys == 2 ? REAL(ref2) : NULL, NULL,
+                         REAL(t1), REAL(t2), REAL(lz), NULL, NULL, NULL, NULL));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)); SET_VECTOR_ELT(out, 0, t1); SET_VECTOR_ELT(out, 1, t2); SET_VECTOR_ELT(out, 2, lz);
+  UNPROTECT(4); return out;
+}
+/* coupled_ccpf_chains + H_bar for R replicates (R/debiasing_algorithm.R:23-111); rb = TRUE also returns the Rao-Blackwellised H_bar */
+SEXP cpimh_R_coupled_ccpf(SEXP cfg_raw, SEXP obs, SEXP R_, SEXP k_, SEXP K_, SEXP maxit, SEXP with_as, SEXP rb) {
+  const cpimh_config* cfg = (const cpimh_config*)RAW(cfg_raw);
+  int R = Rf_asInteger(R_), P = cfg->dim * (cfg->nobs + 1), want_rb = Rf_asLogical(rb);
+  SEXP hbar = PROTECT(Rf_allocMatrix(REALSXP, P, R)), hrb = PROTECT(Rf_allocMatrix(REALSXP, P, want_rb ? R : 0));
+  SEXP tau = PROTECT(Rf_allocVector(INTSXP, R)), it = PROTECT(Rf_allocVector(INTSXP, R));
+  cpimh_chain_out o = {REAL(hbar), INTEGER(tau), INTEGER(it), NULL, NULL, NULL, NULL, want_rb ? REAL(hrb) : NULL, NULL, NULL};
+  check(cpimh_coupled_ccpf(cfg, REAL(obs), R, seed_from_R(), 0, Rf_asInteger(k_), Rf_asInteger(K_), Rf_asInteger(maxit), Rf_asLogical(with_as), &o));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, hbar); SET_VECTOR_ELT(out, 1, tau); SET_VECTOR_ELT(out, 2, it); SET_VECTOR_ELT(out, 3, hrb);
+  UNPROTECT(5); return out;
+}
+
 #define ENTRY(name, n) {#name, (DL_FUNC)&name, n}
 static const R_CallMethodDef CallEntries[] = {
   ENTRY(_CoupledPIMH_systematic_resampling_n_, 3), ENTRY(_CoupledPIMH_multinomial_resampling_n_, 2),
@@ -179,5 +203,6 @@ static const R_CallMethodDef CallEntries[] = {
   ENTRY(_CoupledPIMH_rinitial_SVLevy_cpp, 5), ENTRY(_CoupledPIMH_rtransition_SVLevy_cpp, 6), ENTRY(_CoupledPIMH_dobs_SVLevy_cpp, 5),
   ENTRY(cpimh_R_tree_new, 3), ENTRY(cpimh_R_tree_init, 2), ENTRY(cpimh_R_tree_update, 3), ENTRY(cpimh_R_tree_get_path, 2),
   ENTRY(cpimh_R_tree_retrieve_xgeneration, 2), ENTRY(cpimh_R_pf_batch, 3), ENTRY(cpimh_R_coupled_pimh, 6),
+  ENTRY(cpimh_R_ccpf, 5), ENTRY(cpimh_R_coupled_ccpf, 8),
   {NULL, NULL, 0}};
 void R_init_CoupledPIMH(DllInfo* dll) { R_registerRoutines(dll, NULL, CallEntries, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }

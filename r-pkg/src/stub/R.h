@@ -14,7 +14,7 @@ typedef int R_xlen_t;
 extern SEXP R_NilValue;
 double* REAL(SEXP); int* INTEGER(SEXP); unsigned char* RAW(SEXP);
 int LENGTH(SEXP); int Rf_nrows(SEXP); int Rf_ncols(SEXP);
-int Rf_asInteger(SEXP); double Rf_asReal(SEXP);
+int Rf_asInteger(SEXP); double Rf_asReal(SEXP); int Rf_asLogical(SEXP); int Rf_isNull(SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t); SEXP Rf_allocMatrix(unsigned int, int, int); SEXP Rf_alloc3DArray(unsigned int, int, int, int);
 SEXP Rf_protect(SEXP); void Rf_unprotect(int);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
