@@ -58,6 +58,7 @@ std::vector<double> api_precompute(const cpimh_config& c) {
     double hl = 0;
     for (int i = 0; i < d; i++) hl += log(c.theta[1]);
     pre[(size_t)d * d] = -(hl) - (d * CPIMH_HALF_LOG_2PI_TRUNC);
+    pre.push_back(1.0 / c.theta[1]);
   } else if (c.model == CPIMH_MODEL_LEVY_SV) {
     const double xi = c.theta[2], w2 = c.theta[3], lambda = c.theta[4];
     pre.push_back(exp(-lambda));                       // src/SVLevy_functions.cpp:66 exp(-lambda)
@@ -77,10 +78,15 @@ std::vector<double> api_precompute(const cpimh_config& c) {
     }
     pre.push_back((double)F.size());
     pre.insert(pre.end(), F.begin(), F.end());
+  } else if (c.model == CPIMH_MODEL_SK) {
+    const double sd = sqrt(c.theta[0]);                 // R/model_stochastic_kinetic.R:151 dnorm(..., sd = sqrt(s2_obs), log = TRUE)
+    pre.push_back(1.0 / sd);
+    pre.push_back(log(sd));
   } else if (c.model == CPIMH_MODEL_LORENZ) {
     double hl = 0;
     for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);
     pre.push_back(-(hl) - (c.dim * CPIMH_HALF_LOG_2PI_TRUNC));
+    pre.push_back(1.0 / c.theta[2]);
   }
   return pre;
 }

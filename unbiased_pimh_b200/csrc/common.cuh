@@ -229,6 +229,7 @@ __device__ __forceinline__ int count_lt(const double* c, int n, double u) {
 }
 
 #define CPIMH_M_LN_SQRT_2PI 0.918938533204672741780329736406   // R's dnorm(log=TRUE) constant
+#define CPIMH_INV_SQRT_10 0.31622776601683794                   // 1 / sqrt(10)
 #define CPIMH_LOG_SQRT_10 0x1.26bb1bbb55516p+0                 // log(sqrt(10.0)) as libm rounds it (gss measurement sd)
 #define CPIMH_HALF_LOG_2PI_TRUNC 0.9189385                      // src/mvnorm.cpp:73,98,121 (truncated on purpose)
 

@@ -64,7 +64,7 @@ struct GssModel {
   }
   __device__ static double logw(const ModelCtx&, const double* x, const double* y) {
     // dnorm(y, x^2 / 20, sd = sqrt(10), log = TRUE) (R/model_get_gss.R:36) with log(sd) folded into a constant
-    const double z = (y[0] - (x[0] * x[0]) / 20.0) / sqrt(10.0);
+    const double z = (y[0] - (x[0] * x[0]) / 20.0) * CPIMH_INV_SQRT_10;
     return -(CPIMH_M_LN_SQRT_2PI + 0.5 * z * z + CPIMH_LOG_SQRT_10);
   }
 };
@@ -126,10 +126,10 @@ struct ArModel {
     return 0;
   }
   __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
-    const double sy = c.theta[1];
+    const double isy = c.pre[D * D + 1];                  // 1 / theta[2]: the triangular solve of src/mvnorm.cpp:127 with L = sy I
     double sq = 0.0;
 #pragma unroll
-    for (int k = 0; k < D; k++) { double r = (x[k] - y[k]) / sy; sq += r * r; }
+    for (int k = 0; k < D; k++) { double r = (x[k] - y[k]) * isy; sq += r * r; }
     return -0.5 * sq + c.pre[D * D];
   }
 };
@@ -230,8 +230,9 @@ struct LevySvModel {
   // w / sum(w) and log(mean(w)), so the per-particle log(v) (and the exp that undoes it) is replaced by one rsqrt.
   __device__ static __forceinline__ void weight_parts(const ModelCtx& c, const double* x, const double* y, double& a, double& f) {
     const double r = y[0] - (c.theta[0] + c.theta[1] * x[0]);
-    a = -(0.5 * (r * r) / x[0]);
     f = rsqrt(x[0]);
+    const double rf = r * f;
+    a = -0.5 * (rf * rf);
   }
   __device__ static __forceinline__ double w_const() { return -CPIMH_M_LN_SQRT_2PI; }
 };
@@ -321,7 +322,7 @@ struct SkModel {
     return flags;
   }
   __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
-    const double sd = sqrt(c.theta[0]);
+    const double isd = c.pre[0], log_sd = c.pre[1];       // 1 / sqrt(s2_obs) and log(sqrt(s2_obs)): per-filter constants (host precompute)
     const double* A = c.theta + 1;
     double s = 0.0;
 #pragma unroll
@@ -329,7 +330,8 @@ struct SkModel {
       double m = 0.0;
 #pragma unroll
       for (int l = 0; l < 4; l++) m += A[j + 2 * l] * x[l];
-      s += dnorm_log(m, y[j], sd);
+      const double z = (m - y[j]) * isd;                  // dnorm(m, y_j, sd, log = TRUE), R/model_stochastic_kinetic.R:146-153
+      s += -(CPIMH_M_LN_SQRT_2PI + 0.5 * z * z + log_sd);
     }
     return s;
   }
@@ -469,10 +471,10 @@ struct LorenzModel {
   }
   __device__ static double logw(const ModelCtx& c, const double* x, const double* y) {
     if (isnan(y[0])) return 0.0;
-    const double sy = c.theta[2];
+    const double isy = c.pre[1];                          // 1 / sigma_y
     double sq = 0.0;
 #pragma unroll
-    for (int k = 0; k < D; k++) { double r = (x[k] - y[k]) / sy; sq += r * r; }
+    for (int k = 0; k < D; k++) { double r = (x[k] - y[k]) * isy; sq += r * r; }
     return -0.5 * sq + c.pre[0];
   }
 };
