@@ -216,6 +216,10 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nf
 int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, int with_as, cpimh_chain_out* out_host);
 
+/* the RNG specification's transcendental maps (DESIGN.md "RNG"; csrc/common.cuh rng_log / rng_sincos2pi), elementwise on
+ * the device: lg = log(u), sn/cs = sin/cos(2 pi u) for u in (0,1).  Bit-identical to oracle/rngmath.h (tests). */
+int cpimh_rng_transform(const double* u, int64_t n, double* lg, double* sn, double* cs);
+
 /* ============================== primitives (batched over B independent problems) ==============================
  * Bit-exact with the reference natives given identical weights and uniforms.  All pointers are HOST pointers. */
 /* systematic_resampling_n_(weights, ndraws, u)  src/systematic.cpp:7-32 ; w [B][N], u [B], anc [B][ndraws] */

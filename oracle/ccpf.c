@@ -23,6 +23,7 @@
 #include <omp.h>
 #endif
 #include "oracle.h"
+#include "rngmath.h"
 
 int orc_model_rtransition_ex(const orc_config* c, int time, const double* noise, uint64_t seed, uint64_t fid, double* x, int* clamp);
 
@@ -129,7 +130,7 @@ int orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise, u
       double acc = 0;
       for (int i = 0; i <= nd + 1; i++) {
         orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
-        acc = (i == 0) ? -log(ua) : acc + (-log(ua));
+        acc = (i == 0) ? -orc_rng_log(ua) : acc + (-orc_rng_log(ua));
         P[i] = acc;
       }
       if (nsys == 1) {

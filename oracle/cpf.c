@@ -9,6 +9,7 @@
 #include <omp.h>
 #endif
 #include "oracle.h"
+#include "rngmath.h"
 
 int orc_model_rtransition_ex(const orc_config* c, int time, const double* noise, uint64_t seed, uint64_t fid, double* x, int* clamp);
 
@@ -51,11 +52,11 @@ int orc_cpf(const orc_config* cfg, const double* obs, const orc_noise* noise, ui
         double acc = 0, ua, ub;
         for (int i = 0; i < N; i++) {
           orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
-          acc = (i == 0) ? -log(ua) : acc + (-log(ua));
+          acc = (i == 0) ? -orc_rng_log(ua) : acc + (-orc_rng_log(ua));
           ebuf[i] = acc;
         }
         orc_philox_uniform2(seed, (uint32_t)N, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
-        clamp += orc_multinomial_from_ladder(normw, N, N, ebuf, acc - log(ua), anc);
+        clamp += orc_multinomial_from_ladder(normw, N, N, ebuf, acc - orc_rng_log(ua), anc);
       }
       if (cfg->shuffle) {
         const double* us;

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "oracle.h"
+#include "rngmath.h"
 
 #define M_LN_SQRT_2PI_FULL 0.918938533204672741780329736406 /* R's dnorm(log=TRUE) constant (nmath/dnorm.c) */
 #define TWO_PI 6.283185307179586476925286766559
@@ -21,9 +22,10 @@ static inline void uni2(uint64_t seed, uint64_t filter_id, uint32_t i, int t, in
   orc_philox_uniform2(seed, i, c1_of(filter_id, t), (uint32_t)filter_id, (uint32_t)purpose | (draw << 8), ua, ub);
 }
 static inline void normal2(double ua, double ub, double* z0, double* z1) {
-  double r = sqrt(-2.0 * log(ua));
-  *z0 = r * cos(TWO_PI * ub);
-  *z1 = r * sin(TWO_PI * ub);
+  double r = sqrt(-2.0 * orc_rng_log(ua)), s, c;      /* the RNG specification's log / sincos (rngmath.h) */
+  orc_rng_sincos2pi(ub, &s, &c);
+  *z0 = r * c;
+  *z1 = r * s;
 }
 /* R nmath/dnorm.c, give_log branch */
 static inline double dnorm_log(double x, double mu, double sigma) {
@@ -64,7 +66,7 @@ static void sv_jump_sums(const orc_config* c, uint64_t seed, uint64_t fid, uint3
   double a = 0, b = 0, escale = w2 / xi;
   for (int j = 1; j <= k; j++) {
     uni2(seed, fid, i, t, ORC_P_TRANS, (uint32_t)j, &ua, &ub);
-    double e = -log(ub) * escale;            /* rexp(k, rate=xi/w2) = exp_rand() * (w2/xi) */
+    double e = -orc_rng_log(ub) * escale;            /* rexp(k, rate=xi/w2) = exp_rand() * (w2/xi) */
     a += exp(-lambda * ua) * e;              /* exp(-lambda (t - c)), t - c ~ U(0,1) */
     b += e;
   }
@@ -139,7 +141,7 @@ void orc_fill_trans_noise(const orc_config* c, uint64_t seed, uint64_t fid, int 
       for (int i = 0; i < N; i++)
         for (int m = 0; m < M; m++) {
           uni2(seed, fid, i, time, ORC_P_TRANS, (uint32_t)m, &ua, &ub);
-          noise[(size_t)m * N + i] = -log(ua);
+          noise[(size_t)m * N + i] = -orc_rng_log(ua);
           noise[(size_t)(M + m) * N + i] = ub;
         }
       break;
@@ -271,7 +273,7 @@ static const int SK_S[4][8] = {{0, 0, 1, 0, 0, 0, -1, 0}, {0, 0, 0, 1, -2, 2, 0,
 typedef struct { const double* inj; int N, M, i; uint64_t seed, fid; int t; } sk_src;
 static inline void sk_draw(const sk_src* s, int m, double* E, double* U) {
   if (s->inj) { *E = s->inj[(size_t)m * s->N + s->i]; *U = s->inj[(size_t)(s->M + m) * s->N + s->i]; }
-  else { double ua, ub; uni2(s->seed, s->fid, (uint32_t)s->i, s->t, ORC_P_TRANS, (uint32_t)m, &ua, &ub); *E = -log(ua); *U = ub; }
+  else { double ua, ub; uni2(s->seed, s->fid, (uint32_t)s->i, s->t, ORC_P_TRANS, (uint32_t)m, &ua, &ub); *E = -orc_rng_log(ua); *U = ub; }
 }
 static int sk_particle(double* x, const sk_src* src, int* clamp) {
   const double k = 5;                                                              /* :17 */

@@ -35,3 +35,9 @@ void orc_philox_uniform2(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, u
 }
 
 const char* orc_version(void) { return "cpimh-oracle 0.1 (parity unpinned: reference has no tests and cannot run here)"; }
+
+/* elementwise rng_log / rng_sincos2pi (rngmath.h) for the tests */
+#include "rngmath.h"
+void orc_rng_transform(const double* u, int64_t n, double* lg, double* sn, double* cs) {
+  for (int64_t i = 0; i < n; i++) { lg[i] = orc_rng_log(u[i]); orc_rng_sincos2pi(u[i], &sn[i], &cs[i]); }
+}

@@ -21,14 +21,19 @@ MAX_THETA = 32
 def build(force=False):
     """Compile the oracle with gcc (plain `gcc` from PATH; $CC in this image points at a wrapper without OpenMP specs)."""
     srcs = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "oracle.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    deps = srcs + [os.path.join(HERE, "rngmath.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in deps):
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     base = ["gcc", "-O2", "-std=gnu11", "-fPIC", "-ffp-contract=off", "-shared", "-o", LIB_PATH] + srcs[:-1] + ["-lm"]
-    try:
-        subprocess.run(base[:5] + ["-fopenmp"] + base[5:], check=True, capture_output=True, cwd=HERE)
-    except subprocess.CalledProcessError:
-        subprocess.run(base, check=True, cwd=HERE)
+    # -mfma only makes the explicit fma() calls of rngmath.h inline (libm's fma gives the same correctly rounded result)
+    for extra in (["-mfma", "-fopenmp"], ["-fopenmp"], []):
+        try:
+            subprocess.run(base[:5] + extra + base[5:], check=True, capture_output=True, cwd=HERE)
+            return LIB_PATH
+        except subprocess.CalledProcessError:
+            continue
+    subprocess.run(base, check=True, cwd=HERE)
     return LIB_PATH
 
 
@@ -496,3 +501,11 @@ def coupled_ccpf_batch(cfg, obs, seed, first_replicate, nrep, k=0, K=1, max_iter
     if rb:
         out["hbar_rb"] = hrb
     return out
+
+
+def rng_transform(u):
+    """The RNG specification's log and sin/cos(2 pi u) (oracle/rngmath.h) applied elementwise."""
+    u = _f64(np.ravel(u))
+    lg, sn, cs = np.empty_like(u), np.empty_like(u), np.empty_like(u)
+    lib().orc_rng_transform(_p(u), C.c_int64(u.size), _p(lg), _p(sn), _p(cs))
+    return lg, sn, cs

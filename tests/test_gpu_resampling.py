@@ -157,3 +157,16 @@ def test_tree_object_matches_oracle_tree(up, oracle):
         for lag in (0, 3):
             assert np.array_equal(tg.retrieve_xgeneration(lag), to.retrieve_xgeneration(lag))
         tg.close()
+
+
+def test_rng_specification_functions_are_bit_identical_on_the_gpu(oracle):
+    """rng_log / rng_sincos2pi: the same double on the CPU oracle and on the B200 for every uniform (edge cases included)."""
+    from unbiased_pimh_b200 import rng as prng
+    g = np.random.default_rng(6)
+    u = np.concatenate([g.random(300000), 1.0 - g.random(50000) * 1e-9, g.random(50000) * 1e-12, (np.arange(1, 2049) - 0.5) / 2048,
+                        [2.0 ** -53, 1.0 - 2.0 ** -53, 0.5, 0.25, 0.75, 0.125, 0.375, 0.7071067811865476, 0.7071067811865475]])
+    u = u[(u > 0) & (u < 1)]
+    ol, os_, oc = oracle.rng_transform(u)
+    gl, gs, gc = prng.rng_transform(u)
+    assert np.array_equal(ol.view(np.int64), gl.view(np.int64))
+    assert np.array_equal(os_.view(np.int64), gs.view(np.int64)) and np.array_equal(oc.view(np.int64), gc.view(np.int64))

@@ -244,3 +244,24 @@ def test_rmvnorm_family(oracle):
     zn = rng.normal(size=(n, d))
     assert np.allclose(oracle.rmvnorm(n, mean, cov, zn), zn @ L.T + mean[None, :], rtol=1e-12)
     assert np.allclose(oracle.create_A(0.5, 4), [[0.5 ** (1 + abs(i - j)) for j in range(4)] for i in range(4)])
+
+
+def test_rng_specification_log_and_sincos(oracle):
+    """oracle/rngmath.h: the fixed-operation-sequence log and sin/cos(2 pi u) of the RNG specification are 1-ulp accurate."""
+    rng = np.random.default_rng(5)
+    u = np.concatenate([rng.random(200000), 1.0 - rng.random(50000) * 1e-9, rng.random(50000) * 1e-12,
+                        [2.0 ** -53, 1.0 - 2.0 ** -53, 0.5, 0.25, 0.75, 0.125, 0.7071067811865476, 0.7071067811865475]])
+    u = u[(u > 0) & (u < 1)]
+    lg, sn, cs = oracle.rng_transform(u)
+    assert np.max(np.abs(lg - np.log(u)) / np.abs(np.log(u))) < 4.5e-16
+    ang = 2 * np.pi * u.astype(np.longdouble)
+    assert np.max(np.abs(sn - np.sin(ang).astype(np.float64))) < 4e-16 and np.max(np.abs(cs - np.cos(ang).astype(np.float64))) < 4e-16
+    assert np.max(np.abs(sn * sn + cs * cs - 1)) < 1e-15
+    # Box-Muller on top of them gives standard normals (moments and a KS test)
+    from scipy import stats
+    ua, ub = rng.random(400000), rng.random(400000)
+    la, _, _ = oracle.rng_transform(ua)
+    _, s2, c2 = oracle.rng_transform(ub)
+    z = np.concatenate([np.sqrt(-2 * la) * c2, np.sqrt(-2 * la) * s2])
+    assert abs(z.mean()) < 5e-3 and abs(z.var() - 1) < 6e-3 and abs(stats.kurtosis(z)) < 0.02
+    assert stats.kstest(z[:100000], "norm").pvalue > 1e-3

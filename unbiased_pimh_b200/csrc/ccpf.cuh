@@ -186,7 +186,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
 
     // ---- ancestors of the N-1 free particles
     if (!ident) {
-      for (int i = tid; i <= nd + 1; i += NT) sm.P[i] = -log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
+      for (int i = tid; i <= nd + 1; i += NT) sm.P[i] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
       if (nsys == 1) {
         __syncthreads();
         block_scan_inplace<false>(sm.C1, N, sm.dscr);

@@ -66,18 +66,98 @@ __device__ __forceinline__ double philox_u1(const Stream& s, uint32_t i, int t, 
   uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, (uint32_t)purpose | (draw << 8)), make_uint2(s.k0, s.k1));
   return u64_to_unit(r.x, r.y);
 }
+// ---------------------------------------------------------------- transcendental maps of the RNG specification
+// uniforms -> exponential variates (rng_log) and -> Box-Muller angles (rng_sincos2pi).  They belong to the SPECIFICATION of
+// the Philox streams (DESIGN.md "RNG"), not to the reference's arithmetic (R's norm_rand / exp_rand cannot be reproduced on
+// a GPU): fixed sequences of IEEE-754 double operations, written with explicit round-to-nearest intrinsics so that nvcc
+// neither contracts nor reorders them; the CPU oracle runs the same sequence (oracle/rngmath.h), so every uniform maps to the
+// same double on both sides.  About half the instructions of log() / sincospi(): no special cases, no table, 1 ulp.
+// log(u), u a positive normal double < 2: u = 2^e m, m in (sqrt(1/2), sqrt(2)], s = (m-1)/(m+1), log m = 2 atanh(s).
+__device__ __forceinline__ double rng_log(double u) {
+  const long long b0 = __double_as_longlong(u);
+  int e = (int)(b0 >> 52) - 1023;
+  double m = __longlong_as_double((b0 & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll);
+  if (m > 0x1.6a09e667f3bcdp+0) { m = __dmul_rn(m, 0.5); e = e + 1; }
+  const double f = __dadd_rn(m, -1.0), d = __dadd_rn(m, 1.0);
+  const double h = __dmul_rn(d, 0.5);
+  const double t = __dadd_rn(1.0, -h);
+  double r = __fma_rn(t, __dadd_rn(1.0, t), 1.0);          // 1/h to 1e-2, then three Newton steps
+  double eps = __fma_rn(-h, r, 1.0);
+  r = __fma_rn(r, eps, r);
+  eps = __fma_rn(-h, r, 1.0);
+  r = __fma_rn(r, eps, r);
+  eps = __fma_rn(-h, r, 1.0);
+  r = __fma_rn(r, eps, r);
+  const double rd = __dmul_rn(r, 0.5);
+  double s = __dmul_rn(f, rd);
+  const double rem = __fma_rn(-s, d, f);
+  s = __fma_rn(rem, rd, s);                                // s = f/d
+  const double z = __dmul_rn(s, s);
+  double p = 0x1.8618618618618p-5;                         // 1/21, 1/19, ..., 1/3
+  p = __fma_rn(p, z, 0x1.af286bca1af28p-5);
+  p = __fma_rn(p, z, 0x1.e1e1e1e1e1e1ep-5);
+  p = __fma_rn(p, z, 0x1.1111111111111p-4);
+  p = __fma_rn(p, z, 0x1.3b13b13b13b14p-4);
+  p = __fma_rn(p, z, 0x1.745d1745d1746p-4);
+  p = __fma_rn(p, z, 0x1.c71c71c71c71cp-4);
+  p = __fma_rn(p, z, 0x1.2492492492492p-3);
+  p = __fma_rn(p, z, 0x1.999999999999ap-3);
+  p = __fma_rn(p, z, 0x1.5555555555555p-2);
+  const double s2 = __dadd_rn(s, s);
+  const double lm = __fma_rn(__dmul_rn(s2, z), p, s2);
+  return __fma_rn(__int2double_rn(e), 0x1.62e42fefa39efp-1, lm);
+}
+// sin(2 pi a), cos(2 pi a), a in [0, 1]: a = q/4 + r, |r| <= 1/8, Taylor series in r^2, quadrant fix-up
+template <bool WANT_SIN>
+__device__ __forceinline__ void rng_sincos2pi(double a, double& sn, double& cs) {
+  const double q = rint(__dmul_rn(4.0, a));
+  const double r = __fma_rn(-0.25, q, a);
+  const double z = __dmul_rn(r, r);
+  const int qi = (int)q & 3;
+  double sr = 0.0, cr = 0.0;
+  if (WANT_SIN || (qi & 1)) {
+    double ps = 0x1.aaec32af93359p-4;
+    ps = __fma_rn(ps, z, -0x1.6fadb9f155744p-1);
+    ps = __fma_rn(ps, z, 0x1.e8f434d018d63p+1);
+    ps = __fma_rn(ps, z, -0x1.e3074fde8871fp+3);
+    ps = __fma_rn(ps, z, 0x1.50783487ee782p+5);
+    ps = __fma_rn(ps, z, -0x1.32d2cce62bd86p+6);
+    ps = __fma_rn(ps, z, 0x1.466bc6775aae2p+6);
+    ps = __fma_rn(ps, z, -0x1.4abbce625be53p+5);
+    ps = __fma_rn(ps, z, 0x1.921fb54442d18p+2);
+    sr = __dmul_rn(r, ps);
+  }
+  if (WANT_SIN || !(qi & 1)) {
+    double pc = -0x1.2a0c591af8314p-5;
+    pc = __fma_rn(pc, z, 0x1.20c62c2f2d7f5p-2);
+    pc = __fma_rn(pc, z, -0x1.b6e24f44b128fp+0);
+    pc = __fma_rn(pc, z, 0x1.f9d38a3763cc3p+2);
+    pc = __fma_rn(pc, z, -0x1.a6d1f2a204a8cp+4);
+    pc = __fma_rn(pc, z, 0x1.e1f506891babbp+5);
+    pc = __fma_rn(pc, z, -0x1.55d3c7e3cbffap+6);
+    pc = __fma_rn(pc, z, 0x1.03c1f081b5ac4p+6);
+    pc = __fma_rn(pc, z, -0x1.3bd3cc9be45dep+4);
+    cr = __fma_rn(z, pc, 1.0);
+  }
+  sn = (qi & 1) ? cr : sr;
+  cs = (qi & 1) ? sr : cr;
+  if (qi == 1 || qi == 2) cs = -cs;
+  if (qi >= 2) sn = -sn;
+}
 // Box-Muller pair: r = sqrt(-2 log ua), angle 2 pi ub
 __device__ __forceinline__ void normal2(double ua, double ub, double& z0, double& z1) {
-  double r = sqrt(-2.0 * log(ua));
+  const double r = sqrt(__dmul_rn(-2.0, rng_log(ua)));
   double s, c;
-  sincospi(2.0 * ub, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
+  rng_sincos2pi<true>(ub, s, c);
+  z0 = __dmul_rn(r, c);
+  z1 = __dmul_rn(r, s);
 }
-
 // first normal of the pair only (models that consume one normal per draw): the same value as normal2's z0
 __device__ __forceinline__ double normal1(double ua, double ub) {
-  return sqrt(-2.0 * log(ua)) * cospi(2.0 * ub);
+  const double r = sqrt(__dmul_rn(-2.0, rng_log(ua)));
+  double s, c;
+  rng_sincos2pi<true>(ub, s, c);
+  return __dmul_rn(r, c);
 }
 
 // ---------------------------------------------------------------- warp / block primitives (fp64)

@@ -161,7 +161,7 @@ struct LevySvModel {
   __device__ static __forceinline__ void jump(const ModelCtx& c, int i, int t, int j, double& wa, double& e) {
     double ua, ub;
     philox_u2(c.stream, i, t, CPIMH_P_TRANS, j, ua, ub);
-    e = -log(ub) * c.pre[2];
+    e = -rng_log(ub) * c.pre[2];
     wa = exp(-c.theta[4] * ua) * e;
   }
   __device__ static void jump_sums(const ModelCtx& c, int i, int t, double upois, double& swe, double& se) {
@@ -281,7 +281,7 @@ struct SkModel {
   }
   __device__ static __forceinline__ void draw(const ModelCtx& c, int t, int i, int m, double& E, double& U) {
     if (c.inj_trans) { E = trans_row(c, t, m)[i]; U = trans_row(c, t, c.sk_M + m)[i]; }
-    else { double ua, ub; philox_u2(c.stream, i, t, CPIMH_P_TRANS, m, ua, ub); E = -log(ua); U = ub; }
+    else { double ua, ub; philox_u2(c.stream, i, t, CPIMH_P_TRANS, m, ua, ub); E = -rng_log(ua); U = ub; }
   }
   // exact Gillespie over one inter-observation interval of 0.1 (:96-129).  Returns 0, or CPIMH_ERR_NOISE_OVERFLOW when
   // the injected event budget is exhausted; bit 8 set if an event index was clamped.

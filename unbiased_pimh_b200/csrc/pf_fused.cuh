@@ -199,13 +199,13 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     if (tree) for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
     const bool draw_res = !ident && !inj_res;
     unsigned long long tok0 = 0ull, tok1 = 0ull;           // 8-bit model tokens of this thread's particles (jump counts)
-    if (draw_res && tid == 0) sm.dscr2[0] = -log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0));   // E_N, read after the scan's barriers
+    if (draw_res && tid == 0) sm.dscr2[0] = -rng_log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0));   // E_N, read after the scan's barriers
     if (draw_res || need_shared_u) {
       int e = 0;
       for (int i = tid; i < N; i += NT, e++) {
         double ua, ub;
         philox_u2(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, ub);
-        if (draw_res) sm.S[i] = -log(ua);                 // exponential spacing E_i (see the ladder comment below)
+        if (draw_res) sm.S[i] = -rng_log(ua);                 // exponential spacing E_i (see the ladder comment below)
         if constexpr (Model::JUMP_LIST) {
           if (jump_list) {                                // the model turns its uniform into a small count right away
             int tk = Model::token(c, ub);

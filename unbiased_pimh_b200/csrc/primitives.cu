@@ -6,7 +6,7 @@
 #include <math.h>
 #include <string.h>
 #include <vector>
-#include "registry.h"
+#include "host_common.h"
 
 namespace cpimh {
 
@@ -335,6 +335,16 @@ __global__ void dfma_kernel(double* out, int iters) {
 
 using namespace cpimh;
 
+namespace cpimh {
+__global__ void rng_transform_kernel(const double* u, long long n, double* lg, double* sn, double* cs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  lg[i] = rng_log(u[i]);
+  double s, c;
+  rng_sincos2pi<true>(u[i], s, c);
+  sn[i] = s; cs[i] = c;
+}
+}  // namespace cpimh
 extern "C" {
 
 int cpimh_systematic_resampling_n(const double* w, int64_t B, int N, int ndraws, const double* u, int32_t* anc) {
@@ -566,6 +576,24 @@ int cpimh_measure_fp64_peak(double* tflops) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
   CPIMH_CUDA_CHECK(cudaGetLastError());
   *tflops = best;
+  return CPIMH_OK;
+}
+
+int cpimh_rng_transform(const double* u, int64_t n, double* lg, double* sn, double* cs) {
+  CPIMH_REQUIRE(u && lg && sn && cs && n >= 1, "null argument");
+  DevBuf du, dl, ds, dc;
+  struct Rel { DevBuf* b[4]; ~Rel() { for (auto x : b) x->release(); } } rel{{&du, &dl, &ds, &dc}};
+  int rc = du.alloc(sizeof(double) * n);
+  if (!rc) rc = dl.alloc(sizeof(double) * n);
+  if (!rc) rc = ds.alloc(sizeof(double) * n);
+  if (!rc) rc = dc.alloc(sizeof(double) * n);
+  if (rc) return rc;
+  CPIMH_CUDA_CHECK(cudaMemcpy(du.p, u, sizeof(double) * n, cudaMemcpyHostToDevice));
+  rng_transform_kernel<<<(unsigned)((n + 255) / 256), 256>>>(du.as<double>(), n, dl.as<double>(), ds.as<double>(), dc.as<double>());
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  CPIMH_CUDA_CHECK(cudaMemcpy(lg, dl.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  CPIMH_CUDA_CHECK(cudaMemcpy(sn, ds.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  CPIMH_CUDA_CHECK(cudaMemcpy(cs, dc.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return CPIMH_OK;
 }
 

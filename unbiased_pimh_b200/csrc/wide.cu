@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
       p.lw[(size_t)b * N + k] = w;        // NOT into C: other warps of this launch are still searching the CDF
       if (prep_next) {
         if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t) * N + k];         // row of step t+1
-        else v = -log(philox_u1(s, (unsigned)k, t + 1, CPIMH_P_RESAMPLE, 0));
+        else v = -rng_log(philox_u1(s, (unsigned)k, t + 1, CPIMH_P_RESAMPLE, 0));
         p.S[(size_t)b * N + k] = v;
         if (p.inj_resample) v = 0.0;
       }
@@ -226,7 +226,7 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   }
   if (ladder && rank == WIDE_CLUSTER - 1 && threadIdx.x == 0) {
     const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
-    p.ptot[b] = vrun - log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
+    p.ptot[b] = vrun - rng_log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
   }
 }
 
