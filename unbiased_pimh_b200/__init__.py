@@ -17,6 +17,6 @@ from .pimh import (get_pimh_kernels, coupled_pimh_chains, H_bar, BC, rheeglynn_e
 from .tree import Tree  # noqa: F401
 from .mvnorm import (fast_dmvnorm, fast_dmvnorm_transpose, fast_dmvnorm_transpose_cholesky, fast_rmvnorm, fast_rmvnorm_transpose,  # noqa: F401
                      fast_rmvnorm_transpose_cholesky, lorenz_transition)
-from .rdata import read_rdata  # noqa: F401
+from .rdata import read_rdata, write_rdata  # noqa: F401
 
 __version__ = "0.1.0"

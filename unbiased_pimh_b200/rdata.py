@@ -164,3 +164,109 @@ def read_rdata(path):
         r.p += n  # native encoding string
     top = r.item()
     return dict((k, v) for k, v in top)
+
+
+# ---------------------------------------------------------------------------------------------- writer
+class _Writer:
+    """Serialises python values in R's XDR format (version 2): the inverse of _Reader for the subset the reference's scripts
+    exchange -- numeric / integer / logical / character vectors and matrices, named lists, NULL, Inf and NA."""
+
+    def __init__(self):
+        self.out = bytearray()
+        self.syms = {}
+
+    def i32(self, v):
+        self.out += struct.pack(">i", int(v))
+
+    def flags(self, t, has_attr=False, has_tag=False, is_obj=False):
+        self.i32(t | (int(is_obj) << 8) | (int(has_attr) << 9) | (int(has_tag) << 10))
+
+    def charsxp(self, s):
+        if s is None:
+            self.i32(9)                      # NA_STRING
+            self.i32(-1)
+            return
+        b = s.encode("utf-8")
+        self.i32(9 | (1 << 18 if b.isascii() else 1 << 15))   # levels << 12: ASCII_MASK (1 << 6) or UTF8_MASK (1 << 3)
+        self.i32(len(b))
+        self.out += b
+
+    def symbol(self, name):
+        if name in self.syms:
+            self.i32((self.syms[name] << 8) | REFSXP)
+            return
+        self.i32(1)
+        self.charsxp(name)
+        self.syms[name] = len(self.syms) + 1
+
+    def attributes(self, attrs):
+        for k, v in attrs:
+            self.flags(2, has_tag=True)
+            self.symbol(k)
+            self.item(v)
+        self.i32(NILVALUE_SXP)
+
+    def item(self, v):
+        if v is None:
+            self.i32(NILVALUE_SXP)
+            return
+        if isinstance(v, dict):
+            self.flags(19, has_attr=True)
+            self.i32(len(v))
+            for x in v.values():
+                self.item(x)
+            self.attributes([("names", [str(k) for k in v.keys()])])
+            return
+        if isinstance(v, (list, tuple)) and v and all(isinstance(x, (str, type(None))) for x in v):
+            self.flags(16)
+            self.i32(len(v))
+            for x in v:
+                self.charsxp(x)
+            return
+        if isinstance(v, (list, tuple)):
+            self.flags(19)
+            self.i32(len(v))
+            for x in v:
+                self.item(x)
+            return
+        if isinstance(v, str):
+            self.item([v])
+            return
+        a = np.asarray(v)
+        attrs = []
+        if a.ndim >= 2:
+            attrs.append(("dim", np.asarray(a.shape, dtype=np.int32)))
+        flat = np.ravel(a, order="F")
+        if a.dtype == np.bool_:
+            self.flags(10, has_attr=bool(attrs))
+            self.i32(flat.size)
+            self.out += flat.astype(">i4").tobytes()
+        elif np.issubdtype(a.dtype, np.integer):
+            self.flags(13, has_attr=bool(attrs))
+            self.i32(flat.size)
+            self.out += flat.astype(">i4").tobytes()
+        else:
+            self.flags(14, has_attr=bool(attrs))
+            self.i32(flat.size)
+            self.out += flat.astype(">f8").tobytes()
+        if attrs:
+            self.attributes(attrs)
+
+
+def write_rdata(path, variables):
+    """Write {name: value} as a gzip'd RDX2 file that R's load() reads (and read_rdata() reads back): numpy arrays become
+    numeric / integer / logical vectors or matrices (column-major, dim attribute), dicts named lists, lists unnamed lists
+    or character vectors, None NULL.  This is how c_chains lists (samples1, samples2, log_pdf1, log_pdf2, meetingtime,
+    iteration, finished -- R/debiasing_algorithm.R:254-263) and data sets travel between this package and the R scripts."""
+    w = _Writer()
+    w.out += b"RDX2\nX\n"
+    w.i32(2)                # serialisation format version
+    w.i32(0x00030603)       # written by "R 3.6.3"
+    w.i32(0x00020300)       # readable from R 2.3.0
+    for name, val in variables.items():
+        w.flags(2, has_tag=True)
+        w.symbol(str(name))
+        w.item(val)
+    w.i32(NILVALUE_SXP)
+    with gzip.open(path, "wb") as f:
+        f.write(bytes(w.out))
