@@ -216,6 +216,16 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nf
 int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, int with_as, cpimh_chain_out* out_host);
 
+/* ============================== pf(): ESS-adaptive bootstrap filter ==============================
+ * pf(y, theta, model, nparticles, ess_threshold = 1, systematic = FALSE) -- R/CPF.R:106-155, B filters at once (the PMMH
+ * likelihood evaluator): propagate, weigh with the carried log-weights, resample iff (1 / sum(w^2)) / N < ess_threshold by
+ * multinomial or systematic resampling.  loglik [B] = sum of the increments; loglik_t [B][T] cumulative (nullable);
+ * pf_means [B][T][d] filtering means (nullable); path [B] x (d x (T+1) col-major); resampled [B][T] flags (nullable);
+ * ancestors [B][T][N] 0-based (nullable). */
+int cpimh_pf_adaptive_batch(const cpimh_config* cfg, const double* obs_host, int64_t nfilters, uint64_t seed, uint64_t first_filter,
+                            double ess_threshold, int systematic, double* loglik, double* loglik_t, double* pf_means, double* path,
+                            int32_t* resampled, int32_t* ancestors);
+
 /* the RNG specification's transcendental maps (DESIGN.md "RNG"; csrc/common.cuh rng_log / rng_sincos2pi), elementwise on
  * the device: lg = log(u), sn/cs = sin/cos(2 pi u) for u in (0,1).  Bit-identical to oracle/rngmath.h (tests). */
 int cpimh_rng_transform(const double* u, int64_t n, double* lg, double* sn, double* cs);

@@ -187,6 +187,20 @@ int  orc_coupled_ccpf_batch(const orc_config* cfg, const double* obs, uint64_t s
                             double* hbar /* [nrep][p] */, double* hbar_rb /* [nrep][p], nullable */, int* meetingtime, int* iterations,
                             long long* nfilters_total);
 
+/* ---- pf(): ESS-adaptive bootstrap filter (R/CPF.R:106-155) ---- */
+typedef struct orc_apf_out {
+  double* path;        /* d x (T+1), required                          */
+  double* pf_means;    /* [T][d] filtering means (nullable)             */
+  double* loglik_t;    /* [T] cumulative log-likelihood (nullable)      */
+  int*    resampled;   /* [T] 1 if the step resampled (nullable)        */
+  int*    ancestors;   /* [T][N] 0-based (nullable)                     */
+  double  loglik;
+  int     path_index;
+  int     clamp_count;
+} orc_apf_out;
+int orc_pf_adaptive(const orc_config* cfg, const double* obs, uint64_t seed, uint64_t filter_id, double ess_threshold, int systematic,
+                    orc_apf_out* out);
+
 const char* orc_version(void);
 
 #ifdef __cplusplus

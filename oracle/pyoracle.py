@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "build", "liboracle.so")
-SOURCES = ["philox.c", "resampling.c", "tree.c", "mvnorm.c", "models.c", "cpf.c", "ccpf.c"]
+SOURCES = ["philox.c", "resampling.c", "tree.c", "mvnorm.c", "models.c", "cpf.c", "ccpf.c", "apf.c"]
 
 MODEL_GSS, MODEL_AR, MODEL_LEVY_SV, MODEL_SK, MODEL_LORENZ = range(5)
 INTEGRATOR_RK4, INTEGRATOR_DOPRI5 = 0, 1
@@ -509,3 +509,28 @@ def rng_transform(u):
     lg, sn, cs = np.empty_like(u), np.empty_like(u), np.empty_like(u)
     lib().orc_rng_transform(_p(u), C.c_int64(u.size), _p(lg), _p(sn), _p(cs))
     return lg, sn, cs
+
+
+class ApfOut(C.Structure):
+    _fields_ = [("path", C.c_void_p), ("pf_means", C.c_void_p), ("loglik_t", C.c_void_p), ("resampled", C.c_void_p), ("ancestors", C.c_void_p),
+                ("loglik", C.c_double), ("path_index", C.c_int), ("clamp_count", C.c_int)]
+
+
+def pf_adaptive(cfg, obs, seed=0, filter_id=0, ess_threshold=1.0, systematic=False, want_ancestors=False):
+    """pf(y, theta, model, nparticles, ess_threshold, systematic) (R/CPF.R:106-155) for the hot-path models."""
+    T, d, N = cfg.nobs, cfg.dim, cfg.nparticles
+    ob = np.asfortranarray(np.asarray(obs, dtype=np.float64).reshape(T, -1))
+    path = np.empty((d, T + 1), order="F"); means = np.empty((T, d)); llt = np.empty(T); res = np.empty(T, dtype=np.int32)
+    anc = np.empty((T, N), dtype=np.int32) if want_ancestors else None
+    o = ApfOut()
+    o.path, o.pf_means, o.loglik_t, o.resampled = path.ctypes.data, means.ctypes.data, llt.ctypes.data, res.ctypes.data
+    o.ancestors = anc.ctypes.data if want_ancestors else None
+    rc = lib().orc_pf_adaptive(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_uint64(seed), C.c_uint64(filter_id), C.c_double(ess_threshold),
+                               C.c_int(int(systematic)), C.byref(o))
+    if rc:
+        raise RuntimeError("oracle pf_adaptive failed (%d)" % rc)
+    out = dict(path=np.ascontiguousarray(path.T), pf_means=means, loglik=float(o.loglik), loglik_t=llt, resampled=res, path_index=int(o.path_index),
+               clamp_count=int(o.clamp_count))
+    if want_ancestors:
+        out["ancestors"] = anc
+    return out

@@ -191,3 +191,47 @@ def test_rao_blackwellised_conditional_filters_and_rheeglynn(up, oracle, golden)
     assert r0["estimate"].shape == (1, 101)
     rc = up.CPF_RB_coupled(N, up.get_ar(1), TH_AR, y, refs[0], refs[1], with_as=False, seed=5)
     assert rc["estimate1"].shape == (1, 101) and not np.array_equal(rc["estimate1"], rc["estimate2"])
+
+
+@pytest.mark.parametrize("name", ["ar1", "gss", "sv", "sk", "ar3"])
+@pytest.mark.parametrize("ess,systematic", [(1.0, False), (0.5, False), (0.5, True)])
+def test_adaptive_pf_matches_oracle(up, oracle, golden, name, ess, systematic):
+    """pf() (R/CPF.R:106-155): same resampling decisions, ancestors, cumulative log-likelihood, filtering means and path."""
+    if name == "ar1":
+        m, th, y, N, oc = up.get_ar(1), TH_AR, golden["lgssm_y"], 96, (oracle.MODEL_AR, 1, 1)
+    elif name == "ar3":
+        m, th, y, N, oc = up.get_ar(3), TH_AR, np.random.default_rng(4).normal(size=(30, 3)), 100, (oracle.MODEL_AR, 3, 3)
+    elif name == "gss":
+        m, th, y, N, oc = up.get_gss(), [], golden["gss_y"][:60], 128, (oracle.MODEL_GSS, 1, 1)
+    elif name == "sv":
+        m, th, y, N, oc = up.get_levy_sv(), golden["sv_theta_mle"], golden["sv_y"][:40], 200, (oracle.MODEL_LEVY_SV, 2, 1)
+    else:
+        m, th, y, N, oc = up.get_stochastic_kinetic(), SK_THETA, golden["sk_y"][:20], 64, (oracle.MODEL_SK, 4, 2)
+    T = y.shape[0]
+    oth = th if name != "sk" else [1.0] + list(A_OBS.flatten(order="F"))
+    cfg = oracle.make_config(oc[0], oc[1], oc[2], N, T, theta=oth)
+    g = up.pf_batch(y, th, m, N, 3, ess_threshold=ess, systematic=systematic, seed=41, first_filter=2, ancestors=True)
+    for b in range(3):
+        o = oracle.pf_adaptive(cfg, y, seed=41, filter_id=2 + b, ess_threshold=ess, systematic=systematic, want_ancestors=True)
+        assert np.array_equal(g["resampled"][b], o["resampled"])
+        assert np.array_equal(g["ancestors"][b], o["ancestors"])
+        assert np.allclose(g["loglik_t"][b], o["loglik_t"], rtol=1e-10, atol=1e-10) and abs(g["loglik"][b] - o["loglik"]) <= 1e-10 * abs(o["loglik"])
+        assert np.allclose(g["pf_means"][b], o["pf_means"], rtol=1e-9, atol=1e-10)
+        assert np.allclose(g["path"][b], o["path"], rtol=1e-9, atol=1e-9)
+    if ess == 1.0:
+        assert g["resampled"].all()
+    else:
+        assert 0 < g["resampled"].mean() < 1
+
+
+def test_adaptive_pf_likelihood_is_unbiased(up, golden):
+    """exp(loglik) is an unbiased estimator of the likelihood: log-mean-exp over 4000 filters matches the Kalman value."""
+    y = golden["lgssm_y"]
+    for ess, systematic in ((1.0, False), (0.5, True)):
+        r = up.pf_batch(y, TH_AR, up.get_ar(1), 256, 4000, ess_threshold=ess, systematic=systematic, seed=9)
+        ll = r["loglik"]
+        lme = np.log(np.mean(np.exp(ll - ll.max()))) + ll.max()
+        assert abs(lme - float(golden["lgssm_kalman_loglik"])) < 0.05
+        assert np.allclose(r["loglik_t"][:, -1], ll, rtol=1e-13)
+    one = up.pf(y, TH_AR, up.get_ar(1), 128, seed=3)
+    assert one["pf_means"].shape == (100, 1) and one["path"].shape == (101, 1) and one["loglik_t"].shape == (100,)

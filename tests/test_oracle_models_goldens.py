@@ -341,3 +341,27 @@ def test_conditional_filters_oracle_properties(oracle, golden):
     assert c["finished"] and c["samples1"].shape == (c["iteration"] + 1, 101) and c["samples2"].shape == (c["iteration"], 101)
     for t in range(int(c["meetingtime"]), c["iteration"] + 1):
         assert np.array_equal(c["samples1"][t], c["samples2"][t - 1])
+
+
+def test_adaptive_pf_oracle(oracle, golden):
+    """oracle/apf.c (pf(), R/CPF.R:106-155): ess_threshold = 1 resamples every step, a low threshold rarely; the likelihood
+    estimator is unbiased for the Kalman value for multinomial and systematic resampling; loglik_t is the running sum."""
+    y = golden["lgssm_y"]
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 256, 100, theta=[0.5, math.sqrt(10.0)])
+    kal = float(golden["lgssm_kalman_loglik"])
+    for ess, systematic in ((1.0, False), (0.5, False), (0.5, True)):
+        rs = [oracle.pf_adaptive(cfg, y, seed=3, filter_id=f, ess_threshold=ess, systematic=systematic, want_ancestors=(f == 0)) for f in range(120)]
+        ll = np.array([r["loglik"] for r in rs])
+        lme = math.log(np.mean(np.exp(ll - ll.max()))) + ll.max()
+        assert abs(lme - kal) < 0.12, (ess, systematic, lme)
+        frac = np.mean([r["resampled"].mean() for r in rs])
+        assert frac == 1.0 if ess == 1.0 else 0.02 < frac < 0.6
+        r0 = rs[0]
+        assert r0["loglik_t"][-1] == r0["loglik"] and np.all(np.diff(r0["loglik_t"]) < 0) and r0["clamp_count"] == 0
+        a = r0["ancestors"]
+        for t in range(100):
+            if r0["resampled"][t]:
+                assert np.all(np.diff(a[t]) >= 0) and a[t].min() >= 0 and a[t].max() < 256      # sorted draws / systematic: ascending
+            else:
+                assert np.array_equal(a[t], np.arange(256))
+        assert r0["pf_means"].shape == (100, 1) and r0["path"].shape == (101, 1)

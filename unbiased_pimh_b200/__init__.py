@@ -10,7 +10,7 @@ from .models import Model, get_gss, get_ar, get_levy_sv, get_stochastic_kinetic,
 from .resampling import (multinomial_resampling_n, multinomial_resampling_n_, systematic_resampling_n, systematic_resampling_n_,  # noqa: F401
                          coupled_multinomial_resampling_n_, indexmatching_cpp, CR_multinomial, CR_systematic, CR_indexmatching,
                          normalize_weight, sorted_uniforms)
-from .filters import CPF, CPF_coupled, CPF_RB, CPF_RB_coupled, ccpf_batch, particlefilter, cpf_batch, PfBatch, pf_get_weighted_average  # noqa: F401
+from .filters import CPF, CPF_coupled, CPF_RB, CPF_RB_coupled, ccpf_batch, pf, pf_batch, particlefilter, cpf_batch, PfBatch, pf_get_weighted_average  # noqa: F401
 from .pimh import (get_pimh_kernels, coupled_pimh_chains, H_bar, BC, rheeglynn_estimator, coupled_pimh_chains_batch, ChainBatch,  # noqa: F401
                    unbiased_estimator_sharded, shard_range, combine_sums, get_cpf_kernels, coupled_ccpf_chains,
                    coupled_ccpf_chains_batch, rheeglynn_estimator_RB)

@@ -1,0 +1,208 @@
+// apf.cuh -- pf(y, theta, model, nparticles, ess_threshold, systematic) (R/CPF.R:106-155): the
+// bootstrap filter with ESS-triggered resampling that the PMMH scripts use as likelihood evaluator.  One CTA per filter.
+// A step is propagate -> weigh with the carried log-weights -> log-likelihood increment, normalised weights, filtering mean
+// -> resample iff (1 / sum(w^2)) / N < ess_threshold (sorted multinomial draws or systematic) -> store the RESAMPLED
+// particles and their ancestors (Tree$update, :149).  Randomness and its order: oracle/apf.c header, DESIGN.md "RNG".
+//
+// Layout: hist_x[ws][t][q][i] holds the resampled particles of every time (the path store), hist_a[ws][t][i] their
+// ancestors, prop[ws][q][i] the propagated particles of the current step (gather source).  Shared memory: weights / CDF,
+// ladder / log-weights, carried log-weights.
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+
+namespace cpimh {
+
+struct ApfParams {
+  int N, T, dy, Npad;
+  long long B;
+  unsigned long long seed, first_filter;
+  double ess_threshold;
+  int systematic;
+  const double* obs; const double* theta; const double* pre;
+  int npre, integrator, substeps, sk_M;
+  double* hist_x;              // [ws][T+1][D][Npad]
+  int* hist_a;                 // [ws][T][Npad]
+  double* prop;                // [ws][D][Npad]
+  double* loglik;              // [B]
+  double* loglik_t;            // [B][T] cumulative, or null
+  double* pf_means;            // [B][T][D] or null
+  double* path;                // [B][T+1][D]
+  int* path_index;             // [B] or null
+  int* resampled;              // [B][T] or null
+  int* anc_rec;                // [B][T][N] or null
+  int* status;                 // [B]
+};
+struct ApfSmem { double* C; double* S; double* LW; double* theta; double* pre; double* dscr; int* iscr; };
+__host__ __device__ inline size_t apf_smem_bytes(int Npad, int npre) {
+  size_t b = (size_t)(3 * Npad + 2) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + 36 * 4;
+  return (b + 15) & ~(size_t)15;
+}
+__device__ inline ApfSmem apf_carve(unsigned char* raw, int Npad, int npre) {
+  ApfSmem s;
+  double* d = reinterpret_cast<double*>(raw);
+  s.C = d; d += Npad;
+  s.S = d; d += Npad + 2;
+  s.LW = d; d += Npad;
+  s.theta = d; d += CPIMH_MAX_THETA;
+  s.pre = d; d += npre + (npre & 1);
+  s.dscr = d; d += 64;
+  s.iscr = reinterpret_cast<int*>(d);
+  return s;
+}
+
+template <class Model>
+__device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, const Stream& stream, long long b) {
+  constexpr int D = Model::D;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int N = p.N, T = p.T, Npad = p.Npad;
+  const size_t xstride = (size_t)D * Npad;
+  double* hx = p.hist_x + (size_t)ws * (T + 1) * xstride;
+  int* ha = p.hist_a + (size_t)ws * T * Npad;
+  double* prop = p.prop + (size_t)ws * xstride;
+  ModelCtx c;
+  c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
+  c.inj_init = nullptr; c.inj_trans = nullptr;
+  c.n_trans = 0; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
+  int st = 0;
+  if (tid == 0) sm.iscr[32] = 0;
+  const double lw0 = log(1.0 / (double)N);
+  for (int i = tid; i < N; i += NT) {                    // R/CPF.R:113-119
+    double x[D];
+    Model::init(c, i, x);
+#pragma unroll
+    for (int q = 0; q < D; q++) hx[(size_t)q * Npad + i] = x[q];
+    sm.LW[i] = lw0;
+  }
+  double cum = 0.0;
+  __syncthreads();
+
+  for (int t = 1; t <= T; t++) {
+    const double* y = p.obs + (size_t)(t - 1) * p.dy;
+    const double sc = Model::step_const(c, t);
+    const double* xprev = hx + (size_t)(t - 1) * xstride;
+    double* xres = hx + (size_t)t * xstride;
+    int* arow = ha + (size_t)(t - 1) * Npad;
+    // ---- propagate and weigh (:124-128)
+    double m = -INFINITY;
+    for (int k = tid; k < N; k += NT) {
+      double x[D];
+#pragma unroll
+      for (int q = 0; q < D; q++) x[q] = xprev[(size_t)q * Npad + k];
+      double ush = 0.5;
+      if (Model::USES_SHARED_U) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
+      st |= Model::transition(c, t, k, x, sc, ush);
+#pragma unroll
+      for (int q = 0; q < D; q++) prop[(size_t)q * Npad + k] = x[q];
+      const double lw = Model::logw(c, x, y) + sm.LW[k];
+      sm.S[k] = lw;
+      m = fmax(m, lw);
+    }
+    m = block_max(m, sm.dscr);
+    double s = 0.0;
+    for (int k = tid; k < N; k += NT) { const double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; }
+    s = block_sum(s, sm.dscr);
+    cum += m + log(s);                                   // :130
+    if (tid == 0 && p.loglik_t) p.loglik_t[(size_t)b * T + (t - 1)] = cum;
+    double s2 = 0.0;
+    for (int k = tid; k < N; k += NT) { const double w = sm.C[k] / s; sm.C[k] = w; s2 += w * w; }   // :131
+    s2 = block_sum(s2, sm.dscr);
+    if (p.pf_means) {                                    // :133
+#pragma unroll
+      for (int q = 0; q < D; q++) {
+        double a = 0.0;
+        for (int k = tid; k < N; k += NT) a += sm.C[k] * prop[(size_t)q * Npad + k];
+        a = block_sum(a, sm.dscr);
+        if (tid == 0) p.pf_means[((size_t)b * T + (t - 1)) * D + q] = a;
+      }
+    }
+    const bool resample = ((1.0 / s2) / (double)N) < p.ess_threshold;     // :135
+    if (tid == 0 && p.resampled) p.resampled[(size_t)b * T + (t - 1)] = resample ? 1 : 0;
+    // ---- resample (:136-147)
+    if (resample) {
+      if (!p.systematic) {
+        for (int i = tid; i <= N; i += NT) sm.S[i] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
+        __syncthreads();
+        block_scan_inplace<false>(sm.C, N, sm.dscr);
+        block_scan_inplace<false>(sm.S, N + 1, sm.dscr);
+        const double scale = sm.C[N - 1] / sm.S[N];
+        for (int k = tid; k < N; k += NT) {
+          int a = count_le(sm.C, N, scale * sm.S[k]);
+          if (a >= N) { a = N - 1; st |= 512; }
+          arow[k] = a;
+        }
+      } else {                                           // systematic_resampling_n(normweights, N, u): src/systematic.cpp:7-32
+        __syncthreads();
+        block_scan_inplace<false>(sm.C, N, sm.dscr);
+        const double u = philox_u1(stream, 0, t, CPIMH_P_AS, 0) / (double)N;
+        for (int k = tid; k < N; k += NT) {
+          int a = count_lt(sm.C, N, u + (double)k * (1.0 / (double)N));
+          if (a >= N) { a = N - 1; st |= 512; }
+          arow[k] = a;
+        }
+      }
+      __syncthreads();
+      for (int k = tid; k < N; k += NT) sm.LW[k] = lw0;
+    } else {
+      for (int k = tid; k < N; k += NT) { arow[k] = k; sm.LW[k] = log(sm.C[k]); }
+      __syncthreads();
+      if (t == T) block_scan_inplace<false>(sm.C, N, sm.dscr);           // the final draw needs the CDF
+    }
+    // ---- the tree keeps the resampled particles (:148-149)
+    for (int k = tid; k < N; k += NT) {
+      const int a = arow[k];
+#pragma unroll
+      for (int q = 0; q < D; q++) xres[(size_t)q * Npad + k] = prop[(size_t)q * Npad + a];
+      if (p.anc_rec) p.anc_rec[((size_t)b * T + (t - 1)) * N + k] = a;
+    }
+    __syncthreads();
+  }
+  // ---- sample(1:N, 1, prob = normweights) (:152) by inversion of the last CDF, then Tree$get_path
+  if (st) atomicOr(&sm.iscr[32], st);
+  __syncthreads();
+  int kidx = count_lt(sm.C, N, philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0));
+  if (kidx >= N) kidx = N - 1;
+  const int flags = sm.iscr[32];
+  if (tid == 0) {
+    p.loglik[b] = cum;
+    if (p.path_index) p.path_index[b] = kidx;
+    p.status[b] = flags & 255;
+  }
+  if (tid < 32) {
+    double* tr = p.path + (size_t)b * (T + 1) * D;
+    int j = kidx;
+    for (int step = T; step >= 0; step--) {
+      for (int q = tid; q < D; q += 32) tr[(size_t)step * D + q] = hx[(size_t)step * xstride + (size_t)q * Npad + j];
+      if (step > 0) j = ha[(size_t)(step - 1) * Npad + j];
+    }
+  }
+  __syncthreads();
+}
+
+template <class Model>
+__global__ void __launch_bounds__(512, 1) apf_kernel(ApfParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ApfSmem sm = apf_carve(smem_raw, p.Npad, p.npre);
+  for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
+  for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
+  __syncthreads();
+  for (long long b = blockIdx.x; b < p.B; b += gridDim.x)
+    run_apf<Model>(p, sm, blockIdx.x, make_stream(p.seed, p.first_filter + (unsigned long long)b), b);
+}
+
+struct ApfLaunch { int grid, threads; size_t smem; };
+template <class Model>
+int launch_apf(const ApfParams& p, const ApfLaunch& L, cudaStream_t stream) {
+  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(apf_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  apf_kernel<Model><<<L.grid, L.threads, L.smem, stream>>>(p);
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  return CPIMH_OK;
+}
+template <class Model>
+int occupancy_apf(int threads, size_t smem, int* blocks_per_sm) {
+  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(apf_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CPIMH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, apf_kernel<Model>, threads, smem));
+  return CPIMH_OK;
+}
+
+}  // namespace cpimh

@@ -1,4 +1,5 @@
-// api_ccpf.cu -- C ABI of the conditional particle filters: CPF(ref_trajectory, with_as)
+// api_ccpf.cu -- C ABI of the filters beyond the bootstrap hot path: pf() with ESS-adaptive resampling (R/CPF.R:106-155,
+// kernel apf.cuh) and the conditional particle filters: CPF(ref_trajectory, with_as)
 // (R/CPF.R:14-78), CPF_coupled (R/CPF_coupled.R:14-112), the CCPF kernels (R/pf_kernels.R:236-265) and
 // coupled_ccpf_chains + H_bar (R/debiasing_algorithm.R:23-111, 284-316).  Kernels: ccpf.cuh.
 #include <cstring>
@@ -388,6 +389,82 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
     if (o->sum_hbar_rb) memcpy(o->sum_hbar_rb, hs.data(), sizeof(double) * PD);
     if (o->sum_hbar_rb_sq) memcpy(o->sum_hbar_rb_sq, hs.data() + PD, sizeof(double) * PD);
   }
+  return CPIMH_OK;
+}
+
+int cpimh_pf_adaptive_batch(const cpimh_config* cfg_in, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
+                            double ess_threshold, int systematic, double* loglik, double* loglik_t, double* pf_means, double* path,
+                            int32_t* resampled, int32_t* ancestors) {
+  CPIMH_REQUIRE(cfg_in && obs_host && loglik && path, "null argument");
+  CPIMH_REQUIRE(B >= 1, "nfilters must be >= 1");
+  cpimh_config c = *cfg_in;
+  int rc = api_validate(&c);
+  if (rc) return rc;
+  const ModelEntry* e = find_entry(c.model, c.dim);
+  CPIMH_REQUIRE(e != nullptr, "model %d with dimension %d has no adaptive-filter kernel", c.model, c.dim);
+  int dev = 0;
+  CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CPIMH_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  CPIMH_REQUIRE(prop.major >= 10, "libcpimh is built for sm_100a (Blackwell); device %d is sm_%d%d", dev, prop.major, prop.minor);
+  std::vector<double> pre = api_precompute(c);
+  const int N = c.nparticles, T = c.nobs, D = c.dim, Npad = (N + 31) & ~31;
+  const size_t smem = apf_smem_bytes(Npad, (int)pre.size());
+  CPIMH_REQUIRE(smem <= prop.sharedMemPerBlockOptin, "pf() keeps 24 bytes per particle in shared memory: N=%d needs %zu bytes (max %zu)", N, smem,
+                (size_t)prop.sharedMemPerBlockOptin);
+  int threads = 32;
+  while (threads < 512 && threads * 8 < N) threads <<= 1;
+  int bps = 1;
+  rc = e->occupancy_apf(threads, smem, &bps);
+  if (rc) return rc;
+  if (bps < 1) bps = 1;
+  const int64_t resident = (int64_t)bps * prop.multiProcessorCount;
+  const int grid = (int)(B < resident ? B : resident);
+  const size_t PD = (size_t)(T + 1) * D;
+  DevBuf obs, theta, dpre, hx, ha, pr, ll, llt, pm, pa, rs, an, stt;
+  struct Rel { DevBuf* b[13]; ~Rel() { for (auto x : b) x->release(); } } rel{{&obs, &theta, &dpre, &hx, &ha, &pr, &ll, &llt, &pm, &pa, &rs, &an, &stt}};
+  rc = obs.alloc(sizeof(double) * (size_t)T * c.dim_y);
+  if (!rc) rc = theta.alloc(sizeof(double) * CPIMH_MAX_THETA);
+  if (!rc) rc = dpre.alloc(sizeof(double) * (pre.size() + 1));
+  if (!rc) rc = hx.alloc(sizeof(double) * (size_t)grid * (T + 1) * D * Npad);
+  if (!rc) rc = ha.alloc(sizeof(int) * (size_t)grid * T * Npad);
+  if (!rc) rc = pr.alloc(sizeof(double) * (size_t)grid * D * Npad);
+  if (!rc) rc = ll.alloc(sizeof(double) * B);
+  if (!rc) rc = llt.alloc(sizeof(double) * B * T);
+  if (!rc) rc = pm.alloc(sizeof(double) * B * T * D);
+  if (!rc) rc = pa.alloc(sizeof(double) * B * PD);
+  if (!rc) rc = rs.alloc(sizeof(int) * B * T);
+  if (!rc) rc = stt.alloc(sizeof(int) * B);
+  if (!rc && ancestors) rc = an.alloc(sizeof(int) * (size_t)B * T * N);
+  if (rc) return rc;
+  CPIMH_CUDA_CHECK(cudaMemcpy(theta.p, c.theta, sizeof(double) * CPIMH_MAX_THETA, cudaMemcpyHostToDevice));
+  if (!pre.empty()) CPIMH_CUDA_CHECK(cudaMemcpy(dpre.p, pre.data(), sizeof(double) * pre.size(), cudaMemcpyHostToDevice));
+  rc = api_upload_obs(c, obs_host, obs.p);
+  if (rc) return rc;
+  ApfParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.T = T; p.dy = c.dim_y; p.Npad = Npad; p.B = B; p.seed = seed; p.first_filter = first_filter;
+  p.ess_threshold = ess_threshold; p.systematic = systematic ? 1 : 0;
+  p.obs = obs.as<double>(); p.theta = theta.as<double>(); p.pre = dpre.as<double>(); p.npre = (int)pre.size();
+  p.integrator = c.integrator; p.substeps = c.substeps; p.sk_M = c.sk_max_events;
+  p.hist_x = hx.as<double>(); p.hist_a = ha.as<int>(); p.prop = pr.as<double>();
+  p.loglik = ll.as<double>(); p.loglik_t = llt.as<double>(); p.pf_means = pm.as<double>(); p.path = pa.as<double>();
+  p.resampled = rs.as<int>(); p.anc_rec = ancestors ? an.as<int>() : nullptr; p.status = stt.as<int>();
+  ApfLaunch L;
+  L.grid = grid; L.threads = threads; L.smem = smem;
+  rc = e->launch_apf(p, L, nullptr);
+  if (rc) return rc;
+  CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<int> st((size_t)B);
+  CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), stt.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
+  for (int64_t b = 0; b < B; b++)
+    if (st[(size_t)b]) { set_error("adaptive filter %lld failed with status %d", (long long)b, st[(size_t)b]); return st[(size_t)b]; }
+  CPIMH_CUDA_CHECK(cudaMemcpy(loglik, ll.p, sizeof(double) * B, cudaMemcpyDeviceToHost));
+  CPIMH_CUDA_CHECK(cudaMemcpy(path, pa.p, sizeof(double) * B * PD, cudaMemcpyDeviceToHost));
+  if (loglik_t) CPIMH_CUDA_CHECK(cudaMemcpy(loglik_t, llt.p, sizeof(double) * B * T, cudaMemcpyDeviceToHost));
+  if (pf_means) CPIMH_CUDA_CHECK(cudaMemcpy(pf_means, pm.p, sizeof(double) * B * T * D, cudaMemcpyDeviceToHost));
+  if (resampled) CPIMH_CUDA_CHECK(cudaMemcpy(resampled, rs.p, sizeof(int) * B * T, cudaMemcpyDeviceToHost));
+  if (ancestors) CPIMH_CUDA_CHECK(cudaMemcpy(ancestors, an.p, an.bytes, cudaMemcpyDeviceToHost));
   return CPIMH_OK;
 }
 

@@ -3,6 +3,7 @@
 #include "pf_fused.cuh"
 #include "chains.cuh"
 #include "ccpf.cuh"
+#include "apf.cuh"
 
 namespace cpimh {
 
@@ -16,6 +17,8 @@ struct ModelEntry {
   int (*launch_model_op)(const ModelOpParams&, cudaStream_t);
   int (*launch_ccpf)(const CcpfParams&, const CcpfLaunch&, cudaStream_t);
   int (*occupancy_ccpf)(int threads, size_t smem, int* blocks_per_sm);
+  int (*launch_apf)(const ApfParams&, const ApfLaunch&, cudaStream_t);
+  int (*occupancy_apf)(int threads, size_t smem, int* blocks_per_sm);
 };
 template <class Model>
 ModelEntry make_entry(int model) {
@@ -28,6 +31,8 @@ ModelEntry make_entry(int model) {
   e.launch_model_op = &launch_model_op<Model>;
   e.launch_ccpf = &launch_ccpf<Model>;
   e.occupancy_ccpf = &occupancy_ccpf<Model>;
+  e.launch_apf = &launch_apf<Model>;
+  e.occupancy_apf = &occupancy_apf<Model>;
   return e;
 }
 const ModelEntry* entries_gss(int* n);

@@ -244,6 +244,34 @@ def CPF_RB_coupled(nparticles, model, theta, observations, ref_trajectory1, ref_
             "estimate1": np.ascontiguousarray(r["exp_path1"][0]), "estimate2": np.ascontiguousarray(r["exp_path2"][0])}
 
 
+def pf_batch(y, theta, model, nparticles, nfilters, ess_threshold=1, systematic=False, seed=None, first_filter=0, ancestors=False, **kw):
+    """B runs of pf() (cpimh_pf_adaptive_batch): loglik (B,), loglik_t (B, T) cumulative, pf_means (B, T, d), path (B, T+1, d),
+    resampled (B, T) flags [, ancestors (B, T, N)]."""
+    obs = np.asarray(y, dtype=np.float64)
+    T = obs.shape[0]
+    cfg = model.config(nparticles, theta, nobs=T, **kw)
+    ob = L.obs_matrix(obs, T)
+    B, d, N = int(nfilters), model.dimension, int(nparticles)
+    ll, llt, pm, pa = np.empty(B), np.empty((B, T)), np.empty((B, T, d)), np.empty((B, T + 1, d))
+    rs = np.empty((B, T), dtype=np.int32)
+    anc = np.empty((B, T, N), dtype=np.int32) if ancestors else None
+    seed = rng.next_seed() if seed is None else int(seed)
+    L.check(L.lib().cpimh_pf_adaptive_batch(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_int64(B), C.c_uint64(seed), C.c_uint64(int(first_filter)),
+                                             C.c_double(float(ess_threshold)), C.c_int(int(bool(systematic))), L.ptr(ll), L.ptr(llt), L.ptr(pm), L.ptr(pa),
+                                             L.ptr(rs), L.ptr(anc)))
+    out = {"loglik": ll, "loglik_t": llt, "pf_means": pm, "path": pa, "resampled": rs}
+    if ancestors:
+        out["ancestors"] = anc
+    return out
+
+
+def pf(y, theta, model, nparticles, ess_threshold=1, systematic=False, seed=None, filter_id=0, **kw):
+    """pf(y, theta, model, nparticles, ess_threshold = 1, systematic = FALSE) -- R/CPF.R:106-155: bootstrap filter with
+    ESS-triggered resampling.  Returns {"pf_means": T x d, "loglik": float, "path": (T+1) x d, "loglik_t": cumulative (T,)}."""
+    r = pf_batch(y, theta, model, nparticles, 1, ess_threshold=ess_threshold, systematic=systematic, seed=seed, first_filter=filter_id, **kw)
+    return {"pf_means": r["pf_means"][0], "loglik": float(r["loglik"][0]), "path": r["path"][0], "loglik_t": r["loglik_t"][0]}
+
+
 def particlefilter(nparticles, model, theta, observations, seed=None, filter_id=0, noise=None, **kw):
     """particlefilter(nparticles, model, theta, observations) -- R/particlefilter.R:11-44.
     Returns {"trajectories": d x (T+1) x N, "weights": N}."""
