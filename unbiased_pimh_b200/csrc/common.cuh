@@ -289,6 +289,74 @@ __device__ __forceinline__ void block_scan2_inplace(double* a, double* b, int n,
   __syncthreads();
 }
 
+// ---------------------------------------------------------------- padded layout + chunked scans (fused filter)
+// The fused filter keeps its two per-particle shared arrays with one pad slot per 16 elements: element i lives at
+// pad16(i).  Striped accesses (lane l -> element base + l, base a multiple of 16 per half-warp) stay conflict-free, and so
+// do CHUNKED accesses (thread t -> the 8 contiguous elements 8t..8t+7: half-warp start slots 8t + t/2 cover all 16 bank
+// pairs), which lets a scan run thread-serially over 8 elements in registers instead of log-stepping through shuffles.
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+__host__ __device__ inline int padded_len(int n) { return n + (n >> 4) + 1; }
+
+// In-place inclusive scans of a[0..n) (and b[0..n) when TWO) in the padded layout.  Thread t scans chunk t (8 elements)
+// serially, chunk totals are scanned across the warp (shuffles) and across warps (scratch), prefixes are added on the way
+// out.  More than blockDim chunks: further passes with a running carry.  `scratch` needs 64 doubles.  Ends with a barrier.
+template <bool TWO>
+__device__ __forceinline__ void block_scan_chunked(double* a, double* b, int n, double* scratch) {
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (NT + 31) >> 5;
+  const int nchunks = (n + 7) >> 3;
+  double carry_a = 0.0, carry_b = 0.0;
+  for (int c0 = 0; c0 < nchunks; c0 += NT) {
+    const int ch = c0 + tid, i0 = ch << 3;
+    const int base = pad16(i0);                       // the 8 elements of a chunk never straddle a pad slot
+    double va[8], vb[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const bool in = (i0 + j) < n;
+      va[j] = in ? a[base + j] : 0.0;
+      if (TWO) vb[j] = in ? b[base + j] : 0.0;
+    }
+#pragma unroll
+    for (int j = 1; j < 8; j++) { va[j] += va[j - 1]; if (TWO) vb[j] += vb[j - 1]; }
+    const double ta = va[7], ia = warp_incl_scan(ta, lane);
+    double tb = 0.0, ib = 0.0;
+    if (TWO) { tb = vb[7]; ib = warp_incl_scan(tb, lane); }
+    if (lane == 31) { scratch[wid] = ia; if (TWO) scratch[32 + wid] = ib; }
+    __syncthreads();
+    const double wa = (lane < nw) ? scratch[lane] : 0.0;
+    const double wia = warp_incl_scan(wa, lane);
+    const double offa = carry_a + (__shfl_sync(0xffffffffu, wia, wid) - __shfl_sync(0xffffffffu, wa, wid)) + (ia - ta);
+    carry_a += __shfl_sync(0xffffffffu, wia, nw - 1);
+    double offb = 0.0;
+    if (TWO) {
+      const double wb = (lane < nw) ? scratch[32 + lane] : 0.0;
+      const double wib = warp_incl_scan(wb, lane);
+      offb = carry_b + (__shfl_sync(0xffffffffu, wib, wid) - __shfl_sync(0xffffffffu, wb, wid)) + (ib - tb);
+      carry_b += __shfl_sync(0xffffffffu, wib, nw - 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if ((i0 + j) < n) { a[base + j] = va[j] + offa; if (TWO) b[base + j] = vb[j] + offb; }
+    }
+    __syncthreads();
+  }
+}
+// counts over a padded ascending array (same rules as count_le / count_lt below)
+__device__ __forceinline__ int count_le_p(const double* c, int lo, int hi, double u) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (c[pad16(mid)] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int count_lt_p(const double* c, int n, double u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (c[pad16(mid)] < u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // number of entries of the (ascending) shared array c[0..n) that are <= u   (src/multinomial.cpp:25-27 rule)
 __device__ __forceinline__ int count_le(const double* c, int n, double u) {
   int lo = 0, hi = n;

@@ -60,8 +60,8 @@ struct PfParams {
 };
 
 struct PfSmem {
-  double* C;        // [Npad] normalised weights, then their inclusive CDF
-  double* S;        // [Npad] log(u)/i -> suffix sums -> log-weights
+  double* C;        // [padded_len(Npad)] weights, then their inclusive CDF          (element i at pad16(i))
+  double* S;        // [padded_len(Npad)] exponential spacings -> prefix sums -> log-weights (element i at pad16(i))
   int* leaf;        // [Npad] l_star                                   (PATH_TREE, or shuffle scratch)
   int* bpar;        // [Npad] ancestors, then parent slots b = l_star[a] (PATH_TREE, or shuffle scratch)
   unsigned* off32;  // [Npad/2] 16-bit offspring counters              (PATH_TREE)
@@ -75,7 +75,7 @@ struct PfSmem {
 };
 __host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
   size_t b = 0;
-  b += (size_t)Npad * 8 * 2;                 // C, S
+  b += (size_t)padded_len(Npad) * 8 * 2;     // C, S (padded layout, common.cuh pad16)
   b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64 + 2) * 8;
   if (path_mode == PATH_TREE) {
     b += (size_t)Npad * 4 * 2;               // leaf, bpar
@@ -91,8 +91,8 @@ __host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int p
 __device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre, int path_mode, int shuffle) {
   PfSmem s;
   double* d = reinterpret_cast<double*>(raw);
-  s.C = d; d += Npad;
-  s.S = d; d += Npad;
+  s.C = d; d += padded_len(Npad);
+  s.S = d; d += padded_len(Npad);
   s.theta = d; d += CPIMH_MAX_THETA;
   s.pre = d; d += npre + (npre & 1);
   s.dscr = d; d += 64;
@@ -183,7 +183,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       a_star[i] = -2;
       sm.leaf[i] = i;
     }
-    sm.C[i] = 1.0 / N;
+    sm.C[pad16(i)] = 1.0 / N;
   }
   double logz_sum = 0.0;
   __syncthreads();
@@ -205,7 +205,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       for (int i = tid; i < N; i += NT, e++) {
         double ua, ub;
         philox_u2(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, ub);
-        if (draw_res) sm.S[i] = -rng_log(ua);                 // exponential spacing E_i (see the ladder comment below)
+        if (draw_res) sm.S[pad16(i)] = -rng_log(ua);                 // exponential spacing E_i (see the ladder comment below)
         if constexpr (Model::JUMP_LIST) {
           if (jump_list) {                                // the model turns its uniform into a small count right away
             int tk = Model::token(c, ub);
@@ -216,21 +216,21 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       }
     }
     if (!ident) {
-      if (inj_res) for (int i = tid; i < N; i += NT) sm.S[i] = inj_res[(size_t)(t - 1) * N + i];
+      if (inj_res) for (int i = tid; i < N; i += NT) sm.S[pad16(i)] = inj_res[(size_t)(t - 1) * N + i];
       __syncthreads();
       // Sorted uniforms.  Injected: S holds the ascending e_i of src/multinomial.cpp:22-24 and u_i = sumw e_i (:24).
       // Philox: the same order statistics from exponential spacings, e_i = (E_0+..+E_i) / (E_0+..+E_N) (one log per
       // particle instead of the recurrence's log + divide + exp; DESIGN.md "RNG"): S becomes the prefix sums P_i and
       // u_i = (sumw / total) P_i.
-      if (inj_res) block_scan_inplace<false>(sm.C, N, sm.dscr);
-      else block_scan2_inplace(sm.C, sm.S, N, sm.dscr);
-      sumw = sm.C[N - 1];
-      if (!inj_res) sumw = sumw / (sm.S[N - 1] + sm.dscr2[0]);   // total = P_{N-1} + E_N
+      if (inj_res) block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
+      else block_scan_chunked<true>(sm.C, sm.S, N, sm.dscr);
+      sumw = sm.C[pad16(N - 1)];
+      if (!inj_res) sumw = sumw / (sm.S[pad16(N - 1)] + sm.dscr2[0]);   // total = P_{N-1} + E_N
       // every 32nd sorted uniform gets a full search; the others then search only between their neighbours' results
       const int nrows = (N + 31) >> 5;
       for (int r = tid; r <= nrows; r += NT) {
         int a = N;
-        if (r < nrows) a = count_le(sm.C, N, sumw * sm.S[r << 5]);
+        if (r < nrows) a = count_le_p(sm.C, 0, N, sumw * sm.S[pad16(r << 5)]);
         sm.coarse[r] = a;
       }
       __syncthreads();
@@ -241,7 +241,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // -- ancestors: count of CDF knots <= u (:25-28), clamped
     auto ancestor_of = [&](int k) -> int {
       if (ident) return k;
-      int a = count_le_bounded(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * sm.S[k]);
+      int a = count_le_p(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * sm.S[pad16(k)]);
       if (a >= N) { a = N - 1; st |= 512; }
       return a;
     };
@@ -255,10 +255,10 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
       double lw;
       if constexpr (Model::SPLIT_W) {
-        if (split_w) { double f; Model::weight_parts(c, x, y, lw, f); sm.C[k] = f; }
+        if (split_w) { double f; Model::weight_parts(c, x, y, lw, f); sm.C[pad16(k)] = f; }
         else lw = Model::logw(c, x, y);
       } else lw = Model::logw(c, x, y);
-      sm.S[k] = lw;
+      sm.S[pad16(k)] = lw;
       m = fmax(m, lw);
       if (dense) hist_a[(size_t)(t - 1) * Npad + k] = a;
       if (tree) {                                      // src/tree.cpp:39-42, 90-94
@@ -318,7 +318,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
             sa += wa;
             sb += ev;
             if (++j > kj) {
-              sm.S[tid + e * NT] = sa; sm.C[tid + e * NT] = sb;
+              sm.S[pad16(tid + e * NT)] = sa; sm.C[pad16(tid + e * NT)] = sb;
               sa = 0.0; sb = 0.0; j = 1;
               rem &= ~(255ull << sh);
               if (rem == 0ull && ebase == 0) { rem = tok1; ebase = 8; }
@@ -331,7 +331,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
 #pragma unroll
           for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
           if (c.inj_trans) { swe = trans_row(c, t, 0)[k]; se = trans_row(c, t, 1)[k]; }
-          else if (tok(e) > 0) { swe = sm.S[k]; se = sm.C[k]; }
+          else if (tok(e) > 0) { swe = sm.S[pad16(k)]; se = sm.C[pad16(k)]; }
           Model::finish(c, x, swe, se);
           finish_particle(k, a, x);
         }
@@ -366,12 +366,12 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // -- weights and log Z increment: R/CPF.R:61-63,66
     m = block_max(m, sm.dscr);
     double s = 0.0;
-    if (split_w) { for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m) * sm.C[k]; sm.C[k] = w; s += w; } }
-    else { for (int k = tid; k < N; k += NT) { double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; } }
+    if (split_w) { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m) * sm.C[kp]; sm.C[kp] = w; s += w; } }
+    else { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m); sm.C[kp] = w; s += w; } }
     s = block_sum(s, sm.dscr);
     // normweights = w / sum(w) (R/CPF.R:63).  Between steps only ratios matter (the ancestor search scales its
     // uniforms by the CDF total), so the division pass is done once, for the weights the filter returns.
-    if (t == T) for (int k = tid; k < N; k += NT) sm.C[k] = sm.C[k] / s;
+    if (t == T) for (int k = tid; k < N; k += NT) sm.C[pad16(k)] = sm.C[pad16(k)] / s;
     if (tid == 0) {                                      // only thread 0 reports log Z
       double lz = log(s / (double)N) + m;
       if constexpr (Model::SPLIT_W) { if (split_w) lz += Model::w_const(); }
@@ -434,7 +434,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
 
   // ---------------- path selection: systematic_resampling_n(normweights, 1, runif(1)) + Tree$get_path (R/CPF.R:69)
   if (st) atomicOr(&sm.iscr[32], st);
-  if (out.normw) for (int k = tid; k < N; k += NT) out.normw[k] = sm.C[k];
+  if (out.normw) for (int k = tid; k < N; k += NT) out.normw[k] = sm.C[pad16(k)];
   if (out.leaf_out && tree) for (int k = tid; k < N; k += NT) out.leaf_out[k] = sm.leaf[k];
   if (out.exp_path && (tree || dense)) {
     // pf_get_weighted_average (R/CPF.R:84-92) over sapply(0:(N-1), Tree$get_path) (:73-74): all N leaves walk to the root
@@ -447,7 +447,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       for (int q = 0; q < D; q++) {
         double acc = 0.0;
         for (int n = tid; n < N; n += NT)
-          acc += (tree ? x_star[(size_t)q * M + cur[n]] : hx[(size_t)step * xstride + (size_t)q * Npad + cur[n]]) * sm.C[n];
+          acc += (tree ? x_star[(size_t)q * M + cur[n]] : hx[(size_t)step * xstride + (size_t)q * Npad + cur[n]]) * sm.C[pad16(n)];
         acc = block_sum(acc, sm.dscr);
         if (tid == 0) out.exp_path[(size_t)step * D + q] = acc;
       }
@@ -455,9 +455,9 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     }
   }
   __syncthreads();
-  block_scan_inplace<false>(sm.C, N, sm.dscr);
+  block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
   double u = p.inj_path ? p.inj_path[inj] : philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0);
-  int kidx = count_lt(sm.C, N, u);          // smallest j with csw_j >= u (src/systematic.cpp:15-18), n = 1
+  int kidx = count_lt_p(sm.C, N, u);          // smallest j with csw_j >= u (src/systematic.cpp:15-18), n = 1
   int flags = sm.iscr[32];
   if (kidx >= N) { kidx = N - 1; flags |= 512; }
   if (tid == 0) {
