@@ -50,16 +50,16 @@ struct CcpfSmem {
   double* theta; double* pre; double* dscr; int* iscr;
 };
 __host__ __device__ inline size_t ccpf_smem_bytes(int Npad, int npre) {
-  size_t b = (size_t)(4 * Npad + 64) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + (size_t)Npad * 4 + 36 * 4;
+  size_t b = (size_t)(4 * padded_len(Npad + 32)) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + (size_t)Npad * 4 + 36 * 4;
   return (b + 15) & ~(size_t)15;
 }
 __device__ inline CcpfSmem ccpf_carve(unsigned char* raw, int Npad, int npre) {
   CcpfSmem s;
   double* d = reinterpret_cast<double*>(raw);
-  s.C1 = d; d += Npad;
-  s.C2 = d; d += Npad;
-  s.V = d; d += Npad + 32;
-  s.P = d; d += Npad + 32;
+  s.C1 = d; d += padded_len(Npad + 32);      // all four in the padded layout (element i at pad16(i), common.cuh)
+  s.C2 = d; d += padded_len(Npad + 32);
+  s.V = d; d += padded_len(Npad + 32);
+  s.P = d; d += padded_len(Npad + 32);
   s.theta = d; d += CPIMH_MAX_THETA;
   s.pre = d; d += npre + (npre & 1);
   s.dscr = d; d += 64;
@@ -76,19 +76,19 @@ __device__ __forceinline__ int clampN(int a, int N) { return a >= N ? N - 1 : a;
 __device__ inline void im_single_draw(double* A, double* Bv, int N, double uc, double ud, double* dscr, int& a1, int& a2) {
   const int tid = threadIdx.x, NT = blockDim.x;
   double al = 0.0;
-  for (int k = tid; k < N; k += NT) al += fmin(A[k], Bv[k]);
+  for (int k = tid; k < N; k += NT) al += fmin(A[pad16(k)], Bv[pad16(k)]);
   al = block_sum(al, dscr);
   if (uc < al) {
-    for (int k = tid; k < N; k += NT) A[k] = fmin(A[k], Bv[k]);
+    for (int k = tid; k < N; k += NT) A[pad16(k)] = fmin(A[pad16(k)], Bv[pad16(k)]);
     __syncthreads();
-    block_scan_inplace<false>(A, N, dscr);
-    a1 = a2 = clampN(count_le(A, N, ud * A[N - 1]), N);
+    block_scan_chunked<false>(A, nullptr, N, dscr);
+    a1 = a2 = clampN(count_le_p(A, 0, N, ud * A[pad16(N - 1)]), N);
   } else {
-    for (int k = tid; k < N; k += NT) { const double nu = fmin(A[k], Bv[k]); A[k] -= nu; Bv[k] -= nu; }
+    for (int k = tid; k < N; k += NT) { const double nu = fmin(A[pad16(k)], Bv[pad16(k)]); A[pad16(k)] -= nu; Bv[pad16(k)] -= nu; }
     __syncthreads();
-    block_scan2_inplace(A, Bv, N, dscr);
-    a1 = clampN(count_le(A, N, ud * A[N - 1]), N);
-    a2 = clampN(count_le(Bv, N, ud * Bv[N - 1]), N);
+    block_scan_chunked<true>(A, Bv, N, dscr);
+    a1 = clampN(count_le_p(A, 0, N, ud * A[pad16(N - 1)]), N);
+    a2 = clampN(count_le_p(Bv, 0, N, ud * Bv[pad16(N - 1)]), N);
   }
   __syncthreads();
 }
@@ -126,7 +126,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     for (int s = 0; s < nsys; s++) {
 #pragma unroll
       for (int q = 0; q < D; q++) hx[s][(size_t)q * Npad + i] = (i == N - 1) ? ref[s][q] : x[q];
-      Wk[s][i] = 1.0;
+      Wk[s][pad16(i)] = 1.0;
     }
   }
   double ssum[2] = {(double)N, (double)N};
@@ -144,7 +144,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     // normweights = w / sum(w)  (R/CPF.R:63; index matching compares the two systems' NORMALISED weights)
 #pragma unroll
     for (int s = 0; s < nsys; s++)
-      for (int k = tid; k < N; k += NT) Wk[s][k] = Wk[s][k] / ssum[s];
+      for (int k = tid; k < N; k += NT) Wk[s][pad16(k)] = Wk[s][pad16(k)] / ssum[s];
     __syncthreads();
 
     // ---- ancestor of the reference particle: R/CPF.R:47-57, R/CPF_coupled.R:64-84
@@ -161,22 +161,22 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
             double x[D];
 #pragma unroll
             for (int q = 0; q < D; q++) x[q] = xprev[s][(size_t)q * Npad + k];
-            const double lm = log(Wk[s][k]) + Model::dtrans(c, next, x, t, sc);
-            Lk[s][k] = lm;
+            const double lm = log(Wk[s][pad16(k)]) + Model::dtrans(c, next, x, t, sc);
+            Lk[s][pad16(k)] = lm;
             m = fmax(m, lm);
           }
           m = block_max(m, sm.dscr);
           double sum = 0.0;
-          for (int k = tid; k < N; k += NT) { const double w = exp(Lk[s][k] - m); Lk[s][k] = w; sum += w; }
+          for (int k = tid; k < N; k += NT) { const double w = exp(Lk[s][pad16(k)] - m); Lk[s][pad16(k)] = w; sum += w; }
           sum = block_sum(sum, sm.dscr);
-          for (int k = tid; k < N; k += NT) Lk[s][k] = Lk[s][k] / sum;
+          for (int k = tid; k < N; k += NT) Lk[s][pad16(k)] = Lk[s][pad16(k)] / sum;
         }
         __syncthreads();
         double ua, ub;
         philox_u2(stream, 0, t, CPIMH_P_AS, 0, ua, ub);
         if (nsys == 1) {
-          block_scan_inplace<false>(Lk[0], N, sm.dscr);
-          aref[0] = clampN(count_lt(Lk[0], N, ua), N);                       // systematic_resampling_n(w_as, 1, u)
+          block_scan_chunked<false>(Lk[0], nullptr, N, sm.dscr);
+          aref[0] = clampN(count_lt_p(Lk[0], N, ua), N);                       // systematic_resampling_n(w_as, 1, u)
           __syncthreads();
         } else {
           im_single_draw(Lk[0], Lk[1], N, ua, ub, sm.dscr, aref[0], aref[1]);  // CR_indexmatching(w_as1, w_as2, ntrials = 1)
@@ -186,22 +186,22 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
 
     // ---- ancestors of the N-1 free particles
     if (!ident) {
-      for (int i = tid; i <= nd + 1; i += NT) sm.P[i] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
+      for (int i = tid; i <= nd + 1; i += NT) sm.P[pad16(i)] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
       if (nsys == 1) {
         __syncthreads();
-        block_scan_inplace<false>(sm.C1, N, sm.dscr);
-        block_scan_inplace<false>(sm.P, nd + 1, sm.dscr);
-        const double scale = sm.C1[N - 1] / sm.P[nd];
+        block_scan_chunked<false>(sm.C1, nullptr, N, sm.dscr);
+        block_scan_chunked<false>(sm.P, nullptr, nd + 1, sm.dscr);
+        const double scale = sm.C1[pad16(N - 1)] / sm.P[pad16(nd)];
         for (int k = tid; k < nd; k += NT) {
-          int a = count_le(sm.C1, N, scale * sm.P[k]);
+          int a = count_le_p(sm.C1, 0, N, scale * sm.P[pad16(k)]);
           if (a >= N) { a = N - 1; st |= 512; }
           arow[0][k] = a;
         }
       } else {
         double al = 0.0;                                                     // coupledresamplingindexmatching.cpp:13-21
         for (int k = tid; k < N; k += NT) {
-          const double nu = fmin(sm.C1[k], sm.C2[k]);
-          sm.V[k] = nu; sm.C1[k] -= nu; sm.C2[k] -= nu;
+          const double nu = fmin(sm.C1[pad16(k)], sm.C2[pad16(k)]);
+          sm.V[pad16(k)] = nu; sm.C1[pad16(k)] -= nu; sm.C2[pad16(k)] -= nu;
           al += nu;
         }
         al = block_sum(al, sm.dscr);
@@ -213,20 +213,20 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
         int jc = block_excl_scan_int(cnt, sm.iscr, &nc);
         int jr = i0 - jc;
         for (int i = i0; i < i1; i++) { if (sm.R[i]) sm.R[i] = jc++; else sm.R[i] = ~(jr++); }
-        block_scan2_inplace(sm.C1, sm.C2, N, sm.dscr);
-        block_scan_inplace<false>(sm.V, N, sm.dscr);
-        block_scan_inplace<false>(sm.P, nd + 2, sm.dscr);
-        const double Pnc = sm.P[nc], den = sm.P[nd + 1] - Pnc;
-        const double totV = sm.V[N - 1], tot1 = sm.C1[N - 1], tot2 = sm.C2[N - 1];
+        block_scan_chunked<true>(sm.C1, sm.C2, N, sm.dscr);
+        block_scan_chunked<false>(sm.V, nullptr, N, sm.dscr);
+        block_scan_chunked<false>(sm.P, nullptr, nd + 2, sm.dscr);
+        const double Pnc = sm.P[pad16(nc)], den = sm.P[pad16(nd + 1)] - Pnc;
+        const double totV = sm.V[pad16(N - 1)], tot1 = sm.C1[pad16(N - 1)], tot2 = sm.C2[pad16(N - 1)];
         for (int k = tid; k < nd; k += NT) {
           const int r = sm.R[k];
           int a1, a2;
           if (r >= 0) {                                                      // :36-38 common draw from mu = nu / alpha
-            a1 = a2 = clampN(count_le(sm.V, N, (sm.P[r] / Pnc) * totV), N);
+            a1 = a2 = clampN(count_le_p(sm.V, 0, N, (sm.P[pad16(r)] / Pnc) * totV), N);
           } else {                                                           // :40-42 residuals with a common uniform
-            const double u = (sm.P[nc + 1 + (~r)] - Pnc) / den;
-            a1 = clampN(count_le(sm.C1, N, u * tot1), N);
-            a2 = clampN(count_le(sm.C2, N, u * tot2), N);
+            const double u = (sm.P[pad16(nc + 1 + (~r))] - Pnc) / den;
+            a1 = clampN(count_le_p(sm.C1, 0, N, u * tot1), N);
+            a2 = clampN(count_le_p(sm.C2, 0, N, u * tot2), N);
           }
           arow[0][k] = a1; arow[1][k] = a2;
         }
@@ -262,7 +262,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
 #pragma unroll
         for (int q = 0; q < D; q++) xcur[s][(size_t)q * Npad + k] = x[q];
         const double lw = Model::logw(c, x, y);
-        Lk[s][k] = lw;
+        Lk[s][pad16(k)] = lw;
         m[s] = fmax(m[s], lw);
       }
     }
@@ -272,7 +272,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     for (int s = 0; s < nsys; s++) {
       const double ms = block_max(m[s], sm.dscr);
       double sum = 0.0;
-      for (int k = tid; k < N; k += NT) { const double w = exp(Lk[s][k] - ms); Wk[s][k] = w; sum += w; }
+      for (int k = tid; k < N; k += NT) { const double w = exp(Lk[s][pad16(k)] - ms); Wk[s][pad16(k)] = w; sum += w; }
       ssum[s] = block_sum(sum, sm.dscr);
       if (s == 0) logz_sum += log(ssum[0] / (double)N) + ms;
     }
@@ -283,7 +283,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   if (st) atomicOr(&sm.iscr[32], st);
 #pragma unroll
   for (int s = 0; s < nsys; s++)
-    for (int k = tid; k < N; k += NT) Wk[s][k] = Wk[s][k] / ssum[s];
+    for (int k = tid; k < N; k += NT) Wk[s][pad16(k)] = Wk[s][pad16(k)] / ssum[s];
   __syncthreads();
   if (p.exp1) {
     // estimate = sum_k normweights[k] * Tree$get_path(k) (R/rheeglynn_estimator_RB.R:50-56, test_function = identity): all N
@@ -296,7 +296,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
 #pragma unroll
         for (int q = 0; q < D; q++) {
           double acc = 0.0;
-          for (int n = tid; n < N; n += NT) acc += hx[s][(size_t)step * xstride + (size_t)q * Npad + sm.R[n]] * Wk[s][n];
+          for (int n = tid; n < N; n += NT) acc += hx[s][(size_t)step * xstride + (size_t)q * Npad + sm.R[n]] * Wk[s][pad16(n)];
           acc = block_sum(acc, sm.dscr);
           if (tid == 0) ex[(size_t)step * D + q] = acc;
         }
@@ -309,8 +309,8 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   philox_u2(stream, 0, T + 1, CPIMH_P_PATH, 0, ua, ub);
   int kidx[2] = {0, 0};
   if (nsys == 1) {
-    block_scan_inplace<false>(sm.C1, N, sm.dscr);
-    kidx[0] = clampN(count_lt(sm.C1, N, ua), N);
+    block_scan_chunked<false>(sm.C1, nullptr, N, sm.dscr);
+    kidx[0] = clampN(count_lt_p(sm.C1, N, ua), N);
   } else {
     im_single_draw(sm.C1, sm.C2, N, ua, ub, sm.dscr, kidx[0], kidx[1]);
   }
