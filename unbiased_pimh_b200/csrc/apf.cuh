@@ -35,14 +35,14 @@ struct ApfParams {
 };
 struct ApfSmem { double* C; double* S; double* LW; double* theta; double* pre; double* dscr; int* iscr; };
 __host__ __device__ inline size_t apf_smem_bytes(int Npad, int npre) {
-  size_t b = (size_t)(3 * Npad + 2) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + 36 * 4;
+  size_t b = (size_t)(2 * padded_len(Npad + 16) + Npad) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + 36 * 4;
   return (b + 15) & ~(size_t)15;
 }
 __device__ inline ApfSmem apf_carve(unsigned char* raw, int Npad, int npre) {
   ApfSmem s;
   double* d = reinterpret_cast<double*>(raw);
-  s.C = d; d += Npad;
-  s.S = d; d += Npad + 2;
+  s.C = d; d += padded_len(Npad + 16);       // C and S in the padded layout (element i at pad16(i), common.cuh)
+  s.S = d; d += padded_len(Npad + 16);
   s.LW = d; d += Npad;
   s.theta = d; d += CPIMH_MAX_THETA;
   s.pre = d; d += npre + (npre & 1);
@@ -95,23 +95,23 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
 #pragma unroll
       for (int q = 0; q < D; q++) prop[(size_t)q * Npad + k] = x[q];
       const double lw = Model::logw(c, x, y) + sm.LW[k];
-      sm.S[k] = lw;
+      sm.S[pad16(k)] = lw;
       m = fmax(m, lw);
     }
     m = block_max(m, sm.dscr);
     double s = 0.0;
-    for (int k = tid; k < N; k += NT) { const double w = exp(sm.S[k] - m); sm.C[k] = w; s += w; }
+    for (int k = tid; k < N; k += NT) { const double w = exp(sm.S[pad16(k)] - m); sm.C[pad16(k)] = w; s += w; }
     s = block_sum(s, sm.dscr);
     cum += m + log(s);                                   // :130
     if (tid == 0 && p.loglik_t) p.loglik_t[(size_t)b * T + (t - 1)] = cum;
     double s2 = 0.0;
-    for (int k = tid; k < N; k += NT) { const double w = sm.C[k] / s; sm.C[k] = w; s2 += w * w; }   // :131
+    for (int k = tid; k < N; k += NT) { const double w = sm.C[pad16(k)] / s; sm.C[pad16(k)] = w; s2 += w * w; }   // :131
     s2 = block_sum(s2, sm.dscr);
     if (p.pf_means) {                                    // :133
 #pragma unroll
       for (int q = 0; q < D; q++) {
         double a = 0.0;
-        for (int k = tid; k < N; k += NT) a += sm.C[k] * prop[(size_t)q * Npad + k];
+        for (int k = tid; k < N; k += NT) a += sm.C[pad16(k)] * prop[(size_t)q * Npad + k];
         a = block_sum(a, sm.dscr);
         if (tid == 0) p.pf_means[((size_t)b * T + (t - 1)) * D + q] = a;
       }
@@ -121,22 +121,22 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
     // ---- resample (:136-147)
     if (resample) {
       if (!p.systematic) {
-        for (int i = tid; i <= N; i += NT) sm.S[i] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
+        for (int i = tid; i <= N; i += NT) sm.S[pad16(i)] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
         __syncthreads();
-        block_scan_inplace<false>(sm.C, N, sm.dscr);
-        block_scan_inplace<false>(sm.S, N + 1, sm.dscr);
-        const double scale = sm.C[N - 1] / sm.S[N];
+        block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
+        block_scan_chunked<false>(sm.S, nullptr, N + 1, sm.dscr);
+        const double scale = sm.C[pad16(N - 1)] / sm.S[pad16(N)];
         for (int k = tid; k < N; k += NT) {
-          int a = count_le(sm.C, N, scale * sm.S[k]);
+          int a = count_le_p(sm.C, 0, N, scale * sm.S[pad16(k)]);
           if (a >= N) { a = N - 1; st |= 512; }
           arow[k] = a;
         }
       } else {                                           // systematic_resampling_n(normweights, N, u): src/systematic.cpp:7-32
         __syncthreads();
-        block_scan_inplace<false>(sm.C, N, sm.dscr);
+        block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
         const double u = philox_u1(stream, 0, t, CPIMH_P_AS, 0) / (double)N;
         for (int k = tid; k < N; k += NT) {
-          int a = count_lt(sm.C, N, u + (double)k * (1.0 / (double)N));
+          int a = count_lt_p(sm.C, N, u + (double)k * (1.0 / (double)N));
           if (a >= N) { a = N - 1; st |= 512; }
           arow[k] = a;
         }
@@ -144,9 +144,9 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
       __syncthreads();
       for (int k = tid; k < N; k += NT) sm.LW[k] = lw0;
     } else {
-      for (int k = tid; k < N; k += NT) { arow[k] = k; sm.LW[k] = log(sm.C[k]); }
+      for (int k = tid; k < N; k += NT) { arow[k] = k; sm.LW[k] = log(sm.C[pad16(k)]); }
       __syncthreads();
-      if (t == T) block_scan_inplace<false>(sm.C, N, sm.dscr);           // the final draw needs the CDF
+      if (t == T) block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);           // the final draw needs the CDF
     }
     // ---- the tree keeps the resampled particles (:148-149)
     for (int k = tid; k < N; k += NT) {
@@ -160,7 +160,7 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
   // ---- sample(1:N, 1, prob = normweights) (:152) by inversion of the last CDF, then Tree$get_path
   if (st) atomicOr(&sm.iscr[32], st);
   __syncthreads();
-  int kidx = count_lt(sm.C, N, philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0));
+  int kidx = count_lt_p(sm.C, N, philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0));
   if (kidx >= N) kidx = N - 1;
   const int flags = sm.iscr[32];
   if (tid == 0) {
