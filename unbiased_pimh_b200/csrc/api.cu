@@ -127,6 +127,9 @@ int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, i
   CPIMH_REQUIRE(N <= 32768, "the CTA-per-filter kernel supports N <= 32768 particles (got %d)", N);
   // CTA size: about 8 particles per thread, snapped to a compiled variant (128/256/512/1024 threads)
   int threads = c.threads_per_filter > 0 ? c.threads_per_filter : next_pow2((N + 7) / 8);
+  // 2048 < N <= 4096: three 256-thread CTAs per SM (80 registers per thread, 16 particles per thread) beat two 512-thread
+  // CTAs (64 registers, spills) by ~10 % on levy_sv; larger N keeps 8 per thread (token lists and event lists hold 16)
+  if (c.threads_per_filter <= 0 && threads == 512) threads = 256;
   g->variant = pf_variant_for(threads);
   if (threads >= 128) threads = pf_variant_threads(g->variant);
   else threads = threads <= 32 ? 32 : 64;                      // small filters: one or two warps (no cross-warp barriers to pay for)
