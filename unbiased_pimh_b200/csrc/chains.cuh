@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
 template <class Model, class F>
 int chains_with_kernel(int variant, F&& f) {
   switch (variant) {
-    case PF_VARIANT_128x8: return f(chains_kernel<Model, 128, (Model::D > 4 ? 4 : 6)>);
+    case PF_VARIANT_128x8: return f(chains_kernel<Model, 128, (Model::D > 4 ? 5 : 6)>);
     case PF_VARIANT_256x3: return f(chains_kernel<Model, 256, (Model::D > 4 ? 2 : 3)>);
     case PF_VARIANT_512x2: return f(chains_kernel<Model, 512, (Model::D > 4 ? 1 : 2)>);
     default: return f(chains_kernel<Model, 1024, 1>);

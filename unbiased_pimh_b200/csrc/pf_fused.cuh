@@ -518,7 +518,7 @@ int pf_with_kernel(int variant, F&& f) {
   switch (variant) {
     // wide states (d > 4) keep x, noise and the matvec in registers: trade residency for 128 registers per thread; the
     // narrow ones run best at ~80 registers (768 resident threads per SM): 6 x 128 or 3 x 256 (the enum names are historic)
-    case PF_VARIANT_128x8: return f(pf_batch_kernel<Model, 128, (Model::D > 4 ? 4 : 6)>);
+    case PF_VARIANT_128x8: return f(pf_batch_kernel<Model, 128, (Model::D > 4 ? 5 : 6)>);
     case PF_VARIANT_256x3: return f(pf_batch_kernel<Model, 256, (Model::D > 4 ? 2 : 3)>);
     case PF_VARIANT_512x2: return f(pf_batch_kernel<Model, 512, (Model::D > 4 ? 1 : 2)>);
     default: return f(pf_batch_kernel<Model, 1024, 1>);
