@@ -78,6 +78,7 @@ std::vector<double> api_precompute(const cpimh_config& c) {
     }
     pre.push_back((double)F.size());
     pre.insert(pre.end(), F.begin(), F.end());
+    for (int k = 0; k < 3; k++) pre.push_back(2.0);    // guard knots for the unrolled head of the table search (models.cuh poisson_tab)
   } else if (c.model == CPIMH_MODEL_SK) {
     const double sd = sqrt(c.theta[0]);                 // R/model_stochastic_kinetic.R:151 dnorm(..., sd = sqrt(s2_obs), log = TRUE)
     pre.push_back(1.0 / sd);

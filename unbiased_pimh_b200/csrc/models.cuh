@@ -142,9 +142,11 @@ struct ArModel {
 __device__ __forceinline__ int poisson_tab(const double* pre, double u) {
   const int L = (int)pre[3];
   const double* F = pre + 4;
-  int k = 0;
-  while (k < L && u > F[k]) k++;
-  return k == L ? 1000 : k;          // beyond the saturated CDF the sequential search only stops at its cap of 1000
+  // the first three knots without a dependent loop (the table is padded with three entries > 1 behind F_{L-1}); for the
+  // rates of interest they hold > 99 % of the mass
+  int k = (u > F[0] ? 1 : 0) + (u > F[1] ? 1 : 0) + (u > F[2] ? 1 : 0);
+  if (k == 3) { while (k < L && u > F[k]) k++; }
+  return k >= L ? 1000 : k;          // beyond the saturated CDF the sequential search only stops at its cap of 1000
 }
 struct LevySvModel {
   static constexpr int D = 2;

@@ -325,11 +325,23 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
             }
           }
         }
+        // software pipeline over the thread's particles: the ancestor of particle e+2 and the gathered state of particle
+        // e+1 are in flight (L2 latency) while particle e is finished and weighed
+        int a_cur = E > 0 ? arow[tid] : 0, a_nxt = E > 1 ? arow[tid + NT] : 0;
+        double x_nxt[D];
+#pragma unroll
+        for (int q = 0; q < D; q++) x_nxt[q] = E > 0 ? xold[(size_t)q * Npad + a_cur] : 0.0;
         for (int e = 0; e < E; e++) {
-          const int k = tid + e * NT, a = arow[k];
+          const int k = tid + e * NT, a = a_cur;
           double x[D], swe = 0.0, se = 0.0;
 #pragma unroll
-          for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
+          for (int q = 0; q < D; q++) x[q] = x_nxt[q];
+          a_cur = a_nxt;
+          if (e + 1 < E) {
+#pragma unroll
+            for (int q = 0; q < D; q++) x_nxt[q] = xold[(size_t)q * Npad + a_cur];
+          }
+          a_nxt = (e + 2 < E) ? arow[k + 2 * NT] : 0;
           if (c.inj_trans) { swe = trans_row(c, t, 0)[k]; se = trans_row(c, t, 1)[k]; }
           else if (tok(e) > 0) { swe = sm.S[pad16(k)]; se = sm.C[pad16(k)]; }
           Model::finish(c, x, swe, se);
