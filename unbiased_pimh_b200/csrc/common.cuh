@@ -348,6 +348,16 @@ __device__ __forceinline__ int count_le_p(const double* c, int lo, int hi, doubl
   }
   return lo;
 }
+// two independent bounded searches advanced together: the two chains of dependent shared-memory loads overlap
+__device__ __forceinline__ void count_le_p2(const double* c, int lo1, int hi1, double u1, int lo2, int hi2, double u2, int& r1, int& r2) {
+  while (lo1 < hi1 || lo2 < hi2) {
+    const int m1 = (lo1 + hi1) >> 1, m2 = (lo2 + hi2) >> 1;
+    const double v1 = c[pad16(m1)], v2 = c[pad16(m2)];
+    if (lo1 < hi1) { if (v1 <= u1) lo1 = m1 + 1; else hi1 = m1; }
+    if (lo2 < hi2) { if (v2 <= u2) lo2 = m2 + 1; else hi2 = m2; }
+  }
+  r1 = lo1; r2 = lo2;
+}
 __device__ __forceinline__ int count_lt_p(const double* c, int n, double u) {
   int lo = 0, hi = n;
   while (lo < hi) {

@@ -298,7 +298,23 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         // (2) every thread walks the jumps of ALL its particles as one list, parking each particle's sums in that
         // particle's own slots of S and C; (3) gather, finish the transition, weigh.
         int* arow = dense ? hist_a + (size_t)(t - 1) * Npad : p.ascr + (size_t)ws * Npad;
-        for (int k = tid; k < N; k += NT) arow[k] = shuffled ? sm.bpar[k] : ancestor_of(k);
+        if (shuffled || ident) {
+          for (int k = tid; k < N; k += NT) arow[k] = shuffled ? sm.bpar[k] : k;
+        } else {
+          // two of the thread's searches at a time (independent chains of shared-memory loads)
+          for (int k = tid; k < N; k += 2 * NT) {
+            const int k2 = k + NT;
+            const bool two = k2 < N;
+            const int kk = two ? k2 : k;
+            int a1, a2;
+            count_le_p2(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * sm.S[pad16(k)],
+                        sm.coarse[kk >> 5], sm.coarse[(kk >> 5) + 1], sumw * sm.S[pad16(kk)], a1, a2);
+            if (a1 >= N) { a1 = N - 1; st |= 512; }
+            if (a2 >= N) { a2 = N - 1; st |= 512; }
+            arow[k] = a1;
+            if (two) arow[k2] = a2;
+          }
+        }
         __syncthreads();
         const int E = (N - tid + NT - 1) / NT;
         auto tok = [&](int e) -> int { return (int)(((e < 8 ? tok0 >> (8 * e) : tok1 >> (8 * (e - 8)))) & 255ull); };
