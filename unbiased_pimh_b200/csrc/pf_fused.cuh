@@ -160,7 +160,8 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   const double* inj_shf = p.inj_shuffle ? p.inj_shuffle + (size_t)inj * T * (N - 1) : nullptr;
   const bool need_shared_u = Model::USES_SHARED_U && !c.inj_trans;
   int st = 0;
-  double ukeep[Model::JUMP_LIST ? 1 : CPIMH_MAX_E];   // second uniform of each owned particle's resampling Philox block (local memory)
+  // second uniform of each owned particle's resampling Philox block, for the models that consume it (local memory)
+  double ukeep[(Model::JUMP_LIST || !Model::USES_SHARED_U) ? 1 : CPIMH_MAX_E];
   const bool jump_list = Model::JUMP_LIST && (N + NT - 1) / NT <= 16;   // tokens of <= 16 own particles fit two 64-bit registers
 
   // ---------------- initialisation: R/CPF.R:17-28, Tree::Tree + Tree::init (src/tree.cpp:6-34)
@@ -212,7 +213,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
             if (tk > 255) { tk = 255; st |= CPIMH_ERR_INVALID; }
             if (e < 8) tok0 |= (unsigned long long)tk << (8 * e); else tok1 |= (unsigned long long)tk << (8 * (e - 8));
           } else ukeep[0] = ub;
-        } else ukeep[e] = ub;
+        } else if constexpr (Model::USES_SHARED_U) ukeep[e] = ub;
       }
     }
     if (!ident) {
@@ -271,7 +272,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       double x[D];
 #pragma unroll
       for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
-      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[Model::JUMP_LIST ? 0 : e] : 0.5);
+      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[(Model::JUMP_LIST || !Model::USES_SHARED_U) ? 0 : e] : 0.5);
       finish_particle(k, a, x);
     };
     if (p.shuffle && !ident) {
