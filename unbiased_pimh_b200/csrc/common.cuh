@@ -257,38 +257,6 @@ __device__ __forceinline__ void block_scan_inplace(double* a, int n, double* scr
   __syncthreads();
 }
 
-// Two forward in-place inclusive scans (a and b, same length) sharing the row loop, the barriers and the carry logic.
-// `scratch` needs 64 doubles.
-__device__ __forceinline__ void block_scan2_inplace(double* a, double* b, int n, double* scratch) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  const int rows = (n + 31) >> 5;
-  const int rpw = (rows + nw - 1) / nw;
-  const int r0 = wid * rpw, r1 = min(rows, r0 + rpw);
-  double ca = 0.0, cb = 0.0;
-  for (int r = r0; r < r1; r++) {
-    const int j = r * 32 + lane;
-    double va = (j < n) ? a[j] : 0.0, vb = (j < n) ? b[j] : 0.0;
-    va = warp_incl_scan(va, lane) + ca;
-    vb = warp_incl_scan(vb, lane) + cb;
-    if (j < n) { a[j] = va; b[j] = vb; }
-    ca = __shfl_sync(0xffffffffu, va, 31);
-    cb = __shfl_sync(0xffffffffu, vb, 31);
-  }
-  if (lane == 0) { scratch[wid] = ca; scratch[32 + wid] = cb; }
-  __syncthreads();
-  const double wa = (lane < nw) ? scratch[lane] : 0.0, wb = (lane < nw) ? scratch[32 + lane] : 0.0;
-  const double ia = warp_incl_scan(wa, lane), ib = warp_incl_scan(wb, lane);
-  const double oa = __shfl_sync(0xffffffffu, ia, wid) - __shfl_sync(0xffffffffu, wa, wid);
-  const double ob = __shfl_sync(0xffffffffu, ib, wid) - __shfl_sync(0xffffffffu, wb, wid);
-  if (wid > 0) {
-    for (int r = r0; r < r1; r++) {
-      const int j = r * 32 + lane;
-      if (j < n) { a[j] += oa; b[j] += ob; }
-    }
-  }
-  __syncthreads();
-}
-
 // ---------------------------------------------------------------- padded layout + chunked scans (fused filter)
 // The fused filter keeps its two per-particle shared arrays with one pad slot per 16 elements: element i lives at
 // pad16(i).  Striped accesses (lane l -> element base + l, base a multiple of 16 per half-warp) stay conflict-free, and so
@@ -340,7 +308,8 @@ __device__ __forceinline__ void block_scan_chunked(double* a, double* b, int n, 
     __syncthreads();
   }
 }
-// counts over a padded ascending array (same rules as count_le / count_lt below)
+// counts over a padded ascending array: number of entries <= u in [lo, hi) (src/multinomial.cpp:25-27 rule) and number of
+// entries < u (src/systematic.cpp:15-18 rule: smallest j with csw_j >= u)
 __device__ __forceinline__ int count_le_p(const double* c, int lo, int hi, double u) {
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -367,24 +336,6 @@ __device__ __forceinline__ int count_lt_p(const double* c, int n, double u) {
   return lo;
 }
 
-// number of entries of the (ascending) shared array c[0..n) that are <= u   (src/multinomial.cpp:25-27 rule)
-__device__ __forceinline__ int count_le(const double* c, int n, double u) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (c[mid] <= u) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-// number of entries < u   (src/systematic.cpp:15-18 rule: smallest j with csw_j >= u)
-__device__ __forceinline__ int count_lt(const double* c, int n, double u) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (c[mid] < u) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 #define CPIMH_M_LN_SQRT_2PI 0.918938533204672741780329736406   // R's dnorm(log=TRUE) constant
 #define CPIMH_INV_SQRT_10 0.31622776601683794                   // 1 / sqrt(10)

@@ -112,15 +112,6 @@ __device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre,
   return s;
 }
 
-// count of c[j] <= u, known to lie in [lo, hi]
-__device__ __forceinline__ int count_le_bounded(const double* c, int lo, int hi, double u) {
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (c[mid] <= u) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
 struct FilterOut {
   double* logz; double* logz_t; double* traj; int* path_index; int* status; double* normw; int* leaf_out; int* anc_rec; double* exp_path;
 };
