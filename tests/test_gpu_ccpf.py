@@ -235,3 +235,38 @@ def test_adaptive_pf_likelihood_is_unbiased(up, golden):
         assert np.allclose(r["loglik_t"][:, -1], ll, rtol=1e-13)
     one = up.pf(y, TH_AR, up.get_ar(1), 128, seed=3)
     assert one["pf_means"].shape == (100, 1) and one["path"].shape == (101, 1) and one["loglik_t"].shape == (100,)
+
+
+def test_conditional_filters_with_missing_observations_and_lorenz(up, oracle):
+    """R/CPF.R:38-40 / R/CPF_coupled.R:45-48: no resampling after a row whose first entry is NA (get_lorenz's dmeasurement
+    returns 0 there); Lorenz-96 (d = 8, rk4) through the conditional kernels, one and two systems."""
+    rng = np.random.default_rng(3)
+    y = rng.normal(size=(12, 8)) * 2 + 2
+    y[[3, 4, 8], :] = np.nan
+    N, seed = 96, 11
+    m, th = up.get_lorenz(1.0, 8, "rk4", 1), [8.0, 0.4]
+    ocfg = oracle.make_config(oracle.MODEL_LORENZ, 8, 8, N, 12, theta=[8.0, 0.4, 1.0], integrator=0, substeps=1)
+    refs = [oracle.cpf(ocfg, y, seed=5, filter_id=50 + i)["trajectory"] for i in range(4)]
+    g1 = up.ccpf_batch(N, m, th, y, refs[:2], seed=seed, ancestors=True)
+    g2 = up.ccpf_batch(N, m, th, y, refs[:2], refs[2:], seed=seed, ancestors=True)
+    ident = np.arange(N)
+    for b in range(2):
+        o1 = oracle.ccpf(ocfg, y, refs[b], seed=seed, filter_id=b, want_ancestors=True)
+        o2 = oracle.ccpf(ocfg, y, refs[b], refs[2 + b], seed=seed, filter_id=b, want_ancestors=True)
+        assert np.array_equal(g1["ancestors"][b, 0], o1["ancestors1"])
+        assert np.array_equal(g2["ancestors"][b, 0], o2["ancestors1"]) and np.array_equal(g2["ancestors"][b, 1], o2["ancestors2"])
+        for t in (0, 4, 5, 9):                                   # time 1 and the steps after an NA row: identity ancestors
+            assert np.array_equal(g2["ancestors"][b, 0][t], ident) and np.array_equal(g2["ancestors"][b, 1][t], ident)
+        assert np.allclose(g1["trajectory1"][b], o1["trajectory1"], rtol=1e-9, atol=1e-9)
+        assert np.allclose(g2["trajectory1"][b], o2["trajectory1"], rtol=1e-9, atol=1e-9)
+        assert np.allclose(g2["trajectory2"][b], o2["trajectory2"], rtol=1e-9, atol=1e-9)
+        assert abs(g1["logz"][b] - o1["logz"]) <= 1e-9 * abs(o1["logz"])
+
+
+def test_sharded_ccpf_estimator_single_process(up, golden):
+    y = golden["lgssm_y"]
+    est = up.unbiased_ccpf_estimator_sharded(up.get_ar(1), TH_AR, y, 64, 300, K=4, k=1, with_as=True, seed=3)
+    g = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 64, 300, K=4, k=1, with_as=True, seed=3)
+    assert est["nreplicates"] == 300 and est["nfilters"] == g["nfilters"]
+    assert np.allclose(est["mean"], g["hbar"].mean(axis=0), rtol=1e-12, atol=1e-12)
+    assert np.allclose(est["se"], g["hbar"].std(axis=0, ddof=1) / math.sqrt(300), rtol=1e-9, atol=1e-12)

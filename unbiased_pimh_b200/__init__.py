@@ -13,7 +13,7 @@ from .resampling import (multinomial_resampling_n, multinomial_resampling_n_, sy
 from .filters import CPF, CPF_coupled, CPF_RB, CPF_RB_coupled, ccpf_batch, pf, pf_batch, particlefilter, cpf_batch, PfBatch, pf_get_weighted_average  # noqa: F401
 from .pimh import (get_pimh_kernels, coupled_pimh_chains, H_bar, BC, rheeglynn_estimator, coupled_pimh_chains_batch, ChainBatch,  # noqa: F401
                    unbiased_estimator_sharded, shard_range, combine_sums, get_cpf_kernels, coupled_ccpf_chains,
-                   coupled_ccpf_chains_batch, rheeglynn_estimator_RB)
+                   coupled_ccpf_chains_batch, rheeglynn_estimator_RB, unbiased_ccpf_estimator_sharded)
 from .tree import Tree  # noqa: F401
 from .mvnorm import (fast_dmvnorm, fast_dmvnorm_transpose, fast_dmvnorm_transpose_cholesky, fast_rmvnorm, fast_rmvnorm_transpose,  # noqa: F401
                      fast_rmvnorm_transpose_cholesky, lorenz_transition)

@@ -396,6 +396,28 @@ def rheeglynn_estimator_RB(observations, model, theta, algoparameters, test_func
     return {"estimate": r["hbar_rb"][0], "iteration": int(r["iteration"][0]), "meetingtime": math.inf if tau < 0 else tau}
 
 
+def unbiased_ccpf_estimator_sharded(model, theta, observations, nparticles, nreplicates, K=1, k=0, max_iterations=math.inf, with_as=False,
+                                    seed=0, rb=False, **kw):
+    """The coupled-CCPF estimator over all ranks of torch.distributed (or one process): rank g runs the replicates
+    shard_range(nreplicates, g, G) of coupled_ccpf_chains_batch and ONE all-reduce combines [sum H_bar, sum H_bar^2, filters,
+    replicates] -- the multi-GPU form of foreach(r) coupled_ccpf_chains + H_bar.  Returns mean / standard error per component."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_range(nreplicates, rank, world)
+    g = coupled_ccpf_chains_batch(model, theta, observations, nparticles, hi - lo, K=K, k=k, max_iterations=max_iterations, with_as=with_as,
+                                  seed=seed, first_replicate=lo, rb=rb, **kw)
+    key, key2 = ("sum_hbar_rb", "sum_hbar_rb_sq") if rb else ("sum_hbar", "sum_hbar_sq")
+    buf = np.concatenate([g[key].T.ravel(), g[key2].T.ravel(), [g["nfilters"], hi - lo]])     # [T+1][d] order of combine_sums
+    t = torch.tensor(buf, dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+    if world > 1:
+        dist.all_reduce(t)
+    out = combine_sums(t.cpu().numpy(), model.dimension, np.asarray(observations).shape[0])
+    out["meetingtime_local"] = g["meetingtime"]
+    return out
+
+
 def shard_range(nreplicates, rank, world_size):
     """Replicates [lo, hi) owned by `rank`: contiguous blocks, remainder spread over the first ranks."""
     base, rem = divmod(int(nreplicates), int(world_size))
