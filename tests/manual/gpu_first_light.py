@@ -8,7 +8,7 @@ import traceback
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import unbiased_pimh_b200 as up  # noqa: E402
 from oracle import pyoracle as O  # noqa: E402
