@@ -322,20 +322,24 @@ def main():
         m1, th1 = up.get_ar(1), [0.5, float(np.sqrt(10.0))]
         lo, hi = up.shard_range(Rcc, rank, world)
         up.coupled_ccpf_chains_batch(m1, th1, obs1, 128, min(hi - lo, 2000), K=10, k=3, with_as=True, seed=5, first_replicate=lo)   # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        g = up.coupled_ccpf_chains_batch(m1, th1, obs1, 128, hi - lo, K=10, k=3, with_as=True, seed=6, first_replicate=lo)
-        sums = torch.tensor(np.concatenate([g["sum_hbar"].ravel(), g["sum_hbar_sq"].ravel(), [g["nfilters"], hi - lo]]), dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(sums)
-        barrier()
-        tcc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tcc, op=dist.ReduceOp.MAX)
+        times = []
+        for rep in range(3):                 # the one-shot entry allocates per call: report the median of three whole calls
+            barrier()
+            t0 = time.perf_counter()
+            g = up.coupled_ccpf_chains_batch(m1, th1, obs1, 128, hi - lo, K=10, k=3, with_as=True, seed=6 + rep, first_replicate=lo)
+            sums = torch.tensor(np.concatenate([g["sum_hbar"].ravel(), g["sum_hbar_sq"].ravel(), [g["nfilters"], hi - lo]]), dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(sums)
+            barrier()
+            tcc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tcc, op=dist.ReduceOp.MAX)
+            times.append(float(tcc.item()))
         nf = float(sums[-2].item())
-        cc_extra = {"metric": "coupled-CCPF estimator replicates/sec", "value": Rcc / float(tcc.item()), "replicates": Rcc, "filters_run": int(nf),
-                    "mean_meeting_time": float(np.mean(g["meetingtime"])),
-                    "workload": "get_ar(1) N=128 T=100 k=3 K=10 ancestor sampling; host wall time incl. allocation, H2D/D2H and the all-reduce"}
+        tmed = sorted(times)[1]
+        cc_extra = {"metric": "coupled-CCPF estimator replicates/sec", "value": Rcc / tmed, "replicates": Rcc, "filters_run": int(nf),
+                    "mean_meeting_time": float(np.mean(g["meetingtime"])), "seconds_per_call": times,
+                    "workload": "get_ar(1) N=128 T=100 k=3 K=10 ancestor sampling; median of 3 calls, host wall time incl. allocation, H2D/D2H and the all-reduce"}
 
     if rank == 0:
         peak, which = load_peaks()
