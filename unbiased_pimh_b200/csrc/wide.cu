@@ -25,7 +25,7 @@ struct WideParams {
   int N, T, D, B, GX, G, gshift, pgrid, substeps;   // GX = number of warp groups (softmax blocks), G = 1 << gshift particles each
   unsigned long long seed, first_filter;
   const double* obs;          // [T][D]
-  double F, sx, sy, cst;
+  double F, sx, sy, isy, cst;     // isy = 1 / sy
   double* hist_x; int* hist_a;
   double* lw; double* C; double* S;
   double* pmax; double* psum; double* pv; double* mstep; double* ptot;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
       for (int c = 0; c < C; c++) {
         v[c] = v[c] + p.sx * z[c];                                                      // :29
         xnew[(size_t)kk * D + lane * C + c] = v[c];
-        const double r = (v[c] - yv[c]) / p.sy;
+        const double r = (v[c] - yv[c]) * p.isy;
         sq += r * r;
       }
       sq = warp_sum(sq);
@@ -398,7 +398,7 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.GX = h->GX; p.G = h->G; p.gshift = h->gshift; p.pgrid = h->pgrid; p.substeps = c.substeps < 1 ? 1 : c.substeps;
   p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>();
-  p.F = c.theta[0]; p.sx = c.theta[1]; p.sy = c.theta[2];
+  p.F = c.theta[0]; p.sx = c.theta[1]; p.sy = c.theta[2]; p.isy = 1.0 / c.theta[2];
   double hl = 0;
   for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);                               // src/mvnorm.cpp:120-121
   p.cst = -(hl) - (c.dim * CPIMH_HALF_LOG_2PI_TRUNC);
