@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
       if (p.anc_rec) p.anc_rec[((size_t)b * p.T + (t - 1)) * N + k] = a;
     }
     double mylw = -INFINITY;
+#pragma unroll 2
     for (int j = 0; j < G && base + j < N; j++) {
       const int aj = __shfl_sync(0xffffffffu, a, j);
       const long long kk = base + j;
@@ -294,7 +295,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   h->cfg = cfg; h->maxB = max_filters; h->lastB = 0; h->launches = 0; h->bytes = 0; h->record_anc = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
   wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->gshift, &h->GX);
-  h->pgrid = prop.multiProcessorCount * 8;                  // __launch_bounds__(128, 8): one resident wave
+  h->pgrid = prop.multiProcessorCount * 8;                  // at least one resident wave of wide_propagate CTAs
   CPIMH_REQUIRE((h->GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER <= WIDE_MAX_BLOCKS_PER_CTA, "N too large for the cluster scan");
   const size_t B = (size_t)max_filters, N = cfg.nparticles, T = cfg.nobs, D = cfg.dim;
   size_t free_b = 0, total_b = 0;
