@@ -374,6 +374,7 @@ void api_fill_pf_params(const cpimh_config& c, const Geometry& g, int npre, PfPa
   p->shuffle = c.shuffle; p->path_mode = g.path_mode;
   p->npre = npre; p->integrator = c.integrator; p->substeps = c.substeps;
   p->n_init = api_n_init(c); p->n_trans = api_n_trans(c); p->sk_M = c.sk_max_events;
+  pf_layout(g.Npad, g.M, npre, g.path_mode, c.shuffle, &p->lay);
 }
 }  // namespace cpimh
 extern "C" {

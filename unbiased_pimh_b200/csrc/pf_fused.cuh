@@ -23,7 +23,12 @@ namespace cpimh {
 enum { PATH_NONE = 0, PATH_DENSE = 1, PATH_TREE = 2 };
 #define CPIMH_MAX_E 32        // particles per thread (N <= CPIMH_MAX_E * blockDim.x)
 
+// byte offsets of the shared-memory arrays inside the dynamic window (filled on the host by pf_layout, so that the kernel
+// re-derives a pointer with one add from the constant bank instead of recomputing the carve arithmetic)
+struct PfLayout { int S, theta, pre, dscr, dscr2, leaf, bpar, off32, bits, coarse, iscr; };
+
 struct PfParams {
+  PfLayout lay;
   int N, T, dy, Npad;
   int M;                       // tree capacity per filter (multiple of 32)
   long long B;                 // filters in this launch
@@ -73,42 +78,47 @@ struct PfSmem {
   int* coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
   int* iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
 };
-__host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
+// layout of the dynamic shared-memory window; returns its size in bytes
+__host__ __device__ inline size_t pf_layout(int Npad, int M, int npre, int path_mode, int shuffle, PfLayout* L) {
   size_t b = 0;
-  b += (size_t)padded_len(Npad) * 8 * 2;     // C, S (padded layout, common.cuh pad16)
-  b += (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64 + 2) * 8;
+  PfLayout l;
+  b += (size_t)padded_len(Npad) * 8;         // C at offset 0 (padded layout, common.cuh pad16)
+  l.S = (int)b; b += (size_t)padded_len(Npad) * 8;
+  l.theta = (int)b; b += (size_t)CPIMH_MAX_THETA * 8;
+  l.pre = (int)b; b += (size_t)(npre + (npre & 1)) * 8;
+  l.dscr = (int)b; b += 64 * 8;
+  l.dscr2 = (int)b; b += 2 * 8;
+  l.leaf = l.bpar = l.off32 = l.bits = -1;
   if (path_mode == PATH_TREE) {
-    b += (size_t)Npad * 4 * 2;               // leaf, bpar
-    b += (size_t)(Npad / 2) * 4;             // off32
-    b += (size_t)(M / 32) * 4;               // bits
+    l.leaf = (int)b; b += (size_t)Npad * 4;
+    l.bpar = (int)b; b += (size_t)Npad * 4;
+    l.off32 = (int)b; b += (size_t)(Npad / 2) * 4;
+    l.bits = (int)b; b += (size_t)(M / 32) * 4;
   } else if (shuffle) {
-    b += (size_t)Npad * 4;                   // bpar (ancestors to permute)
+    l.bpar = (int)b; b += (size_t)Npad * 4;  // ancestors to permute
   }
-  b += (size_t)(Npad / 32 + 4) * 4;          // coarse
-  b += 36 * 4;
+  l.coarse = (int)b; b += (size_t)(Npad / 32 + 4) * 4;
+  l.iscr = (int)b; b += 36 * 4;
+  if (L) *L = l;
   return (b + 15) & ~(size_t)15;
 }
-__device__ inline PfSmem pf_carve(unsigned char* raw, int Npad, int M, int npre, int path_mode, int shuffle) {
+__host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
+  return pf_layout(Npad, M, npre, path_mode, shuffle, nullptr);
+}
+__device__ __forceinline__ PfSmem pf_carve(unsigned char* raw, const PfLayout& l) {
   PfSmem s;
-  double* d = reinterpret_cast<double*>(raw);
-  s.C = d; d += padded_len(Npad);
-  s.S = d; d += padded_len(Npad);
-  s.theta = d; d += CPIMH_MAX_THETA;
-  s.pre = d; d += npre + (npre & 1);
-  s.dscr = d; d += 64;
-  s.dscr2 = d; d += 2;
-  int* i = reinterpret_cast<int*>(d);
-  s.leaf = nullptr; s.bpar = nullptr; s.off32 = nullptr; s.bits = nullptr;
-  if (path_mode == PATH_TREE) {
-    s.leaf = i; i += Npad;
-    s.bpar = i; i += Npad;
-    s.off32 = reinterpret_cast<unsigned*>(i); i += Npad / 2;
-    s.bits = reinterpret_cast<unsigned*>(i); i += M / 32;
-  } else if (shuffle) {
-    s.bpar = i; i += Npad;
-  }
-  s.coarse = i; i += Npad / 32 + 4;
-  s.iscr = i;
+  s.C = reinterpret_cast<double*>(raw);
+  s.S = reinterpret_cast<double*>(raw + l.S);
+  s.theta = reinterpret_cast<double*>(raw + l.theta);
+  s.pre = reinterpret_cast<double*>(raw + l.pre);
+  s.dscr = reinterpret_cast<double*>(raw + l.dscr);
+  s.dscr2 = reinterpret_cast<double*>(raw + l.dscr2);
+  s.leaf = l.leaf >= 0 ? reinterpret_cast<int*>(raw + l.leaf) : nullptr;
+  s.bpar = l.bpar >= 0 ? reinterpret_cast<int*>(raw + l.bpar) : nullptr;
+  s.off32 = l.off32 >= 0 ? reinterpret_cast<unsigned*>(raw + l.off32) : nullptr;
+  s.bits = l.bits >= 0 ? reinterpret_cast<unsigned*>(raw + l.bits) : nullptr;
+  s.coarse = reinterpret_cast<int*>(raw + l.coarse);
+  s.iscr = reinterpret_cast<int*>(raw + l.iscr);
   return s;
 }
 
@@ -507,7 +517,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
 template <class Model, int NT_MAX, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PfSmem sm = pf_carve(smem_raw, p.Npad, p.M, p.npre, p.path_mode, p.shuffle);
+  PfSmem sm = pf_carve(smem_raw, p.lay);
   for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
   for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
   __syncthreads();
