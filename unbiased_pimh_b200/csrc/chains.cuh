@@ -38,10 +38,9 @@ struct ChainParams {
 
 template <class Model, int NT_MAX, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams cp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int D = Model::D;
   const PfParams& p = cp.pf;
-  PfSmem sm = pf_carve(smem_raw, p.lay);
+  PfSmem sm = pf_carve(p.lay);
   const int tid = threadIdx.x, NT = blockDim.x, P = p.T + 1;
   for (int i = tid; i < CPIMH_MAX_THETA; i += NT) sm.theta[i] = p.theta[i];
   for (int i = tid; i < p.npre; i += NT) sm.pre[i] = p.pre[i];

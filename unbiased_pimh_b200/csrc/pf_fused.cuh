@@ -64,19 +64,32 @@ struct PfParams {
   int n_init, n_trans, sk_M;
 };
 
+// A shared-memory array addressed as (dynamic window symbol + byte offset) at every use, never as a stored generic pointer:
+// the compiler then emits LDS/STS with the offset as an operand, instead of re-deriving a generic address (special-register
+// read of the CTA's cluster rank + address arithmetic) each time a spilled pointer is rematerialised.
+template <class T>
+struct SmemArr {
+  int off;          // byte offset in the dynamic shared-memory window
+  __device__ __forceinline__ T* ptr() const {
+    extern __shared__ __align__(16) unsigned char cpimh_dyn_smem[];
+    return reinterpret_cast<T*>(cpimh_dyn_smem + off);
+  }
+  __device__ __forceinline__ T& operator[](int i) const { return ptr()[i]; }
+  __device__ __forceinline__ operator T*() const { return ptr(); }
+};
 struct PfSmem {
-  double* C;        // [padded_len(Npad)] weights, then their inclusive CDF          (element i at pad16(i))
-  double* S;        // [padded_len(Npad)] exponential spacings -> prefix sums -> log-weights (element i at pad16(i))
-  int* leaf;        // [Npad] l_star                                   (PATH_TREE, or shuffle scratch)
-  int* bpar;        // [Npad] ancestors, then parent slots b = l_star[a] (PATH_TREE, or shuffle scratch)
-  unsigned* off32;  // [Npad/2] 16-bit offspring counters              (PATH_TREE)
-  unsigned* bits;   // [M/32] free-slot bitmap (1 = free)              (PATH_TREE)
-  double* theta;    // [CPIMH_MAX_THETA]
-  double* pre;      // [npre]
-  double* dscr;     // [64]
-  double* dscr2;    // [2]   E_N of the ladder (written by thread 0 before the scans)
-  int* coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
-  int* iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
+  SmemArr<double> C;        // [padded_len(Npad)] weights, then their inclusive CDF          (element i at pad16(i))
+  SmemArr<double> S;        // [padded_len(Npad)] exponential spacings -> prefix sums -> log-weights (element i at pad16(i))
+  SmemArr<int> leaf;        // [Npad] l_star                                   (PATH_TREE, or shuffle scratch)
+  SmemArr<int> bpar;        // [Npad] ancestors, then parent slots b = l_star[a] (PATH_TREE, or shuffle scratch)
+  SmemArr<unsigned> off32;  // [Npad/2] 16-bit offspring counters              (PATH_TREE)
+  SmemArr<unsigned> bits;   // [M/32] free-slot bitmap (1 = free)              (PATH_TREE)
+  SmemArr<double> theta;    // [CPIMH_MAX_THETA]
+  SmemArr<double> pre;      // [npre]
+  SmemArr<double> dscr;     // [64]
+  SmemArr<double> dscr2;    // [2]   E_N of the ladder (written by thread 0 before the scans)
+  SmemArr<int> coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
+  SmemArr<int> iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
 };
 // layout of the dynamic shared-memory window; returns its size in bytes
 __host__ __device__ inline size_t pf_layout(int Npad, int M, int npre, int path_mode, int shuffle, PfLayout* L) {
@@ -105,20 +118,11 @@ __host__ __device__ inline size_t pf_layout(int Npad, int M, int npre, int path_
 __host__ __device__ inline size_t pf_smem_bytes(int Npad, int M, int npre, int path_mode, int shuffle) {
   return pf_layout(Npad, M, npre, path_mode, shuffle, nullptr);
 }
-__device__ __forceinline__ PfSmem pf_carve(unsigned char* raw, const PfLayout& l) {
+__device__ __forceinline__ PfSmem pf_carve(const PfLayout& l) {
   PfSmem s;
-  s.C = reinterpret_cast<double*>(raw);
-  s.S = reinterpret_cast<double*>(raw + l.S);
-  s.theta = reinterpret_cast<double*>(raw + l.theta);
-  s.pre = reinterpret_cast<double*>(raw + l.pre);
-  s.dscr = reinterpret_cast<double*>(raw + l.dscr);
-  s.dscr2 = reinterpret_cast<double*>(raw + l.dscr2);
-  s.leaf = l.leaf >= 0 ? reinterpret_cast<int*>(raw + l.leaf) : nullptr;
-  s.bpar = l.bpar >= 0 ? reinterpret_cast<int*>(raw + l.bpar) : nullptr;
-  s.off32 = l.off32 >= 0 ? reinterpret_cast<unsigned*>(raw + l.off32) : nullptr;
-  s.bits = l.bits >= 0 ? reinterpret_cast<unsigned*>(raw + l.bits) : nullptr;
-  s.coarse = reinterpret_cast<int*>(raw + l.coarse);
-  s.iscr = reinterpret_cast<int*>(raw + l.iscr);
+  s.C.off = 0; s.S.off = l.S; s.theta.off = l.theta; s.pre.off = l.pre; s.dscr.off = l.dscr; s.dscr2.off = l.dscr2;
+  s.leaf.off = l.leaf; s.bpar.off = l.bpar; s.off32.off = l.off32; s.bits.off = l.bits;   // -1 when absent (never dereferenced then)
+  s.coarse.off = l.coarse; s.iscr.off = l.iscr;
   return s;
 }
 
@@ -280,7 +284,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       for (int k = tid; k < N; k += NT) sm.bpar[k] = ancestor_of(k);
       __syncthreads();
       // std::random_shuffle with randWrapper (src/multinomial.cpp:6-10,30): for i = 1..n-1 swap(a[i], a[floor(u_i (i+1))])
-      int* jidx = reinterpret_cast<int*>(sm.S);
+      int* jidx = reinterpret_cast<int*>(sm.S.ptr());
       for (int i = 1 + tid; i < N; i += NT) {
         double u = inj_shf ? inj_shf[(size_t)(t - 1) * (N - 1) + (i - 1)] : philox_u1(stream, i, t, CPIMH_P_SHUFFLE, 0);
         int j = (int)floor(u * (double)(i + 1));
@@ -469,7 +473,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   if (out.exp_path && (tree || dense)) {
     // pf_get_weighted_average (R/CPF.R:84-92) over sapply(0:(N-1), Tree$get_path) (:73-74): all N leaves walk to the root
     // in lock step; per generation and component one block reduction of w_n x.  S is free and holds the walkers.
-    int* cur = reinterpret_cast<int*>(sm.S);
+    int* cur = reinterpret_cast<int*>(sm.S.ptr());
     const double* hx = dense ? p.hist_x + (size_t)ws * (T + 1) * xstride : nullptr;
     for (int n = tid; n < N; n += NT) cur[n] = tree ? sm.leaf[n] : n;
     for (int step = T; step >= 0; step--) {
@@ -516,8 +520,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
 
 template <class Model, int NT_MAX, int MIN_BLOCKS>
 __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  PfSmem sm = pf_carve(smem_raw, p.lay);
+  PfSmem sm = pf_carve(p.lay);
   for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
   for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
   __syncthreads();
