@@ -33,7 +33,7 @@ struct ApfParams {
   int* anc_rec;                // [B][T][N] or null
   int* status;                 // [B]
 };
-struct ApfSmem { double* C; double* S; double* LW; double* theta; double* pre; double* dscr; int* iscr; };
+struct ApfSmem { double* C; double* S; double* LW; double* theta; double* pre; double* dscr; int* iscr; int theta_off, pre_off; };
 __host__ __device__ inline size_t apf_smem_bytes(int Npad, int npre) {
   size_t b = (size_t)(2 * padded_len(Npad + 16) + Npad) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + 36 * 4;
   return (b + 15) & ~(size_t)15;
@@ -44,8 +44,8 @@ __device__ inline ApfSmem apf_carve(unsigned char* raw, int Npad, int npre) {
   s.C = d; d += padded_len(Npad + 16);       // C and S in the padded layout (element i at pad16(i), common.cuh)
   s.S = d; d += padded_len(Npad + 16);
   s.LW = d; d += Npad;
-  s.theta = d; d += CPIMH_MAX_THETA;
-  s.pre = d; d += npre + (npre & 1);
+  s.theta = d; s.theta_off = (int)(reinterpret_cast<unsigned char*>(d) - raw); d += CPIMH_MAX_THETA;
+  s.pre = d; s.pre_off = (int)(reinterpret_cast<unsigned char*>(d) - raw); d += npre + (npre & 1);
   s.dscr = d; d += 64;
   s.iscr = reinterpret_cast<int*>(d);
   return s;
@@ -61,7 +61,7 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
   int* ha = p.hist_a + (size_t)ws * T * Npad;
   double* prop = p.prop + (size_t)ws * xstride;
   ModelCtx c;
-  c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
+  c.theta.off = sm.theta_off; c.pre.off = sm.pre_off; c.stream = stream; c.N = N; c.T = T;
   c.inj_init = nullptr; c.inj_trans = nullptr;
   c.n_trans = 0; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
   int st = 0;

@@ -48,6 +48,7 @@ struct CcpfSmem {
   double* P;                   // [Npad + 32] ladder prefix sums ; log-weights of system 2
   int* R;                      // [Npad] rank among the coupled (>= 0) or the residual (~rank < 0) indices
   double* theta; double* pre; double* dscr; int* iscr;
+  int theta_off, pre_off;      // byte offsets of theta / pre in the dynamic window (ModelCtx addresses them as symbol + offset)
 };
 __host__ __device__ inline size_t ccpf_smem_bytes(int Npad, int npre) {
   size_t b = (size_t)(4 * padded_len(Npad + 32)) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + (size_t)Npad * 4 + 36 * 4;
@@ -60,8 +61,8 @@ __device__ inline CcpfSmem ccpf_carve(unsigned char* raw, int Npad, int npre) {
   s.C2 = d; d += padded_len(Npad + 32);
   s.V = d; d += padded_len(Npad + 32);
   s.P = d; d += padded_len(Npad + 32);
-  s.theta = d; d += CPIMH_MAX_THETA;
-  s.pre = d; d += npre + (npre & 1);
+  s.theta = d; s.theta_off = (int)(reinterpret_cast<unsigned char*>(d) - raw); d += CPIMH_MAX_THETA;
+  s.pre = d; s.pre_off = (int)(reinterpret_cast<unsigned char*>(d) - raw); d += npre + (npre & 1);
   s.dscr = d; d += 64;
   int* i = reinterpret_cast<int*>(d);
   s.R = i; i += Npad;
@@ -111,7 +112,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   double* Wk[2] = {sm.C1, sm.C2};
   double* Lk[2] = {sm.V, sm.P};
   ModelCtx c;
-  c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
+  c.theta.off = sm.theta_off; c.pre.off = sm.pre_off; c.stream = stream; c.N = N; c.T = T;
   c.inj_init = p.inj_init ? p.inj_init + (size_t)inj * p.n_init * N : nullptr;
   c.inj_trans = p.inj_trans ? p.inj_trans + (size_t)inj * T * p.n_trans * N : nullptr;
   c.n_trans = p.n_trans; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;

@@ -178,14 +178,12 @@ struct ModelOpParams {
 template <class Model>
 __global__ void model_op_kernel(ModelOpParams q) {
   constexpr int D = Model::D;
-  __shared__ double theta[CPIMH_MAX_THETA];
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* pre = reinterpret_cast<double*>(smem_raw);
-  for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) theta[i] = q.theta[i];
-  for (int i = threadIdx.x; i < q.npre; i += blockDim.x) pre[i] = q.pre[i];
+  ModelCtx c;                                  // dynamic window: theta [CPIMH_MAX_THETA] then pre [npre]
+  c.theta.off = 0; c.pre.off = CPIMH_MAX_THETA * (int)sizeof(double);
+  for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) c.theta[i] = q.theta[i];
+  for (int i = threadIdx.x; i < q.npre; i += blockDim.x) c.pre[i] = q.pre[i];
   __syncthreads();
-  ModelCtx c;
-  c.theta = theta; c.pre = pre; c.stream = make_stream(q.seed, q.filter_id); c.N = q.N; c.T = q.T;
+  c.stream = make_stream(q.seed, q.filter_id); c.N = q.N; c.T = q.T;
   c.inj_init = q.op == 0 ? q.noise : nullptr;
   // rtransition with injected noise: present the single step as row `time` of a [T][n][N] array
   c.inj_trans = (q.op == 1 && q.noise) ? q.noise - (size_t)(q.time - 1) * q.n_trans * q.N : nullptr;
@@ -211,7 +209,7 @@ __global__ void model_op_kernel(ModelOpParams q) {
 template <class Model>
 int launch_model_op(const ModelOpParams& q, cudaStream_t stream) {
   const int threads = 128, grid = (q.N + threads - 1) / threads;
-  model_op_kernel<Model><<<grid, threads, (size_t)(q.npre + 1) * sizeof(double), stream>>>(q);
+  model_op_kernel<Model><<<grid, threads, (size_t)(CPIMH_MAX_THETA + q.npre + 1) * sizeof(double), stream>>>(q);
   CPIMH_CUDA_CHECK(cudaGetLastError());
   return CPIMH_OK;
 }

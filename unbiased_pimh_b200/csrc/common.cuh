@@ -257,6 +257,20 @@ __device__ __forceinline__ void block_scan_inplace(double* a, int n, double* scr
   __syncthreads();
 }
 
+// A shared-memory array addressed as (dynamic window symbol + byte offset) at every use, never as a stored generic pointer:
+// the compiler then emits LDS/STS with the offset as an operand, instead of re-deriving a generic address (special-register
+// read of the CTA's cluster rank + address arithmetic) each time a spilled pointer is rematerialised.
+template <class T>
+struct SmemArr {
+  int off;          // byte offset in the dynamic shared-memory window
+  __device__ __forceinline__ T* ptr() const {
+    extern __shared__ __align__(16) unsigned char cpimh_dyn_smem[];
+    return reinterpret_cast<T*>(cpimh_dyn_smem + off);
+  }
+  __device__ __forceinline__ T& operator[](int i) const { return ptr()[i]; }
+  __device__ __forceinline__ operator T*() const { return ptr(); }
+};
+
 // ---------------------------------------------------------------- padded layout + chunked scans (fused filter)
 // The fused filter keeps its two per-particle shared arrays with one pad slot per 16 elements: element i lives at
 // pad16(i).  Striped accesses (lane l -> element base + l, base a multiple of 16 per half-warp) stay conflict-free, and so

@@ -12,8 +12,8 @@
 namespace cpimh {
 
 struct ModelCtx {
-  const double* theta;      // shared-memory copy of cfg.theta
-  const double* pre;        // shared-memory model precompute (AR: A col-major then cst; LORENZ: cst)
+  SmemArr<double> theta;    // shared-memory copy of cfg.theta (dynamic window offset, see common.cuh SmemArr)
+  SmemArr<double> pre;      // shared-memory model precompute (AR: A col-major then cst; LORENZ: cst)
   Stream stream;
   int N;                    // particles
   int T;

@@ -64,19 +64,6 @@ struct PfParams {
   int n_init, n_trans, sk_M;
 };
 
-// A shared-memory array addressed as (dynamic window symbol + byte offset) at every use, never as a stored generic pointer:
-// the compiler then emits LDS/STS with the offset as an operand, instead of re-deriving a generic address (special-register
-// read of the CTA's cluster rank + address arithmetic) each time a spilled pointer is rematerialised.
-template <class T>
-struct SmemArr {
-  int off;          // byte offset in the dynamic shared-memory window
-  __device__ __forceinline__ T* ptr() const {
-    extern __shared__ __align__(16) unsigned char cpimh_dyn_smem[];
-    return reinterpret_cast<T*>(cpimh_dyn_smem + off);
-  }
-  __device__ __forceinline__ T& operator[](int i) const { return ptr()[i]; }
-  __device__ __forceinline__ operator T*() const { return ptr(); }
-};
 struct PfSmem {
   SmemArr<double> C;        // [padded_len(Npad)] weights, then their inclusive CDF          (element i at pad16(i))
   SmemArr<double> S;        // [padded_len(Npad)] exponential spacings -> prefix sums -> log-weights (element i at pad16(i))
