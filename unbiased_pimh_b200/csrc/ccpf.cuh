@@ -43,30 +43,30 @@ struct CcpfParams {
 };
 
 struct CcpfSmem {
-  double* C1; double* C2;      // [Npad] weights of system 1 / 2 -> residual CDFs
-  double* V;                   // [Npad + 32] nu -> its CDF ; log-weights of system 1 ; ancestor-sampling weights
-  double* P;                   // [Npad + 32] ladder prefix sums ; log-weights of system 2
-  int* R;                      // [Npad] rank among the coupled (>= 0) or the residual (~rank < 0) indices
-  double* theta; double* pre; double* dscr; int* iscr;
-  int theta_off, pre_off;      // byte offsets of theta / pre in the dynamic window (ModelCtx addresses them as symbol + offset)
+  SmemArr<double> C1, C2;      // [Npad] weights of system 1 / 2 -> residual CDFs
+  SmemArr<double> V;           // [Npad + 32] nu -> its CDF ; log-weights of system 1 ; ancestor-sampling weights
+  SmemArr<double> P;           // [Npad + 32] ladder prefix sums ; log-weights of system 2
+  SmemArr<int> R;              // [Npad] rank among the coupled (>= 0) or the residual (~rank < 0) indices
+  SmemArr<double> theta, pre, dscr;
+  SmemArr<int> iscr;
 };
 __host__ __device__ inline size_t ccpf_smem_bytes(int Npad, int npre) {
   size_t b = (size_t)(4 * padded_len(Npad + 32)) * 8 + (size_t)(CPIMH_MAX_THETA + npre + (npre & 1) + 64) * 8 + (size_t)Npad * 4 + 36 * 4;
   return (b + 15) & ~(size_t)15;
 }
-__device__ inline CcpfSmem ccpf_carve(unsigned char* raw, int Npad, int npre) {
+__device__ __forceinline__ CcpfSmem ccpf_carve(int Npad, int npre) {
   CcpfSmem s;
-  double* d = reinterpret_cast<double*>(raw);
-  s.C1 = d; d += padded_len(Npad + 32);      // all four in the padded layout (element i at pad16(i), common.cuh)
-  s.C2 = d; d += padded_len(Npad + 32);
-  s.V = d; d += padded_len(Npad + 32);
-  s.P = d; d += padded_len(Npad + 32);
-  s.theta = d; s.theta_off = (int)(reinterpret_cast<unsigned char*>(d) - raw); d += CPIMH_MAX_THETA;
-  s.pre = d; s.pre_off = (int)(reinterpret_cast<unsigned char*>(d) - raw); d += npre + (npre & 1);
-  s.dscr = d; d += 64;
-  int* i = reinterpret_cast<int*>(d);
-  s.R = i; i += Npad;
-  s.iscr = i;
+  int b = 0;
+  const int arr = padded_len(Npad + 32) * 8;   // all four in the padded layout (element i at pad16(i), common.cuh)
+  s.C1.off = b; b += arr;
+  s.C2.off = b; b += arr;
+  s.V.off = b; b += arr;
+  s.P.off = b; b += arr;
+  s.theta.off = b; b += CPIMH_MAX_THETA * 8;
+  s.pre.off = b; b += (npre + (npre & 1)) * 8;
+  s.dscr.off = b; b += 64 * 8;
+  s.R.off = b; b += Npad * 4;
+  s.iscr.off = b;
   return s;
 }
 
@@ -109,10 +109,10 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     hx[s] = p.hist_x + ((size_t)ws * 2 + s) * (T + 1) * xstride;
     ha[s] = p.hist_a + ((size_t)ws * 2 + s) * T * Npad;
   }
-  double* Wk[2] = {sm.C1, sm.C2};
-  double* Lk[2] = {sm.V, sm.P};
+  const SmemArr<double> Wk[2] = {sm.C1, sm.C2};
+  const SmemArr<double> Lk[2] = {sm.V, sm.P};
   ModelCtx c;
-  c.theta.off = sm.theta_off; c.pre.off = sm.pre_off; c.stream = stream; c.N = N; c.T = T;
+  c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
   c.inj_init = p.inj_init ? p.inj_init + (size_t)inj * p.n_init * N : nullptr;
   c.inj_trans = p.inj_trans ? p.inj_trans + (size_t)inj * T * p.n_trans * N : nullptr;
   c.n_trans = p.n_trans; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
@@ -342,8 +342,7 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
 
 template <class Model>
 __global__ void __launch_bounds__(512, 1) ccpf_kernel(CcpfParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CcpfSmem sm = ccpf_carve(smem_raw, p.Npad, p.npre);
+  CcpfSmem sm = ccpf_carve(p.Npad, p.npre);
   for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
   for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
   __syncthreads();
