@@ -137,6 +137,9 @@ int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ance
 /* device pointers of the resident outputs (valid until destroy): logz [B], trajectory [B][T+1][d] */
 int cpimh_pf_device_outputs(cpimh_pf* h, double** d_logz, double** d_trajectory);
 int cpimh_pf_device_exp_paths(cpimh_pf* h, double** d_exp_path);   /* [B][T+1][d]; after cpimh_pf_all_particles(h, 1) */
+/* number of time steps each filter of the last run repeated with sequential-order sums because a sorted uniform came within
+ * rounding distance of a CDF knot (DESIGN.md "Exact ancestors"): repeats [B] */
+int cpimh_pf_fetch_exact_repeats(cpimh_pf* h, int64_t nfilters, void* stream, int32_t* repeats);
 int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status);   /* [B] per-filter status of the last run (0 = ok) */
 /* kernels launched by this handle so far (bench.py's gpu_launches) and bytes of HBM it holds */
 int64_t cpimh_pf_launch_count(const cpimh_pf* h);

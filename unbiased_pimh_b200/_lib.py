@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcpimh.so")
+LIB_PATH = os.environ.get("CPIMH_LIB") or os.path.join(HERE, "libcpimh.so")   # CPIMH_LIB: A/B builds of the same ABI (tools/)
 MAX_THETA = 32
 
 MODEL_GSS, MODEL_AR, MODEL_LEVY_SV, MODEL_SK, MODEL_LORENZ = range(5)

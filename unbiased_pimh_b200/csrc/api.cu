@@ -214,7 +214,7 @@ struct cpimh_pf {
   int record_anc, all_particles;
   int64_t launches, bytes;
   int grid;
-  DevBuf hist_x, hist_a, ascr;
+  DevBuf hist_x, hist_a, ascr, wscr, exact;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, logz, logz_t, traj, path_index, status, normw, leaf_out, anc_rec, exp_path;
   DevBuf inj_init, inj_trans, inj_resample, inj_shuffle, inj_path;
   bool have_inj[5];
@@ -271,6 +271,8 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   const size_t G = (size_t)h->grid;          // HBM workspaces belong to resident CTAs, not to filters
   if (!rc && g.path_mode != PATH_DENSE) rc = A(h->xbuf, sizeof(double) * G * 2 * D * g.Npad);
   if (!rc && g.path_mode != PATH_DENSE) rc = A(h->ascr, sizeof(int) * G * g.Npad);
+  if (!rc) rc = A(h->wscr, sizeof(double) * G * g.Npad);
+  if (!rc) rc = A(h->exact, sizeof(int) * B);
   if (!rc && g.path_mode == PATH_DENSE) {
     rc = A(h->hist_x, sizeof(double) * G * g.hist_x_elems);
     if (!rc) rc = A(h->hist_a, sizeof(int) * G * g.hist_a_elems);
@@ -299,7 +301,7 @@ int cpimh_pf_destroy(cpimh_pf* h) {
   if (!h) return CPIMH_OK;
   if (h->wide) { wide_destroy(h->wide); delete h; return CPIMH_OK; }
   DevBuf* all[] = {&h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->logz, &h->logz_t, &h->traj, &h->path_index,
-                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->exp_path, &h->hist_x, &h->hist_a, &h->ascr, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
+                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->exp_path, &h->hist_x, &h->hist_a, &h->ascr, &h->wscr, &h->exact, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
   return CPIMH_OK;
@@ -389,6 +391,7 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   p.B = B; p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>(); p.theta = h->theta.as<double>(); p.pre = h->pre.as<double>();
   p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.ascr = h->ascr.as<int>();
+  p.wscr = h->wscr.as<double>(); p.exact_repeats = h->exact.as<int>();
   p.xbuf = h->xbuf.as<double>(); p.a_star = h->a_star.as<int>(); p.o_star = h->o_star.as<int>(); p.x_star = h->x_star.as<double>();
   p.logz = h->logz.as<double>(); p.logz_t = h->logz_t.as<double>(); p.traj = h->traj.as<double>();
   p.path_index = h->path_index.as<int>(); p.status = h->status.as<int>(); p.normw = h->normw.as<double>();
@@ -501,6 +504,16 @@ int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* e
   a.hist_a = h->hist_a.as<int>() ? h->hist_a.as<int>() + (size_t)b * h->geo.hist_a_elems : nullptr;
   a.normw = h->normw.as<double>() + (size_t)b * N;
   return api_all_particles(a, s, exp_path, trajectories, normweights);
+}
+
+int cpimh_pf_fetch_exact_repeats(cpimh_pf* h, int64_t B, void* stream, int32_t* repeats) {
+  CPIMH_REQUIRE(h && repeats, "null argument");
+  CPIMH_REQUIRE(!h->wide, "not available for the wide (d = 32/64) filter");
+  CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
+  cudaStream_t s = (cudaStream_t)stream;
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(repeats, h->exact.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CPIMH_OK;
 }
 
 int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status) {

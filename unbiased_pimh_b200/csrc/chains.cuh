@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
     int p1 = 0, p2 = -1, pp = 1;           // buffer indices: chain 1, chain 2 (none yet), next proposal
     int id1 = 0, id2 = -1;                  // iteration index of the proposal each chain currently holds
     FilterOut out;
-    out.logz = lzbuf; out.logz_t = nullptr; out.path_index = nullptr; out.status = ibuf; out.normw = nullptr; out.leaf_out = nullptr; out.anc_rec = nullptr; out.exp_path = nullptr;
+    out.logz = lzbuf; out.status = ibuf;
     // pimh_init (R/pf_kernels.R:134-139)
     out.traj = sbuf + (size_t)p1 * P * D;
     run_filter<Model>(p, sm, ws, make_stream(p.seed, (unsigned long long)rep), -1, out);

@@ -351,6 +351,37 @@ __device__ __forceinline__ int count_lt_p(const double* c, int n, double u) {
 }
 
 
+// ---------------------------------------------------------------- CTA-size independent reductions
+// Block sum of f(0) + ... + f(n-1) evaluated as ONE fixed tree whatever the CTA size (a multiple of 32 threads), so that a
+// filter returns the same bits from a 32-, 256- or 1024-thread CTA.  The tree: segments of 1024 consecutive terms; inside a
+// segment lane l of one warp adds f(1024 g + l), f(1024 g + l + 32), ... in that order, an xor butterfly combines the 32
+// lanes; the segment totals are then added left to right.  All threads must call; `scratch` needs 32 doubles (n <= 32768)
+// and must be free; begins and ends with a barrier.
+template <class F>
+__device__ __forceinline__ double block_sum_canonical(F f, int n, double* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nseg = (n + 1023) >> 10;
+  __syncthreads();
+  for (int g = wid; g < nseg; g += nw) {
+    const int k0 = (g << 10) + lane, k1 = min(n, (g + 1) << 10);
+    double part = 0.0;
+    for (int k = k0; k < k1; k += 32) part += f(k);
+    part = warp_sum(part);
+    if (lane == 0) scratch[g] = part;
+  }
+  __syncthreads();
+  double r = scratch[0];
+  for (int g = 1; g < nseg; g++) r += scratch[g];
+  __syncthreads();
+  return r;
+}
+// In-place inclusive prefix sums of a padded array by ONE thread, left to right: r[i] = r[i-1] + x[i], the order of
+// Rcpp::cumsum (src/multinomial.cpp:17) and of the running sum in src/systematic.cpp:13-17.
+__device__ __forceinline__ void sequential_cumsum_p(double* a, int n) {
+  double acc = a[0];
+  for (int i = 1; i < n; i++) { acc += a[pad16(i)]; a[pad16(i)] = acc; }
+}
+
 #define CPIMH_M_LN_SQRT_2PI 0.918938533204672741780329736406   // R's dnorm(log=TRUE) constant
 #define CPIMH_INV_SQRT_10 0.31622776601683794                   // 1 / sqrt(10)
 #define CPIMH_LOG_SQRT_10 0x1.26bb1bbb55516p+0                 // log(sqrt(10.0)) as libm rounds it (gss measurement sd)

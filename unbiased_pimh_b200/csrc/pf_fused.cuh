@@ -17,6 +17,9 @@
 #pragma once
 #include "common.cuh"
 #include "models.cuh"
+#ifndef CPIMH_EXP
+#define CPIMH_EXP 0      // A/B switches of tools/build_variant.sh (0 in the product)
+#endif
 
 namespace cpimh {
 
@@ -45,7 +48,9 @@ struct PfParams {
   double* xbuf;                // PATH_NONE/TREE: [ws][2][D][Npad]
   double* hist_x;              // PATH_DENSE:     [ws][T+1][D][Npad]
   int* hist_a;                 // PATH_DENSE:     [ws][T][Npad]
-  int* ascr;                   // [ws][Npad] ancestor scratch (jump-list models when the path store is not dense)
+  int* ascr;                   // [ws][Npad] this step's ancestors when the path store is not dense
+  double* wscr;                // [ws][Npad] last step's unnormalised weights (exact-order repeat of a resampling step)
+  int* exact_repeats;          // [B] or null: number of steps a filter repeated with sequential-order sums
   int* a_star;                 // PATH_TREE:      [ws][M]
   int* o_star;                 // PATH_TREE:      [ws][M]
   double* x_star;              // PATH_TREE:      [ws][D][M]
@@ -74,9 +79,9 @@ struct PfSmem {
   SmemArr<double> theta;    // [CPIMH_MAX_THETA]
   SmemArr<double> pre;      // [npre]
   SmemArr<double> dscr;     // [64]
-  SmemArr<double> dscr2;    // [2]   E_N of the ladder (written by thread 0 before the scans)
+  SmemArr<double> dscr2;    // [4]   E_N of the ladder (written by thread 0 before the scans), sum of the last weights, knot margin, running log Z
   SmemArr<int> coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
-  SmemArr<int> iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item)
+  SmemArr<int> iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item, [34] exact-order repeats, [35] near-knot flag)
 };
 // layout of the dynamic shared-memory window; returns its size in bytes
 __host__ __device__ inline size_t pf_layout(int Npad, int M, int npre, int path_mode, int shuffle, PfLayout* L) {
@@ -87,7 +92,7 @@ __host__ __device__ inline size_t pf_layout(int Npad, int M, int npre, int path_
   l.theta = (int)b; b += (size_t)CPIMH_MAX_THETA * 8;
   l.pre = (int)b; b += (size_t)(npre + (npre & 1)) * 8;
   l.dscr = (int)b; b += 64 * 8;
-  l.dscr2 = (int)b; b += 2 * 8;
+  l.dscr2 = (int)b; b += 4 * 8;
   l.leaf = l.bpar = l.off32 = l.bits = -1;
   if (path_mode == PATH_TREE) {
     l.leaf = (int)b; b += (size_t)Npad * 4;
@@ -113,20 +118,25 @@ __device__ __forceinline__ PfSmem pf_carve(const PfLayout& l) {
   return s;
 }
 
+// Where one filter's results go.  Only the three outputs that the chain kernel redirects are pointers; everything else is
+// addressed at its (rare) use as PfParams array + filter index `fb`, which costs no registers in the hot loop (the arrays are
+// kernel parameters in the constant bank; a null array switches the output off; fb < 0 means "no per-filter arrays").
 struct FilterOut {
-  double* logz; double* logz_t; double* traj; int* path_index; int* status; double* normw; int* leaf_out; int* anc_rec; double* exp_path;
+  double* logz; double* traj; int* status;
 };
 
 __device__ __forceinline__ void set_free_bit(unsigned* bits, int slot) { atomicOr(&bits[slot >> 5], 1u << (slot & 31)); }
 
-// Runs one whole filter with the calling CTA.  `ws` selects the HBM workspace, `inj` the row of the injected
-// noise arrays (ignored when they are null).  All threads of the CTA must call.
-template <class Model>
-__device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, const Stream& stream, long long inj, const FilterOut& out) {
+// Runs one whole filter with the calling CTA.  `ws` selects the HBM workspace, `fb` the filter's row in the per-filter
+// output arrays and in the injected noise arrays of PfParams (ignored when they are null).  All threads of the CTA must call.
+// LEAN (the production configuration: dense path store, Philox noise, no shuffle, no ancestor recording) compiles the tree, the
+// injection pointers and the shuffle out of the kernel: their registers are what the hot loops otherwise spill.
+template <class Model, bool LEAN = false>
+__device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, const Stream& stream, long long fb, const FilterOut& out) {
   constexpr int D = Model::D;
   const int tid = threadIdx.x, NT = blockDim.x;
   const int N = p.N, T = p.T, Npad = p.Npad, M = p.M, W = M >> 5;
-  const bool tree = p.path_mode == PATH_TREE, dense = p.path_mode == PATH_DENSE;
+  const bool tree = !LEAN && p.path_mode == PATH_TREE, dense = LEAN || p.path_mode == PATH_DENSE;
   const size_t xstride = (size_t)D * Npad;
   double* xold;                // state at time t-1 (SoA [D][Npad])
   double* xnew;
@@ -145,19 +155,17 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
 
   ModelCtx c;
   c.theta = sm.theta; c.pre = sm.pre; c.stream = stream; c.N = N; c.T = T;
-  c.inj_init = p.inj_init ? p.inj_init + (size_t)inj * p.n_init * N : nullptr;
-  c.inj_trans = p.inj_trans ? p.inj_trans + (size_t)inj * T * p.n_trans * N : nullptr;
+  c.inj_init = (!LEAN && p.inj_init) ? p.inj_init + (size_t)fb * p.n_init * N : nullptr;
+  c.inj_trans = (!LEAN && p.inj_trans) ? p.inj_trans + (size_t)fb * T * p.n_trans * N : nullptr;
   c.n_trans = p.n_trans; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
-  const double* inj_res = p.inj_resample ? p.inj_resample + (size_t)inj * T * N : nullptr;
-  const double* inj_shf = p.inj_shuffle ? p.inj_shuffle + (size_t)inj * T * (N - 1) : nullptr;
+  const bool inj_res = !LEAN && p.inj_resample != nullptr;      // injected arrays are addressed at their use (no pointers held across the loop)
   const bool need_shared_u = Model::USES_SHARED_U && !c.inj_trans;
-  int st = 0;
-  // second uniform of each owned particle's resampling Philox block, for the models that consume it (local memory)
-  double ukeep[(Model::JUMP_LIST || !Model::USES_SHARED_U) ? 1 : CPIMH_MAX_E];
+  // status / clamp flags are rare events: they go straight to shared memory (no register held across the filter)
+  auto flag_status = [&](int f) { if (f) atomicOr(&sm.iscr[32], f); };
   const bool jump_list = Model::JUMP_LIST && (N + NT - 1) / NT <= 16;   // tokens of <= 16 own particles fit two 64-bit registers
 
   // ---------------- initialisation: R/CPF.R:17-28, Tree::Tree + Tree::init (src/tree.cpp:6-34)
-  if (tid == 0) sm.iscr[32] = 0;
+  if (tid == 0) { sm.iscr[32] = 0; sm.iscr[34] = 0; sm.C[pad16(N)] = INFINITY; }   // status flags, exact-order repeats, CDF sentinel (check_knots)
   if (tree) {
     for (int j = tid; j < M; j += NT) o_star[j] = 0;
     for (int w = tid; w < W; w += NT) {
@@ -178,7 +186,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     }
     sm.C[pad16(i)] = 1.0 / N;
   }
-  double logz_sum = 0.0;
+  if (tid == 0) sm.dscr2[3] = 0.0;                       // sum of the log Z increments (thread 0 only)
   __syncthreads();
 
   // ---------------- hot loop: R/CPF.R:35-67
@@ -186,14 +194,27 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     const bool ident = (t == 1) || isnan(p.obs[(size_t)(t - 2) * p.dy]);     // R/CPF.R:38-40
     const double* y = p.obs + (size_t)(t - 1) * p.dy;
     const double sc = Model::step_const(c, t);
+    // models whose weight factorises as exp(a) f (Model::SPLIT_W) park f in C next to a in S: both arrays are dead once
+    // all ancestors are known, which the jump-list path guarantees
+    const bool split_w = Model::SPLIT_W && jump_list;
+    const bool shuffled = !LEAN && p.shuffle && !ident;
+    double m = -INFINITY;                                  // running max of this thread's log-weights
+    // The step runs once with parallel-scan sums.  If a sorted uniform came within rounding distance of a CDF knot (near != 0
+    // somewhere in the CTA), it runs a second time with the reference's own operation order (exact): see "ancestors" below.
+    bool exact = false;
+    for (;;) {
     double sumw = 1.0;
+    m = -INFINITY;
+    if (tid == 0 && !exact) sm.iscr[35] = 0;             // near-knot flag (set by check_knots, read by vote_repeat); the repeat pass ignores it
+    // block-wide vote at a barrier the step has anyway; true => repeat the step in exact order
+    auto vote_repeat = [&]() -> bool { __syncthreads(); return sm.iscr[35] != 0 && !exact; };
 
     // -- sorted uniforms (src/multinomial.cpp:18-24) and CDF (:17); zero the offspring counters
     if (tree) for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
     const bool draw_res = !ident && !inj_res;
     unsigned long long tok0 = 0ull, tok1 = 0ull;           // 8-bit model tokens of this thread's particles (jump counts)
     if (draw_res && tid == 0) sm.dscr2[0] = -rng_log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0));   // E_N, read after the scan's barriers
-    if (draw_res || need_shared_u) {
+    if (draw_res || (need_shared_u && jump_list)) {
       int e = 0;
       for (int i = tid; i < N; i += NT, e++) {
         double ua, ub;
@@ -202,22 +223,34 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         if constexpr (Model::JUMP_LIST) {
           if (jump_list) {                                // the model turns its uniform into a small count right away
             int tk = Model::token(c, ub);
-            if (tk > 255) { tk = 255; st |= CPIMH_ERR_INVALID; }
+            if (tk > 255) { tk = 255; flag_status(CPIMH_ERR_INVALID); }
             if (e < 8) tok0 |= (unsigned long long)tk << (8 * e); else tok1 |= (unsigned long long)tk << (8 * (e - 8));
-          } else ukeep[0] = ub;
-        } else if constexpr (Model::USES_SHARED_U) ukeep[e] = ub;
+          }
+        }
       }
     }
     if (!ident) {
-      if (inj_res) for (int i = tid; i < N; i += NT) sm.S[pad16(i)] = inj_res[(size_t)(t - 1) * N + i];
+      if (inj_res) for (int i = tid; i < N; i += NT) sm.S[pad16(i)] = p.inj_resample[((size_t)fb * T + (t - 1)) * N + i];
+      if (exact) for (int i = tid; i < N; i += NT) sm.C[pad16(i)] = p.wscr[(size_t)ws * Npad + i] / sm.dscr2[1];      // normweights, R/CPF.R:63 (dscr2[1]: last step's sum)
       __syncthreads();
       // Sorted uniforms.  Injected: S holds the ascending e_i of src/multinomial.cpp:22-24 and u_i = sumw e_i (:24).
       // Philox: the same order statistics from exponential spacings, e_i = (E_0+..+E_i) / (E_0+..+E_N) (one log per
       // particle instead of the recurrence's log + divide + exp; DESIGN.md "RNG"): S becomes the prefix sums P_i and
       // u_i = (sumw / total) P_i.
-      if (inj_res) block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
-      else block_scan_chunked<true>(sm.C, sm.S, N, sm.dscr);
+      if (!exact) {
+        if (inj_res) block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
+        else block_scan_chunked<true>(sm.C, sm.S, N, sm.dscr);
+      } else {                                             // Rcpp::cumsum's order (src/multinomial.cpp:17): one thread, left to right
+        if (tid == 0) sequential_cumsum_p(sm.C, N);
+        if (!inj_res && tid == (NT > 32 ? 32 : 0)) sequential_cumsum_p(sm.S, N);
+        if (tid == 0) sm.iscr[34] += 1;                    // exact-order repeats of this filter
+        __syncthreads();
+      }
       sumw = sm.C[pad16(N - 1)];
+      // A knot within `margin` of a uniform could fall on its other side under another summation order: two orders of the same
+      // non-negative terms differ by at most 2 gamma_N of the total, likewise the two u_k; 12 (N + 2) 2^-53 sum(w) bounds the
+      // sum of all those differences (DESIGN.md "Exact ancestors").
+      if (tid == 0) sm.dscr2[2] = exact ? 0.0 : (double)(N + 2) * 0x1.8p-50 * sumw;      // read after the barrier below
       if (!inj_res) sumw = sumw / (sm.S[pad16(N - 1)] + sm.dscr2[0]);   // total = P_{N-1} + E_N
       // every 32nd sorted uniform gets a full search; the others then search only between their neighbours' results
       const int nrows = (N + 31) >> 5;
@@ -231,18 +264,24 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       __syncthreads();
     }
 
-    // -- ancestors: count of CDF knots <= u (:25-28), clamped
+    // -- ancestors: count of CDF knots <= u (:25-28), clamped.  The CDF above is a parallel scan, the reference's a
+    // left-to-right sum.  When no u_k comes within `margin` of the knots on either side of it, the ancestors found here ARE the
+    // reference's (whatever the search did on the way: the two knots are re-read and compared).  Otherwise (a few times per
+    // 10^4 steps at N = 4096) the CTA repeats the step with normalised weights and left-to-right sums by one thread.
+    auto check_knots = [&](int a, double u) {
+      if (CPIMH_EXP & 4) return;
+      const double prev = sm.C[pad16(a > 0 ? a - 1 : 0)], cur = sm.C[pad16(a)], margin = sm.dscr2[2];      // C carries a +infinity sentinel at N
+      if ((a > 0 && u - prev < margin) || (cur - u <= margin)) sm.iscr[35] = 1;
+    };
     auto ancestor_of = [&](int k) -> int {
       if (ident) return k;
-      int a = count_le_p(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * sm.S[pad16(k)]);
-      if (a >= N) { a = N - 1; st |= 512; }
+      const double u = sumw * sm.S[pad16(k)];
+      int a = count_le_p(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], u);
+      check_knots(a, u);
+      if (a >= N) { a = N - 1; flag_status(512); }
       return a;
     };
     // -- gather (R/CPF.R:41) -> rtransition (:44) -> dmeasurement (:60) ; path bookkeeping
-    double m = -INFINITY;                                // running max of this thread's log-weights
-    // models whose weight factorises as exp(a) f (Model::SPLIT_W) park f in C next to a in S: both arrays are dead once
-    // all ancestors are known, which the jump-list path guarantees
-    const bool split_w = Model::SPLIT_W && jump_list;
     auto finish_particle = [&](int k, int a, const double* x) {
 #pragma unroll
       for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
@@ -258,22 +297,26 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         sm.bpar[k] = sm.leaf[a];
         atomicAdd(&sm.off32[a >> 1], 1u << ((a & 1) << 4));
       }
-      if (out.anc_rec) out.anc_rec[(size_t)(t - 1) * N + k] = a;
+      if (!LEAN && p.anc_rec) p.anc_rec[((size_t)fb * T + (t - 1)) * N + k] = a;
     };
-    auto propagate = [&](int k, int a, int e) {
+    auto propagate = [&](int k, int a) {
       double x[D];
 #pragma unroll
       for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
-      st |= Model::transition(c, t, k, x, sc, need_shared_u ? ukeep[(Model::JUMP_LIST || !Model::USES_SHARED_U) ? 0 : e] : 0.5);
+      double ush = 0.5;
+      if constexpr (Model::USES_SHARED_U) {              // second uniform of the particle's OWN resampling block (DESIGN.md "RNG")
+        if (!c.inj_trans) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
+      }
+      flag_status(Model::transition(c, t, k, x, sc, ush));
       finish_particle(k, a, x);
     };
-    if (p.shuffle && !ident) {
+    if (shuffled) {
       for (int k = tid; k < N; k += NT) sm.bpar[k] = ancestor_of(k);
-      __syncthreads();
+      if (vote_repeat()) { exact = true; continue; }
       // std::random_shuffle with randWrapper (src/multinomial.cpp:6-10,30): for i = 1..n-1 swap(a[i], a[floor(u_i (i+1))])
       int* jidx = reinterpret_cast<int*>(sm.S.ptr());
       for (int i = 1 + tid; i < N; i += NT) {
-        double u = inj_shf ? inj_shf[(size_t)(t - 1) * (N - 1) + (i - 1)] : philox_u1(stream, i, t, CPIMH_P_SHUFFLE, 0);
+        double u = p.inj_shuffle ? p.inj_shuffle[((size_t)fb * T + (t - 1)) * (N - 1) + (i - 1)] : philox_u1(stream, i, t, CPIMH_P_SHUFFLE, 0);
         int j = (int)floor(u * (double)(i + 1));
         jidx[i] = j > i ? i : j;
       }
@@ -282,7 +325,6 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         for (int i = 1; i < N; i++) { int j = jidx[i]; int tmp = sm.bpar[i]; sm.bpar[i] = sm.bpar[j]; sm.bpar[j] = tmp; }
       __syncthreads();
     }
-    const bool shuffled = p.shuffle && !ident;
     bool done = false;
     if constexpr (Model::JUMP_LIST) {
       if (jump_list) {
@@ -300,15 +342,17 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
             const bool two = k2 < N;
             const int kk = two ? k2 : k;
             int a1, a2;
-            count_le_p2(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], sumw * sm.S[pad16(k)],
-                        sm.coarse[kk >> 5], sm.coarse[(kk >> 5) + 1], sumw * sm.S[pad16(kk)], a1, a2);
-            if (a1 >= N) { a1 = N - 1; st |= 512; }
-            if (a2 >= N) { a2 = N - 1; st |= 512; }
+            const double u1 = sumw * sm.S[pad16(k)], u2 = sumw * sm.S[pad16(kk)];
+            count_le_p2(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], u1, sm.coarse[kk >> 5], sm.coarse[(kk >> 5) + 1], u2, a1, a2);
+            check_knots(a1, u1);
+            check_knots(a2, u2);
+            if (a1 >= N) { a1 = N - 1; flag_status(512); }
+            if (a2 >= N) { a2 = N - 1; flag_status(512); }
             arow[k] = a1;
             if (two) arow[k2] = a2;
           }
         }
-        __syncthreads();
+        if (vote_repeat()) { exact = true; continue; }
         const int E = (N - tid + NT - 1) / NT;
         auto tok = [&](int e) -> int { return (int)(((e < 8 ? tok0 >> (8 * e) : tok1 >> (8 * (e - 8)))) & 255ull); };
         if (!c.inj_trans) {
@@ -372,32 +416,37 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
 #pragma unroll
             for (int q = 0; q < D; q++) xl[E][q] = xold[(size_t)q * Npad + a];
           }
-          if (E > 0) st |= Model::transition_multi(c, t, E, tid, NT, xl, ukeep, sc);
+          if (E > 0) flag_status(Model::transition_multi(c, t, E, tid, NT, xl, nullptr, sc));
           for (int e = 0; e < E; e++) finish_particle(tid + e * NT, al[e], xl[e]);
           done = true;
         }
       }
     }
     if (!done) {
-      int e = 0;
-      for (int k = tid; k < N; k += NT, e++) propagate(k, shuffled ? sm.bpar[k] : ancestor_of(k), e);
+      for (int k = tid; k < N; k += NT) propagate(k, shuffled ? sm.bpar[k] : ancestor_of(k));
     }
-    __syncthreads();
+    // the barrier that ends the propagation also carries the vote
+    if (vote_repeat()) { exact = true; continue; }
+    break;
+    }
 
     // -- weights and log Z increment: R/CPF.R:61-63,66
     m = block_max(m, sm.dscr);
-    double s = 0.0;
-    if (split_w) { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m) * sm.C[kp]; sm.C[kp] = w; s += w; } }
-    else { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m); sm.C[kp] = w; s += w; } }
-    s = block_sum(s, sm.dscr);
+    double sloc = 0.0;
+    double* wscr = p.wscr + (size_t)ws * Npad;             // this step's unnormalised weights, for an exact-order repeat of the next step
+    if (split_w) { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m) * sm.C[kp]; sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
+    else { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m); sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
+    // the sum is evaluated as one fixed tree, whatever the CTA size (common.cuh block_sum_canonical)
+    const double s = (CPIMH_EXP & 1) ? block_sum(sloc, sm.dscr) : block_sum_canonical([&](int k) { return sm.C[pad16(k)]; }, N, sm.dscr);
+    if (tid == 0) sm.dscr2[1] = s;
     // normweights = w / sum(w) (R/CPF.R:63).  Between steps only ratios matter (the ancestor search scales its
     // uniforms by the CDF total), so the division pass is done once, for the weights the filter returns.
     if (t == T) for (int k = tid; k < N; k += NT) sm.C[pad16(k)] = sm.C[pad16(k)] / s;
     if (tid == 0) {                                      // only thread 0 reports log Z
       double lz = log(s / (double)N) + m;
       if constexpr (Model::SPLIT_W) { if (split_w) lz += Model::w_const(); }
-      logz_sum += lz;
-      if (out.logz_t) out.logz_t[t - 1] = lz;
+      sm.dscr2[3] += lz;
+      if (p.logz_t) p.logz_t[(size_t)fb * T + (t - 1)] = lz;
     }
 
     // -- Tree::update (src/tree.cpp:88-99)
@@ -454,10 +503,9 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   }
 
   // ---------------- path selection: systematic_resampling_n(normweights, 1, runif(1)) + Tree$get_path (R/CPF.R:69)
-  if (st) atomicOr(&sm.iscr[32], st);
-  if (out.normw) for (int k = tid; k < N; k += NT) out.normw[k] = sm.C[pad16(k)];
-  if (out.leaf_out && tree) for (int k = tid; k < N; k += NT) out.leaf_out[k] = sm.leaf[k];
-  if (out.exp_path && (tree || dense)) {
+  if (p.normw) for (int k = tid; k < N; k += NT) p.normw[(size_t)fb * N + k] = sm.C[pad16(k)];
+  if (p.leaf_out && tree) for (int k = tid; k < N; k += NT) p.leaf_out[(size_t)ws * N + k] = sm.leaf[k];
+  if (p.exp_path && (tree || dense)) {
     // pf_get_weighted_average (R/CPF.R:84-92) over sapply(0:(N-1), Tree$get_path) (:73-74): all N leaves walk to the root
     // in lock step; per generation and component one block reduction of w_n x.  S is free and holds the walkers.
     int* cur = reinterpret_cast<int*>(sm.S.ptr());
@@ -466,25 +514,25 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     for (int step = T; step >= 0; step--) {
 #pragma unroll
       for (int q = 0; q < D; q++) {
-        double acc = 0.0;
-        for (int n = tid; n < N; n += NT)
-          acc += (tree ? x_star[(size_t)q * M + cur[n]] : hx[(size_t)step * xstride + (size_t)q * Npad + cur[n]]) * sm.C[pad16(n)];
-        acc = block_sum(acc, sm.dscr);
-        if (tid == 0) out.exp_path[(size_t)step * D + q] = acc;
+        const double acc = block_sum_canonical([&](int n) {
+          return (tree ? x_star[(size_t)q * M + cur[n]] : hx[(size_t)step * xstride + (size_t)q * Npad + cur[n]]) * sm.C[pad16(n)]; }, N, sm.dscr);
+        if (tid == 0) p.exp_path[((size_t)fb * (T + 1) + step) * D + q] = acc;
       }
       if (step > 0) for (int n = tid; n < N; n += NT) cur[n] = tree ? a_star[cur[n]] : hist_a[(size_t)(step - 1) * Npad + cur[n]];
     }
   }
   __syncthreads();
-  block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
-  double u = p.inj_path ? p.inj_path[inj] : philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0);
+  if (tid == 0) sequential_cumsum_p(sm.C, N);   // csw of src/systematic.cpp:13-17: left to right, once per filter
+  __syncthreads();
+  double u = (!LEAN && p.inj_path) ? p.inj_path[fb] : philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0);
   int kidx = count_lt_p(sm.C, N, u);          // smallest j with csw_j >= u (src/systematic.cpp:15-18), n = 1
   int flags = sm.iscr[32];
   if (kidx >= N) { kidx = N - 1; flags |= 512; }
   if (tid == 0) {
-    *out.logz = logz_sum;
-    if (out.path_index) *out.path_index = kidx;
+    *out.logz = sm.dscr2[3];
+    if (p.path_index) p.path_index[fb] = kidx;
     *out.status = flags & 255;
+    if (p.exact_repeats) p.exact_repeats[fb] = sm.iscr[34];
   }
   if (out.traj && tid < 32) {               // Tree::get_path (src/tree.cpp:118-129): one warp, lane q carries component q
     if (tree) {
@@ -505,7 +553,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
   __syncthreads();
 }
 
-template <class Model, int NT_MAX, int MIN_BLOCKS>
+template <class Model, int NT_MAX, int MIN_BLOCKS, bool LEAN>
 __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p) {
   PfSmem sm = pf_carve(p.lay);
   for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
@@ -515,15 +563,9 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) pf_batch_kernel(PfParams p
     Stream s = make_stream(p.seed, p.stream_ids ? p.stream_ids[b] : p.first_filter + (unsigned long long)b);
     FilterOut out;
     out.logz = p.logz + b;
-    out.logz_t = p.logz_t ? p.logz_t + (size_t)b * p.T : nullptr;
     out.traj = p.traj ? p.traj + (size_t)b * (p.T + 1) * Model::D : nullptr;
-    out.path_index = p.path_index ? p.path_index + b : nullptr;
     out.status = p.status + b;
-    out.normw = p.normw ? p.normw + (size_t)b * p.N : nullptr;
-    out.leaf_out = p.leaf_out ? p.leaf_out + (size_t)blockIdx.x * p.N : nullptr;
-    out.anc_rec = p.anc_rec ? p.anc_rec + (size_t)b * p.T * p.N : nullptr;
-    out.exp_path = p.exp_path ? p.exp_path + (size_t)b * (p.T + 1) * Model::D : nullptr;
-    run_filter<Model>(p, sm, blockIdx.x, s, b, out);
+    run_filter<Model, LEAN>(p, sm, blockIdx.x, s, b, out);
   }
 }
 
@@ -533,29 +575,34 @@ enum { PF_VARIANT_128x8 = 0, PF_VARIANT_256x3 = 1, PF_VARIANT_512x2 = 2, PF_VARI
 inline int pf_variant_threads(int v) { return v == PF_VARIANT_128x8 ? 128 : v == PF_VARIANT_256x3 ? 256 : v == PF_VARIANT_512x2 ? 512 : 1024; }
 inline int pf_variant_for(int threads) { return threads <= 128 ? PF_VARIANT_128x8 : threads <= 256 ? PF_VARIANT_256x3 : threads <= 512 ? PF_VARIANT_512x2 : PF_VARIANT_1024x1; }
 
-template <class Model, class F>
+template <class Model, bool LEAN, class F>
 int pf_with_kernel(int variant, F&& f) {
   switch (variant) {
     // wide states (d > 4) keep x, noise and the matvec in registers: trade residency for 128 registers per thread; the
     // narrow ones run best at ~80 registers (768 resident threads per SM): 6 x 128 or 3 x 256 (the enum names are historic)
-    case PF_VARIANT_128x8: return f(pf_batch_kernel<Model, 128, (Model::D > 4 ? 5 : 6)>);
-    case PF_VARIANT_256x3: return f(pf_batch_kernel<Model, 256, (Model::D > 4 ? 2 : 3)>);
-    case PF_VARIANT_512x2: return f(pf_batch_kernel<Model, 512, (Model::D > 4 ? 1 : 2)>);
-    default: return f(pf_batch_kernel<Model, 1024, 1>);
+    case PF_VARIANT_128x8: return f(pf_batch_kernel<Model, 128, (Model::D > 4 ? 5 : 6), LEAN>);
+    case PF_VARIANT_256x3: return f(pf_batch_kernel<Model, 256, (Model::D > 4 ? 2 : 3), LEAN>);
+    case PF_VARIANT_512x2: return f(pf_batch_kernel<Model, 512, (Model::D > 4 ? 1 : 2), LEAN>);
+    default: return f(pf_batch_kernel<Model, 1024, 1, LEAN>);
   }
+}
+// the production configuration runs the lean instantiation (see run_filter)
+inline bool pf_is_lean(const PfParams& p) {
+  return p.path_mode == PATH_DENSE && !p.shuffle && !p.anc_rec && !p.inj_init && !p.inj_trans && !p.inj_resample && !p.inj_shuffle && !p.inj_path;
 }
 template <class Model>
 int launch_pf_batch(const PfParams& p, const PfLaunch& L, cudaStream_t stream) {
-  return pf_with_kernel<Model>(L.variant, [&](auto kernel) -> int {
+  auto go = [&](auto kernel) -> int {
     CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     kernel<<<L.grid, L.threads, L.smem, stream>>>(p);
     CPIMH_CUDA_CHECK(cudaGetLastError());
     return CPIMH_OK;
-  });
+  };
+  return pf_is_lean(p) ? pf_with_kernel<Model, true>(L.variant, go) : pf_with_kernel<Model, false>(L.variant, go);
 }
 template <class Model>
 int occupancy_pf_batch(int variant, int threads, size_t smem, int* blocks_per_sm) {
-  return pf_with_kernel<Model>(variant, [&](auto kernel) -> int {
+  return pf_with_kernel<Model, false>(variant, [&](auto kernel) -> int {
     CPIMH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CPIMH_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem));
     return CPIMH_OK;

@@ -102,6 +102,14 @@ class PfBatch:
         L.check(L.lib().cpimh_pf_fetch_ancestors(self.h, C.c_int64(int(b)), C.c_void_p(stream or 0), L.ptr(anc)))
         return anc
 
+    def fetch_exact_repeats(self, nfilters=None, stream=None):
+        """Steps each filter of the last run repeated with sequential-order sums (a sorted uniform within rounding distance
+        of a CDF knot; DESIGN.md "Exact ancestors")."""
+        B = int(nfilters if nfilters is not None else self.max_filters)
+        rep = np.empty(B, dtype=np.int32)
+        L.check(L.lib().cpimh_pf_fetch_exact_repeats(self.h, C.c_int64(B), C.c_void_p(stream or 0), L.ptr(rep)))
+        return rep
+
     def device_outputs(self):
         a, b = C.c_void_p(), C.c_void_p()
         L.check(L.lib().cpimh_pf_device_outputs(self.h, C.byref(a), C.byref(b)))
