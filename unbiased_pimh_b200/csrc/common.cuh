@@ -355,7 +355,7 @@ __device__ __forceinline__ int count_lt_p(const double* c, int n, double u) {
 // Block sum of f(0) + ... + f(n-1) evaluated as ONE fixed tree whatever the CTA size (a multiple of 32 threads), so that a
 // filter returns the same bits from a 32-, 256- or 1024-thread CTA.  The tree: segments of 1024 consecutive terms; inside a
 // segment lane l of one warp adds f(1024 g + l), f(1024 g + l + 32), ... in that order, an xor butterfly combines the 32
-// lanes; the segment totals are then added left to right.  All threads must call; `scratch` needs 32 doubles (n <= 32768)
+// lanes; the segment totals are then added left to right.  f(k, kp) gets the term index and its padded slot.  All threads must call; `scratch` needs 32 doubles (n <= 32768)
 // and must be free; begins and ends with a barrier.
 template <class F>
 __device__ __forceinline__ double block_sum_canonical(F f, int n, double* scratch) {
@@ -365,7 +365,7 @@ __device__ __forceinline__ double block_sum_canonical(F f, int n, double* scratc
   for (int g = wid; g < nseg; g += nw) {
     const int k0 = (g << 10) + lane, k1 = min(n, (g + 1) << 10);
     double part = 0.0;
-    for (int k = k0; k < k1; k += 32) part += f(k);
+    for (int k = k0, kp = pad16(k0); k < k1; k += 32, kp += 34) part += f(k, kp);     // kp = pad16(k)
     part = warp_sum(part);
     if (lane == 0) scratch[g] = part;
   }

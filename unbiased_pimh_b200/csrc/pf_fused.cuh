@@ -135,6 +135,8 @@ template <class Model, bool LEAN = false>
 __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, const Stream& stream, long long fb, const FilterOut& out) {
   constexpr int D = Model::D;
   const int tid = threadIdx.x, NT = blockDim.x;
+  // striped particle k = tid + e NT lives at padded slot pad16(k) = kp0 + e NTP (NT is a multiple of 32)
+  const int kp0 = pad16(tid), NTP = NT + (NT >> 4);
   const int N = p.N, T = p.T, Npad = p.Npad, M = p.M, W = M >> 5;
   const bool tree = !LEAN && p.path_mode == PATH_TREE, dense = LEAN || p.path_mode == PATH_DENSE;
   const size_t xstride = (size_t)D * Npad;
@@ -203,7 +205,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // somewhere in the CTA), it runs a second time with the reference's own operation order (exact): see "ancestors" below.
     bool exact = false;
     for (;;) {
-    double sumw = 1.0;
+    double sumw = 1.0, margin_r = 0.0;
     m = -INFINITY;
     if (tid == 0 && !exact) sm.iscr[35] = 0;             // near-knot flag (set by check_knots, read by vote_repeat); the repeat pass ignores it
     // block-wide vote at a barrier the step has anyway; true => repeat the step in exact order
@@ -216,10 +218,13 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     if (draw_res && tid == 0) sm.dscr2[0] = -rng_log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0));   // E_N, read after the scan's barriers
     if (draw_res || (need_shared_u && jump_list)) {
       int e = 0;
-      for (int i = tid; i < N; i += NT, e++) {
+#if (CPIMH_EXP & 8)
+#pragma unroll 2
+#endif
+      for (int i = tid, ip = kp0; i < N; i += NT, ip += NTP, e++) {
         double ua, ub;
         philox_u2(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, ub);
-        if (draw_res) sm.S[pad16(i)] = -rng_log(ua);                 // exponential spacing E_i (see the ladder comment below)
+        if (draw_res) sm.S[ip] = -rng_log(ua);                 // exponential spacing E_i (see the ladder comment below)
         if constexpr (Model::JUMP_LIST) {
           if (jump_list) {                                // the model turns its uniform into a small count right away
             int tk = Model::token(c, ub);
@@ -251,6 +256,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       // non-negative terms differ by at most 2 gamma_N of the total, likewise the two u_k; 12 (N + 2) 2^-53 sum(w) bounds the
       // sum of all those differences (DESIGN.md "Exact ancestors").
       if (tid == 0) sm.dscr2[2] = exact ? 0.0 : (double)(N + 2) * 0x1.8p-50 * sumw;      // read after the barrier below
+      margin_r = exact ? 0.0 : (double)(N + 2) * 0x1.8p-50 * sumw;
       if (!inj_res) sumw = sumw / (sm.S[pad16(N - 1)] + sm.dscr2[0]);   // total = P_{N-1} + E_N
       // every 32nd sorted uniform gets a full search; the others then search only between their neighbours' results
       const int nrows = (N + 31) >> 5;
@@ -270,27 +276,27 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // 10^4 steps at N = 4096) the CTA repeats the step with normalised weights and left-to-right sums by one thread.
     auto check_knots = [&](int a, double u) {
       if (CPIMH_EXP & 4) return;
-      const double prev = sm.C[pad16(a > 0 ? a - 1 : 0)], cur = sm.C[pad16(a)], margin = sm.dscr2[2];      // C carries a +infinity sentinel at N
+      const double prev = sm.C[pad16(a > 0 ? a - 1 : 0)], cur = sm.C[pad16(a)], margin = (CPIMH_EXP & 16) ? margin_r : sm.dscr2[2];      // C carries a +infinity sentinel at N
       if ((a > 0 && u - prev < margin) || (cur - u <= margin)) sm.iscr[35] = 1;
     };
-    auto ancestor_of = [&](int k) -> int {
+    auto ancestor_of = [&](int k, int kp) -> int {
       if (ident) return k;
-      const double u = sumw * sm.S[pad16(k)];
+      const double u = sumw * sm.S[kp];
       int a = count_le_p(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], u);
       check_knots(a, u);
       if (a >= N) { a = N - 1; flag_status(512); }
       return a;
     };
     // -- gather (R/CPF.R:41) -> rtransition (:44) -> dmeasurement (:60) ; path bookkeeping
-    auto finish_particle = [&](int k, int a, const double* x) {
+    auto finish_particle = [&](int k, int kp, int a, const double* x) {
 #pragma unroll
       for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
       double lw;
       if constexpr (Model::SPLIT_W) {
-        if (split_w) { double f; Model::weight_parts(c, x, y, lw, f); sm.C[pad16(k)] = f; }
+        if (split_w) { double f; Model::weight_parts(c, x, y, lw, f); sm.C[kp] = f; }
         else lw = Model::logw(c, x, y);
       } else lw = Model::logw(c, x, y);
-      sm.S[pad16(k)] = lw;
+      sm.S[kp] = lw;
       m = fmax(m, lw);
       if (dense) hist_a[(size_t)(t - 1) * Npad + k] = a;
       if (tree) {                                      // src/tree.cpp:39-42, 90-94
@@ -299,7 +305,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       }
       if (!LEAN && p.anc_rec) p.anc_rec[((size_t)fb * T + (t - 1)) * N + k] = a;
     };
-    auto propagate = [&](int k, int a) {
+    auto propagate = [&](int k, int kp, int a) {
       double x[D];
 #pragma unroll
       for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
@@ -308,10 +314,10 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         if (!c.inj_trans) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
       }
       flag_status(Model::transition(c, t, k, x, sc, ush));
-      finish_particle(k, a, x);
+      finish_particle(k, kp, a, x);
     };
     if (shuffled) {
-      for (int k = tid; k < N; k += NT) sm.bpar[k] = ancestor_of(k);
+      for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP) sm.bpar[k] = ancestor_of(k, kp);
       if (vote_repeat()) { exact = true; continue; }
       // std::random_shuffle with randWrapper (src/multinomial.cpp:6-10,30): for i = 1..n-1 swap(a[i], a[floor(u_i (i+1))])
       int* jidx = reinterpret_cast<int*>(sm.S.ptr());
@@ -337,12 +343,12 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
           for (int k = tid; k < N; k += NT) arow[k] = shuffled ? sm.bpar[k] : k;
         } else {
           // two of the thread's searches at a time (independent chains of shared-memory loads)
-          for (int k = tid; k < N; k += 2 * NT) {
+          for (int k = tid, kp = kp0; k < N; k += 2 * NT, kp += 2 * NTP) {
             const int k2 = k + NT;
             const bool two = k2 < N;
             const int kk = two ? k2 : k;
             int a1, a2;
-            const double u1 = sumw * sm.S[pad16(k)], u2 = sumw * sm.S[pad16(kk)];
+            const double u1 = sumw * sm.S[kp], u2 = sumw * sm.S[two ? kp + NTP : kp];
             count_le_p2(sm.C, sm.coarse[k >> 5], sm.coarse[(k >> 5) + 1], u1, sm.coarse[kk >> 5], sm.coarse[(kk >> 5) + 1], u2, a1, a2);
             check_knots(a1, u1);
             check_knots(a2, u2);
@@ -371,7 +377,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
             sa += wa;
             sb += ev;
             if (++j > kj) {
-              sm.S[pad16(tid + e * NT)] = sa; sm.C[pad16(tid + e * NT)] = sb;
+              sm.S[kp0 + e * NTP] = sa; sm.C[kp0 + e * NTP] = sb;
               sa = 0.0; sb = 0.0; j = 1;
               rem &= ~(255ull << sh);
               if (rem == 0ull && ebase == 0) { rem = tok1; ebase = 8; }
@@ -384,7 +390,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         double x_nxt[D];
 #pragma unroll
         for (int q = 0; q < D; q++) x_nxt[q] = E > 0 ? xold[(size_t)q * Npad + a_cur] : 0.0;
-        for (int e = 0; e < E; e++) {
+        for (int e = 0, kp = kp0; e < E; e++, kp += NTP) {
           const int k = tid + e * NT, a = a_cur;
           double x[D], swe = 0.0, se = 0.0;
 #pragma unroll
@@ -396,9 +402,9 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
           }
           a_nxt = (e + 2 < E) ? arow[k + 2 * NT] : 0;
           if (c.inj_trans) { swe = trans_row(c, t, 0)[k]; se = trans_row(c, t, 1)[k]; }
-          else if (tok(e) > 0) { swe = sm.S[pad16(k)]; se = sm.C[pad16(k)]; }
+          else if (tok(e) > 0) { swe = sm.S[kp]; se = sm.C[kp]; }
           Model::finish(c, x, swe, se);
-          finish_particle(k, a, x);
+          finish_particle(k, kp, a, x);
         }
         done = true;
       }
@@ -410,20 +416,20 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
           double xl[CPIMH_MULTI_MAX_E][D];
           int al[CPIMH_MULTI_MAX_E];
           int E = 0;
-          for (int k = tid; k < N; k += NT, E++) {
-            const int a = shuffled ? sm.bpar[k] : ancestor_of(k);
+          for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP, E++) {
+            const int a = shuffled ? sm.bpar[k] : ancestor_of(k, kp);
             al[E] = a;
 #pragma unroll
             for (int q = 0; q < D; q++) xl[E][q] = xold[(size_t)q * Npad + a];
           }
           if (E > 0) flag_status(Model::transition_multi(c, t, E, tid, NT, xl, nullptr, sc));
-          for (int e = 0; e < E; e++) finish_particle(tid + e * NT, al[e], xl[e]);
+          for (int e = 0; e < E; e++) finish_particle(tid + e * NT, kp0 + e * NTP, al[e], xl[e]);
           done = true;
         }
       }
     }
     if (!done) {
-      for (int k = tid; k < N; k += NT) propagate(k, shuffled ? sm.bpar[k] : ancestor_of(k));
+      for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP) propagate(k, kp, shuffled ? sm.bpar[k] : ancestor_of(k, kp));
     }
     // the barrier that ends the propagation also carries the vote
     if (vote_repeat()) { exact = true; continue; }
@@ -434,10 +440,10 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     m = block_max(m, sm.dscr);
     double sloc = 0.0;
     double* wscr = p.wscr + (size_t)ws * Npad;             // this step's unnormalised weights, for an exact-order repeat of the next step
-    if (split_w) { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m) * sm.C[kp]; sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
-    else { for (int k = tid; k < N; k += NT) { const int kp = pad16(k); double w = exp(sm.S[kp] - m); sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
+    if (split_w) { for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP) { double w = exp(sm.S[kp] - m) * sm.C[kp]; sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
+    else { for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP) { double w = exp(sm.S[kp] - m); sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
     // the sum is evaluated as one fixed tree, whatever the CTA size (common.cuh block_sum_canonical)
-    const double s = (CPIMH_EXP & 1) ? block_sum(sloc, sm.dscr) : block_sum_canonical([&](int k) { return sm.C[pad16(k)]; }, N, sm.dscr);
+    const double s = (CPIMH_EXP & 1) ? block_sum(sloc, sm.dscr) : block_sum_canonical([&](int, int kp) { return sm.C[kp]; }, N, sm.dscr);
     if (tid == 0) sm.dscr2[1] = s;
     // normweights = w / sum(w) (R/CPF.R:63).  Between steps only ratios matter (the ancestor search scales its
     // uniforms by the CDF total), so the division pass is done once, for the weights the filter returns.
@@ -514,8 +520,8 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     for (int step = T; step >= 0; step--) {
 #pragma unroll
       for (int q = 0; q < D; q++) {
-        const double acc = block_sum_canonical([&](int n) {
-          return (tree ? x_star[(size_t)q * M + cur[n]] : hx[(size_t)step * xstride + (size_t)q * Npad + cur[n]]) * sm.C[pad16(n)]; }, N, sm.dscr);
+        const double acc = block_sum_canonical([&](int n, int np) {
+          return (tree ? x_star[(size_t)q * M + cur[n]] : hx[(size_t)step * xstride + (size_t)q * Npad + cur[n]]) * sm.C[np]; }, N, sm.dscr);
         if (tid == 0) p.exp_path[((size_t)fb * (T + 1) + step) * D + q] = acc;
       }
       if (step > 0) for (int n = tid; n < N; n += NT) cur[n] = tree ? a_star[cur[n]] : hist_a[(size_t)(step - 1) * Npad + cur[n]];
