@@ -147,9 +147,12 @@ int64_t cpimh_pf_device_bytes(const cpimh_pf* h);
 int cpimh_pf_effective_config(const cpimh_pf* h, cpimh_config* out);
 
 /* One-shot host API: H2D observations (+ injected noise), run, D2H results.  This is the call the
- * R shim's CPF()/particlefilter()/batched twins make. */
+ * R shim's CPF()/particlefilter()/batched twins make (r-pkg/src/shim.c cpimh_R_pf_batch), once per PIMH sweep: the HBM
+ * workspaces stay cached in the library between calls with the same configuration (they are 24 GB for BASELINE configs[1]);
+ * cpimh_release_cached() frees them, and so does any allocation that would otherwise run out of memory. */
 int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nfilters, uint64_t seed, uint64_t first_filter,
                    const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index);
+int cpimh_release_cached(void);
 
 /* ============================== coupled PIMH ==============================
  * Batched coupled_pimh_chains(single_kernel, coupled_kernel, pimh_init, N, K) + H_bar(c_chains, h=identity on
@@ -284,6 +287,9 @@ int cpimh_tree_arrays(cpimh_tree* t, int32_t* a_star, int32_t* o_star, int32_t* 
 /* FP64 FMA peak of the current device, measured with a register-resident DFMA kernel (TFLOP/s);
  * used by bench.py as the secondary (compute) bound for Lorenz-96. */
 int cpimh_measure_fp64_peak(double* tflops);
+/* measured peak warp-instruction issue rate of the device (independent integer / fp32 chains, 32 warps per SM), in 1e9 warp
+ * instructions per second: the denominator of bench.py's roofline_secondary */
+int cpimh_measure_issue_peak(double* gwarp_instr_per_s);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "host_common.h"
 #include "wide.h"
@@ -550,21 +551,46 @@ int cpimh_pf_effective_config(const cpimh_pf* h, cpimh_config* out) {
   return CPIMH_OK;
 }
 
+// The one-shot entry is what the R shim calls once per PIMH sweep (r-pkg/src/shim.c cpimh_R_pf_batch): its HBM workspaces
+// (24 GB for BASELINE configs[1]) stay cached in a handle between calls with the same configuration instead of being
+// allocated and freed every time.  cpimh_release_cached() frees them; so does any allocation that runs out of memory.
+static std::recursive_mutex g_cache_mu;   // recursive: an allocation inside the cached call may ask for the cache to be dropped
+static cpimh_pf* g_cached = nullptr;
+static cpimh_config g_cached_cfg;
+static int64_t g_cached_B = 0;
+
+int cpimh_release_cached(void) {
+  std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
+  if (g_cached) { cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0; }
+  return CPIMH_OK;
+}
+
 int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
                    const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
   CPIMH_REQUIRE(cfg && obs_host, "null argument");
+  CPIMH_REQUIRE(B >= 1, "nfilters must be >= 1");
+  std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
   cpimh_config c = *cfg;
   for (int attempt = 0; attempt < 4; attempt++) {
-    cpimh_pf* h = nullptr;
-    int rc = cpimh_pf_create(&c, B, &h);
-    if (rc) return rc;
+    int rc = CPIMH_OK;
+    if (!(g_cached && g_cached_B >= B && memcmp(&g_cached_cfg, &c, sizeof(c)) == 0)) {
+      if (g_cached) { cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0; }
+      rc = cpimh_pf_create(&c, B, &g_cached);
+      if (rc) { g_cached = nullptr; return rc; }
+      g_cached_cfg = c; g_cached_B = B;
+    }
+    cpimh_pf* h = g_cached;
     rc = cpimh_pf_set_observations(h, obs_host);
-    if (!rc && noise_host) rc = cpimh_pf_set_noise(h, B, noise_host);
+    if (!rc) rc = cpimh_pf_set_noise(h, B, noise_host);                 // NULL clears noise left by an earlier call
+    if (!rc) rc = cpimh_pf_record_ancestors(h, 0);
     if (!rc) rc = cpimh_pf_run(h, B, seed, first_filter, nullptr);
     if (!rc) rc = cpimh_pf_fetch(h, B, nullptr, logz, logz_t, trajectory, path_index);
-    int M = h->geo.M;
-    cpimh_pf_destroy(h);
-    if (rc != CPIMH_ERR_TREE_OVERFLOW) return rc;
+    if (rc != CPIMH_ERR_TREE_OVERFLOW) {
+      if (rc) { cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0; }   // do not keep a handle in an unknown state
+      return rc;
+    }
+    const int M = h->wide ? 0 : h->geo.M;
+    cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0;
     c.tree_capacity = 2 * M;
     c.store_paths = 3;          // Tree::double_size (src/tree.cpp:101-116): rerun with twice the capacity (same streams => same draws)
   }

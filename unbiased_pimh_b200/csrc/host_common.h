@@ -13,6 +13,11 @@ struct DevBuf {
     if (p) { cudaFree(p); if (total) *total -= (int64_t)bytes; p = nullptr; bytes = 0; }
     if (n == 0) return CPIMH_OK;
     cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaErrorMemoryAllocation) {        // drop the workspaces cached by the one-shot entries (api.cu) and try once more
+      cudaGetLastError();
+      cpimh_release_cached();
+      e = cudaMalloc(&p, n);
+    }
     if (e != cudaSuccess) {
       set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
       p = nullptr;

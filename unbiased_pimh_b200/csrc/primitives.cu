@@ -320,6 +320,25 @@ __global__ void lorenz_kernel(const double* xin, long long n, double t0, double 
 // wide state (d up to 64 per warp pass): one warp per particle, lane l owns components l and l + 32
 __global__ void lorenz_wide_rk4_kernel(const double* xin, long long n, int d, double t0, double t1, double F, int substeps, double* xout);
 
+// ---------------------------------------------------------------- warp-instruction issue peak
+// 8 independent chains per thread, fp32 FMA (fma pipe) alternating with integer xor-add (alu pipe): every scheduler can issue
+// one warp instruction per clock when its four warps of the eight resident ones always have an independent instruction ready
+__global__ void issue_kernel(unsigned* out, int iters) {
+  float f0 = threadIdx.x * 1e-9f, f1 = f0 + 1, f2 = f0 + 2, f3 = f0 + 3;
+  unsigned i0 = threadIdx.x, i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3;
+  const float m = 1.0000001f, c = 1e-7f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      f0 = fmaf(f0, m, c); i0 = (i0 ^ 0x9E3779B9u) + i1;
+      f1 = fmaf(f1, m, c); i1 = (i1 ^ 0x85EBCA6Bu) + i2;
+      f2 = fmaf(f2, m, c); i2 = (i2 ^ 0xC2B2AE35u) + i3;
+      f3 = fmaf(f3, m, c); i3 = (i3 ^ 0x27D4EB2Fu) + i0;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = i0 + i1 + i2 + i3 + (unsigned)(f0 + f1 + f2 + f3);
+}
+
 // ---------------------------------------------------------------- FP64 FMA peak
 __global__ void dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -576,6 +595,35 @@ int cpimh_measure_fp64_peak(double* tflops) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
   CPIMH_CUDA_CHECK(cudaGetLastError());
   *tflops = best;
+  return CPIMH_OK;
+}
+
+int cpimh_measure_issue_peak(double* gwarp) {
+  CPIMH_REQUIRE(gwarp, "null argument");
+  int dev = 0; cudaDeviceProp prop;
+  CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
+  CPIMH_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  const int threads = 256, grid = prop.multiProcessorCount * 4, iters = 1 << 12;
+  unsigned* out;
+  CPIMH_CUDA_CHECK(cudaMalloc(&out, sizeof(unsigned) * (size_t)threads * grid));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  issue_kernel<<<grid, threads>>>(out, 64);
+  double best = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    issue_kernel<<<grid, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    // per thread and iteration: 16 x (4 FFMA + 4 LOP3 + 4 IADD) = 192 instructions (xor-add may fuse to fewer: a lower bound)
+    const double winst = 192.0 * (double)iters * (threads / 32) * grid;
+    const double g = winst / (ms * 1e-3) / 1e9;
+    if (g > best) best = g;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  *gwarp = best;
   return CPIMH_OK;
 }
 
