@@ -43,7 +43,8 @@ enum {
   CPIMH_ERR_CUDA = 2,           /* CUDA runtime error (message has the CUDA string)    */
   CPIMH_ERR_TREE_OVERFLOW = 3,  /* ancestor tree capacity exhausted (Tree::double_size) */
   CPIMH_ERR_NOISE_OVERFLOW = 4, /* injected SK noise ran out of events                  */
-  CPIMH_ERR_NOMEM = 5
+  CPIMH_ERR_NOMEM = 5,
+  CPIMH_ERR_NOT_MET = 6         /* coupled chains: max_iterations reached before the chains met (R: finished = FALSE) */
 };
 
 /* ---- models shipped by name (R/model_get_gss.R, model_get_ar.R, model_levy_sv.R,
@@ -157,7 +158,8 @@ int cpimh_release_cached(void);
 /* ============================== coupled PIMH ==============================
  * Batched coupled_pimh_chains(single_kernel, coupled_kernel, pimh_init, N, K) + H_bar(c_chains, h=identity on
  * state component 1, k, K) -- R/pf_kernels.R:86-145, R/debiasing_algorithm.R:140-265,284-316.
- * One persistent CTA runs a whole replicate (init filter, then proposals until iter >= max(tau, K)).
+ * One persistent kernel runs all replicates (owner CTAs replay each chain in order, idle CTAs run proposals ahead for the
+ * replicates still unfinished: csrc/chains.cuh), until iter >= max(tau, K) for every replicate.
  * Replicate r uses Philox stream id r for its filters (iteration in counter word 1) and its MH uniforms. */
 typedef struct cpimh_chain_out {
   double*  hbar;         /* [R] x (d x (T+1) col-major)  H_bar_{k:K} per replicate, all state components (nullable) */
@@ -173,6 +175,11 @@ typedef struct cpimh_chain_out {
   double*  hbar_rb;        /* [R] x (d x (T+1))  (nullable) */
   double*  sum_hbar_rb;    /* [d x (T+1)]        (nullable) */
   double*  sum_hbar_rb_sq; /* [d x (T+1)]        (nullable) */
+  /* `finished` of the reference's c_chains list (R/debiasing_algorithm.R:262): 0 for a replicate that reached max_iterations
+   * before its chains met.  Such replicates are left OUT of sum_hbar / sum_hbar_sq (H_bar refuses them in the reference);
+   * nfinished is the number of replicates the sums hold. */
+  int32_t* finished;       /* [R]                (nullable) */
+  int64_t* nfinished;      /* [1]                (nullable) */
 } cpimh_chain_out;
 int cpimh_coupled_pimh(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, cpimh_chain_out* out_host);

@@ -14,7 +14,7 @@ MAX_THETA = 32
 
 MODEL_GSS, MODEL_AR, MODEL_LEVY_SV, MODEL_SK, MODEL_LORENZ = range(5)
 INTEGRATOR_RK4, INTEGRATOR_DOPRI5 = 0, 1
-OK, ERR_INVALID, ERR_CUDA, ERR_TREE_OVERFLOW, ERR_NOISE_OVERFLOW, ERR_NOMEM = range(6)
+OK, ERR_INVALID, ERR_CUDA, ERR_TREE_OVERFLOW, ERR_NOISE_OVERFLOW, ERR_NOMEM, ERR_NOT_MET = range(7)
 
 
 class CpimhError(RuntimeError):
@@ -37,7 +37,8 @@ class Noise(C.Structure):
 class ChainOut(C.Structure):
     _fields_ = [("hbar", C.c_void_p), ("meetingtime", C.c_void_p), ("iteration", C.c_void_p), ("sum_hbar", C.c_void_p),
                 ("sum_hbar_sq", C.c_void_p), ("nfilters", C.c_void_p), ("bc", C.c_void_p),
-                ("hbar_rb", C.c_void_p), ("sum_hbar_rb", C.c_void_p), ("sum_hbar_rb_sq", C.c_void_p)]
+                ("hbar_rb", C.c_void_p), ("sum_hbar_rb", C.c_void_p), ("sum_hbar_rb_sq", C.c_void_p),
+                ("finished", C.c_void_p), ("nfinished", C.c_void_p)]
 
 
 _lib = None

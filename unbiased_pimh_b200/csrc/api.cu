@@ -19,7 +19,8 @@ void set_error(const char* fmt, ...) {
 }
 
 const ModelEntry* find_entry(int model, int dim) {
-  const ModelEntry* (*tables[])(int*) = {entries_gss, entries_ar, entries_ar_hi, entries_sv, entries_sk, entries_lorenz};
+  const ModelEntry* (*tables[])(int*) = {entries_gss, entries_ar1, entries_ar2, entries_ar3, entries_ar4, entries_ar5, entries_ar8, entries_ar10, entries_ar16,
+                                          entries_sv, entries_sk, entries_lorenz4, entries_lorenz8, entries_lorenz16};
   for (auto tf : tables) {
     int n = 0;
     const ModelEntry* e = tf(&n);

@@ -9,15 +9,18 @@ namespace cpimh {
 
 // deterministic reduction of the per-replicate estimators into the all-reduce buffer:
 // sums[0..P) = sum_r hbar[r][j], sums[P..2P) = sum_r hbar[r][j]^2, sums[2P] = filters run, sums[2P+1] = replicates
-__global__ void reduce_hbar_kernel(const double* hbar, long long R, int P, const unsigned long long* nfilters, double* sums) {
+__global__ void reduce_hbar_kernel(const double* hbar, const int* status, long long R, int P, const unsigned long long* nfilters, double* sums) {
   __shared__ double scr[32];
   const int j = blockIdx.x;
-  if (j == P) {
-    if (threadIdx.x == 0) { sums[2 * P] = (double)(*nfilters); sums[2 * P + 1] = (double)R; }
+  if (j == P) {          // replicates that entered the sums: those that finished (status 0); capped ones (CPIMH_ERR_NOT_MET) are left out
+    double n = 0;
+    for (long long r = threadIdx.x; r < R; r += blockDim.x) n += (status[r] == 0) ? 1.0 : 0.0;
+    n = block_sum(n, scr);
+    if (threadIdx.x == 0) { sums[2 * P] = (double)(*nfilters); sums[2 * P + 1] = n; }
     return;
   }
   double s = 0, s2 = 0;
-  for (long long r = threadIdx.x; r < R; r += blockDim.x) { double v = hbar[(size_t)r * P + j]; s += v; s2 += v * v; }
+  for (long long r = threadIdx.x; r < R; r += blockDim.x) { if (status[r] != 0) continue; double v = hbar[(size_t)r * P + j]; s += v; s2 += v * v; }
   s = block_sum(s, scr);
   s2 = block_sum(s2, scr);
   if (threadIdx.x == 0) { sums[j] = s; sums[P + j] = s2; }
@@ -128,7 +131,7 @@ __global__ void rounds_accept_kernel(RoundParams q) {
       }
     }
     if (tau > 0 && iter >= max(tau, q.K)) finished = 1;                        // :245
-    if (q.max_it >= 0 && iter >= q.max_it) finished = 1;
+    if (!finished && q.max_it >= 0 && iter >= q.max_it) { finished = 1; status = CPIMH_ERR_NOT_MET; }   // R: finished = FALSE
   }
   __syncthreads();
   if (finished) {
@@ -253,7 +256,8 @@ struct cpimh_chains {
   DevBuf bc;
   int all_particles;
   DevBuf r_exp, r_e1, r_e2, r_accHe, r_accDe, hbar_rb, sums_rb;
-  DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, state, acc, scal, iscal, hbar, mt, it, status, nfilters, counter, sums;
+  DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, state, acc, estate, eacc, hbar, mt, it, status, nfilters, counter, sums;
+  DevBuf ring_traj, ring_exp, ring_logz, ring_status, ring_tag, next_it, it_done, slot_rep, unfinished;   // persistent kernel: proposal rings per resident CTA
   DevBuf samples1, samples2, log_pdf1, log_pdf2;
   // round-based driver
   int mode; int64_t filters_launched;
@@ -270,7 +274,7 @@ extern "C" {
 
 int cpimh_chains_destroy(cpimh_chains* h) {
   if (!h) return CPIMH_OK;
-  DevBuf* all[] = {&h->bc, &h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe, &h->hbar_rb, &h->sums_rb, &h->hist_x, &h->hist_a, &h->ascr, &h->wscr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->scal, &h->iscal, &h->hbar, &h->mt,
+  DevBuf* all[] = {&h->bc, &h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe, &h->hbar_rb, &h->sums_rb, &h->hist_x, &h->hist_a, &h->ascr, &h->wscr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->estate, &h->eacc, &h->ring_traj, &h->ring_exp, &h->ring_logz, &h->ring_status, &h->ring_tag, &h->next_it, &h->it_done, &h->slot_rep, &h->unfinished, &h->hbar, &h->mt,
                    &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2,
                    &h->r_logz, &h->r_traj, &h->r_status, &h->r_ids, &h->r_lz1, &h->r_lz2, &h->r_id1, &h->r_id2, &h->r_meet, &h->r_iter, &h->r_tau,
                    &h->r_st1, &h->r_st2, &h->r_accH, &h->r_accD, &h->r_act0, &h->r_act1, &h->r_cnt};
@@ -314,16 +318,22 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
     if (!rc) rc = h->x_star.alloc(sizeof(double) * G * D * g.M);
   }
   if (!rc) rc = h->wscr.alloc(sizeof(double) * G * g.Npad);
-  if (!rc) rc = h->state.alloc(sizeof(double) * G * 3 * P * D);
+  if (!rc) rc = h->state.alloc(sizeof(double) * G * 2 * P * D);
   if (!rc) rc = h->acc.alloc(sizeof(double) * G * 2 * P * D);
-  if (!rc) rc = h->scal.alloc(sizeof(double) * G * 4);
-  if (!rc) rc = h->iscal.alloc(sizeof(int) * G * 4);
+  if (!rc) rc = h->ring_traj.alloc(sizeof(double) * G * CPIMH_RING * P * D);
+  if (!rc) rc = h->ring_logz.alloc(sizeof(double) * G * CPIMH_RING);
+  if (!rc) rc = h->ring_status.alloc(sizeof(int) * G * CPIMH_RING);
+  if (!rc) rc = h->ring_tag.alloc(sizeof(int) * G * CPIMH_RING);
+  if (!rc) rc = h->next_it.alloc(sizeof(int) * G);
+  if (!rc) rc = h->it_done.alloc(sizeof(int) * G);
+  if (!rc) rc = h->slot_rep.alloc(sizeof(int) * G);
+  if (!rc) rc = h->unfinished.alloc(sizeof(int));
   if (!rc) rc = h->hbar.alloc(sizeof(double) * R * P * D);
   if (!rc) rc = h->bc.alloc(sizeof(double) * R * P * D);
   if (!rc) rc = h->mt.alloc(sizeof(int) * R);
   if (!rc) rc = h->it.alloc(sizeof(int) * R);
   if (!rc) rc = h->status.alloc(sizeof(int) * R);
-  if (!rc) rc = h->nfilters.alloc(sizeof(unsigned long long));
+  if (!rc) rc = h->nfilters.alloc(2 * sizeof(unsigned long long));
   if (!rc) rc = h->counter.alloc(sizeof(int));
   if (!rc) rc = h->sums.alloc(sizeof(double) * (2 * P * D + 2));
   if (!rc && h->record) {
@@ -473,19 +483,19 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   CPIMH_REQUIRE(max_iterations < 0 || max_iterations >= K, "max_iterations must be >= K or negative (unbounded)");
   CPIMH_REQUIRE(max_iterations < 4096, "iteration index must fit 12 bits of the Philox counter (max_iterations < 4096)");
   cudaStream_t s = (cudaStream_t)stream;
-  const bool rounds = h->all_particles || h->mode == 2 || (h->mode == 0 && !h->record);
+  const bool rounds = h->mode == 2;       // default (0) and 1: the persistent owner / helper kernel (chains.cuh)
   if (rounds) {
-    CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, sizeof(unsigned long long), s));
+    CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, 2 * sizeof(unsigned long long), s));
     CPIMH_CUDA_CHECK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * (size_t)R, s));
     int rcr = chains_run_rounds(h, R, seed, first_replicate, k, K, max_iterations < 0 ? 4095 : max_iterations, s);
     if (rcr) return rcr;
     const int Pr = (h->cfg.nobs + 1) * h->cfg.dim;
     double* sums_r = d_sums ? d_sums : h->sums.as<double>();
-    reduce_hbar_kernel<<<Pr + 1, 256, 0, s>>>(h->hbar.as<double>(), R, Pr, h->nfilters.as<unsigned long long>(), sums_r);
+    reduce_hbar_kernel<<<Pr + 1, 256, 0, s>>>(h->hbar.as<double>(), h->status.as<int>(), R, Pr, h->nfilters.as<unsigned long long>(), sums_r);
     CPIMH_CUDA_CHECK(cudaGetLastError());
     if (d_sums) CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->sums.p, d_sums, sizeof(double) * (2 * Pr + 2), cudaMemcpyDeviceToDevice, s));
     if (h->all_particles) {
-      reduce_hbar_kernel<<<Pr + 1, 256, 0, s>>>(h->hbar_rb.as<double>(), R, Pr, h->nfilters.as<unsigned long long>(), h->sums_rb.as<double>());
+      reduce_hbar_kernel<<<Pr + 1, 256, 0, s>>>(h->hbar_rb.as<double>(), h->status.as<int>(), R, Pr, h->nfilters.as<unsigned long long>(), h->sums_rb.as<double>());
       CPIMH_CUDA_CHECK(cudaGetLastError());
       h->launches += 1;
     }
@@ -499,49 +509,76 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   cp.pf.obs = h->obs.as<double>(); cp.pf.theta = h->theta.as<double>(); cp.pf.pre = h->pre.as<double>();
   cp.pf.hist_x = h->hist_x.as<double>(); cp.pf.hist_a = h->hist_a.as<int>(); cp.pf.ascr = h->ascr.as<int>(); cp.pf.wscr = h->wscr.as<double>();
   cp.pf.xbuf = h->xbuf.as<double>(); cp.pf.a_star = h->a_star.as<int>(); cp.pf.o_star = h->o_star.as<int>(); cp.pf.x_star = h->x_star.as<double>();
+  // the proposal rings are the filter's per-filter outputs (entry = slot * RING + iteration mod RING)
+  cp.pf.traj = h->ring_traj.as<double>(); cp.pf.logz = h->ring_logz.as<double>(); cp.pf.status = h->ring_status.as<int>();
+  cp.pf.exp_path = h->all_particles ? h->ring_exp.as<double>() : nullptr;
   cp.R = R; cp.first_replicate = first_replicate; cp.k = k; cp.K = K; cp.max_iterations = max_iterations < 0 ? 4095 : max_iterations;
-  cp.state = h->state.as<double>(); cp.acc = h->acc.as<double>(); cp.scal = h->scal.as<double>(); cp.iscal = h->iscal.as<int>();
-  cp.hbar = h->hbar.as<double>(); cp.bc = h->bc.as<double>(); cp.meetingtime = h->mt.as<int>(); cp.iteration = h->it.as<int>(); cp.status = h->status.as<int>();
+  cp.state = h->state.as<double>(); cp.acc = h->acc.as<double>();
+  cp.estate = h->all_particles ? h->estate.as<double>() : nullptr; cp.eacc = h->all_particles ? h->eacc.as<double>() : nullptr;
+  cp.ring_tag = h->ring_tag.as<int>(); cp.next_iter = h->next_it.as<int>(); cp.iter_done = h->it_done.as<int>(); cp.slot_rep = h->slot_rep.as<int>();
+  cp.unfinished = h->unfinished.as<int>();
+  cp.hbar = h->hbar.as<double>(); cp.bc = h->bc.as<double>(); cp.hbar_rb = h->all_particles ? h->hbar_rb.as<double>() : nullptr;
+  cp.meetingtime = h->mt.as<int>(); cp.iteration = h->it.as<int>(); cp.status = h->status.as<int>();
   cp.nfilters = h->nfilters.as<unsigned long long>(); cp.work_counter = h->counter.as<int>();
   if (h->record) {
     cp.samples1 = h->samples1.as<double>(); cp.samples2 = h->samples2.as<double>();
     cp.log_pdf1 = h->log_pdf1.as<double>(); cp.log_pdf2 = h->log_pdf2.as<double>(); cp.max_rec = h->max_rec;
   }
-  CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, sizeof(unsigned long long), s));
+  const int Ri = (int)R;
+  CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, 2 * sizeof(unsigned long long), s));
   CPIMH_CUDA_CHECK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), s));
+  CPIMH_CUDA_CHECK(cudaMemsetAsync(h->slot_rep.p, 0xff, sizeof(int) * (size_t)h->grid, s));      // -1: no slot owns a replicate yet
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->unfinished.p, &Ri, sizeof(int), cudaMemcpyHostToDevice, s));  // pageable source: copied before the call returns
   PfLaunch L;
   L.threads = h->geo.threads; L.smem = h->geo.smem; L.variant = h->geo.variant;
-  L.grid = (int)(R < h->grid ? R : h->grid);
+  L.grid = h->grid;        // every resident CTA takes part: owners while replicates last, then helpers
   int rc = h->entry->launch_chains(cp, L, s);
   if (rc) return rc;
   const int P = (h->cfg.nobs + 1) * h->cfg.dim;     // estimator entries per replicate: d x (T+1)
   double* sums = d_sums ? d_sums : h->sums.as<double>();
-  reduce_hbar_kernel<<<P + 1, 256, 0, s>>>(h->hbar.as<double>(), R, P, h->nfilters.as<unsigned long long>(), sums);
+  reduce_hbar_kernel<<<P + 1, 256, 0, s>>>(h->hbar.as<double>(), h->status.as<int>(), R, P, h->nfilters.as<unsigned long long>(), sums);
   CPIMH_CUDA_CHECK(cudaGetLastError());
   if (d_sums) CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->sums.p, d_sums, sizeof(double) * (2 * P + 2), cudaMemcpyDeviceToDevice, s));
+  if (h->all_particles) {
+    reduce_hbar_kernel<<<P + 1, 256, 0, s>>>(h->hbar_rb.as<double>(), h->status.as<int>(), R, P, h->nfilters.as<unsigned long long>(), h->sums_rb.as<double>());
+    CPIMH_CUDA_CHECK(cudaGetLastError());
+    h->launches += 1;
+  }
   h->launches += 2; h->lastR = R; h->filters_launched = -1;
   return CPIMH_OK;
 }
 
 int cpimh_chains_set_all_particles(cpimh_chains* h, int on) {
   CPIMH_REQUIRE(h, "null handle");
-  CPIMH_REQUIRE(!on || (!h->record && h->mode != 1), "all_particles runs on the round-based driver: no recorded samples, mode 0 or 2");
   h->all_particles = on ? 1 : 0;
   if (!on) return CPIMH_OK;
-  const size_t n = sizeof(double) * (size_t)h->maxR * (h->cfg.nobs + 1) * h->cfg.dim;
-  DevBuf* bufs[] = {&h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe, &h->hbar_rb};
-  for (auto b : bufs) { int rc = b->alloc(n); if (rc) return rc; }
-  return h->sums_rb.alloc(sizeof(double) * (2 * (size_t)(h->cfg.nobs + 1) * h->cfg.dim + 2));
+  const size_t PD = (size_t)(h->cfg.nobs + 1) * h->cfg.dim, G = (size_t)h->grid;
+  int rc = h->hbar_rb.alloc(sizeof(double) * (size_t)h->maxR * PD);
+  if (!rc) rc = h->estate.alloc(sizeof(double) * G * 2 * PD);
+  if (!rc) rc = h->eacc.alloc(sizeof(double) * G * 2 * PD);
+  if (!rc) rc = h->ring_exp.alloc(sizeof(double) * G * CPIMH_RING * PD);
+  if (!rc) rc = h->sums_rb.alloc(sizeof(double) * (2 * PD + 2));
+  if (!rc && h->mode == 2) {                  // the round-based driver keeps per-replicate copies
+    DevBuf* bufs[] = {&h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe};
+    for (auto b : bufs) { rc = b->alloc(sizeof(double) * (size_t)h->maxR * PD); if (rc) break; }
+  }
+  return rc;
 }
 
 int cpimh_chains_set_mode(cpimh_chains* h, int mode) {
-  CPIMH_REQUIRE(h && mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (persistent CTA per replicate) or 2 (rounds)");
-  CPIMH_REQUIRE(!(mode == 2 && h->record), "recording samples needs the persistent kernel (mode 1)");
-  CPIMH_REQUIRE(!(mode == 1 && h->all_particles), "all_particles runs on the round-based driver (mode 0 or 2)");
+  CPIMH_REQUIRE(h && mode >= 0 && mode <= 2, "mode must be 0 (default: persistent kernel), 1 (the same) or 2 (host-driven rounds, round 1's driver)");
+  CPIMH_REQUIRE(!(mode == 2 && h->record), "recording samples needs the persistent kernel (mode 0 / 1)");
   h->mode = mode;
+  if (mode == 2 && h->all_particles) return cpimh_chains_set_all_particles(h, 1);
   return CPIMH_OK;
 }
-int64_t cpimh_chains_filters_launched(const cpimh_chains* h) { return h ? h->filters_launched : 0; }
+int64_t cpimh_chains_filters_launched(const cpimh_chains* h) {     // including discarded speculative proposals
+  if (!h) return 0;
+  if (h->filters_launched >= 0) return h->filters_launched;          // round-based driver: counted on the host
+  unsigned long long n[2] = {0, 0};                                  // persistent kernel: counted on the device
+  if (cudaMemcpy(n, h->nfilters.p, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)n[1];
+}
 
 int cpimh_chains_fetch(cpimh_chains* h, int64_t R, void* stream, cpimh_chain_out* o) {
   CPIMH_REQUIRE(h && o, "null argument");
@@ -551,7 +588,7 @@ int cpimh_chains_fetch(cpimh_chains* h, int64_t R, void* stream, cpimh_chain_out
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(st.data(), h->status.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
   for (int64_t r = 0; r < R; r++)
-    if (st[(size_t)r]) {
+    if (st[(size_t)r] && st[(size_t)r] != CPIMH_ERR_NOT_MET) {     // a capped replicate is reported through `finished`, not as a failure
       if (st[(size_t)r] == CPIMH_ERR_TREE_OVERFLOW) set_error("replicate %lld: ancestor tree capacity exhausted; raise cfg.tree_capacity", (long long)r);
       else set_error("replicate %lld failed with status %d", (long long)r, st[(size_t)r]);
       return st[(size_t)r];
@@ -571,6 +608,8 @@ int cpimh_chains_fetch(cpimh_chains* h, int64_t R, void* stream, cpimh_chain_out
   if (o->sum_hbar) memcpy(o->sum_hbar, sums.data(), sizeof(double) * P);
   if (o->sum_hbar_sq) memcpy(o->sum_hbar_sq, sums.data() + P, sizeof(double) * P);
   if (o->nfilters) *o->nfilters = (int64_t)sums[2 * P];
+  if (o->nfinished) *o->nfinished = (int64_t)sums[2 * P + 1];
+  if (o->finished) for (int64_t r = 0; r < R; r++) o->finished[r] = st[(size_t)r] == 0 ? 1 : 0;
   if (o->sum_hbar_rb) memcpy(o->sum_hbar_rb, sums_rb.data(), sizeof(double) * P);
   if (o->sum_hbar_rb_sq) memcpy(o->sum_hbar_rb_sq, sums_rb.data() + P, sizeof(double) * P);
   return CPIMH_OK;

@@ -1,0 +1,9 @@
+// model_ar16.cu -- kernel instantiations for get_ar(16) (one translation unit per dimension: they compile in parallel)
+#include "registry.h"
+namespace cpimh {
+const ModelEntry* entries_ar16(int* n) {
+  static const ModelEntry e[] = {make_entry<ArModel<16>>(CPIMH_MODEL_AR)};
+  *n = 1;
+  return e;
+}
+}  // namespace cpimh

@@ -1,0 +1,9 @@
+// model_lorenz16.cu -- kernel instantiations for get_lorenz with d = 16 (thread-per-particle; d = 32 / 64 live in wide.cu)
+#include "registry.h"
+namespace cpimh {
+const ModelEntry* entries_lorenz16(int* n) {
+  static const ModelEntry e[] = {make_entry<LorenzModel<16>>(CPIMH_MODEL_LORENZ)};
+  *n = 1;
+  return e;
+}
+}  // namespace cpimh

@@ -1,0 +1,9 @@
+// model_lorenz8.cu -- kernel instantiations for get_lorenz with d = 8 (thread-per-particle; d = 32 / 64 live in wide.cu)
+#include "registry.h"
+namespace cpimh {
+const ModelEntry* entries_lorenz8(int* n) {
+  static const ModelEntry e[] = {make_entry<LorenzModel<8>>(CPIMH_MODEL_LORENZ)};
+  *n = 1;
+  return e;
+}
+}  // namespace cpimh

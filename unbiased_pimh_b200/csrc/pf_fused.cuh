@@ -28,7 +28,7 @@ enum { PATH_NONE = 0, PATH_DENSE = 1, PATH_TREE = 2 };
 
 // byte offsets of the shared-memory arrays inside the dynamic window (filled on the host by pf_layout, so that the kernel
 // re-derives a pointer with one add from the constant bank instead of recomputing the carve arithmetic)
-struct PfLayout { int S, theta, pre, dscr, dscr2, leaf, bpar, off32, bits, coarse, iscr; };
+struct PfLayout { int S, theta, pre, dscr, dscr2, leaf, bpar, off32, bits, coarse, iscr, own; };
 
 struct PfParams {
   PfLayout lay;
@@ -81,6 +81,7 @@ struct PfSmem {
   SmemArr<double> dscr;     // [64]
   SmemArr<double> dscr2;    // [4]   E_N of the ladder (written by thread 0 before the scans), sum of the last weights, knot margin, running log Z
   SmemArr<int> coarse;      // [Npad/32 + 1] ancestor of every 32nd sorted uniform (bounds for the per-particle search)
+  SmemArr<double> own;      // [16]  the chain kernel's per-replicate scalars (kept out of registers across run_filter)
   SmemArr<int> iscr;        // [36]  (32 scan scratch, [32] status flag, [33] work item, [34] exact-order repeats, [35] near-knot flag)
 };
 // layout of the dynamic shared-memory window; returns its size in bytes
@@ -104,6 +105,8 @@ __host__ __device__ inline size_t pf_layout(int Npad, int M, int npre, int path_
   }
   l.coarse = (int)b; b += (size_t)(Npad / 32 + 4) * 4;
   l.iscr = (int)b; b += 36 * 4;
+  b = (b + 7) & ~(size_t)7;
+  l.own = (int)b; b += 16 * 8;               // chain-owner state (chains.cuh), untouched by run_filter
   if (L) *L = l;
   return (b + 15) & ~(size_t)15;
 }
@@ -114,7 +117,7 @@ __device__ __forceinline__ PfSmem pf_carve(const PfLayout& l) {
   PfSmem s;
   s.C.off = 0; s.S.off = l.S; s.theta.off = l.theta; s.pre.off = l.pre; s.dscr.off = l.dscr; s.dscr2.off = l.dscr2;
   s.leaf.off = l.leaf; s.bpar.off = l.bpar; s.off32.off = l.off32; s.bits.off = l.bits;   // -1 when absent (never dereferenced then)
-  s.coarse.off = l.coarse; s.iscr.off = l.iscr;
+  s.coarse.off = l.coarse; s.iscr.off = l.iscr; s.own.off = l.own;
   return s;
 }
 

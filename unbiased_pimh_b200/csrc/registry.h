@@ -36,11 +36,19 @@ ModelEntry make_entry(int model) {
   return e;
 }
 const ModelEntry* entries_gss(int* n);
-const ModelEntry* entries_ar(int* n);
-const ModelEntry* entries_ar_hi(int* n);
+const ModelEntry* entries_ar1(int* n);
+const ModelEntry* entries_ar2(int* n);
+const ModelEntry* entries_ar3(int* n);
+const ModelEntry* entries_ar4(int* n);
+const ModelEntry* entries_ar5(int* n);
+const ModelEntry* entries_ar8(int* n);
+const ModelEntry* entries_ar10(int* n);
+const ModelEntry* entries_ar16(int* n);
 const ModelEntry* entries_sv(int* n);
 const ModelEntry* entries_sk(int* n);
-const ModelEntry* entries_lorenz(int* n);
+const ModelEntry* entries_lorenz4(int* n);
+const ModelEntry* entries_lorenz8(int* n);
+const ModelEntry* entries_lorenz16(int* n);
 const ModelEntry* find_entry(int model, int dim);
 
 }  // namespace cpimh

@@ -307,6 +307,9 @@ class ChainBatch:
         o.bc = bcv.ctypes.data if bc else None
         o.meetingtime, o.iteration = mt.ctypes.data, it.ctypes.data
         o.sum_hbar, o.sum_hbar_sq, o.nfilters = s.ctypes.data, s2.ctypes.data, nf.ctypes.data
+        fin = np.empty(R, dtype=np.int32)
+        nfin = np.zeros(1, dtype=np.int64)
+        o.finished, o.nfinished = fin.ctypes.data, nfin.ctypes.data
         rb = self.all_particles
         hrb = np.empty((R, P, d)) if (rb and hbar) else None
         srb, srb2 = (np.empty((P, d)), np.empty((P, d))) if rb else (None, None)
@@ -314,7 +317,10 @@ class ChainBatch:
             o.hbar_rb = hrb.ctypes.data if hbar else None
             o.sum_hbar_rb, o.sum_hbar_rb_sq = srb.ctypes.data, srb2.ctypes.data
         L.check(L.lib().cpimh_chains_fetch(self.h, C.c_int64(R), C.c_void_p(stream or 0), C.byref(o)))
-        out = {"meetingtime": mt, "iteration": it, "sum_hbar": s.T.copy(), "sum_hbar_sq": s2.T.copy(), "nfilters": int(nf[0])}
+        # finished[r] is False when max_iterations was reached before the chains met (c_chains$finished, R/debiasing_algorithm.R:262);
+        # the sums hold the finished replicates only
+        out = {"meetingtime": mt, "iteration": it, "sum_hbar": s.T.copy(), "sum_hbar_sq": s2.T.copy(), "nfilters": int(nf[0]),
+               "finished": fin.astype(bool), "nfinished": int(nfin[0])}
         if hbar:
             out["hbar"] = hb.transpose(0, 2, 1)       # (R, d, T+1)
         if bc:
