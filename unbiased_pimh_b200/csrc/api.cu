@@ -560,10 +560,13 @@ static cpimh_pf* g_cached = nullptr;
 static cpimh_config g_cached_cfg;
 static int64_t g_cached_B = 0;
 
+int cpimh_ccpf_release_cached(void);
 int cpimh_release_cached(void) {
-  std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
-  if (g_cached) { cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0; }
-  return CPIMH_OK;
+  {
+    std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
+    if (g_cached) { cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0; }
+  }
+  return cpimh_ccpf_release_cached();
 }
 
 int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,

@@ -3,6 +3,7 @@
 // (R/CPF.R:14-78), CPF_coupled (R/CPF_coupled.R:14-112), the CCPF kernels (R/pf_kernels.R:236-265) and
 // coupled_ccpf_chains + H_bar (R/debiasing_algorithm.R:23-111, 284-316).  Kernels: ccpf.cuh.
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "host_common.h"
 
@@ -76,20 +77,6 @@ static int ccpf_launch(CcpfWork& w, const CcpfParams& p, cudaStream_t s) {
   return w.entry->launch_ccpf(p, L, s);
 }
 
-// ------------------------------------------------------------------ coupled_ccpf_chains state machine
-struct CcRound {
-  int PD, k, K, max_it, it;
-  unsigned first_replicate;
-  const int* active; int nA; int* next_active; int* next_count;
-  unsigned long long* stream_ids;
-  const double* new1; const double* new2; const double* new_logz; const int* new_status;
-  double* st1; double* st2; double* lz1; double* lz2;
-  int* single; int* iter; int* tau; int* status;
-  double* accH; double* accD; double* hbar; double* bc;
-  unsigned long long* nfilters;
-  // Rao-Blackwellised twin (null when off): exp paths of the new filters / of the current states, accumulators, output
-  const double* newe1; const double* newe2; double* e1; double* e2; double* accHe; double* accDe; double* hbar_rb;
-};
 __global__ void cc_prepare_kernel(CcRound q) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= q.nA) return;
@@ -110,77 +97,24 @@ __global__ void cc_init_kernel(CcRound q, const int* pf_status1, const int* pf_s
     int st = pf_status1[rep] | pf_status2[rep];
     if (st == 0 && (isnan(q.lz1[rep]) || isnan(q.lz2[rep]))) st = CPIMH_ERR_INVALID;
     q.status[rep] = st;
-    if (st == 0) q.next_active[atomicAdd(q.next_count, 1)] = rep;
+    if (st == 0 && q.next_active) q.next_active[atomicAdd(q.next_count, 1)] = rep;
   }
 }
-__global__ void cc_accept_kernel(CcRound q) {
-  const int rep = q.active[blockIdx.x];
-  const int PD = q.PD, it = q.it;
-  double* x1 = q.st1 + (size_t)rep * PD;
-  double* x2 = q.st2 + (size_t)rep * PD;
-  const double* n1 = q.new1 + (size_t)rep * PD;
-  const double* n2 = q.new2 + (size_t)rep * PD;
-  double* accH = q.accH + (size_t)rep * PD;
-  double* accD = q.accD + (size_t)rep * PD;
-  const int single = q.single[rep];
-  int tau = q.tau[rep];
-  int status = q.new_status[rep];
-  if (status == 0 && isnan(q.new_logz[rep])) status = CPIMH_ERR_INVALID;
-  const int t = it - 1;
-  const bool mcmc = (it >= q.k && it <= q.K);
-  const double coef = (double)min(t - q.k + 1, q.K - q.k + 1);
-  int same = 1;
-  for (int j = threadIdx.x; j < PD; j += blockDim.x) {
-    const double xa = n1[j];
-    // iteration 1 moves chain 1 only; after the meeting both chains take the single kernel's output (:68-73)
-    const double xb = (it == 1) ? x2[j] : (single ? xa : n2[j]);
-    x1[j] = xa; x2[j] = xb;
-    if (xa != xb) same = 0;
-  }
-  same = __syncthreads_and(same);
-  int finished = 0;
-  if (status) finished = 1;
-  if (it >= 2 && !single && same && tau < 0) tau = it;                         // :82-86 all(chain_state1 == chain_state2)
-  if (tau > 0 && it >= max(tau, q.K)) finished = 1;                            // :104-106
-  if (q.max_it >= 0 && it >= q.max_it) finished = 1;
-  // H_bar (debiasing_algorithm.R:296-312): MCMC sum over k..K plus coef_t (X_{t+1} - Y_t) for k <= t <= tau - 1, skipped
-  // altogether when tau <= k + 1 (:303).  For the states the skipped term is zero; for the weighted-average paths it is not.
-  const bool bias = (t >= q.k) && !(tau > 0 && tau <= q.k + 1);
-  for (int j = threadIdx.x; j < PD; j += blockDim.x) {
-    const double xa = x1[j], xb = x2[j];
-    if (mcmc) accH[j] += xa;
-    if (bias) accD[j] = accD[j] + coef * (xa - xb);
-    if (q.e1) {                                                                // the same recursion over the filters' weighted-average paths
-      const size_t o = (size_t)rep * PD + j;
-      const double ea = q.newe1[o];
-      const double eb = (it == 1) ? q.e2[o] : (single ? ea : q.newe2[o]);
-      q.e1[o] = ea; q.e2[o] = eb;
-      if (mcmc) q.accHe[o] += ea;
-      if (bias) q.accDe[o] = q.accDe[o] + coef * (ea - eb);
-    }
-  }
-  if (finished) {
-    const double denom = (double)(q.K - q.k + 1);
-    for (int j = threadIdx.x; j < PD; j += blockDim.x) {
-      q.hbar[(size_t)rep * PD + j] = (accH[j] + accD[j]) / denom;
-      q.bc[(size_t)rep * PD + j] = accD[j] / denom;
-      if (q.e1) q.hbar_rb[(size_t)rep * PD + j] = (q.accHe[(size_t)rep * PD + j] + q.accDe[(size_t)rep * PD + j]) / denom;
-    }
-  }
-  if (threadIdx.x == 0) {
-    if (it == 1 || single) { q.lz1[rep] = q.new_logz[rep]; if (it > 1) q.lz2[rep] = q.new_logz[rep]; }   // coupled kernel leaves log_pdf unchanged
-    q.single[rep] = (tau > 0) ? 1 : 0;
-    q.iter[rep] = it; q.tau[rep] = tau;
-    if (status) q.status[rep] = status;
-    if (finished) atomicAdd(q.nfilters, (unsigned long long)(2 + it));
-    else q.next_active[atomicAdd(q.next_count, 1)] = rep;
-  }
-}
-__global__ void cc_reduce_kernel(const double* hbar, long long R, int P, double* sums) {
-  const int j = blockIdx.x;
-  double s = 0.0, s2 = 0.0;
-  for (long long r = threadIdx.x; r < R; r += blockDim.x) { const double v = hbar[(size_t)r * P + j]; s += v; s2 += v * v; }
+__global__ void cc_accept_kernel(CcRound q) { cc_accept(q, q.active[blockIdx.x], q.it); }
+// deterministic sums over the finished replicates (status 0): sums[0..P) = sum hbar, [P..2P) = sum hbar^2, [2P] = filters run,
+// [2P+1] = replicates that entered the sums (a replicate capped by max_iterations is left out: CPIMH_ERR_NOT_MET)
+__global__ void cc_reduce_kernel(const double* hbar, const int* status, long long R, int P, const unsigned long long* nfilters, double* sums) {
   __shared__ double scr[64];
+  const int j = blockIdx.x;
+  if (j == P) {
+    double n = 0;
+    for (long long r = threadIdx.x; r < R; r += blockDim.x) n += (status[r] == 0) ? 1.0 : 0.0;
+    n = block_sum(n, scr);
+    if (threadIdx.x == 0) { sums[2 * P] = (double)(*nfilters); sums[2 * P + 1] = n; }
+    return;
+  }
+  double s = 0.0, s2 = 0.0;
+  for (long long r = threadIdx.x; r < R; r += blockDim.x) { if (status[r] != 0) continue; const double v = hbar[(size_t)r * P + j]; s += v; s2 += v * v; }
   s = block_sum(s, scr);
   s2 = block_sum(s2, scr);
   if (threadIdx.x == 0) { sums[j] = s; sums[P + j] = s2; }
@@ -260,16 +194,43 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B,
   return CPIMH_OK;
 }
 
+// Workspaces of the one-shot chain entry, kept between calls (grow-only buffers, the bootstrap-filter handle of the initial
+// states): the R shim calls this entry once per estimator batch.  cpimh_release_cached() frees them.
+struct CcChainCache {
+  CcpfWork w;
+  cpimh_pf* pf = nullptr;
+  cpimh_config pf_cfg;
+  int64_t pf_R = 0;
+  DevBuf st1, st2, n1, n2, lz1, lz2, nlz, nst, single, iter, tau, status, accH, accD, hbar, bc, cnt, nf, sums, pst1, pst2;
+  DevBuf e1, e2, ne1, ne2, accHe, accDe, hbar_rb, sums_rb;
+  void release() {
+    DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &cnt, &nf, &sums, &pst1, &pst2,
+                     &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb, &w.obs, &w.theta, &w.pre, &w.hist_x, &w.hist_a};
+    for (auto x : all) x->release();
+    if (pf) { cpimh_pf_destroy(pf); pf = nullptr; pf_R = 0; }
+  }
+};
+static CcChainCache g_cc;
+static std::recursive_mutex g_cc_mu;
+
+int cpimh_ccpf_release_cached(void) {
+  std::lock_guard<std::recursive_mutex> lk(g_cc_mu);
+  g_cc.release();
+  return CPIMH_OK;
+}
+
 int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, int with_as, cpimh_chain_out* o) {
   CPIMH_REQUIRE(cfg && obs_host && o, "null argument");
   CPIMH_REQUIRE(R >= 1, "nreplicates must be >= 1");
   CPIMH_REQUIRE(k >= 0 && K >= k, "need 0 <= k <= K (got k=%d K=%d)", k, K);
   CPIMH_REQUIRE(max_iterations < 0 || max_iterations >= (K > 1 ? K : 1), "max_iterations must be >= max(K, 1) or negative (unbounded)");
-  CPIMH_REQUIRE(max_iterations < 4096, "iteration index must fit 12 bits of the Philox counter (max_iterations < 4096)");
+  CPIMH_REQUIRE(max_iterations < 4095, "iteration index must fit 12 bits of the Philox counter and 0xFFF is the second initial filter (max_iterations <= 4094)");
   const bool rb = o->hbar_rb || o->sum_hbar_rb || o->sum_hbar_rb_sq;
   const int max_it = max_iterations < 0 ? 4094 : max_iterations;
-  CcpfWork w;
+  std::lock_guard<std::recursive_mutex> lk(g_cc_mu);
+  CcChainCache& g = g_cc;
+  CcpfWork& w = g.w;
   int rc = ccpf_work_init(&w, cfg, obs_host, R);
   if (rc) return rc;
   const cpimh_config& c = w.cfg;
@@ -278,31 +239,29 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   // ---- initial states: two independent bootstrap filters per replicate (iteration indices 0 and 0xFFF)
   cpimh_config cpf = c;
   cpf.store_paths = cpf.store_paths == 0 ? 1 : cpf.store_paths;
-  cpimh_pf* pf = nullptr;
-  rc = cpimh_pf_create(&cpf, R, &pf);
-  if (rc) return rc;
-  DevBuf st1, st2, n1, n2, lz1, lz2, nlz, nst, single, iter, tau, status, accH, accD, hbar, bc, act0, act1, cnt, ids, nf, sums, pst1, pst2;
-  DevBuf e1, e2, ne1, ne2, accHe, accDe, hbar_rb, sums_rb;
-  DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &act0, &act1, &cnt, &ids, &nf, &sums, &pst1, &pst2,
-                   &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb};
-  struct Rel { DevBuf** b; size_t n; cpimh_pf** pf; ~Rel() { for (size_t i = 0; i < n; i++) b[i]->release(); if (*pf) cpimh_pf_destroy(*pf); } } rel{all, sizeof(all) / sizeof(all[0]), &pf};
-  const size_t RPD = sizeof(double) * (size_t)R * PD;
-  DevBuf* dbl[] = {&st1, &st2, &n1, &n2, &accH, &accD, &hbar, &bc};
-  for (auto b : dbl) { rc = b->alloc(RPD); if (rc) return rc; }
-  if (rb) {
-    DevBuf* dre[] = {&e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb};
-    for (auto b : dre) { rc = b->alloc(RPD); if (rc) return rc; }
-    rc = sums_rb.alloc(sizeof(double) * (2 * (size_t)PD)); if (rc) return rc;
-    rc = cpimh_pf_all_particles(pf, 1); if (rc) return rc;
+  if (!(g.pf && g.pf_R >= R && memcmp(&g.pf_cfg, &cpf, sizeof(cpf)) == 0)) {
+    if (g.pf) { cpimh_pf_destroy(g.pf); g.pf = nullptr; g.pf_R = 0; }
+    rc = cpimh_pf_create(&cpf, R, &g.pf);
+    if (rc) { g.pf = nullptr; return rc; }
+    g.pf_cfg = cpf; g.pf_R = R;
   }
-  DevBuf* dR[] = {&lz1, &lz2, &nlz};
+  cpimh_pf* pf = g.pf;
+  const size_t RPD = sizeof(double) * (size_t)R * PD;
+  DevBuf* dbl[] = {&g.st1, &g.st2, &g.n1, &g.n2, &g.accH, &g.accD, &g.hbar, &g.bc};
+  for (auto b : dbl) { rc = b->alloc(RPD); if (rc) return rc; }
+  rc = cpimh_pf_all_particles(pf, rb ? 1 : 0); if (rc) return rc;
+  if (rb) {
+    DevBuf* dre[] = {&g.e1, &g.e2, &g.ne1, &g.ne2, &g.accHe, &g.accDe, &g.hbar_rb};
+    for (auto b : dre) { rc = b->alloc(RPD); if (rc) return rc; }
+    rc = g.sums_rb.alloc(sizeof(double) * (2 * (size_t)PD + 2)); if (rc) return rc;
+  }
+  DevBuf* dR[] = {&g.lz1, &g.lz2, &g.nlz};
   for (auto b : dR) { rc = b->alloc(sizeof(double) * (size_t)R); if (rc) return rc; }
-  DevBuf* iR[] = {&nst, &single, &iter, &tau, &status, &act0, &act1, &pst1, &pst2};
+  DevBuf* iR[] = {&g.nst, &g.single, &g.iter, &g.tau, &g.status, &g.pst1, &g.pst2};
   for (auto b : iR) { rc = b->alloc(sizeof(int) * (size_t)R); if (rc) return rc; }
-  rc = cnt.alloc(sizeof(int)); if (rc) return rc;
-  rc = ids.alloc(sizeof(unsigned long long) * (size_t)R); if (rc) return rc;
-  rc = nf.alloc(sizeof(unsigned long long)); if (rc) return rc;
-  rc = sums.alloc(sizeof(double) * (2 * (size_t)PD)); if (rc) return rc;
+  rc = g.cnt.alloc(sizeof(int)); if (rc) return rc;
+  rc = g.nf.alloc(sizeof(unsigned long long)); if (rc) return rc;
+  rc = g.sums.alloc(sizeof(double) * (2 * (size_t)PD + 2)); if (rc) return rc;
   rc = cpimh_pf_set_observations(pf, obs_host);
   if (rc) return rc;
   double *d_lz = nullptr, *d_tr = nullptr;
@@ -317,75 +276,62 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
     const uint64_t first = (uint64_t)first_replicate | (which ? ((uint64_t)0xFFF << 32) : 0ull);
     rc = cpimh_pf_run(pf, R, seed, first, s);
     if (rc) return rc;
-    CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? st2.p : st1.p, d_tr, RPD, cudaMemcpyDeviceToDevice, s));
-    CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? lz2.p : lz1.p, d_lz, sizeof(double) * (size_t)R, cudaMemcpyDeviceToDevice, s));
-    CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? pst2.p : pst1.p, d_st, sizeof(int) * (size_t)R, cudaMemcpyDeviceToDevice, s));
-    if (rb) CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? e2.p : e1.p, d_ex, RPD, cudaMemcpyDeviceToDevice, s));
+    CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? g.st2.p : g.st1.p, d_tr, RPD, cudaMemcpyDeviceToDevice, s));
+    CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? g.lz2.p : g.lz1.p, d_lz, sizeof(double) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+    CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? g.pst2.p : g.pst1.p, d_st, sizeof(int) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+    if (rb) CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? g.e2.p : g.e1.p, d_ex, RPD, cudaMemcpyDeviceToDevice, s));
   }
   CcRound q;
   memset(&q, 0, sizeof(q));
   q.PD = PD; q.k = k; q.K = K; q.max_it = max_it; q.first_replicate = first_replicate;
-  q.stream_ids = ids.as<unsigned long long>();
-  q.new1 = n1.as<double>(); q.new2 = n2.as<double>(); q.new_logz = nlz.as<double>(); q.new_status = nst.as<int>();
-  q.st1 = st1.as<double>(); q.st2 = st2.as<double>(); q.lz1 = lz1.as<double>(); q.lz2 = lz2.as<double>();
-  q.single = single.as<int>(); q.iter = iter.as<int>(); q.tau = tau.as<int>(); q.status = status.as<int>();
-  q.accH = accH.as<double>(); q.accD = accD.as<double>(); q.hbar = hbar.as<double>(); q.bc = bc.as<double>();
-  q.nfilters = nf.as<unsigned long long>(); q.next_count = cnt.as<int>();
+  q.new1 = g.n1.as<double>(); q.new2 = g.n2.as<double>(); q.new_logz = g.nlz.as<double>(); q.new_status = g.nst.as<int>();
+  q.st1 = g.st1.as<double>(); q.st2 = g.st2.as<double>(); q.lz1 = g.lz1.as<double>(); q.lz2 = g.lz2.as<double>();
+  q.single = g.single.as<int>(); q.iter = g.iter.as<int>(); q.tau = g.tau.as<int>(); q.status = g.status.as<int>();
+  q.accH = g.accH.as<double>(); q.accD = g.accD.as<double>(); q.hbar = g.hbar.as<double>(); q.bc = g.bc.as<double>();
+  q.nfilters = g.nf.as<unsigned long long>();
+  q.next_active = nullptr; q.next_count = nullptr;       // no active lists: the persistent kernel takes replicates from a ticket counter
   if (rb) {
-    q.newe1 = ne1.as<double>(); q.newe2 = ne2.as<double>(); q.e1 = e1.as<double>(); q.e2 = e2.as<double>();
-    q.accHe = accHe.as<double>(); q.accDe = accDe.as<double>(); q.hbar_rb = hbar_rb.as<double>();
+    q.newe1 = g.ne1.as<double>(); q.newe2 = g.ne2.as<double>(); q.e1 = g.e1.as<double>(); q.e2 = g.e2.as<double>();
+    q.accHe = g.accHe.as<double>(); q.accDe = g.accDe.as<double>(); q.hbar_rb = g.hbar_rb.as<double>();
   }
-  CPIMH_CUDA_CHECK(cudaMemsetAsync(nf.p, 0, sizeof(unsigned long long), s));
-  CPIMH_CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(int), s));
-  q.next_active = act0.as<int>();
-  cc_init_kernel<<<(unsigned)R, 128, 0, s>>>(q, pst1.as<int>(), pst2.as<int>());
-  int nA = 0, flip = 0;
-  CPIMH_CUDA_CHECK(cudaMemcpyAsync(&nA, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  CPIMH_CUDA_CHECK(cudaMemsetAsync(g.nf.p, 0, sizeof(unsigned long long), s));
+  CPIMH_CUDA_CHECK(cudaMemsetAsync(g.cnt.p, 0, sizeof(int), s));
+  cc_init_kernel<<<(unsigned)R, 128, 0, s>>>(q, g.pst1.as<int>(), g.pst2.as<int>());
   CcpfParams p;
   ccpf_fill(w, &p);
-  p.with_as = with_as ? 1 : 0; p.seed = seed; p.stream_ids = ids.as<unsigned long long>();
-  p.single = single.as<int>();
-  p.ref1 = st1.as<double>(); p.ref2 = st2.as<double>();
-  p.traj1 = n1.as<double>(); p.traj2 = n2.as<double>(); p.logz = nlz.as<double>(); p.status = nst.as<int>();
-  if (rb) { p.exp1 = ne1.as<double>(); p.exp2 = ne2.as<double>(); }
-  int64_t filters = 2 * R;
-  for (int it = 1; nA > 0; it++) {
-    q.it = it;
-    q.active = flip ? act1.as<int>() : act0.as<int>();
-    q.next_active = flip ? act0.as<int>() : act1.as<int>();
-    q.nA = nA;
-    CPIMH_CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, sizeof(int), s));
-    cc_prepare_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, s>>>(q);
-    p.B = nA; p.slot = q.active;
-    rc = ccpf_launch(w, p, s);
-    if (rc) return rc;
-    cc_accept_kernel<<<(unsigned)nA, 128, 0, s>>>(q);
-    filters += nA;
-    CPIMH_CUDA_CHECK(cudaMemcpyAsync(&nA, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
-    flip ^= 1;
-  }
-  cc_reduce_kernel<<<PD, 256, 0, s>>>(hbar.as<double>(), R, PD, sums.as<double>());
-  if (rb) cc_reduce_kernel<<<PD, 256, 0, s>>>(hbar_rb.as<double>(), R, PD, sums_rb.as<double>());
+  p.with_as = with_as ? 1 : 0; p.seed = seed;
+  p.single = g.single.as<int>();
+  p.ref1 = g.st1.as<double>(); p.ref2 = g.st2.as<double>();
+  p.traj1 = g.n1.as<double>(); p.traj2 = g.n2.as<double>(); p.logz = g.nlz.as<double>(); p.status = g.nst.as<int>();
+  if (rb) { p.exp1 = g.ne1.as<double>(); p.exp2 = g.ne2.as<double>(); }
+  // ---- the chains: one persistent kernel, every resident CTA runs whole replicates (ccpf.cuh ccpf_chains_kernel)
+  CcpfLaunch L;
+  L.threads = w.threads; L.smem = w.smem; L.grid = (int)(R < w.grid_max ? R : w.grid_max);
+  rc = w.entry->launch_ccpf_chains(p, q, R, g.cnt.as<int>(), L, s);
+  if (rc) return rc;
+  w.launches++;
+  cc_reduce_kernel<<<PD + 1, 256, 0, s>>>(g.hbar.as<double>(), g.status.as<int>(), R, PD, g.nf.as<unsigned long long>(), g.sums.as<double>());
+  if (rb) cc_reduce_kernel<<<PD + 1, 256, 0, s>>>(g.hbar_rb.as<double>(), g.status.as<int>(), R, PD, g.nf.as<unsigned long long>(), g.sums_rb.as<double>());
   CPIMH_CUDA_CHECK(cudaGetLastError());
   std::vector<int> stv((size_t)R);
-  CPIMH_CUDA_CHECK(cudaMemcpyAsync(stv.data(), status.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(stv.data(), g.status.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
   for (int64_t r = 0; r < R; r++)
-    if (stv[(size_t)r]) { set_error("replicate %lld failed with status %d", (long long)r, stv[(size_t)r]); return stv[(size_t)r]; }
-  std::vector<double> hs(2 * (size_t)PD);
-  CPIMH_CUDA_CHECK(cudaMemcpy(hs.data(), sums.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost));
-  if (o->hbar) CPIMH_CUDA_CHECK(cudaMemcpy(o->hbar, hbar.p, RPD, cudaMemcpyDeviceToHost));
-  if (o->bc) CPIMH_CUDA_CHECK(cudaMemcpy(o->bc, bc.p, RPD, cudaMemcpyDeviceToHost));
-  if (o->meetingtime) CPIMH_CUDA_CHECK(cudaMemcpy(o->meetingtime, tau.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost));
-  if (o->iteration) CPIMH_CUDA_CHECK(cudaMemcpy(o->iteration, iter.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost));
+    if (stv[(size_t)r] && stv[(size_t)r] != CPIMH_ERR_NOT_MET) { set_error("replicate %lld failed with status %d", (long long)r, stv[(size_t)r]); return stv[(size_t)r]; }
+  std::vector<double> hs(2 * (size_t)PD + 2);
+  CPIMH_CUDA_CHECK(cudaMemcpy(hs.data(), g.sums.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost));
+  if (o->hbar) CPIMH_CUDA_CHECK(cudaMemcpy(o->hbar, g.hbar.p, RPD, cudaMemcpyDeviceToHost));
+  if (o->bc) CPIMH_CUDA_CHECK(cudaMemcpy(o->bc, g.bc.p, RPD, cudaMemcpyDeviceToHost));
+  if (o->meetingtime) CPIMH_CUDA_CHECK(cudaMemcpy(o->meetingtime, g.tau.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost));
+  if (o->iteration) CPIMH_CUDA_CHECK(cudaMemcpy(o->iteration, g.iter.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost));
   if (o->sum_hbar) memcpy(o->sum_hbar, hs.data(), sizeof(double) * PD);
   if (o->sum_hbar_sq) memcpy(o->sum_hbar_sq, hs.data() + PD, sizeof(double) * PD);
-  if (o->nfilters) *o->nfilters = filters;
+  if (o->nfilters) *o->nfilters = (int64_t)hs[2 * (size_t)PD];
+  if (o->nfinished) *o->nfinished = (int64_t)hs[2 * (size_t)PD + 1];
+  if (o->finished) for (int64_t r = 0; r < R; r++) o->finished[r] = stv[(size_t)r] == 0 ? 1 : 0;
   if (rb) {
-    CPIMH_CUDA_CHECK(cudaMemcpy(hs.data(), sums_rb.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost));
-    if (o->hbar_rb) CPIMH_CUDA_CHECK(cudaMemcpy(o->hbar_rb, hbar_rb.p, RPD, cudaMemcpyDeviceToHost));
+    CPIMH_CUDA_CHECK(cudaMemcpy(hs.data(), g.sums_rb.p, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost));
+    if (o->hbar_rb) CPIMH_CUDA_CHECK(cudaMemcpy(o->hbar_rb, g.hbar_rb.p, RPD, cudaMemcpyDeviceToHost));
     if (o->sum_hbar_rb) memcpy(o->sum_hbar_rb, hs.data(), sizeof(double) * PD);
     if (o->sum_hbar_rb_sq) memcpy(o->sum_hbar_rb_sq, hs.data() + PD, sizeof(double) * PD);
   }

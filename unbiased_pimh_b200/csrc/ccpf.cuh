@@ -355,12 +355,129 @@ __global__ void __launch_bounds__(512, 1) ccpf_kernel(CcpfParams p) {
   }
 }
 
+// ------------------------------------------------------------------ coupled_ccpf_chains state machine
+struct CcRound {
+  int PD, k, K, max_it, it;
+  unsigned first_replicate;
+  const int* active; int nA; int* next_active; int* next_count;
+  unsigned long long* stream_ids;
+  const double* new1; const double* new2; const double* new_logz; const int* new_status;
+  double* st1; double* st2; double* lz1; double* lz2;
+  int* single; int* iter; int* tau; int* status;
+  double* accH; double* accD; double* hbar; double* bc;
+  unsigned long long* nfilters;
+  // Rao-Blackwellised twin (null when off): exp paths of the new filters / of the current states, accumulators, output
+  const double* newe1; const double* newe2; double* e1; double* e2; double* accHe; double* accDe; double* hbar_rb;
+};
+// one step of the lag-one recursion of replicate `rep` after its iteration-`it` filter(s) (R/debiasing_algorithm.R:50-106, 296-312);
+// all threads of the CTA call; returns != 0 when the replicate is finished
+__device__ inline int cc_accept(const CcRound& q, int rep, int it) {
+  const int PD = q.PD;
+  double* x1 = q.st1 + (size_t)rep * PD;
+  double* x2 = q.st2 + (size_t)rep * PD;
+  const double* n1 = q.new1 + (size_t)rep * PD;
+  const double* n2 = q.new2 + (size_t)rep * PD;
+  double* accH = q.accH + (size_t)rep * PD;
+  double* accD = q.accD + (size_t)rep * PD;
+  const int single = q.single[rep];
+  int tau = q.tau[rep];
+  int status = q.new_status[rep];
+  if (status == 0 && isnan(q.new_logz[rep])) status = CPIMH_ERR_INVALID;
+  const int t = it - 1;
+  const bool mcmc = (it >= q.k && it <= q.K);
+  const double coef = (double)min(t - q.k + 1, q.K - q.k + 1);
+  int same = 1;
+  for (int j = threadIdx.x; j < PD; j += blockDim.x) {
+    const double xa = n1[j];
+    // iteration 1 moves chain 1 only; after the meeting both chains take the single kernel's output (:68-73)
+    const double xb = (it == 1) ? x2[j] : (single ? xa : n2[j]);
+    x1[j] = xa; x2[j] = xb;
+    if (xa != xb) same = 0;
+  }
+  same = __syncthreads_and(same);
+  int finished = 0;
+  if (status) finished = 1;
+  if (it >= 2 && !single && same && tau < 0) tau = it;                         // :82-86 all(chain_state1 == chain_state2)
+  if (tau > 0 && it >= max(tau, q.K)) finished = 1;                            // :104-106
+  if (!finished && q.max_it >= 0 && it >= q.max_it) { finished = 1; status = CPIMH_ERR_NOT_MET; }   // R: finished = FALSE
+  // H_bar (debiasing_algorithm.R:296-312): MCMC sum over k..K plus coef_t (X_{t+1} - Y_t) for k <= t <= tau - 1, skipped
+  // altogether when tau <= k + 1 (:303).  For the states the skipped term is zero; for the weighted-average paths it is not.
+  const bool bias = (t >= q.k) && !(tau > 0 && tau <= q.k + 1);
+  for (int j = threadIdx.x; j < PD; j += blockDim.x) {
+    const double xa = x1[j], xb = x2[j];
+    if (mcmc) accH[j] += xa;
+    if (bias) accD[j] = accD[j] + coef * (xa - xb);
+    if (q.e1) {                                                                // the same recursion over the filters' weighted-average paths
+      const size_t o = (size_t)rep * PD + j;
+      const double ea = q.newe1[o];
+      const double eb = (it == 1) ? q.e2[o] : (single ? ea : q.newe2[o]);
+      q.e1[o] = ea; q.e2[o] = eb;
+      if (mcmc) q.accHe[o] += ea;
+      if (bias) q.accDe[o] = q.accDe[o] + coef * (ea - eb);
+    }
+  }
+  if (finished) {
+    const double denom = (double)(q.K - q.k + 1);
+    for (int j = threadIdx.x; j < PD; j += blockDim.x) {
+      q.hbar[(size_t)rep * PD + j] = (accH[j] + accD[j]) / denom;
+      q.bc[(size_t)rep * PD + j] = accD[j] / denom;
+      if (q.e1) q.hbar_rb[(size_t)rep * PD + j] = (q.accHe[(size_t)rep * PD + j] + q.accDe[(size_t)rep * PD + j]) / denom;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (it == 1 || single) { q.lz1[rep] = q.new_logz[rep]; if (it > 1) q.lz2[rep] = q.new_logz[rep]; }   // coupled kernel leaves log_pdf unchanged
+    q.single[rep] = (tau > 0) ? 1 : 0;
+    q.iter[rep] = it; q.tau[rep] = tau;
+    if (status) q.status[rep] = status;
+    if (finished) atomicAdd(q.nfilters, (unsigned long long)(2 + it));
+    else if (q.next_active) q.next_active[atomicAdd(q.next_count, 1)] = rep;
+  }
+  return finished;
+}
+
+// coupled_ccpf_chains as ONE persistent kernel: a CTA takes a replicate from the ticket counter and runs its whole chain --
+// conditional filter(s) on the current states, accept / meet / H_bar recursion -- until iteration max(tau, K); no host round
+// trip per iteration (round 1: a cudaMemcpy + stream synchronise after every iteration, 0.87 scaling efficiency at 8 GPUs).
+// Unlike PIMH, a conditional filter depends on the chain state, so a replicate's iterations are inherently sequential.
+template <class Model>
+__global__ void __launch_bounds__(512, 1) ccpf_chains_kernel(CcpfParams p, CcRound q, long long R, int* work_counter) {
+  CcpfSmem sm = ccpf_carve(p.Npad, p.npre);
+  for (int i = threadIdx.x; i < CPIMH_MAX_THETA; i += blockDim.x) sm.theta[i] = p.theta[i];
+  for (int i = threadIdx.x; i < p.npre; i += blockDim.x) sm.pre[i] = p.pre[i];
+  __syncthreads();
+  for (;;) {
+    if (threadIdx.x == 0) sm.iscr[33] = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const long long r = sm.iscr[33];
+    __syncthreads();
+    if (r >= R) break;
+    if (q.status[r] != 0) continue;                          // an initial bootstrap filter failed
+    for (int it = 1;; it++) {
+      const Stream s = make_stream(p.seed, (unsigned long long)(q.first_replicate + (unsigned)r) | ((unsigned long long)it << 32));
+      if (q.single[r]) run_ccpf<Model, 1>(p, sm, blockIdx.x, s, r, r);
+      else run_ccpf<Model, 2>(p, sm, blockIdx.x, s, r, r);
+      __syncthreads();
+      const int fin = cc_accept(q, (int)r, it);
+      __syncthreads();
+      if (fin) break;
+    }
+  }
+}
+
 struct CcpfLaunch { int grid, threads; size_t smem; };
 template <class Model>
 int launch_ccpf(const CcpfParams& p, const CcpfLaunch& L, cudaStream_t stream) {
   if (p.with_as && !Model::HAS_DTRANS) { set_error("ancestor sampling needs model$dtransition: defined for get_gss and get_ar only"); return CPIMH_ERR_INVALID; }
   CPIMH_CUDA_CHECK(cudaFuncSetAttribute(ccpf_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
   ccpf_kernel<Model><<<L.grid, L.threads, L.smem, stream>>>(p);
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  return CPIMH_OK;
+}
+template <class Model>
+int launch_ccpf_chains(const CcpfParams& p, const CcRound& q, long long R, int* work_counter, const CcpfLaunch& L, cudaStream_t stream) {
+  if (p.with_as && !Model::HAS_DTRANS) { set_error("ancestor sampling needs model$dtransition: defined for get_gss and get_ar only"); return CPIMH_ERR_INVALID; }
+  CPIMH_CUDA_CHECK(cudaFuncSetAttribute(ccpf_chains_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  ccpf_chains_kernel<Model><<<L.grid, L.threads, L.smem, stream>>>(p, q, R, work_counter);
   CPIMH_CUDA_CHECK(cudaGetLastError());
   return CPIMH_OK;
 }

@@ -17,6 +17,7 @@ struct ModelEntry {
   int (*launch_model_op)(const ModelOpParams&, cudaStream_t);
   int (*launch_ccpf)(const CcpfParams&, const CcpfLaunch&, cudaStream_t);
   int (*occupancy_ccpf)(int threads, size_t smem, int* blocks_per_sm);
+  int (*launch_ccpf_chains)(const CcpfParams&, const CcRound&, long long, int*, const CcpfLaunch&, cudaStream_t);
   int (*launch_apf)(const ApfParams&, const ApfLaunch&, cudaStream_t);
   int (*occupancy_apf)(int threads, size_t smem, int* blocks_per_sm);
 };
@@ -31,6 +32,7 @@ ModelEntry make_entry(int model) {
   e.launch_model_op = &launch_model_op<Model>;
   e.launch_ccpf = &launch_ccpf<Model>;
   e.occupancy_ccpf = &occupancy_ccpf<Model>;
+  e.launch_ccpf_chains = &launch_ccpf_chains<Model>;
   e.launch_apf = &launch_apf<Model>;
   e.occupancy_apf = &occupancy_apf<Model>;
   return e;
