@@ -62,7 +62,7 @@ def test_no_cpu_fallback_and_argument_checks():
         up.cpf_batch(0, up.get_gss(), [], y, 2, seed=1)
     assert ei.value.code == 1 and "nparticles" in str(ei.value)
     with pytest.raises(up.CpimhError) as ei:
-        up.cpf_batch(16, up.get_ar(7), [0.5, 1.0], np.zeros((5, 7)), 1, seed=1)   # no compiled kernel for d = 7
+        up.cpf_batch(16, up.get_ar(17), [0.5, 1.0], np.zeros((5, 17)), 1, seed=1)   # get_ar(d) is compiled for every d <= 16
     assert "dimension" in str(ei.value)
     with pytest.raises(up.CpimhError) as ei:          # conditional filters: argument checks come before any CUDA call
         up.CPF(16, up.get_gss(), [], y, ref_trajectory=np.zeros((1, 6)), shuffle=1)

@@ -248,3 +248,28 @@ def test_multi_wave_batches_and_tail_launch(up, golden):
     c = pb.fetch(path_index=True)
     assert np.array_equal(a["logz"], c["logz"]) and np.array_equal(a["trajectory"], c["trajectory"])
     pb.close()
+
+
+@pytest.mark.parametrize("d", [6, 7, 9, 11, 12, 13, 14, 15])
+def test_get_ar_every_dimension_up_to_sixteen(up, oracle, d):
+    """R/model_get_ar.R:11-46 accepts any dimension: every d <= 16 has a kernel (round 1: only 1,2,3,4,5,8,10,16).  Injected
+    noise: identical ancestors and log Z; Philox seed for seed."""
+    rng = np.random.default_rng(d)
+    N, T, B = 96, 12, 2
+    th = [0.4, 1.3]
+    obs = rng.normal(size=(T, d)) * 1.5
+    ocfg = oracle.make_config(oracle.MODEL_AR, d, d, N, T, theta=th)
+    nz = injected_noise(rng, oracle, ocfg, B, N, T, 0)
+    pb = up.PfBatch(up.get_ar(d), th, obs, N, B)
+    pb.record_ancestors(True); pb.set_noise(B, nz); pb.run(B, 0)
+    r = pb.fetch(logz_t=True, path_index=True)
+    for b in range(B):
+        o = oracle.cpf(ocfg, obs, noise={k: v[b] for k, v in nz.items()}, want_ancestors=True)
+        assert np.array_equal(pb.fetch_ancestors(b), o["ancestors"])
+        assert np.max(np.abs(r["logz_t"][b] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ
+        assert np.allclose(r["trajectory"][b], o["trajectory"], rtol=1e-9, atol=1e-9)
+    pb.close()
+    r = up.cpf_batch(N, up.get_ar(d), th, obs, 2, seed=5, logz_t=True)
+    for b in range(2):
+        o = oracle.cpf(ocfg, obs, seed=5, filter_id=b)
+        assert np.max(np.abs(r["logz_t"][b] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ and int(r["path_index"][b]) == o["path_index"]

@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libcpimh.so")
-UNITS = (["model_ar16.cu", "model_ar10.cu", "model_lorenz16.cu", "model_ar8.cu", "model_lorenz8.cu", "model_ar5.cu", "model_sk.cu", "model_sv.cu", "model_lorenz4.cu",
-          "model_ar4.cu", "model_ar3.cu", "model_ar2.cu", "model_ar1.cu", "model_gss.cu"]      # slowest first
+UNITS = (["model_ar%d.cu" % d for d in range(16, 4, -1)] + ["model_lorenz16.cu", "model_lorenz8.cu", "model_sk.cu", "model_sv.cu", "model_lorenz4.cu",
+          "model_ar4.cu", "model_ar3.cu", "model_ar2.cu", "model_ar1.cu", "model_gss.cu"]      # slowest first; get_ar(d) for every d <= 16
          + ["api.cu", "api_chains.cu", "api_ccpf.cu", "primitives.cu", "lorenz_wide.cu", "wide.cu"])
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 }
 
 const ModelEntry* find_entry(int model, int dim) {
-  const ModelEntry* (*tables[])(int*) = {entries_gss, entries_ar1, entries_ar2, entries_ar3, entries_ar4, entries_ar5, entries_ar8, entries_ar10, entries_ar16,
+  const ModelEntry* (*tables[])(int*) = {entries_gss, entries_ar1, entries_ar2, entries_ar3, entries_ar4, entries_ar5, entries_ar6, entries_ar7, entries_ar8, entries_ar9, entries_ar10, entries_ar11, entries_ar12, entries_ar13, entries_ar14, entries_ar15, entries_ar16,
                                           entries_sv, entries_sk, entries_lorenz4, entries_lorenz8, entries_lorenz16};
   for (auto tf : tables) {
     int n = 0;

@@ -24,7 +24,7 @@
 
 namespace cpimh {
 
-#define CPIMH_RING 32          // proposals of one replicate that may be in flight / waiting for the in-order replay
+#define CPIMH_RING 128         // proposals of one replicate that may be in flight / waiting for the in-order replay (a power of two)
 
 struct ChainParams {
   PfParams pf;                 // workspace slot = blockIdx.x.  pf.traj / pf.logz / pf.status / pf.exp_path ARE the proposal rings:
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
         else { ist[9] = 1; ist[10] = (int)r; ist[11] = slot; ist[12] = 0; ist[13] = (int)r; cp.next_iter[slot] = 1; cp.iter_done[slot] = 0; }
       }
       // nobody else touches this slot now: helpers exist only once the tickets have run out, and then no slot starts a new replicate
-      if (tid < CPIMH_RING) cp.ring_tag[slot * CPIMH_RING + tid] = -1;
+      for (int i = tid; i < CPIMH_RING; i += NT) cp.ring_tag[slot * CPIMH_RING + i] = -1;
       __syncthreads();
     } else if (ist[9] == 1) {                                                     // owner: claim the replicate's next proposal
       __syncthreads();

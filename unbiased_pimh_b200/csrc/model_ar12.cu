@@ -1,0 +1,9 @@
+// model_ar12.cu -- kernel instantiations for get_ar(12) (one translation unit per dimension: they compile in parallel)
+#include "registry.h"
+namespace cpimh {
+const ModelEntry* entries_ar12(int* n) {
+  static const ModelEntry e[] = {make_entry<ArModel<12>>(CPIMH_MODEL_AR)};
+  *n = 1;
+  return e;
+}
+}  // namespace cpimh

@@ -1,0 +1,9 @@
+// model_ar13.cu -- kernel instantiations for get_ar(13) (one translation unit per dimension: they compile in parallel)
+#include "registry.h"
+namespace cpimh {
+const ModelEntry* entries_ar13(int* n) {
+  static const ModelEntry e[] = {make_entry<ArModel<13>>(CPIMH_MODEL_AR)};
+  *n = 1;
+  return e;
+}
+}  // namespace cpimh

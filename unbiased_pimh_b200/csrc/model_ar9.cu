@@ -1,0 +1,9 @@
+// model_ar9.cu -- kernel instantiations for get_ar(9) (one translation unit per dimension: they compile in parallel)
+#include "registry.h"
+namespace cpimh {
+const ModelEntry* entries_ar9(int* n) {
+  static const ModelEntry e[] = {make_entry<ArModel<9>>(CPIMH_MODEL_AR)};
+  *n = 1;
+  return e;
+}
+}  // namespace cpimh

@@ -43,8 +43,16 @@ const ModelEntry* entries_ar2(int* n);
 const ModelEntry* entries_ar3(int* n);
 const ModelEntry* entries_ar4(int* n);
 const ModelEntry* entries_ar5(int* n);
+const ModelEntry* entries_ar6(int* n);
+const ModelEntry* entries_ar7(int* n);
 const ModelEntry* entries_ar8(int* n);
+const ModelEntry* entries_ar9(int* n);
 const ModelEntry* entries_ar10(int* n);
+const ModelEntry* entries_ar11(int* n);
+const ModelEntry* entries_ar12(int* n);
+const ModelEntry* entries_ar13(int* n);
+const ModelEntry* entries_ar14(int* n);
+const ModelEntry* entries_ar15(int* n);
 const ModelEntry* entries_ar16(int* n);
 const ModelEntry* entries_sv(int* n);
 const ModelEntry* entries_sk(int* n);
