@@ -153,6 +153,10 @@ int cpimh_pf_effective_config(const cpimh_pf* h, cpimh_config* out);
  * cpimh_release_cached() frees them, and so does any allocation that would otherwise run out of memory. */
 int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nfilters, uint64_t seed, uint64_t first_filter,
                    const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index);
+/* CPF(..., all_particles = TRUE) for B filters (R/CPF.R:73-76, the *_all_particles PIMH kernels R/pf_kernels.R:147-223):
+ * exp_path [B] x (d x (T+1)) is the weighted average of all N paths of each filter */
+int cpimh_pf_batch_all_particles(const cpimh_config* cfg, const double* obs_host, int64_t nfilters, uint64_t seed, uint64_t first_filter,
+                                 double* logz, double* trajectory, double* exp_path);
 int cpimh_release_cached(void);
 
 /* ============================== coupled PIMH ==============================

@@ -8,6 +8,7 @@
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
 #include <R_ext/Random.h>
+#include <math.h>
 #include <stdint.h>
 #include "cpimh.h"
 
@@ -127,7 +128,8 @@ SEXP _CoupledPIMH_dobs_SVLevy_cpp(SEXP Yt, SEXP Xts, SEXP mu, SEXP beta, SEXP lo
   double* x = (double*)R_alloc(2 * N, sizeof(double));
   for (int i = 0; i < N; i++) { x[2 * i] = REAL(Xts)[i]; x[2 * i + 1] = REAL(Xts)[N + i]; }
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, 1, N));
-  check(cpimh_model_dmeasurement(&c, x, REAL(Yt), REAL(out)));
+  check(cpimh_model_dmeasurement(&c, x, REAL(Yt), REAL(out)));                            /* log density */
+  if (!Rf_asLogical(log_)) for (int i = 0; i < N; i++) REAL(out)[i] = exp(REAL(out)[i]);  /* dobs_SVLevy_cpp(..., log = FALSE), src/SVLevy_functions.cpp:78 */
   UNPROTECT(1); return out;
 }
 
@@ -148,15 +150,42 @@ SEXP cpimh_R_tree_retrieve_xgeneration(SEXP p, SEXP lag) {
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, N)); check(cpimh_tree_retrieve_xgeneration(t, Rf_asInteger(lag), REAL(out))); UNPROTECT(1); return out;
 }
 
+/* fields of the module class (src/tree.cpp:146-154): which = 0 N, 1 M, 2 dimx, 3 nsteps, 4 a_star, 5 o_star, 6 x_star, 7 l_star */
+SEXP cpimh_R_tree_field(SEXP p, SEXP which) {
+  cpimh_tree* t = (cpimh_tree*)R_ExternalPtrAddr(p); int N, M, d, ns, w = Rf_asInteger(which);
+  check(cpimh_tree_fields(t, &N, &M, &d, &ns));
+  if (w < 4) { SEXP out = PROTECT(Rf_allocVector(INTSXP, 1)); INTEGER(out)[0] = w == 0 ? N : w == 1 ? M : w == 2 ? d : ns; UNPROTECT(1); return out; }
+  if (w == 6) { SEXP out = PROTECT(Rf_allocMatrix(REALSXP, d, M)); check(cpimh_tree_arrays(t, NULL, NULL, NULL, REAL(out))); UNPROTECT(1); return out; }
+  SEXP out = PROTECT(Rf_allocVector(INTSXP, w == 7 ? N : M));
+  check(cpimh_tree_arrays(t, w == 4 ? INTEGER(out) : NULL, w == 5 ? INTEGER(out) : NULL, w == 7 ? INTEGER(out) : NULL, NULL));
+  UNPROTECT(1); return out;
+}
+SEXP cpimh_R_tree_reset(SEXP p) { check(cpimh_tree_reset((cpimh_tree*)R_ExternalPtrAddr(p))); return R_NilValue; }
+
 /* ---- batched entries the R closures dispatch to by model name ---- */
-SEXP cpimh_R_pf_batch(SEXP cfg_raw, SEXP obs, SEXP nfilters) {                           /* CPF(ref=NULL), R/CPF.R:14-78, B at once */
+SEXP cpimh_R_pf_batch(SEXP cfg_raw, SEXP obs, SEXP nfilters, SEXP all_particles) {       /* CPF(ref=NULL[, all_particles]), R/CPF.R:14-78, B at once */
   const cpimh_config* cfg = (const cpimh_config*)RAW(cfg_raw);
-  int B = Rf_asInteger(nfilters), d = cfg->dim, T = cfg->nobs;
+  int B = Rf_asInteger(nfilters), d = cfg->dim, T = cfg->nobs, ap = Rf_asLogical(all_particles);
   SEXP logz = PROTECT(Rf_allocVector(REALSXP, B));
   SEXP traj = PROTECT(Rf_alloc3DArray(REALSXP, d, T + 1, B));
-  check(cpimh_pf_batch(cfg, REAL(obs), B, seed_from_R(), 0, NULL, REAL(logz), NULL, REAL(traj), NULL));
-  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2)); SET_VECTOR_ELT(out, 0, logz); SET_VECTOR_ELT(out, 1, traj);
-  UNPROTECT(3); return out;
+  SEXP expp = PROTECT(Rf_alloc3DArray(REALSXP, d, T + 1, ap ? B : 0));                  /* exp_path (R/CPF.R:73-76) */
+  if (ap) check(cpimh_pf_batch_all_particles(cfg, REAL(obs), B, seed_from_R(), 0, REAL(logz), REAL(traj), REAL(expp)));
+  else check(cpimh_pf_batch(cfg, REAL(obs), B, seed_from_R(), 0, NULL, REAL(logz), NULL, REAL(traj), NULL));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)); SET_VECTOR_ELT(out, 0, logz); SET_VECTOR_ELT(out, 1, traj); SET_VECTOR_ELT(out, 2, expp);
+  UNPROTECT(4); return out;
+}
+/* pf(y, theta, model, nparticles, ess_threshold, systematic) for B filters (R/CPF.R:106-155): log-likelihood, filtering means
+ * per time step, one sampled path */
+SEXP cpimh_R_pf_adaptive(SEXP cfg_raw, SEXP obs, SEXP nfilters, SEXP ess_threshold, SEXP systematic) {
+  const cpimh_config* cfg = (const cpimh_config*)RAW(cfg_raw);
+  int B = Rf_asInteger(nfilters), d = cfg->dim, T = cfg->nobs;
+  SEXP ll = PROTECT(Rf_allocVector(REALSXP, B));
+  SEXP means = PROTECT(Rf_alloc3DArray(REALSXP, d, T, B));                               /* pf_means: [B][T][d] = d x T x B column-major */
+  SEXP path = PROTECT(Rf_alloc3DArray(REALSXP, d, T + 1, B));
+  check(cpimh_pf_adaptive_batch(cfg, REAL(obs), B, seed_from_R(), 0, Rf_asReal(ess_threshold), Rf_asLogical(systematic), REAL(ll), NULL,
+                                REAL(means), REAL(path), NULL, NULL));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3)); SET_VECTOR_ELT(out, 0, ll); SET_VECTOR_ELT(out, 1, means); SET_VECTOR_ELT(out, 2, path);
+  UNPROTECT(4); return out;
 }
 SEXP cpimh_R_coupled_pimh(SEXP cfg_raw, SEXP obs, SEXP R_, SEXP k_, SEXP K_, SEXP maxit) {   /* coupled_pimh_chains + H_bar, R/debiasing_algorithm.R:140-316 */
   const cpimh_config* cfg = (const cpimh_config*)RAW(cfg_raw);
@@ -202,7 +231,8 @@ static const R_CallMethodDef CallEntries[] = {
   ENTRY(_CoupledPIMH_create_A_, 2), ENTRY(_CoupledPIMH_one_step_lorenz_vector, 5),
   ENTRY(_CoupledPIMH_rinitial_SVLevy_cpp, 5), ENTRY(_CoupledPIMH_rtransition_SVLevy_cpp, 6), ENTRY(_CoupledPIMH_dobs_SVLevy_cpp, 5),
   ENTRY(cpimh_R_tree_new, 3), ENTRY(cpimh_R_tree_init, 2), ENTRY(cpimh_R_tree_update, 3), ENTRY(cpimh_R_tree_get_path, 2),
-  ENTRY(cpimh_R_tree_retrieve_xgeneration, 2), ENTRY(cpimh_R_pf_batch, 3), ENTRY(cpimh_R_coupled_pimh, 6),
+  ENTRY(cpimh_R_tree_retrieve_xgeneration, 2), ENTRY(cpimh_R_tree_field, 2), ENTRY(cpimh_R_tree_reset, 1),
+  ENTRY(cpimh_R_pf_batch, 4), ENTRY(cpimh_R_pf_adaptive, 5), ENTRY(cpimh_R_coupled_pimh, 6),
   ENTRY(cpimh_R_ccpf, 5), ENTRY(cpimh_R_coupled_ccpf, 8),
   {NULL, NULL, 0}};
 void R_init_CoupledPIMH(DllInfo* dll) { R_registerRoutines(dll, NULL, CallEntries, NULL, NULL); R_useDynamicSymbols(dll, FALSE); }

@@ -273,3 +273,22 @@ def test_get_ar_every_dimension_up_to_sixteen(up, oracle, d):
     for b in range(2):
         o = oracle.cpf(ocfg, obs, seed=5, filter_id=b)
         assert np.max(np.abs(r["logz_t"][b] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ and int(r["path_index"][b]) == o["path_index"]
+
+
+def test_one_shot_entries_cache_their_workspaces_and_match_the_handle_api(up, golden):
+    """cpimh_pf_batch / cpimh_pf_batch_all_particles (what the R shim calls) keep their HBM workspaces between calls: repeated
+    calls, calls with another configuration in between and calls after cpimh_release_cached() all return the handle API's bits."""
+    th, y = [0.5, math.sqrt(10.0)], golden["lgssm_y"][:30]
+    pb = up.PfBatch(up.get_ar(1), th, y, 128, 6); pb.all_particles(True); pb.run(6, 9, first_filter=2)
+    ref = pb.fetch(); ref_exp = pb.fetch_exp_paths(6); pb.close()
+    for rep in range(3):
+        r = up.cpf_batch(128, up.get_ar(1), th, y, 6, seed=9, first_filter=2)
+        assert np.array_equal(r["logz"], ref["logz"]) and np.array_equal(r["trajectory"], ref["trajectory"])
+        if rep == 0:
+            up.cpf_batch(64, up.get_gss(), [], golden["gss_y"][:10], 3, seed=1)          # evicts the cached handle
+        if rep == 1:
+            up.lib().cpimh_release_cached()
+    ra = up.cpf_batch(128, up.get_ar(1), th, y, 6, seed=9, first_filter=2, all_particles=True)
+    assert np.array_equal(ra["logz"], ref["logz"]) and np.array_equal(ra["exp_path"], ref_exp)
+    r = up.cpf_batch(128, up.get_ar(1), th, y, 4, seed=9, first_filter=2)                  # smaller batch reuses the larger handle
+    assert np.array_equal(r["logz"], ref["logz"][:4])

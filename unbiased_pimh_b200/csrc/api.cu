@@ -569,8 +569,8 @@ int cpimh_release_cached(void) {
   return cpimh_ccpf_release_cached();
 }
 
-int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
-                   const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
+static int pf_batch_cached(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
+                           const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index, double* exp_path) {
   CPIMH_REQUIRE(cfg && obs_host, "null argument");
   CPIMH_REQUIRE(B >= 1, "nfilters must be >= 1");
   std::lock_guard<std::recursive_mutex> lk(g_cache_mu);
@@ -587,8 +587,11 @@ int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, u
     rc = cpimh_pf_set_observations(h, obs_host);
     if (!rc) rc = cpimh_pf_set_noise(h, B, noise_host);                 // NULL clears noise left by an earlier call
     if (!rc) rc = cpimh_pf_record_ancestors(h, 0);
+    if (!rc && !h->wide) rc = cpimh_pf_all_particles(h, exp_path ? 1 : 0);
+    if (!rc && h->wide && exp_path) { set_error("all-particle outputs are not available for the wide (d = 32/64) filter"); rc = CPIMH_ERR_INVALID; }
     if (!rc) rc = cpimh_pf_run(h, B, seed, first_filter, nullptr);
     if (!rc) rc = cpimh_pf_fetch(h, B, nullptr, logz, logz_t, trajectory, path_index);
+    if (!rc && exp_path) rc = cpimh_pf_fetch_exp_paths(h, B, nullptr, exp_path);
     if (rc != CPIMH_ERR_TREE_OVERFLOW) {
       if (rc) { cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0; }   // do not keep a handle in an unknown state
       return rc;
@@ -599,6 +602,16 @@ int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, u
     c.store_paths = 3;          // Tree::double_size (src/tree.cpp:101-116): rerun with twice the capacity (same streams => same draws)
   }
   return CPIMH_ERR_TREE_OVERFLOW;
+}
+
+int cpimh_pf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
+                   const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
+  return pf_batch_cached(cfg, obs_host, B, seed, first_filter, noise_host, logz, logz_t, trajectory, path_index, nullptr);
+}
+int cpimh_pf_batch_all_particles(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
+                                 double* logz, double* trajectory, double* exp_path) {
+  CPIMH_REQUIRE(exp_path, "null argument");
+  return pf_batch_cached(cfg, obs_host, B, seed, first_filter, nullptr, logz, nullptr, trajectory, nullptr, exp_path);
 }
 
 }  // extern "C"

@@ -130,8 +130,20 @@ class PfBatch:
                 "path_storage": {0: "none", 2: "dense", 3: "tree"}.get(c.store_paths, str(c.store_paths))}
 
 
-def cpf_batch(nparticles, model, theta, observations, nfilters, seed=None, first_filter=0, noise=None, logz_t=False, **kw):
-    """B independent CPF(nparticles, model, theta, observations) runs through the one-shot host API (cpimh_pf_batch)."""
+def cpf_batch(nparticles, model, theta, observations, nfilters, seed=None, first_filter=0, noise=None, logz_t=False, all_particles=False, **kw):
+    """B independent CPF(nparticles, model, theta, observations[, all_particles = TRUE]) runs through the one-shot host API
+    (cpimh_pf_batch / cpimh_pf_batch_all_particles: the entries the R shim calls; their HBM workspaces stay cached in the library)."""
+    if all_particles:
+        obs = np.asarray(observations, dtype=np.float64)
+        T = obs.shape[0]
+        cfg = model.config(nparticles, theta, nobs=T, **kw)
+        ob = L.obs_matrix(obs, T)
+        B, d = int(nfilters), model.dimension
+        logz, traj, ep = np.empty(B), np.empty((B, T + 1, d)), np.empty((B, T + 1, d))
+        seed = rng.next_seed() if seed is None else int(seed)
+        L.check(L.lib().cpimh_pf_batch_all_particles(C.byref(cfg), ob.ctypes.data_as(C.c_void_p), C.c_int64(B), C.c_uint64(seed), C.c_uint64(int(first_filter)),
+                                                      L.ptr(logz), L.ptr(traj), L.ptr(ep)))
+        return {"logz": logz, "trajectory": traj.transpose(0, 2, 1), "exp_path": ep.transpose(0, 2, 1)}
     obs = np.asarray(observations, dtype=np.float64)
     T = obs.shape[0]
     cfg = model.config(nparticles, theta, nobs=T, **kw)
