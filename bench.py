@@ -461,6 +461,10 @@ def main():
         roof["note"] = "dominant (only) kernel pf_batch_kernel; bound by warp-instruction issue (fp64 log/exp, Philox), not by HBM: see roofline_secondary"
         if sec is not None:
             sec["fp64_fma_peak_tflops"] = fp64_peak
+            prop = torch.cuda.get_device_properties(local)
+            mhz = (main_res["clocks"] or {}).get("sm_mhz") or 1965.0
+            sec["peak_theoretical"] = prop.multi_processor_count * 4 * mhz * 1e6 / 1e9      # SMs x 4 schedulers x clock
+            sec["frac_of_theoretical"] = sec["achieved"] / sec["peak_theoretical"]
         line = {"metric": "particle-steps/sec", "value": main_res["value"], "unit": "particle-steps/s", "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["name"], "filters_per_gpu": w["B"], "nparticles": w["N"], "nobs": w["T"], "state_dim": w["d"],
