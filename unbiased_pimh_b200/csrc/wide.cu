@@ -28,6 +28,8 @@ struct WideParams {
   double F, sx, sy, isy, cst;     // isy = 1 / sy
   double* hist_x; int* hist_a;
   double* lw; double* C; double* S;
+  // two-level CDF (round 2): per-group inclusive sums instead of per-particle scans; lw is double-buffered by step parity
+  double* lw2; double* GC; double* GP; double* fac; int two_level;
   double* pmax; double* psum; double* pv; double* mstep; double* ptot;
   double* logz_t; double* logz; double* traj; int* path_index;
   const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_path;
@@ -64,7 +66,7 @@ __global__ void wide_init_kernel(WideParams p) {
 }
 
 // ------------------------------------------------------------------ one time step for all particles of all filters
-template <int C>
+template <int C, bool TWO>
 __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, int t, int ident, int prep_next) {
   constexpr int D = 32 * C;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -81,7 +83,14 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
 #pragma unroll
   for (int c = 0; c < C; c++) yv[c] = y[lane * C + c];
   const double h = 0.05 / (double)p.substeps;
-  const double scale = ident ? 0.0 : (p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b]);   // u = sumw e_k  /  (sumw / total) P_k
+  // TWO: the CDF is kept as inclusive sums GC of the G-particle groups (wide_group_scan_kernel) + the group-scaled numerators
+  // lw of the previous step (factor fac per group); likewise the sorted-uniform ladder as group sums GP + the spacings S
+  const double* GCb = TWO ? p.GC + (size_t)b * p.GX : nullptr;
+  const double* GPb = TWO ? p.GP + (size_t)b * p.GX : nullptr;
+  const double* facb = TWO ? p.fac + (size_t)b * p.GX : nullptr;
+  const double* lwold = (TWO ? ((t & 1) ? p.lw2 : p.lw) : p.lw) + (size_t)b * N;           // written by step t-1
+  double* lwnew = (TWO ? ((t & 1) ? p.lw : p.lw2) : p.lw) + (size_t)b * N;
+  const double scale = ident ? 0.0 : (TWO ? GCb[p.GX - 1] / p.ptot[b] : (p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b]));   // u = sumw e_k  /  (sumw / total) P_k
   // persistent warps: group g = G consecutive particles; the grid covers the machine once and strides over the groups
   for (int grp = blockIdx.x * nwarp + warp; grp < p.GX; grp += gridDim.x * nwarp) {
     const long long base = (long long)grp << p.gshift;
@@ -91,10 +100,31 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
     int a = 0;
     if (mine) {
       if (ident) a = (int)k;
-      else {
+      else if (!TWO) {
         a = g_count_le_w(Cb, N, scale * Sb[k]);
         if (a >= N) a = N - 1;
       }
+    }
+    if (TWO && !ident) {
+      // sorted uniform of particle k: (sum of the earlier groups' spacings + prefix inside the group) * scale
+      double e = mine ? Sb[k] : 0.0;
+      e = warp_incl_scan(e, lane);
+      if (mine) {
+        const double u = scale * ((grp > 0 ? GPb[grp - 1] : 0.0) + e);
+        int gs = g_count_le_w(GCb, p.GX, u);                      // groups whose last knot is <= u
+        if (gs >= p.GX) gs = p.GX - 1;
+        double acc = gs > 0 ? GCb[gs - 1] : 0.0;
+        const double f = facb[gs];
+        const long long j0 = (long long)gs << p.gshift;
+        const int cnt = (int)min((long long)G, (long long)N - j0);
+        a = (int)j0 + cnt - 1;
+        for (int j = 0; j < cnt; j++) {                            // knots inside the group, left to right (src/multinomial.cpp:25-28 rule)
+          acc += lwold[j0 + j] * f;
+          if (acc > u) { a = (int)j0 + j; break; }
+        }
+      }
+    }
+    if (mine) {
       ha[k] = a;
       if (p.anc_rec) p.anc_rec[((size_t)b * p.T + (t - 1)) * N + k] = a;
     }
@@ -130,7 +160,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
     double w = 0.0, v = 0.0;
     if (mine) {
       w = (mg == -INFINITY) ? 0.0 : exp(mylw - mg);                                    // R/CPF.R:62, group-local scaling
-      p.lw[(size_t)b * N + k] = w;        // NOT into C: other warps of this launch are still searching the CDF
+      lwnew[k] = w;                       // NOT into C / the buffer being searched: other warps of this launch still read them
       if (prep_next) {
         if (p.inj_resample) v = p.inj_resample[((size_t)b * p.T + t) * N + k];         // row of step t+1
         else v = -rng_log(philox_u1(s, (unsigned)k, t + 1, CPIMH_P_RESAMPLE, 0));
@@ -231,6 +261,44 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   }
 }
 
+// ------------------------------------------------------------------ two-level variant of the step's normalisation (round 2):
+// one CTA per filter turns the per-group maxima / sums that wide_propagate left into (a) log Z_t, (b) the factor exp(m_g - m) of
+// every group, (c) the inclusive CDF over GROUPS and (d) the inclusive ladder sums over groups.  The per-particle CDF and ladder
+// are never materialised: wide_propagate<.., true> searches the group table and then walks the G weights of one group.
+// 4096 groups instead of 65536 particles, no cluster, no per-particle pass: ~5 us instead of ~23 us per step at N = 65536.
+#define WIDE_MAX_GROUPS 8192
+__global__ void __launch_bounds__(1024, 1) wide_group_scan_kernel(WideParams p, int t_done, int prep) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  double* bw = reinterpret_cast<double*>(raw);      // [GX] group weights -> inclusive CDF
+  double* bv = bw + p.GX;                           // [GX] group spacing sums -> inclusive ladder
+  __shared__ double scr[32];
+  const int b = blockIdx.x, GX = p.GX, N = p.N;
+  double m = -INFINITY;
+  for (int g = threadIdx.x; g < GX; g += blockDim.x) m = fmax(m, p.pmax[(size_t)b * GX + g]);
+  m = block_max(m, scr);
+  for (int g = threadIdx.x; g < GX; g += blockDim.x) {
+    const double mc = p.pmax[(size_t)b * GX + g];
+    const double f = (mc == -INFINITY) ? 0.0 : exp(mc - m);
+    p.fac[(size_t)b * GX + g] = f;
+    bw[g] = p.psum[(size_t)b * GX + g] * f;
+    bv[g] = p.pv[(size_t)b * GX + g];
+  }
+  __syncthreads();
+  block_scan_inplace<false>(bw, GX, scr);
+  if (prep) block_scan_inplace<false>(bv, GX, scr);
+  for (int g = threadIdx.x; g < GX; g += blockDim.x) {
+    p.GC[(size_t)b * GX + g] = bw[g];
+    if (prep) p.GP[(size_t)b * GX + g] = bv[g];
+  }
+  if (threadIdx.x == 0) {
+    p.logz_t[(size_t)b * p.T + (t_done - 1)] = log(bw[GX - 1] / (double)N) + m;   // R/CPF.R:66
+    if (prep) {
+      const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+      p.ptot[b] = bv[GX - 1] - rng_log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
+    }
+  }
+}
+
 // ------------------------------------------------------------------ final path: systematic(normw, 1, u) + get_path (R/CPF.R:69)
 template <int C>
 __global__ void wide_path_kernel(WideParams p) {
@@ -262,7 +330,7 @@ struct WideFilter {
   int GX, G, gshift, pgrid, record_anc;
   std::vector<double> obs_host;
   DevBuf ptot;
-  DevBuf obs, hist_x, hist_a, lw, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
+  DevBuf obs, hist_x, hist_a, lw, lw2, GC, GP, fac, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
   DevBuf inj_init, inj_trans, inj_resample, inj_path;
   bool have_inj[4];
 };
@@ -307,6 +375,10 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   if (!rc) rc = A(h->hist_x, sizeof(double) * B * (T + 1) * N * D);
   if (!rc) rc = A(h->hist_a, sizeof(int) * B * T * N);
   if (!rc) rc = A(h->lw, sizeof(double) * B * N);
+  if (!rc) rc = A(h->lw2, sizeof(double) * B * N);
+  if (!rc) rc = A(h->GC, sizeof(double) * B * h->GX);
+  if (!rc) rc = A(h->GP, sizeof(double) * B * h->GX);
+  if (!rc) rc = A(h->fac, sizeof(double) * B * h->GX);
   if (!rc) rc = A(h->C, sizeof(double) * B * N);
   if (!rc) rc = A(h->S, sizeof(double) * B * N);
   if (!rc) rc = A(h->pmax, sizeof(double) * B * h->GX);
@@ -325,7 +397,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
 
 void wide_destroy(WideFilter* h) {
   if (!h) return;
-  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
+  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->lw2, &h->GC, &h->GP, &h->fac, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
                    &h->path_index, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
@@ -374,17 +446,24 @@ static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   auto is_ident = [&](int t) { return (t == 1) || isnan(h->obs_host[(size_t)(t - 2) * p.D]); };   // R/CPF.R:38-40
   const size_t wsmem = (WIDE_TILE + WIDE_MAX_BLOCKS_PER_CTA) * sizeof(double);
   CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_weights_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+  const size_t gsmem = 2 * (size_t)p.GX * sizeof(double);
+  if (p.two_level) CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_group_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
   for (int t = 1; t <= T; t++) {
     const int ident = is_ident(t);
     if (t >= 2) {
-      wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, t - 1, ident ? 0 : 1);
+      if (p.two_level) wide_group_scan_kernel<<<B, 1024, gsmem, s>>>(p, t - 1, ident ? 0 : 1);
+      else wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, t - 1, ident ? 0 : 1);
       h->launches += 1;
     }
     const int prep_next = (t < T && !is_ident(t + 1)) ? 1 : 0;
-    wide_propagate_kernel<C><<<gp, 128, 0, s>>>(p, t, ident, prep_next);
+    if (p.two_level) wide_propagate_kernel<C, true><<<gp, 128, 0, s>>>(p, t, ident, prep_next);
+    else wide_propagate_kernel<C, false><<<gp, 128, 0, s>>>(p, t, ident, prep_next);
     h->launches++;
   }
-  wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, T, 0);
+  // the last step's weights as a normalised per-particle CDF: the final path pick (R/CPF.R:69) and log Z_T
+  WideParams pl = p;
+  if (p.two_level && (T & 1) == 0) pl.lw = p.lw2;           // step T wrote the buffer of its parity
+  wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(pl, T, 0);
   wide_path_kernel<C><<<B, 32, 0, s>>>(p);
   h->launches += 2;
   CPIMH_CUDA_CHECK(cudaGetLastError());
@@ -404,6 +483,9 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);                               // src/mvnorm.cpp:120-121
   p.cst = -(hl) - (c.dim * CPIMH_HALF_LOG_2PI_TRUNC);
   p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.lw = h->lw.as<double>(); p.C = h->C.as<double>(); p.S = h->S.as<double>();
+  p.lw2 = h->lw2.as<double>(); p.GC = h->GC.as<double>(); p.GP = h->GP.as<double>(); p.fac = h->fac.as<double>();
+  // the two-level CDF serves the Philox path; injected sorted uniforms (parity runs) keep the per-particle scans
+  p.two_level = (!h->have_inj[2] && h->GX <= WIDE_MAX_GROUPS) ? 1 : 0;
   p.pmax = h->pmax.as<double>(); p.psum = h->psum.as<double>(); p.pv = h->pv.as<double>(); p.mstep = h->mstep.as<double>(); p.ptot = h->ptot.as<double>();
   p.logz_t = h->logz_t.as<double>(); p.logz = h->logz.as<double>(); p.traj = h->traj.as<double>(); p.path_index = h->path_index.as<int>();
   p.inj_init = h->have_inj[0] ? h->inj_init.as<double>() : nullptr;
