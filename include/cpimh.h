@@ -233,6 +233,13 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nf
 int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, int with_as, cpimh_chain_out* out_host);
 
+/* rheeglynn_estimator(observations, model, theta, algoparameters) -- R/rheeglynn_estimator.R:14-66 -- for R replicates: X_0 +
+ * sum_n (X_n - X~_{n-1}) / (1 - lambda)^n over coupled conditional filters until the references meet or, with lambda > 0, until
+ * the replicate's geometric truncation variable truncation[r] (host, R draws of rgeom(1, lambda); 0 => the estimate is X_0).
+ * lambda = 0: no truncation (truncation may be NULL).  out->hbar holds the estimates, out->iteration the iterations run. */
+int cpimh_rheeglynn(const cpimh_config* cfg, const double* obs_host, int64_t nreplicates, uint64_t seed, uint32_t first_replicate,
+                    double lambda, const int32_t* truncation, int max_iterations, int with_as, cpimh_chain_out* out_host);
+
 /* ============================== pf(): ESS-adaptive bootstrap filter ==============================
  * pf(y, theta, model, nparticles, ess_threshold = 1, systematic = FALSE) -- R/CPF.R:106-155, B filters at once (the PMMH
  * likelihood evaluator): propagate, weigh with the carried log-weights, resample iff (1 / sum(w^2)) / N < ess_threshold by

@@ -270,3 +270,35 @@ def test_sharded_ccpf_estimator_single_process(up, golden):
     assert est["nreplicates"] == 300 and est["nfilters"] == g["nfilters"]
     assert np.allclose(est["mean"], g["hbar"].mean(axis=0), rtol=1e-12, atol=1e-12)
     assert np.allclose(est["se"], g["hbar"].std(axis=0, ddof=1) / math.sqrt(300), rtol=1e-9, atol=1e-12)
+
+
+def test_rheeglynn_estimator_with_geometric_truncation(up, oracle, golden):
+    """rheeglynn_estimator with lambda > 0 (R/rheeglynn_estimator.R:24-31, 58-59): the sum of differences stops at the geometric
+    truncation variable and difference n is divided by the survival probability (1 - lambda)^n.  Expected values are rebuilt from
+    the oracle's recorded coupled chains (samples1[n] = X_n, samples2[n-1] = X~_{n-1}) run to the same truncation."""
+    import ctypes as C
+    from unbiased_pimh_b200 import _lib as L
+    y, th = golden["lgssm_y"][:40], [0.5, math.sqrt(10.0)]
+    N, T, R, seed, lam = 32, 40, 12, 21, 0.2
+    trunc = np.array([0, 1, 2, 3, 5, 8, 50, 50, 4, 1, 2, 50], dtype=np.int32)
+    model = up.get_ar(1)
+    cfg = model.config(N, th, nobs=T)
+    hb, it, mt = np.empty((R, T + 1, 1)), np.empty(R, dtype=np.int32), np.empty(R, dtype=np.int32)
+    o = L.ChainOut(); o.hbar, o.iteration, o.meetingtime = hb.ctypes.data, it.ctypes.data, mt.ctypes.data
+    L.check(L.lib().cpimh_rheeglynn(C.byref(cfg), L.obs_matrix(y, T).ctypes.data_as(C.c_void_p), C.c_int64(R), C.c_uint64(seed), C.c_uint32(3),
+                                    C.c_double(lam), L.ptr(trunc), C.c_int(-1), C.c_int(0), C.byref(o)))
+    ocfg = oracle.make_config(oracle.MODEL_AR, 1, 1, N, T, theta=th)
+    for r in range(R):
+        if trunc[r] == 0:
+            c = oracle.coupled_ccpf_chains(ocfg, y, seed, 3 + r, K=0, max_iterations=1)
+            exp = c["samples1"][0]
+        else:
+            c = oracle.coupled_ccpf_chains(ocfg, y, seed, 3 + r, K=0, max_iterations=int(trunc[r]))
+            exp = c["samples1"][0].copy()
+            for n in range(1, c["iteration"] + 1):
+                exp = exp + (c["samples1"][n] - c["samples2"][n - 1]) / (1.0 - lam) ** n
+            assert it[r] == c["iteration"] <= trunc[r]
+        assert np.allclose(hb[r, :, 0], exp, rtol=1e-9, atol=1e-9), r
+    # the R-shaped front end draws the truncation itself and returns it
+    e = up.rheeglynn_estimator(y, model, th, {"nparticles": N, "with_as": False, "lambda": 0.3}, seed=5)
+    assert e["estimate"].shape == (1, T + 1) and e["truncation"] >= 0 and e["iteration"] <= max(e["truncation"], 0) and np.all(np.isfinite(e["estimate"]))

@@ -200,6 +200,14 @@ def test_round_based_driver_equals_persistent_kernel(up, oracle, golden):
         assert np.allclose(a["sum_hbar"], b["sum_hbar"], rtol=1e-13)
         if mi == 6:
             assert a["iteration"].max() <= 6 and np.any(a["meetingtime"] < 0)      # hit max_iterations before meeting
+            # such replicates are reported as not finished (c_chains$finished, R/debiasing_algorithm.R:262) and stay OUT of the
+            # sums the estimator averages (H_bar refuses a chain with K > iteration); round 1 averaged their truncated H_bar in
+            for r in (a, b):
+                fin = r["finished"]
+                assert np.array_equal(fin, r["meetingtime"] > 0) and r["nfinished"] == int(fin.sum()) and 0 < r["nfinished"] < R
+                assert np.allclose(r["sum_hbar"], r["hbar"][fin].sum(axis=0), rtol=1e-12, atol=1e-12)
+        else:
+            assert a["finished"].all() and a["nfinished"] == R
     cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 20, 100, theta=th)
     o = oracle.coupled_pimh_batch(cfg, y, 12, 3, 200, k=0, K=1)
     assert np.array_equal(b["meetingtime"][:0], o["meetingtime"][:0])

@@ -201,10 +201,10 @@ struct CcChainCache {
   cpimh_pf* pf = nullptr;
   cpimh_config pf_cfg;
   int64_t pf_R = 0;
-  DevBuf st1, st2, n1, n2, lz1, lz2, nlz, nst, single, iter, tau, status, accH, accD, hbar, bc, cnt, nf, sums, pst1, pst2;
+  DevBuf st1, st2, n1, n2, lz1, lz2, nlz, nst, single, iter, tau, status, accH, accD, hbar, bc, cnt, nf, sums, pst1, pst2, trunc;
   DevBuf e1, e2, ne1, ne2, accHe, accDe, hbar_rb, sums_rb;
   void release() {
-    DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &cnt, &nf, &sums, &pst1, &pst2,
+    DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &cnt, &nf, &sums, &pst1, &pst2, &trunc,
                      &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb, &w.obs, &w.theta, &w.pre, &w.hist_x, &w.hist_a};
     for (auto x : all) x->release();
     if (pf) { cpimh_pf_destroy(pf); pf = nullptr; pf_R = 0; }
@@ -219,8 +219,19 @@ int cpimh_ccpf_release_cached(void) {
   return CPIMH_OK;
 }
 
+static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
+                             int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o);
 int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
                        int k, int K, int max_iterations, int with_as, cpimh_chain_out* o) {
+  return coupled_ccpf_impl(cfg, obs_host, R, seed, first_replicate, k, K, max_iterations, with_as, 0.0, nullptr, o);
+}
+int cpimh_rheeglynn(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
+                    double lambda, const int32_t* truncation, int max_iterations, int with_as, cpimh_chain_out* o) {
+  CPIMH_REQUIRE(lambda == 0.0 || (lambda > 0.0 && lambda < 1.0 && truncation), "lambda must be 0, or in (0, 1) with one truncation variable per replicate");
+  return coupled_ccpf_impl(cfg, obs_host, R, seed, first_replicate, 0, 0, max_iterations, with_as, lambda, lambda > 0.0 ? truncation : nullptr, o);
+}
+static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
+                             int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o) {
   CPIMH_REQUIRE(cfg && obs_host && o, "null argument");
   CPIMH_REQUIRE(R >= 1, "nreplicates must be >= 1");
   CPIMH_REQUIRE(k >= 0 && K >= k, "need 0 <= k <= K (got k=%d K=%d)", k, K);
@@ -290,6 +301,11 @@ int cpimh_coupled_ccpf(const cpimh_config* cfg, const double* obs_host, int64_t 
   q.accH = g.accH.as<double>(); q.accD = g.accD.as<double>(); q.hbar = g.hbar.as<double>(); q.bc = g.bc.as<double>();
   q.nfilters = g.nf.as<unsigned long long>();
   q.next_active = nullptr; q.next_count = nullptr;       // no active lists: the persistent kernel takes replicates from a ticket counter
+  if (truncation) {
+    rc = g.trunc.alloc(sizeof(int) * (size_t)R); if (rc) return rc;
+    CPIMH_CUDA_CHECK(cudaMemcpyAsync(g.trunc.p, truncation, sizeof(int) * (size_t)R, cudaMemcpyHostToDevice, s));
+    q.trunc = g.trunc.as<int>(); q.rg_lambda = rg_lambda;
+  }
   if (rb) {
     q.newe1 = g.ne1.as<double>(); q.newe2 = g.ne2.as<double>(); q.e1 = g.e1.as<double>(); q.e2 = g.e2.as<double>();
     q.accHe = g.accHe.as<double>(); q.accDe = g.accDe.as<double>(); q.hbar_rb = g.hbar_rb.as<double>();

@@ -368,6 +368,9 @@ struct CcRound {
   unsigned long long* nfilters;
   // Rao-Blackwellised twin (null when off): exp paths of the new filters / of the current states, accumulators, output
   const double* newe1; const double* newe2; double* e1; double* e2; double* accHe; double* accDe; double* hbar_rb;
+  // Rhee-Glynn estimator with geometric truncation (R/rheeglynn_estimator.R:24-31, 58-59): per-replicate truncation variable (null:
+  // none) and the parameter lambda of its law; difference n is divided by the survival probability (1 - lambda)^n
+  const int* trunc; double rg_lambda;
 };
 // one step of the lag-one recursion of replicate `rep` after its iteration-`it` filter(s) (R/debiasing_algorithm.R:50-106, 296-312);
 // all threads of the CTA call; returns != 0 when the replicate is finished
@@ -385,7 +388,8 @@ __device__ inline int cc_accept(const CcRound& q, int rep, int it) {
   if (status == 0 && isnan(q.new_logz[rep])) status = CPIMH_ERR_INVALID;
   const int t = it - 1;
   const bool mcmc = (it >= q.k && it <= q.K);
-  const double coef = (double)min(t - q.k + 1, q.K - q.k + 1);
+  double coef = (double)min(t - q.k + 1, q.K - q.k + 1);
+  if (q.rg_lambda > 0.0) coef = coef / pow(1.0 - q.rg_lambda, (double)it);             // / survival_probabilities[iteration]
   int same = 1;
   for (int j = threadIdx.x; j < PD; j += blockDim.x) {
     const double xa = n1[j];
@@ -399,6 +403,7 @@ __device__ inline int cc_accept(const CcRound& q, int rep, int it) {
   if (status) finished = 1;
   if (it >= 2 && !single && same && tau < 0) tau = it;                         // :82-86 all(chain_state1 == chain_state2)
   if (tau > 0 && it >= max(tau, q.K)) finished = 1;                            // :104-106
+  if (!finished && q.trunc && it >= q.trunc[rep]) finished = 1;                          // the truncation variable ends the sum (:45)
   if (!finished && q.max_it >= 0 && it >= q.max_it) { finished = 1; status = CPIMH_ERR_NOT_MET; }   // R: finished = FALSE
   // H_bar (debiasing_algorithm.R:296-312): MCMC sum over k..K plus coef_t (X_{t+1} - Y_t) for k <= t <= tau - 1, skipped
   // altogether when tau <= k + 1 (:303).  For the states the skipped term is zero; for the weighted-average paths it is not.
@@ -452,6 +457,15 @@ __global__ void __launch_bounds__(512, 1) ccpf_chains_kernel(CcpfParams p, CcRou
     __syncthreads();
     if (r >= R) break;
     if (q.status[r] != 0) continue;                          // an initial bootstrap filter failed
+    if (q.trunc && q.trunc[r] <= 0) {                        // truncation = 0: the estimate is X_0 alone (R/rheeglynn_estimator.R:37-39)
+      const double denom = (double)(q.K - q.k + 1);
+      for (int j = threadIdx.x; j < q.PD; j += blockDim.x) {
+        q.hbar[(size_t)r * q.PD + j] = q.accH[(size_t)r * q.PD + j] / denom; q.bc[(size_t)r * q.PD + j] = 0.0;
+        if (q.e1) q.hbar_rb[(size_t)r * q.PD + j] = q.accHe[(size_t)r * q.PD + j] / denom;
+      }
+      if (threadIdx.x == 0) atomicAdd(q.nfilters, 2ull);
+      continue;
+    }
     for (int it = 1;; it++) {
       const Stream s = make_stream(p.seed, (unsigned long long)(q.first_replicate + (unsigned)r) | ((unsigned long long)it << 32));
       if (q.single[r]) run_ccpf<Model, 1>(p, sm, blockIdx.x, s, r, r);

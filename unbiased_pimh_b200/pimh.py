@@ -379,10 +379,26 @@ def rheeglynn_estimator(observations, model, theta, algoparameters, force_nitera
     """rheeglynn_estimator(observations, model, theta, algoparameters, force_niterations = 0, max_niterations = 0)
     -- R/rheeglynn_estimator.R:14-66: X_0 + sum_{n >= 1} (X_n - X~_{n-1}) over coupled conditional particle filters until the two
     reference trajectories meet, i.e. H_bar with k = K = 0 over coupled_ccpf_chains.  algoparameters: nparticles, with_as,
-    coupled_resampling (index matching is what is fused), lambda (geometric truncation; must be 0).  The shipped R function
+    coupled_resampling (index matching is what is fused), lambda (geometric truncation).  The shipped R function
     adds the lists returned by CPF(); this is the estimator it intends, for all state components."""
-    if algoparameters.get("lambda", 0) and algoparameters["lambda"] > 0:
-        raise NotImplementedError("geometric truncation (lambda > 0) is not fused; use lambda = 0")
+    lam = float(algoparameters.get("lambda", 0) or 0)
+    if lam > 0:
+        # truncation <- rgeom(1, lambda) (:27): failures before the first success; difference n is divided by (1 - lambda)^n (:58)
+        seed = rng.next_seed() if seed is None else int(seed)
+        trunc = int(np.random.default_rng([seed, int(replicate), 0x7267]).geometric(lam)) - 1
+        if force_niterations:
+            raise NotImplementedError("force_niterations with lambda > 0")
+        obs = np.asarray(observations, dtype=np.float64)
+        T, d = obs.shape[0], model.dimension
+        cfg = model.config(int(algoparameters["nparticles"]), theta, nobs=T)
+        hb, it, mt = np.empty((1, T + 1, d)), np.empty(1, dtype=np.int32), np.empty(1, dtype=np.int32)
+        o = L.ChainOut()
+        o.hbar, o.iteration, o.meetingtime = hb.ctypes.data, it.ctypes.data, mt.ctypes.data
+        tr = np.array([trunc], dtype=np.int32)
+        L.check(L.lib().cpimh_rheeglynn(C.byref(cfg), L.obs_matrix(obs, T).ctypes.data_as(C.c_void_p), C.c_int64(1), C.c_uint64(seed), C.c_uint32(int(replicate)),
+                                        C.c_double(lam), L.ptr(tr), C.c_int(int(max_niterations) if max_niterations else -1),
+                                        C.c_int(int(bool(algoparameters.get("with_as", False)))), C.byref(o)))
+        return {"estimate": hb[0].T.copy(), "iteration": int(it[0]) if trunc > 0 else 0, "truncation": trunc}
     mi = int(force_niterations) if force_niterations else (int(max_niterations) if max_niterations else math.inf)
     r = coupled_ccpf_chains_batch(model, theta, observations, int(algoparameters["nparticles"]), 1, K=0, k=0, max_iterations=mi,
                                   with_as=bool(algoparameters.get("with_as", False)), seed=seed, first_replicate=replicate)
