@@ -55,6 +55,9 @@ enum { CPIMH_INTEGRATOR_RK4 = 0, CPIMH_INTEGRATOR_DOPRI5 = 1 };
 enum { CPIMH_P_RESAMPLE = 1, CPIMH_P_INIT = 2, CPIMH_P_TRANS = 3, CPIMH_P_PATH = 4, CPIMH_P_MH = 5, CPIMH_P_SHUFFLE = 6, CPIMH_P_COUPLE = 7, CPIMH_P_AS = 8 };
 
 #define CPIMH_MAX_THETA 32
+/* chain iterations live in 20 bits of the Philox counter: max_iterations < CPIMH_MAX_ITERATION; the value itself is the stream
+ * of the second initial bootstrap filter of coupled_ccpf_chains (never a chain iteration) */
+#define CPIMH_MAX_ITERATION 0xFFFFF
 
 /* Model + filter configuration.  theta layout per model:
  *   GSS      : (none)
@@ -226,7 +229,7 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t nf
 /* coupled_ccpf_chains(single_kernel, coupled_kernel, pimh_init, N, K, max_iterations) with get_cpf_kernels(with_as) and
  * pimh_init of get_pimh_kernels, + H_bar(c_chains, k, K) and BC -- R/debiasing_algorithm.R:23-111, R/pf_kernels.R:236-265,134-145.
  * R replicates advance together, one launch of conditional filters per iteration; replicate r uses stream id
- * first_replicate + r with the iteration index in counter word 1 (0 and 0xFFF: the two initial bootstrap filters).
+ * first_replicate + r with the iteration index in the counter (0 and CPIMH_MAX_ITERATION: the two initial bootstrap filters).
  * Requesting hbar_rb / sum_hbar_rb* also carries every filter's weighted average of all N paths through the chains:
  * with k = K = 0 that is rheeglynn_estimator_RB, with k = K = m rheeglynn_estimator_RB2 (R/rheeglynn_estimator_RB.R:170-265);
  * k = K = 0 without it is rheeglynn_estimator with lambda = 0 (R/rheeglynn_estimator.R:14-66). */

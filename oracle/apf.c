@@ -17,6 +17,8 @@
 
 int orc_model_rtransition_ex(const orc_config* c, int time, const double* noise, uint64_t seed, uint64_t fid, double* x, int* clamp);
 static inline uint32_t c1_of(uint64_t filter_id, int t) { return (uint32_t)t | ((uint32_t)(filter_id >> 32) << 20); }
+/* bits 12..19 of the iteration (high word of the filter id) go to the top byte of counter word 3 (DESIGN.md "RNG") */
+static inline uint32_t c3_of(uint64_t filter_id, uint32_t c3) { return c3 | ((((uint32_t)(filter_id >> 32)) << 12) & 0xff000000u); }
 
 int orc_pf_adaptive(const orc_config* cfg, const double* obs, uint64_t seed, uint64_t fid, double ess_threshold, int systematic,
                     orc_apf_out* out) {
@@ -67,15 +69,15 @@ int orc_pf_adaptive(const orc_config* cfg, const double* obs, uint64_t seed, uin
       if (!systematic) {                                                 /* :137 N iid draws, here as sorted uniforms */
         double acc = 0, ua, ub;
         for (int i = 0; i < N; i++) {
-          orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
+          orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_RESAMPLE), &ua, &ub);
           acc = (i == 0) ? -orc_rng_log(ua) : acc + (-orc_rng_log(ua));
           P[i] = acc;
         }
-        orc_philox_uniform2(seed, (uint32_t)N, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
+        orc_philox_uniform2(seed, (uint32_t)N, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_RESAMPLE), &ua, &ub);
         clamp += orc_multinomial_from_ladder(normw, N, N, P, acc - orc_rng_log(ua), anc);
       } else {                                                           /* :139 */
         double ua, ub;
-        orc_philox_uniform2(seed, 0, c1_of(fid, time), (uint32_t)fid, ORC_P_AS, &ua, &ub);
+        orc_philox_uniform2(seed, 0, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_AS), &ua, &ub);
         clamp += orc_systematic_resampling_n(normw, N, N, ua, anc);
       }
       for (int i = 0; i < N; i++) log_W[i] = log(1.0 / N);               /* :142 */
@@ -89,7 +91,7 @@ int orc_pf_adaptive(const orc_config* cfg, const double* obs, uint64_t seed, uin
   }
   {
     double ua, ub;
-    orc_philox_uniform2(seed, 0, c1_of(fid, T + 1), (uint32_t)fid, ORC_P_PATH, &ua, &ub);
+    orc_philox_uniform2(seed, 0, c1_of(fid, T + 1), (uint32_t)fid, c3_of(fid, ORC_P_PATH), &ua, &ub);
     int k;
     clamp += orc_systematic_resampling_n(normw, N, 1, ua, &k);           /* :152 one draw from normweights, by inversion */
     orc_tree_get_path(tree, k, out->path);

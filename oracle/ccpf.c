@@ -28,6 +28,8 @@
 int orc_model_rtransition_ex(const orc_config* c, int time, const double* noise, uint64_t seed, uint64_t fid, double* x, int* clamp);
 
 static inline uint32_t c1_of(uint64_t filter_id, int t) { return (uint32_t)t | ((uint32_t)(filter_id >> 32) << 20); }
+/* bits 12..19 of the iteration (high word of the filter id) go to the top byte of counter word 3 (DESIGN.md "RNG") */
+static inline uint32_t c3_of(uint64_t filter_id, uint32_t c3) { return c3 | ((((uint32_t)(filter_id >> 32)) << 12) & 0xff000000u); }
 
 /* number of cdf knots <= u, clamped to n-1 (src/multinomial.cpp:25-28 read as a count) */
 static int count_le(const double* cdf, int n, double u) {
@@ -129,7 +131,7 @@ int orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise, u
     } else {
       double acc = 0;
       for (int i = 0; i <= nd + 1; i++) {
-        orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
+        orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_RESAMPLE), &ua, &ub);
         acc = (i == 0) ? -orc_rng_log(ua) : acc + (-orc_rng_log(ua));
         P[i] = acc;
       }
@@ -142,7 +144,7 @@ int orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise, u
         cumsum(s0, N, s0); cumsum(s1, N, s1); cumsum(s2, N, s2);
         int nc = 0;
         for (int i = 0; i < nd; i++) {                                   /* :26-33 */
-          orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_COUPLE, &ua, &ub);
+          orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_COUPLE), &ua, &ub);
           anc[0][i] = ua < alpha;
           nc += anc[0][i];
         }
@@ -171,7 +173,7 @@ int orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise, u
         for (int i = 0; i < N; i++) { was[s][i] = exp(was[s][i] - m); sum += was[s][i]; }
         for (int i = 0; i < N; i++) was[s][i] = was[s][i] / sum;
       }
-      orc_philox_uniform2(seed, 0, c1_of(fid, time), (uint32_t)fid, ORC_P_AS, &ua, &ub);
+      orc_philox_uniform2(seed, 0, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_AS), &ua, &ub);
       if (nsys == 1) { int k; clamp += orc_systematic_resampling_n(was[0], N, 1, ua, &k); anc[0][N - 1] = k; }
       else im_single_draw(was[0], was[1], N, ua, ub, s0, s1, s2, &anc[0][N - 1], &anc[1][N - 1]);
     } else {
@@ -197,7 +199,7 @@ int orc_ccpf(const orc_config* cfg, const double* obs, const orc_noise* noise, u
   }
   {
     double ua, ub;
-    orc_philox_uniform2(seed, 0, c1_of(fid, T + 1), (uint32_t)fid, ORC_P_PATH, &ua, &ub);
+    orc_philox_uniform2(seed, 0, c1_of(fid, T + 1), (uint32_t)fid, c3_of(fid, ORC_P_PATH), &ua, &ub);
     int k[2] = {0, 0};
     if (nsys == 1) clamp += orc_systematic_resampling_n(normw[0], N, 1, ua, &k[0]);          /* R/CPF.R:69 */
     else im_single_draw(normw[0], normw[1], N, ua, ub, s0, s1, s2, &k[0], &k[1]);            /* R/CPF_coupled.R:101-103 */
@@ -264,7 +266,7 @@ int orc_coupled_ccpf_chains_rb(const orc_config* cfg, const double* obs, uint64_
   o.trajectory = s1; o.logz = &lz1; o.exp_path = rb ? e1 : NULL;
   rc = orc_cpf(cfg, obs, NULL, seed, (uint64_t)replicate, &o); nf++;                               /* pimh_init: chain_state1 */
   o.trajectory = s2; o.logz = &lz2; o.exp_path = rb ? e2 : NULL;
-  if (!rc) { rc = orc_cpf(cfg, obs, NULL, seed, (uint64_t)replicate | ((uint64_t)0xFFF << 32), &o); nf++; }   /* chain_state2 */
+  if (!rc) { rc = orc_cpf(cfg, obs, NULL, seed, (uint64_t)replicate | ((uint64_t)ORC_MAX_ITERATION << 32), &o); nf++; }   /* chain_state2 */
   if (rc) goto fail;
   for (int t = 0; t < p; t++) { out->samples1[t] = s1[(size_t)t * d]; out->samples2[t] = s2[(size_t)t * d]; }   /* :42-43 */
   out->log_pdf1[0] = lz1; out->log_pdf2[0] = lz2;

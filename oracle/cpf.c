@@ -14,6 +14,8 @@
 int orc_model_rtransition_ex(const orc_config* c, int time, const double* noise, uint64_t seed, uint64_t fid, double* x, int* clamp);
 
 static inline uint32_t c1_of(uint64_t filter_id, int t) { return (uint32_t)t | ((uint32_t)(filter_id >> 32) << 20); }
+/* bits 12..19 of the iteration (high word of the filter id) go to the top byte of counter word 3 (DESIGN.md "RNG") */
+static inline uint32_t c3_of(uint64_t filter_id, uint32_t c3) { return c3 | ((((uint32_t)(filter_id >> 32)) << 12) & 0xff000000u); }
 
 int orc_cpf(const orc_config* cfg, const double* obs, const orc_noise* noise, uint64_t seed, uint64_t fid, orc_pf_out* out) {
   const int N = cfg->nparticles, d = cfg->dim, T = cfg->nobs, dy = cfg->dim_y;
@@ -51,18 +53,18 @@ int orc_cpf(const orc_config* cfg, const double* obs, const orc_noise* noise, ui
          * e_i = (E_0+..+E_i) / (E_0+..+E_N), E_i = -log(u_i); same law as the recurrence of src/multinomial.cpp:20-24 */
         double acc = 0, ua, ub;
         for (int i = 0; i < N; i++) {
-          orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
+          orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_RESAMPLE), &ua, &ub);
           acc = (i == 0) ? -orc_rng_log(ua) : acc + (-orc_rng_log(ua));
           ebuf[i] = acc;
         }
-        orc_philox_uniform2(seed, (uint32_t)N, c1_of(fid, time), (uint32_t)fid, ORC_P_RESAMPLE, &ua, &ub);
+        orc_philox_uniform2(seed, (uint32_t)N, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_RESAMPLE), &ua, &ub);
         clamp += orc_multinomial_from_ladder(normw, N, N, ebuf, acc - orc_rng_log(ua), anc);
       }
       if (cfg->shuffle) {
         const double* us;
         if (noise && noise->shuffle) us = noise->shuffle + (size_t)(time - 1) * (N - 1);
         else {
-          for (int i = 1; i < N; i++) { double ub; orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, ORC_P_SHUFFLE, &ubuf[i - 1], &ub); }
+          for (int i = 1; i < N; i++) { double ub; orc_philox_uniform2(seed, (uint32_t)i, c1_of(fid, time), (uint32_t)fid, c3_of(fid, ORC_P_SHUFFLE), &ubuf[i - 1], &ub); }
           us = ubuf;
         }
         orc_random_shuffle_int(anc, N, us);
@@ -88,7 +90,7 @@ int orc_cpf(const orc_config* cfg, const double* obs, const orc_noise* noise, ui
     if (out->logz_t) { for (int t = 0; t < T; t++) s += out->logz_t[t]; logz_sum = (double)s; }
     double u;
     if (noise && noise->path_u) u = noise->path_u[0];
-    else { double ub; orc_philox_uniform2(seed, 0, c1_of(fid, T + 1), (uint32_t)fid, ORC_P_PATH, &u, &ub); }
+    else { double ub; orc_philox_uniform2(seed, 0, c1_of(fid, T + 1), (uint32_t)fid, c3_of(fid, ORC_P_PATH), &u, &ub); }
     int k;
     clamp += orc_systematic_resampling_n(normw, N, 1, u, &k);            /* :69 */
     orc_tree_get_path(tree, k, out->trajectory);
@@ -178,7 +180,7 @@ int orc_coupled_pimh_chains_ap(const orc_config* cfg, const double* obs, uint64_
   }
   int rc = run_filter(cfg, obs, seed, replicate, 0, s1, &lz1, e1); nf++;     /* pimh_init, R/pf_kernels.R:134-139 (:200-206) */
   if (rc) return rc;
-  if (run_discarded_init) { double lzd; run_filter(cfg, obs, seed, replicate, 0xFFF, prop, &lzd, NULL); nf++; }  /* :140-142, discarded at debiasing_algorithm.R:160-161 */
+  if (run_discarded_init) { double lzd; run_filter(cfg, obs, seed, replicate, ORC_MAX_ITERATION, prop, &lzd, NULL); nf++; }  /* :140-142, discarded at debiasing_algorithm.R:160-161 */
   for (int t = 0; t < p; t++) out->samples1[t] = s1[(size_t)t * d];      /* :156 chain_state1[1,] */
   if (all_particles) for (int t = 0; t < p; t++) out->exp_samples1[t] = e1[(size_t)t * d];   /* :169 */
   out->log_pdf1[0] = lz1;
@@ -188,7 +190,7 @@ int orc_coupled_pimh_chains_ap(const orc_config* cfg, const double* obs, uint64_
     rc = run_filter(cfg, obs, seed, replicate, (uint32_t)iter, prop, &lzp, eprop); nf++;
     if (rc) return rc;
     double u, ub;
-    orc_philox_uniform2(seed, 0, (uint32_t)iter << 20, replicate, ORC_P_MH, &u, &ub);
+    orc_philox_uniform2(seed, 0, (uint32_t)iter << 20, replicate, c3_of((uint64_t)iter << 32, ORC_P_MH), &u, &ub);
     double lu = log(u);
     if (meet) {                                                          /* single_kernel R/pf_kernels.R:88-101 (:147-162) */
       if (lu < (lzp - lz1)) { memcpy(s1, prop, sizeof(double) * psz); lz1 = lzp; if (all_particles) memcpy(e1, eprop, sizeof(double) * psz); }

@@ -18,8 +18,10 @@
 #define TWO_PI 6.283185307179586476925286766559
 
 static inline uint32_t c1_of(uint64_t filter_id, int t) { return (uint32_t)t | ((uint32_t)(filter_id >> 32) << 20); }
+/* bits 12..19 of the iteration (high word of the filter id) go to the top byte of counter word 3 (DESIGN.md "RNG") */
+static inline uint32_t c3_of(uint64_t filter_id, uint32_t c3) { return c3 | ((((uint32_t)(filter_id >> 32)) << 12) & 0xff000000u); }
 static inline void uni2(uint64_t seed, uint64_t filter_id, uint32_t i, int t, int purpose, uint32_t draw, double* ua, double* ub) {
-  orc_philox_uniform2(seed, i, c1_of(filter_id, t), (uint32_t)filter_id, (uint32_t)purpose | (draw << 8), ua, ub);
+  orc_philox_uniform2(seed, i, c1_of(filter_id, t), (uint32_t)filter_id, c3_of(filter_id, (uint32_t)purpose | (draw << 8)), ua, ub);
 }
 static inline void normal2(double ua, double ub, double* z0, double* z1) {
   double r = sqrt(-2.0 * orc_rng_log(ua)), s, c;      /* the RNG specification's log / sincos (rngmath.h) */

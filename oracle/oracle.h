@@ -32,6 +32,7 @@ extern "C" {
 /* ---- model ids / flags: numerically identical to include/cpimh.h (checked by tests) ---- */
 enum { ORC_MODEL_GSS = 0, ORC_MODEL_AR = 1, ORC_MODEL_LEVY_SV = 2, ORC_MODEL_SK = 3, ORC_MODEL_LORENZ = 4 };
 enum { ORC_INTEGRATOR_RK4 = 0, ORC_INTEGRATOR_DOPRI5 = 1 };
+#define ORC_MAX_ITERATION 0xFFFFF   /* chain iterations use 20 bits of the Philox counter; this value is the stream of the second initial filter of coupled_ccpf_chains */
 enum { ORC_P_RESAMPLE = 1, ORC_P_INIT = 2, ORC_P_TRANS = 3, ORC_P_PATH = 4, ORC_P_MH = 5, ORC_P_SHUFFLE = 6, ORC_P_COUPLE = 7, ORC_P_AS = 8 };
 
 #define ORC_MAX_THETA 32

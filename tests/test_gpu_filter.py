@@ -292,3 +292,18 @@ def test_one_shot_entries_cache_their_workspaces_and_match_the_handle_api(up, go
     assert np.array_equal(ra["logz"], ref["logz"]) and np.array_equal(ra["exp_path"], ref_exp)
     r = up.cpf_batch(128, up.get_ar(1), th, y, 4, seed=9, first_filter=2)                  # smaller batch reuses the larger handle
     assert np.array_equal(r["logz"], ref["logz"][:4])
+
+
+def test_chain_iteration_index_has_twenty_bits(up, oracle, golden):
+    """The iteration of a chain is the high word of the 64-bit filter id; 20 bits of it reach the Philox counter (round 1: 12, so
+    iteration 4096 + x replayed the draws of iteration x).  CPU and GPU agree seed for seed above 4095, and nothing aliases."""
+    th, y = [0.5, math.sqrt(10.0)], golden["lgssm_y"][:15]
+    ocfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 64, 15, theta=th)
+    lz = {}
+    for it in (5, 4096 + 5, 70000, 0xFFFFF):
+        fid = 7 | (it << 32)
+        r = up.cpf_batch(64, up.get_ar(1), th, y, 1, seed=3, first_filter=fid, logz_t=True)
+        o = oracle.cpf(ocfg, y, seed=3, filter_id=fid)
+        assert np.max(np.abs(r["logz_t"][0] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ and int(r["path_index"][0]) == o["path_index"]
+        lz[it] = r["logz"][0]
+    assert len(set(lz.values())) == 4

@@ -3,6 +3,8 @@
 // (R/CPF.R:14-78), CPF_coupled (R/CPF_coupled.R:14-112), the CCPF kernels (R/pf_kernels.R:236-265) and
 // coupled_ccpf_chains + H_bar (R/debiasing_algorithm.R:23-111, 284-316).  Kernels: ccpf.cuh.
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include "host_common.h"
@@ -236,10 +238,13 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
   CPIMH_REQUIRE(R >= 1, "nreplicates must be >= 1");
   CPIMH_REQUIRE(k >= 0 && K >= k, "need 0 <= k <= K (got k=%d K=%d)", k, K);
   CPIMH_REQUIRE(max_iterations < 0 || max_iterations >= (K > 1 ? K : 1), "max_iterations must be >= max(K, 1) or negative (unbounded)");
-  CPIMH_REQUIRE(max_iterations < 4095, "iteration index must fit 12 bits of the Philox counter and 0xFFF is the second initial filter (max_iterations <= 4094)");
+  CPIMH_REQUIRE(max_iterations < CPIMH_MAX_ITERATION, "iteration index must fit 20 bits of the Philox counter; the last value is the second initial filter (max_iterations < %d)", CPIMH_MAX_ITERATION);
   const bool rb = o->hbar_rb || o->sum_hbar_rb || o->sum_hbar_rb_sq;
-  const int max_it = max_iterations < 0 ? 4094 : max_iterations;
+  const int max_it = max_iterations < 0 ? CPIMH_MAX_ITERATION - 1 : max_iterations;
   std::lock_guard<std::recursive_mutex> lk(g_cc_mu);
+  const bool timing = getenv("CPIMH_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
   CcChainCache& g = g_cc;
   CcpfWork& w = g.w;
   int rc = ccpf_work_init(&w, cfg, obs_host, R);
@@ -247,7 +252,7 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
   const cpimh_config& c = w.cfg;
   const int D = c.dim, P = c.nobs + 1, PD = P * D;
   cudaStream_t s = nullptr;
-  // ---- initial states: two independent bootstrap filters per replicate (iteration indices 0 and 0xFFF)
+  // ---- initial states: two independent bootstrap filters per replicate (iteration indices 0 and CPIMH_MAX_ITERATION = 0xFFFFF, which no chain iteration can reach)
   cpimh_config cpf = c;
   cpf.store_paths = cpf.store_paths == 0 ? 1 : cpf.store_paths;
   if (!(g.pf && g.pf_R >= R && memcmp(&g.pf_cfg, &cpf, sizeof(cpf)) == 0)) {
@@ -284,7 +289,7 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
   double* d_ex = nullptr;
   if (rb) { rc = cpimh_pf_device_exp_paths(pf, &d_ex); if (rc) return rc; }
   for (int which = 0; which < 2; which++) {
-    const uint64_t first = (uint64_t)first_replicate | (which ? ((uint64_t)0xFFF << 32) : 0ull);
+    const uint64_t first = (uint64_t)first_replicate | (which ? ((uint64_t)CPIMH_MAX_ITERATION << 32) : 0ull);
     rc = cpimh_pf_run(pf, R, seed, first, s);
     if (rc) return rc;
     CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? g.st2.p : g.st1.p, d_tr, RPD, cudaMemcpyDeviceToDevice, s));
@@ -292,6 +297,8 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
     CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? g.pst2.p : g.pst1.p, d_st, sizeof(int) * (size_t)R, cudaMemcpyDeviceToDevice, s));
     if (rb) CPIMH_CUDA_CHECK(cudaMemcpyAsync(which ? g.e2.p : g.e1.p, d_ex, RPD, cudaMemcpyDeviceToDevice, s));
   }
+  if (timing) { cudaStreamSynchronize(s); fprintf(stderr, "[ccpf] setup + init filters %.1f ms\n", now() - t_start); }
+  const double t_chain = now();
   CcRound q;
   memset(&q, 0, sizeof(q));
   q.PD = PD; q.k = k; q.K = K; q.max_it = max_it; q.first_replicate = first_replicate;
@@ -329,6 +336,8 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
   cc_reduce_kernel<<<PD + 1, 256, 0, s>>>(g.hbar.as<double>(), g.status.as<int>(), R, PD, g.nf.as<unsigned long long>(), g.sums.as<double>());
   if (rb) cc_reduce_kernel<<<PD + 1, 256, 0, s>>>(g.hbar_rb.as<double>(), g.status.as<int>(), R, PD, g.nf.as<unsigned long long>(), g.sums_rb.as<double>());
   CPIMH_CUDA_CHECK(cudaGetLastError());
+  if (timing) { cudaStreamSynchronize(s); fprintf(stderr, "[ccpf] chain kernel + reduce %.1f ms\n", now() - t_chain); }
+  const double t_out = now();
   std::vector<int> stv((size_t)R);
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(stv.data(), g.status.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -351,6 +360,7 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
     if (o->sum_hbar_rb) memcpy(o->sum_hbar_rb, hs.data(), sizeof(double) * PD);
     if (o->sum_hbar_rb_sq) memcpy(o->sum_hbar_rb_sq, hs.data() + PD, sizeof(double) * PD);
   }
+  if (timing) fprintf(stderr, "[ccpf] outputs %.1f ms, total %.1f ms\n", now() - t_out, now() - t_start);
   return CPIMH_OK;
 }
 

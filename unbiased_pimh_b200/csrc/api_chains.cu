@@ -481,13 +481,13 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   CPIMH_REQUIRE(R >= 1 && R <= h->maxR, "nreplicates %lld outside [1, %lld]", (long long)R, (long long)h->maxR);
   CPIMH_REQUIRE(k >= 0 && K >= k, "need 0 <= k <= K (got k=%d K=%d)", k, K);
   CPIMH_REQUIRE(max_iterations < 0 || max_iterations >= K, "max_iterations must be >= K or negative (unbounded)");
-  CPIMH_REQUIRE(max_iterations < 4096, "iteration index must fit 12 bits of the Philox counter (max_iterations < 4096)");
+  CPIMH_REQUIRE(max_iterations < CPIMH_MAX_ITERATION, "iteration index must fit 20 bits of the Philox counter (max_iterations < %d)", CPIMH_MAX_ITERATION);
   cudaStream_t s = (cudaStream_t)stream;
   const bool rounds = h->mode == 2;       // default (0) and 1: the persistent owner / helper kernel (chains.cuh)
   if (rounds) {
     CPIMH_CUDA_CHECK(cudaMemsetAsync(h->nfilters.p, 0, 2 * sizeof(unsigned long long), s));
     CPIMH_CUDA_CHECK(cudaMemsetAsync(h->status.p, 0, sizeof(int) * (size_t)R, s));
-    int rcr = chains_run_rounds(h, R, seed, first_replicate, k, K, max_iterations < 0 ? 4095 : max_iterations, s);
+    int rcr = chains_run_rounds(h, R, seed, first_replicate, k, K, max_iterations < 0 ? CPIMH_MAX_ITERATION - 1 : max_iterations, s);
     if (rcr) return rcr;
     const int Pr = (h->cfg.nobs + 1) * h->cfg.dim;
     double* sums_r = d_sums ? d_sums : h->sums.as<double>();
@@ -512,7 +512,7 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   // the proposal rings are the filter's per-filter outputs (entry = slot * RING + iteration mod RING)
   cp.pf.traj = h->ring_traj.as<double>(); cp.pf.logz = h->ring_logz.as<double>(); cp.pf.status = h->ring_status.as<int>();
   cp.pf.exp_path = h->all_particles ? h->ring_exp.as<double>() : nullptr;
-  cp.R = R; cp.first_replicate = first_replicate; cp.k = k; cp.K = K; cp.max_iterations = max_iterations < 0 ? 4095 : max_iterations;
+  cp.R = R; cp.first_replicate = first_replicate; cp.k = k; cp.K = K; cp.max_iterations = max_iterations < 0 ? CPIMH_MAX_ITERATION - 1 : max_iterations;
   cp.state = h->state.as<double>(); cp.acc = h->acc.as<double>();
   cp.estate = h->all_particles ? h->estate.as<double>() : nullptr; cp.eacc = h->all_particles ? h->eacc.as<double>() : nullptr;
   cp.ring_tag = h->ring_tag.as<int>(); cp.next_iter = h->next_it.as<int>(); cp.iter_done = h->it_done.as<int>(); cp.slot_rep = h->slot_rep.as<int>();

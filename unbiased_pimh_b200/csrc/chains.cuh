@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
       // nobody else touches this slot now: helpers exist only once the tickets have run out, and then no slot starts a new replicate
       for (int i = tid; i < CPIMH_RING; i += NT) cp.ring_tag[slot * CPIMH_RING + i] = -1;
       __syncthreads();
+      // publish the replicate BEFORE its init filter runs: proposals do not depend on the chain state, so helpers may already
+      // run iterations 1, 2, ... while the owner runs iteration 0 (shortens the tail of a call by one filter time)
+      if (tid == 0 && ist[9] == 1) { __threadfence(); st_volatile(cp.slot_rep + slot, ist[10]); }
     } else if (ist[9] == 1) {                                                     // owner: claim the replicate's next proposal
       __syncthreads();
       if (tid == 0) { ist[11] = slot; ist[12] = chains_try_claim(cp, slot); ist[13] = ist[10]; }
@@ -176,7 +179,6 @@ __global__ void __launch_bounds__(NT_MAX, MIN_BLOCKS) chains_kernel(ChainParams 
         if (cp.samples1) cp.log_pdf1[(size_t)r * (cp.max_rec + 1)] = lz;
       }
       __syncthreads();
-      if (tid == 0) { __threadfence(); st_volatile(cp.slot_rep + slot, (int)r); }   // helpers may claim iterations of this replicate from now on
     }
     bool progressed = false;
     while (!ist[6] && !ist[5]) {                                                  // R/debiasing_algorithm.R:180

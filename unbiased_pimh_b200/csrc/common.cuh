@@ -28,7 +28,8 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // ---------------------------------------------------------------- Philox4x32-10 (DESIGN.md "RNG")
-// counter = (c0 particle/draw index, c1 time | iteration << 20, c2 stream id, c3 purpose | draw << 8), key = seed
+// counter = (c0 particle/draw index, c1 time | iteration[0:12) << 20, c2 stream id, c3 purpose | draw << 8 | iteration[12:20) << 24), key = seed
+// (time < 2^20, draw < 2^16, iteration < 2^20: the iteration of a chain is the high word of the 64-bit filter id)
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -47,23 +48,23 @@ __device__ __forceinline__ double u64_to_unit(uint32_t lo, uint32_t hi) {
 }
 struct Stream {               // identifies one filter's random streams
   uint32_t k0, k1;            // seed
-  uint32_t c1hi;              // iteration << 20
+  uint32_t hi;                // high word of the filter id = iteration of a chain (20 bits used)
   uint32_t c2;                // stream id
 };
 __device__ __forceinline__ Stream make_stream(unsigned long long seed, unsigned long long filter_id) {
   Stream s;
   s.k0 = (uint32_t)seed; s.k1 = (uint32_t)(seed >> 32);
-  s.c1hi = ((uint32_t)(filter_id >> 32)) << 20;
+  s.hi = (uint32_t)(filter_id >> 32);
   s.c2 = (uint32_t)filter_id;
   return s;
 }
 __device__ __forceinline__ void philox_u2(const Stream& s, uint32_t i, int t, int purpose, uint32_t draw, double& ua, double& ub) {
-  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, (uint32_t)purpose | (draw << 8)), make_uint2(s.k0, s.k1));
+  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | (s.hi << 20), s.c2, ((uint32_t)purpose | (draw << 8)) | ((s.hi << 12) & 0xff000000u)), make_uint2(s.k0, s.k1));
   ua = u64_to_unit(r.x, r.y);
   ub = u64_to_unit(r.z, r.w);
 }
 __device__ __forceinline__ double philox_u1(const Stream& s, uint32_t i, int t, int purpose, uint32_t draw) {
-  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, (uint32_t)purpose | (draw << 8)), make_uint2(s.k0, s.k1));
+  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | (s.hi << 20), s.c2, ((uint32_t)purpose | (draw << 8)) | ((s.hi << 12) & 0xff000000u)), make_uint2(s.k0, s.k1));
   return u64_to_unit(r.x, r.y);
 }
 // ---------------------------------------------------------------- transcendental maps of the RNG specification
