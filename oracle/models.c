@@ -54,22 +54,34 @@ int orc_model_n_trans(const orc_config* c) {
 }
 
 /* ---------------- Philox noise generation (DESIGN.md "RNG"; mirrored in csrc/models.cuh) ---------------- */
-static int poisson_inv(double rate, double u) {
-  double p = exp(-rate), F = p; int k = 0;
-  while (u > F && k < 1000) { k++; p = p * rate / k; F += p; }
+/* Poisson count by sequential inversion (recurrence p_k = p_{k-1} rate / k) AND the position of u inside its cell,
+ * (u - F_{k-1}) / p_k: uniform on (0,1), independent of k (DESIGN.md "RNG": it is the time of the first jump) */
+static int poisson_inv_cell(double rate, double u, double* cell) {
+  double p = exp(-rate), F = p, Fprev = 0.0; int k = 0;
+  while (u > F && k < 1000) { k++; p = p * rate / k; Fprev = F; F += p; }
+  *cell = (u - Fprev) * (1.0 / p);
   return k;
 }
-/* compound-Poisson sums of the Levy-SV transition for particle i at time t (src/SVLevy_functions.cpp:61-67) */
+/* compound-Poisson sums of the Levy-SV transition for particle i at time t (src/SVLevy_functions.cpp:61-67).  The block whose
+ * first half is the resampling draw of slot i carries, in its second half, two 32-bit uniforms: u_z -> jump count and first jump
+ * time, u_w -> first jump size; jumps j >= 2 use block (i, t, TRANS, j). */
 static void sv_jump_sums(const orc_config* c, uint64_t seed, uint64_t fid, uint32_t i, int t, double* swe, double* se) {
   double xi = c->theta[2], w2 = c->theta[3], lambda = c->theta[4];
-  double ua, ub;
-  uni2(seed, fid, i, t, ORC_P_RESAMPLE, 0, &ua, &ub);   /* shared Philox block: ua = resampling draw of slot i, ub = Poisson uniform */
-  int k = poisson_inv(lambda * xi * xi / w2, ub);
+  double ua, ub, cell;
+  uint32_t z, w;
+  orc_philox_uniform1_raw(seed, i, c1_of(fid, t), (uint32_t)fid, c3_of(fid, ORC_P_RESAMPLE), &ua, &z, &w);
+  const double uz = ((double)z + 0.5) * 0x1p-32, uw = ((double)w + 0.5) * 0x1p-32;
+  int k = poisson_inv_cell(lambda * xi * xi / w2, uz, &cell);
   double a = 0, b = 0, escale = w2 / xi;
-  for (int j = 1; j <= k; j++) {
+  if (k >= 1) {
+    double e = -orc_rng_log(uw) * escale;            /* rexp(k, rate=xi/w2) = exp_rand() * (w2/xi) */
+    a = exp(-lambda * cell) * e;                     /* exp(-lambda (t - c)), t - c ~ U(0,1) */
+    b = e;
+  }
+  for (int j = 2; j <= k; j++) {
     uni2(seed, fid, i, t, ORC_P_TRANS, (uint32_t)j, &ua, &ub);
-    double e = -orc_rng_log(ub) * escale;            /* rexp(k, rate=xi/w2) = exp_rand() * (w2/xi) */
-    a += exp(-lambda * ua) * e;              /* exp(-lambda (t - c)), t - c ~ U(0,1) */
+    double e = -orc_rng_log(ub) * escale;
+    a += exp(-lambda * ua) * e;
     b += e;
   }
   *swe = a; *se = b;

@@ -63,6 +63,7 @@ typedef struct orc_noise {
 
 /* ---- Philox4x32-10 streams (DESIGN.md "RNG") ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_philox_uniform1_raw(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double* ua, uint32_t* z, uint32_t* w);
 void orc_philox_uniform2(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double* ua, double* ub);
 
 void orc_rng_transform(const double* u, int64_t n, double* lg, double* sn, double* cs);   /* rngmath.h, elementwise */

@@ -24,6 +24,14 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* first uniform (52 bits) + the raw words z, w of the same block: models that split the second half into two 32-bit uniforms */
+void orc_philox_uniform1_raw(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double* ua, uint32_t* z, uint32_t* w) {
+  uint32_t ctr[4] = {c0, c1, c2, c3}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, r[4];
+  orc_philox4x32_10(ctr, key, r);
+  uint64_t xa = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+  *ua = ((double)(xa >> 12) + 0.5) * 0x1p-52;
+  *z = r[2]; *w = r[3];
+}
 /* two uniforms in the OPEN interval (0,1): ((x >> 12) + 0.5) * 2^-52, exact in fp64 */
 void orc_philox_uniform2(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, double* ua, double* ub) {
   uint32_t ctr[4] = {c0, c1, c2, c3}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, r[4];
@@ -34,7 +42,7 @@ void orc_philox_uniform2(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, u
   *ub = ((double)(xb >> 12) + 0.5) * 0x1p-52;
 }
 
-const char* orc_version(void) { return "cpimh-oracle 0.1 (parity unpinned: reference has no tests and cannot run here)"; }
+const char* orc_version(void) { return "cpimh-oracle 0.2 (resamplers, tree, create_A_, SVLevy pinned to the reference's own sources: oracle/ref_build; mvnorm / lorenz96 unpinned)"; }
 
 /* elementwise rng_log / rng_sincos2pi (rngmath.h) for the tests */
 #include "rngmath.h"

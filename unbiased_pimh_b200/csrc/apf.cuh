@@ -89,8 +89,8 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
       double x[D];
 #pragma unroll
       for (int q = 0; q < D; q++) x[q] = xprev[(size_t)q * Npad + k];
-      double ush = 0.5;
-      if (Model::USES_SHARED_U) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
+      uint2 ush = make_uint2(0u, 0u);
+      if (Model::USES_SHARED_U) { double ua; philox_u1raw(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
       st |= Model::transition(c, t, k, x, sc, ush);
 #pragma unroll
       for (int q = 0; q < D; q++) prop[(size_t)q * Npad + k] = x[q];

@@ -68,19 +68,20 @@ std::vector<double> api_precompute(const cpimh_config& c) {
     pre.push_back(w2 / xi);                            // rexp(k, xi/w2) = exp_rand() * (w2/xi) (:63)
     // CDF of rpois(lambda xi^2 / w2) (:61) by the sequential-search recurrence, until it stops increasing
     const double rate = lambda * xi * xi / w2;
-    std::vector<double> F;
+    std::vector<double> F, invp;
     double p = exp(-rate), acc = p;
-    F.push_back(acc);
+    F.push_back(acc); invp.push_back(1.0 / p);
     for (int k = 1; k < 1000; k++) {
       p = p * rate / k;
       const double nxt = acc + p;
       if (nxt == acc) break;
       acc = nxt;
-      F.push_back(acc);
+      F.push_back(acc); invp.push_back(1.0 / p);
     }
     pre.push_back((double)F.size());
     pre.insert(pre.end(), F.begin(), F.end());
     for (int k = 0; k < 3; k++) pre.push_back(2.0);    // guard knots for the unrolled head of the table search (models.cuh poisson_tab)
+    pre.insert(pre.end(), invp.begin(), invp.end());   // 1 / p_k: position of the Poisson uniform inside its cell -> first jump time
   } else if (c.model == CPIMH_MODEL_SK) {
     const double sd = sqrt(c.theta[0]);                 // R/model_stochastic_kinetic.R:151 dnorm(..., sd = sqrt(s2_obs), log = TRUE)
     pre.push_back(1.0 / sd);
@@ -216,7 +217,7 @@ struct cpimh_pf {
   int record_anc, all_particles;
   int64_t launches, bytes;
   int grid;
-  DevBuf hist_x, hist_a, ascr, wscr, exact;
+  DevBuf hist_x, hist_a, ascr, wscr, exact, jq;
   DevBuf obs, theta, pre, xbuf, a_star, o_star, x_star, logz, logz_t, traj, path_index, status, normw, leaf_out, anc_rec, exp_path;
   DevBuf inj_init, inj_trans, inj_resample, inj_shuffle, inj_path;
   bool have_inj[5];
@@ -274,6 +275,7 @@ int cpimh_pf_create(const cpimh_config* cfg_in, int64_t max_filters, cpimh_pf** 
   if (!rc && g.path_mode != PATH_DENSE) rc = A(h->xbuf, sizeof(double) * G * 2 * D * g.Npad);
   if (!rc && g.path_mode != PATH_DENSE) rc = A(h->ascr, sizeof(int) * G * g.Npad);
   if (!rc) rc = A(h->wscr, sizeof(double) * G * g.Npad);
+  if (!rc && cfg.model == CPIMH_MODEL_LEVY_SV) rc = A(h->jq, sizeof(uint4) * G * pf_jq_stride(g.Npad));   // per-warp jump queues
   if (!rc) rc = A(h->exact, sizeof(int) * B);
   if (!rc && g.path_mode == PATH_DENSE) {
     rc = A(h->hist_x, sizeof(double) * G * g.hist_x_elems);
@@ -303,7 +305,7 @@ int cpimh_pf_destroy(cpimh_pf* h) {
   if (!h) return CPIMH_OK;
   if (h->wide) { wide_destroy(h->wide); delete h; return CPIMH_OK; }
   DevBuf* all[] = {&h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->logz, &h->logz_t, &h->traj, &h->path_index,
-                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->exp_path, &h->hist_x, &h->hist_a, &h->ascr, &h->wscr, &h->exact, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
+                   &h->status, &h->normw, &h->leaf_out, &h->anc_rec, &h->exp_path, &h->hist_x, &h->hist_a, &h->ascr, &h->wscr, &h->exact, &h->jq, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_shuffle, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
   return CPIMH_OK;
@@ -393,7 +395,7 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   p.B = B; p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>(); p.theta = h->theta.as<double>(); p.pre = h->pre.as<double>();
   p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.ascr = h->ascr.as<int>();
-  p.wscr = h->wscr.as<double>(); p.exact_repeats = h->exact.as<int>();
+  p.wscr = h->wscr.as<double>(); p.exact_repeats = h->exact.as<int>(); p.jq = h->jq.as<uint4>();
   p.xbuf = h->xbuf.as<double>(); p.a_star = h->a_star.as<int>(); p.o_star = h->o_star.as<int>(); p.x_star = h->x_star.as<double>();
   p.logz = h->logz.as<double>(); p.logz_t = h->logz_t.as<double>(); p.traj = h->traj.as<double>();
   p.path_index = h->path_index.as<int>(); p.status = h->status.as<int>(); p.normw = h->normw.as<double>();

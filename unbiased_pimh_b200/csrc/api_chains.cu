@@ -252,7 +252,7 @@ struct cpimh_chains {
   Geometry geo;
   int64_t maxR, lastR, launches;
   int record, max_rec, grid, npre;
-  DevBuf hist_x, hist_a, ascr, wscr;
+  DevBuf hist_x, hist_a, ascr, wscr, jq;
   DevBuf bc;
   int all_particles;
   DevBuf r_exp, r_e1, r_e2, r_accHe, r_accDe, hbar_rb, sums_rb;
@@ -274,7 +274,7 @@ extern "C" {
 
 int cpimh_chains_destroy(cpimh_chains* h) {
   if (!h) return CPIMH_OK;
-  DevBuf* all[] = {&h->bc, &h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe, &h->hbar_rb, &h->sums_rb, &h->hist_x, &h->hist_a, &h->ascr, &h->wscr, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->estate, &h->eacc, &h->ring_traj, &h->ring_exp, &h->ring_logz, &h->ring_status, &h->ring_tag, &h->next_it, &h->it_done, &h->slot_rep, &h->unfinished, &h->hbar, &h->mt,
+  DevBuf* all[] = {&h->bc, &h->r_exp, &h->r_e1, &h->r_e2, &h->r_accHe, &h->r_accDe, &h->hbar_rb, &h->sums_rb, &h->hist_x, &h->hist_a, &h->ascr, &h->wscr, &h->jq, &h->obs, &h->theta, &h->pre, &h->xbuf, &h->a_star, &h->o_star, &h->x_star, &h->state, &h->acc, &h->estate, &h->eacc, &h->ring_traj, &h->ring_exp, &h->ring_logz, &h->ring_status, &h->ring_tag, &h->next_it, &h->it_done, &h->slot_rep, &h->unfinished, &h->hbar, &h->mt,
                    &h->it, &h->status, &h->nfilters, &h->counter, &h->sums, &h->samples1, &h->samples2, &h->log_pdf1, &h->log_pdf2,
                    &h->r_logz, &h->r_traj, &h->r_status, &h->r_ids, &h->r_lz1, &h->r_lz2, &h->r_id1, &h->r_id2, &h->r_meet, &h->r_iter, &h->r_tau,
                    &h->r_st1, &h->r_st2, &h->r_accH, &h->r_accD, &h->r_act0, &h->r_act1, &h->r_cnt};
@@ -318,6 +318,7 @@ int cpimh_chains_create(const cpimh_config* cfg_in, int64_t max_replicates, int 
     if (!rc) rc = h->x_star.alloc(sizeof(double) * G * D * g.M);
   }
   if (!rc) rc = h->wscr.alloc(sizeof(double) * G * g.Npad);
+  if (!rc && cfg.model == CPIMH_MODEL_LEVY_SV) rc = h->jq.alloc(sizeof(uint4) * G * pf_jq_stride(g.Npad));
   if (!rc) rc = h->state.alloc(sizeof(double) * G * 2 * P * D);
   if (!rc) rc = h->acc.alloc(sizeof(double) * G * 2 * P * D);
   if (!rc) rc = h->ring_traj.alloc(sizeof(double) * G * CPIMH_RING * P * D);
@@ -377,6 +378,7 @@ static int chains_rounds_alloc(cpimh_chains* h) {
     if (!rc) rc = h->x_star.alloc(sizeof(double) * G * D * g.M);
   }
   if (!rc) rc = h->wscr.alloc(sizeof(double) * G * g.Npad);
+  if (!rc && h->cfg.model == CPIMH_MODEL_LEVY_SV) rc = h->jq.alloc(sizeof(uint4) * G * pf_jq_stride(g.Npad));
   if (!rc) rc = h->r_logz.alloc(sizeof(double) * R);
   if (!rc) rc = h->r_traj.alloc(sizeof(double) * R * PD);
   if (!rc) rc = h->r_status.alloc(sizeof(int) * R);
@@ -411,7 +413,7 @@ static int chains_run_rounds(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t
   api_fill_pf_params(c, g, h->npre, &p);
   p.seed = seed; p.first_filter = 0; p.b0 = 0;
   p.obs = h->obs.as<double>(); p.theta = h->theta.as<double>(); p.pre = h->pre.as<double>();
-  p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.ascr = h->ascr.as<int>(); p.wscr = h->wscr.as<double>();
+  p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.ascr = h->ascr.as<int>(); p.wscr = h->wscr.as<double>(); p.jq = h->jq.as<uint4>();
   p.xbuf = h->xbuf.as<double>(); p.a_star = h->a_star.as<int>(); p.o_star = h->o_star.as<int>(); p.x_star = h->x_star.as<double>();
   p.logz = h->r_logz.as<double>(); p.traj = h->r_traj.as<double>(); p.status = h->r_status.as<int>();
   p.stream_ids = h->r_ids.as<unsigned long long>();
@@ -507,7 +509,7 @@ int cpimh_chains_run(cpimh_chains* h, int64_t R, uint64_t seed, uint32_t first_r
   api_fill_pf_params(h->cfg, h->geo, h->npre, &cp.pf);
   cp.pf.B = 0; cp.pf.seed = seed; cp.pf.first_filter = 0;
   cp.pf.obs = h->obs.as<double>(); cp.pf.theta = h->theta.as<double>(); cp.pf.pre = h->pre.as<double>();
-  cp.pf.hist_x = h->hist_x.as<double>(); cp.pf.hist_a = h->hist_a.as<int>(); cp.pf.ascr = h->ascr.as<int>(); cp.pf.wscr = h->wscr.as<double>();
+  cp.pf.hist_x = h->hist_x.as<double>(); cp.pf.hist_a = h->hist_a.as<int>(); cp.pf.ascr = h->ascr.as<int>(); cp.pf.wscr = h->wscr.as<double>(); cp.pf.jq = h->jq.as<uint4>();
   cp.pf.xbuf = h->xbuf.as<double>(); cp.pf.a_star = h->a_star.as<int>(); cp.pf.o_star = h->o_star.as<int>(); cp.pf.x_star = h->x_star.as<double>();
   // the proposal rings are the filter's per-filter outputs (entry = slot * RING + iteration mod RING)
   cp.pf.traj = h->ring_traj.as<double>(); cp.pf.logz = h->ring_logz.as<double>(); cp.pf.status = h->ring_status.as<int>();

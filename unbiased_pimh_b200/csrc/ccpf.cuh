@@ -246,8 +246,8 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
     // ---- gather -> common-noise transition -> pin the reference -> weigh  (R/CPF_coupled.R:50-62, 87-88)
     double m[2] = {-INFINITY, -INFINITY};
     for (int k = tid; k < N; k += NT) {
-      double ush = 0.5;
-      if (Model::USES_SHARED_U && !c.inj_trans) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
+      uint2 ush = make_uint2(0u, 0u);
+      if (Model::USES_SHARED_U && !c.inj_trans) { double ua; philox_u1raw(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
 #pragma unroll
       for (int s = 0; s < nsys; s++) {
         double x[D];

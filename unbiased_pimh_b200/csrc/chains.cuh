@@ -347,9 +347,9 @@ __global__ void model_op_kernel(ModelOpParams q) {
   }
   if (q.op == 0) Model::init(c, i, x);
   else if (q.op == 1) {
-    double ua = 0.5, ub = 0.5;
-    if (Model::USES_SHARED_U && !c.inj_trans) philox_u2(c.stream, i, q.time, CPIMH_P_RESAMPLE, 0, ua, ub);
-    int st = Model::transition(c, q.time, i, x, Model::step_const(c, q.time), ub);
+    double ua = 0.5; uint2 zw = make_uint2(0u, 0u);
+    if (Model::USES_SHARED_U && !c.inj_trans) philox_u1raw(c.stream, i, q.time, CPIMH_P_RESAMPLE, 0, ua, zw);
+    int st = Model::transition(c, q.time, i, x, Model::step_const(c, q.time), zw);
     if (st & 255) atomicOr(q.status, st & 255);
   }
   else { q.logw[i] = Model::logw(c, x, q.y); return; }

@@ -53,7 +53,7 @@ struct GssModel {
     else { double ua, ub; philox_u2(c.stream, i, 0, CPIMH_P_INIT, 0, ua, ub); z = normal1(ua, ub); }
     x[0] = sqrt(2.0) * z;
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double drift, double /*ush*/) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double drift, uint2 /*zw*/) {
     double z;
     if (c.inj_trans) z = trans_row(c, t, 0)[i];
     else { double ua, ub; philox_u2(c.stream, i, t, CPIMH_P_TRANS, 0, ua, ub); z = normal1(ua, ub); }
@@ -108,7 +108,7 @@ struct ArModel {
       for (int k = 0; k < D; k++) x[k] = c.inj_init[(size_t)k * c.N + i];
     } else normals(c, i, 0, CPIMH_P_INIT, x);
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double /*ush*/) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, uint2 /*zw*/) {
     double z[D], y[D];
     if (c.inj_trans) {
 #pragma unroll
@@ -137,7 +137,13 @@ struct ArModel {
 // ------------------------------------------------------------------ get_levy_sv (d = 2; x = (v, z))
 // Host precompute (api.cu, libm like the oracle): pre[0] = exp(-lambda), pre[1] = 1/lambda, pre[2] = omega^2/xi
 // (scale of the exponential jumps), pre[3] = L, pre[4..4+L) = F_0..F_{L-1}: the CDF of rpois(lambda xi^2/omega^2)
-// built by the recurrence p_k = p_{k-1} rate / k, F_k = F_{k-1} + p_k until it stops increasing.
+// built by the recurrence p_k = p_{k-1} rate / k, F_k = F_{k-1} + p_k until it stops increasing; three guard knots; then
+// pre[4+L+3 ..) = 1/p_0 .. 1/p_{L-1}.
+// RNG layout (DESIGN.md "RNG"): the Philox block whose first half is the resampling draw of slot i at time t carries, in its
+// second half, TWO 32-bit uniforms for the particle's transition: u_z -> the Poisson count k by inversion AND, through the
+// position of u_z inside its cell, c'_1 = (u_z - F_{k-1}) / p_k -- uniform on (0,1) and independent of k -- the time of the first
+// jump; u_w -> the size of the first jump.  69 % of the particles have no jump and 25 % exactly one: they need no further Philox
+// call.  Jumps j >= 2 use block (i, t, TRANS, j) as before.  (R's own unif_rand() has 32-bit resolution.)
 #define CPIMH_MULTI_MAX_E 16
 __device__ __forceinline__ int poisson_tab(const double* pre, double u) {
   const int L = (int)pre[3];
@@ -150,26 +156,34 @@ __device__ __forceinline__ int poisson_tab(const double* pre, double u) {
 }
 struct LevySvModel {
   static constexpr int D = 2;
-  // the Poisson uniform of particle i at time t is the SECOND uniform of the Philox block whose first uniform is the
-  // resampling draw of slot i at time t (one Philox call serves both; DESIGN.md "RNG")
-  static constexpr bool USES_SHARED_U = true;
+  static constexpr bool USES_SHARED_U = true;  // consumes the second half of the particle's resampling block (see above)
   static constexpr bool MULTI = false;
-  static constexpr bool JUMP_LIST = true;      // pf_fused.cuh walks the Poisson jumps of a thread's particles as one list
+  static constexpr bool JUMP_LIST = true;      // pf_fused.cuh queues the particles that jump and walks the queue with full warps
   static constexpr bool HAS_DTRANS = false;
   static constexpr bool SPLIT_W = true;       // the weight factorises as exp(a) * f without a log (see weight_parts)
-  __device__ static __forceinline__ int token(const ModelCtx& c, double upois) { return poisson_tab(c.pre, upois); }
+  __device__ static __forceinline__ int token(const ModelCtx& c, uint2 zw) { return poisson_tab(c.pre, u32_to_unit(zw.x)); }
   __device__ static double step_const(const ModelCtx& c, int) { return c.pre[0]; }
-  // one jump of the compound Poisson process (src/SVLevy_functions.cpp:62-67): c' = t - c ~ U(0,1), e ~ Exp(rate xi/w2)
+  // first jump of a particle with k >= 1 jumps, from the second half of its resampling block
+  __device__ static __forceinline__ void jump1(const ModelCtx& c, uint2 zw, int k, double& wa, double& e) {
+    const int L = (int)c.pre[3];
+    const double uz = u32_to_unit(zw.x);
+    const double fprev = k >= 2 ? c.pre[4 + k - 1] : (k == 1 ? c.pre[4] : 0.0);            // F_{k-1}
+    const double cp = (uz - fprev) * c.pre[4 + L + 3 + (k < L ? k : L - 1)];            // c' = t - c ~ U(0,1)
+    e = -rng_log(u32_to_unit(zw.y)) * c.pre[2];
+    wa = exp(-c.theta[4] * cp) * e;
+  }
+  // jump j >= 2 of the compound Poisson process (src/SVLevy_functions.cpp:62-67): c' = t - c ~ U(0,1), e ~ Exp(rate xi/w2)
   __device__ static __forceinline__ void jump(const ModelCtx& c, int i, int t, int j, double& wa, double& e) {
     double ua, ub;
     philox_u2(c.stream, i, t, CPIMH_P_TRANS, j, ua, ub);
     e = -rng_log(ub) * c.pre[2];
     wa = exp(-c.theta[4] * ua) * e;
   }
-  __device__ static void jump_sums(const ModelCtx& c, int i, int t, double upois, double& swe, double& se) {
-    int k = poisson_tab(c.pre, upois);
+  __device__ static void jump_sums(const ModelCtx& c, int i, int t, uint2 zw, double& swe, double& se) {
+    const int k = poisson_tab(c.pre, u32_to_unit(zw.x));
     double a = 0.0, b = 0.0;
-    for (int j = 1; j <= k; j++) {
+    if (k >= 1) jump1(c, zw, k, a, b);
+    for (int j = 2; j <= k; j++) {
       double wa, e;
       jump(c, i, t, j, wa, e);
       a += wa;
@@ -202,9 +216,9 @@ struct LevySvModel {
     if (c.inj_init) { z0 = c.inj_init[i]; swe = c.inj_init[(size_t)c.N + i]; se = c.inj_init[(size_t)2 * c.N + i]; }
     else {
       z0 = gamma_mt(c, i, xi * xi / w2, w2 / xi);
-      double ua, ub;
-      philox_u2(c.stream, i, 0, CPIMH_P_RESAMPLE, 0, ua, ub);
-      jump_sums(c, i, 0, ub, swe, se);
+      double ua; uint2 zw;
+      philox_u1raw(c.stream, i, 0, CPIMH_P_RESAMPLE, 0, ua, zw);
+      jump_sums(c, i, 0, zw, swe, se);
     }
     double z1 = c.pre[0] * z0 + swe;
     x[0] = c.pre[1] * (z0 - z1 + se);
@@ -216,10 +230,10 @@ struct LevySvModel {
     x[0] = c.pre[1] * (zold - znew + se);                // :67
     x[1] = znew;
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double ush) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, uint2 zw) {
     double swe, se;
     if (c.inj_trans) { swe = trans_row(c, t, 0)[i]; se = trans_row(c, t, 1)[i]; }
-    else jump_sums(c, i, t, ush, swe, se);
+    else jump_sums(c, i, t, zw, swe, se);
     finish(c, x, swe, se);
     return 0;
   }
@@ -287,7 +301,7 @@ struct SkModel {
   }
   // exact Gillespie over one inter-observation interval of 0.1 (:96-129).  Returns 0, or CPIMH_ERR_NOISE_OVERFLOW when
   // the injected event budget is exhausted; bit 8 set if an event index was clamped.
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, uint2) {
     double tcur = 0.0;
     int flags = 0;
     for (int m = 0;; m++) {
@@ -453,7 +467,7 @@ struct LorenzModel {
 #pragma unroll
     for (int k = 0; k < D; k++) x[k] = -1.0 + 4.0 * (0.5 * erfc(-z[k] / sqrt(2.0)));   // -1 + 4 pnorm(z)
   }
-  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, double /*ush*/) {
+  __device__ static int transition(const ModelCtx& c, int t, int i, double* x, double, uint2 /*zw*/) {
     const double F = c.theta[0], sx = c.theta[1];
     double z[D];
     if (c.inj_trans) {

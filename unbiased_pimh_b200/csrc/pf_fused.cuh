@@ -51,6 +51,7 @@ struct PfParams {
   int* ascr;                   // [ws][Npad] this step's ancestors when the path store is not dense
   double* wscr;                // [ws][Npad] last step's unnormalised weights (exact-order repeat of a resampling step)
   int* exact_repeats;          // [B] or null: number of steps a filter repeated with sequential-order sums
+  uint4* jq;                   // [ws][pf_jq_stride(Npad)] jump-list models: per-warp queues of the particles that jump (L2-resident scratch)
   int* a_star;                 // PATH_TREE:      [ws][M]
   int* o_star;                 // PATH_TREE:      [ws][M]
   double* x_star;              // PATH_TREE:      [ws][D][M]
@@ -124,6 +125,9 @@ __device__ __forceinline__ PfSmem pf_carve(const PfLayout& l) {
 // Where one filter's results go.  Only the three outputs that the chain kernel redirects are pointers; everything else is
 // addressed at its (rare) use as PfParams array + filter index `fb`, which costs no registers in the hot loop (the arrays are
 // kernel parameters in the constant bank; a null array switches the output off; fb < 0 means "no per-filter arrays").
+// entries (16 bytes) of jump-queue scratch per workspace: 32 ceil(N / threads) per warp, threads ceil(N / threads) <= N + threads in all
+__host__ __device__ inline size_t pf_jq_stride(int Npad) { return (size_t)2 * Npad + 512; }
+
 struct FilterOut {
   double* logz; double* traj; int* status;
 };
@@ -217,22 +221,33 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // -- sorted uniforms (src/multinomial.cpp:18-24) and CDF (:17); zero the offspring counters
     if (tree) for (int i = tid; i < (Npad >> 1); i += NT) sm.off32[i] = 0u;
     const bool draw_res = !ident && !inj_res;
-    unsigned long long tok0 = 0ull, tok1 = 0ull;           // 8-bit model tokens of this thread's particles (jump counts)
+    // Jump-list models (levy_sv): a particle's jump count comes from the second half of its resampling block.  The particles
+    // that jump (31 % at the reference's theta) are appended to a queue of the WARP that owns them (4 words per entry in an
+    // L2-resident scratch row), so that the jumps are later computed by full warps instead of the 16 of 32 lanes a per-thread
+    // walk keeps busy.  hasj: bit e = particle e of this thread has jumps (its sums will be in its S / C slots).
+    unsigned hasj = 0u;
+    int nq1 = 0;                                           // entries in this warp's queue (warp-uniform)
+    uint4* jq = Model::JUMP_LIST ? p.jq + (size_t)ws * pf_jq_stride(Npad) + (size_t)(tid >> 5) * 32 * ((N + NT - 1) / NT) : nullptr;   // a warp owns 32 x ceil(N / NT) particles
     if (draw_res && tid == 0) sm.dscr2[0] = -rng_log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0));   // E_N, read after the scan's barriers
     if (draw_res || (need_shared_u && jump_list)) {
       int e = 0;
-#if (CPIMH_EXP & 8)
-#pragma unroll 2
-#endif
-      for (int i = tid, ip = kp0; i < N; i += NT, ip += NTP, e++) {
-        double ua, ub;
-        philox_u2(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, ub);
-        if (draw_res) sm.S[ip] = -rng_log(ua);                 // exponential spacing E_i (see the ladder comment below)
+      const int lane = tid & 31;
+      for (int i0 = tid - lane; i0 < N; i0 += NT, e++) {   // warp-uniform trip count: the queue append votes with all 32 lanes
+        const int i = i0 + lane, ip = kp0 + e * NTP;
+        const bool in = i < N;
+        double ua = 0.5; uint2 zw = make_uint2(0u, 0u);
+        if (in) philox_u1raw(stream, i, t, CPIMH_P_RESAMPLE, 0, ua, zw);
+        if (draw_res && in) sm.S[ip] = -rng_log(ua);                 // exponential spacing E_i (see the ladder comment below)
         if constexpr (Model::JUMP_LIST) {
-          if (jump_list) {                                // the model turns its uniform into a small count right away
-            int tk = Model::token(c, ub);
+          if (jump_list && need_shared_u) {               // the model turns its uniform into a small count right away
+            int tk = in ? Model::token(c, zw) : 0;
             if (tk > 255) { tk = 255; flag_status(CPIMH_ERR_INVALID); }
-            if (e < 8) tok0 |= (unsigned long long)tk << (8 * e); else tok1 |= (unsigned long long)tk << (8 * (e - 8));
+            const unsigned vote = __ballot_sync(0xffffffffu, tk > 0);
+            if (tk > 0) {
+              hasj |= 1u << e;
+              jq[nq1 + __popc(vote & ((1u << lane) - 1u))] = make_uint4((unsigned)i | ((unsigned)tk << 24), zw.x, zw.y, (unsigned)ip);
+            }
+            nq1 += __popc(vote);
           }
         }
       }
@@ -312,9 +327,9 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       double x[D];
 #pragma unroll
       for (int q = 0; q < D; q++) x[q] = xold[(size_t)q * Npad + a];
-      double ush = 0.5;
-      if constexpr (Model::USES_SHARED_U) {              // second uniform of the particle's OWN resampling block (DESIGN.md "RNG")
-        if (!c.inj_trans) { double ua; philox_u2(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
+      uint2 ush = make_uint2(0u, 0u);
+      if constexpr (Model::USES_SHARED_U) {              // second half of the particle's OWN resampling block (DESIGN.md "RNG")
+        if (!c.inj_trans) { double ua; philox_u1raw(stream, k, t, CPIMH_P_RESAMPLE, 0, ua, ush); }
       }
       flag_status(Model::transition(c, t, k, x, sc, ush));
       finish_particle(k, kp, a, x);
@@ -363,29 +378,40 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         }
         if (vote_repeat()) { exact = true; continue; }
         const int E = (N - tid + NT - 1) / NT;
-        auto tok = [&](int e) -> int { return (int)(((e < 8 ? tok0 >> (8 * e) : tok1 >> (8 * (e - 8)))) & 255ull); };
         if (!c.inj_trans) {
-          // walk the non-zero token bytes: the position of the lowest set bit gives the next particle with jumps
-          unsigned long long rem = tok0;
-          int ebase = 0;
-          if (rem == 0ull) { rem = tok1; ebase = 8; }
-          double sa = 0.0, sb = 0.0;
-          int j = 1;
-          while (rem != 0ull) {
-            const int sh = (__ffsll((long long)rem) - 1) & ~7;            // bit offset of the current particle's byte
-            const int e = ebase + (sh >> 3);
-            const int kj = (int)((rem >> sh) & 255ull);
-            double wa, ev;
-            Model::jump(c, tid + e * NT, t, j, wa, ev);
-            sa += wa;
-            sb += ev;
-            if (++j > kj) {
-              sm.S[kp0 + e * NTP] = sa; sm.C[kp0 + e * NTP] = sb;
-              sa = 0.0; sb = 0.0; j = 1;
-              rem &= ~(255ull << sh);
-              if (rem == 0ull && ebase == 0) { rem = tok1; ebase = 8; }
+          // (1) first jumps: the warp's queue, one entry per lane and pass -- every lane busy, no Philox call (the entry carries the
+          // two 32-bit uniforms of the particle's own resampling block); particles with more jumps go to a second queue
+          const int lane = tid & 31;
+          __syncwarp();
+          int nq2 = 0;
+          for (int q0 = 0; q0 < nq1; q0 += 32) {
+            const int q = q0 + lane;
+            const bool on = q < nq1;
+            uint4 en = on ? jq[q] : make_uint4(0u, 0u, 0u, 0u);
+            const int tk = (int)(en.x >> 24);
+            if (on) {
+              double wa, ev;
+              Model::jump1(c, make_uint2(en.y, en.z), tk, wa, ev);
+              sm.S[en.w] = wa; sm.C[en.w] = ev;
+            }
+            const unsigned more = __ballot_sync(0xffffffffu, on && tk > 1);
+            __syncwarp();                                   // entry q0.. has been read by every lane before slot q0.. may be rewritten below
+            if (on && tk > 1) jq[nq2 + __popc(more & ((1u << lane) - 1u))] = en;   // compacted in place: nq2 <= q0 + (lanes before me) <= q
+            nq2 += __popc(more);
+          }
+          __syncwarp();
+          // (2) jumps 2..k of the few particles that have them (6 % of the particles): one Philox block per jump, added in jump order
+          for (int q0 = 0; q0 < nq2; q0 += 32) {
+            const int q = q0 + lane;
+            if (q < nq2) {
+              const uint4 en = jq[q];
+              const int tk = (int)(en.x >> 24), i = (int)(en.x & 0xffffffu);
+              double sa = sm.S[en.w], sb = sm.C[en.w];
+              for (int j = 2; j <= tk; j++) { double wa, ev; Model::jump(c, i, t, j, wa, ev); sa += wa; sb += ev; }
+              sm.S[en.w] = sa; sm.C[en.w] = sb;
             }
           }
+          __syncwarp();                                     // the sums of a particle were written by another lane of ITS OWN warp
         }
         // software pipeline over the thread's particles: the ancestor of particle e+2 and the gathered state of particle
         // e+1 are in flight (L2 latency) while particle e is finished and weighed
@@ -405,7 +431,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
           }
           a_nxt = (e + 2 < E) ? arow[k + 2 * NT] : 0;
           if (c.inj_trans) { swe = trans_row(c, t, 0)[k]; se = trans_row(c, t, 1)[k]; }
-          else if (tok(e) > 0) { swe = sm.S[kp]; se = sm.C[kp]; }
+          else if ((hasj >> e) & 1u) { swe = sm.S[kp]; se = sm.C[kp]; }
           Model::finish(c, x, swe, se);
           finish_particle(k, kp, a, x);
         }
