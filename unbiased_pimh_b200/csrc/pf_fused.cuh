@@ -384,10 +384,12 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
           const int lane = tid & 31;
           __syncwarp();
           int nq2 = 0;
+          uint4 nxt = lane < nq1 ? jq[lane] : make_uint4(0u, 0u, 0u, 0u);
           for (int q0 = 0; q0 < nq1; q0 += 32) {
             const int q = q0 + lane;
             const bool on = q < nq1;
-            uint4 en = on ? jq[q] : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 en = nxt;
+            if (q + 32 < nq1) nxt = jq[q + 32];             // next pass's entry is in flight (L2) while this one is computed
             const int tk = (int)(en.x >> 24);
             if (on) {
               double wa, ev;
