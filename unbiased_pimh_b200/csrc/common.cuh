@@ -48,32 +48,33 @@ __device__ __forceinline__ double u64_to_unit(uint32_t lo, uint32_t hi) {
 }
 struct Stream {               // identifies one filter's random streams
   uint32_t k0, k1;            // seed
-  uint32_t hi;                // high word of the filter id = iteration of a chain (20 bits used)
+  uint32_t c1hi, c3hi;        // iteration of a chain (high word of the filter id, 20 bits): bits 0..11 << 20 for word 1, bits 12..19 << 24 for word 3
   uint32_t c2;                // stream id
 };
 __device__ __forceinline__ Stream make_stream(unsigned long long seed, unsigned long long filter_id) {
   Stream s;
   s.k0 = (uint32_t)seed; s.k1 = (uint32_t)(seed >> 32);
-  s.hi = (uint32_t)(filter_id >> 32);
+  const uint32_t hi = (uint32_t)(filter_id >> 32);
+  s.c1hi = hi << 20; s.c3hi = (hi << 12) & 0xff000000u;
   s.c2 = (uint32_t)filter_id;
   return s;
 }
 __device__ __forceinline__ void philox_u2(const Stream& s, uint32_t i, int t, int purpose, uint32_t draw, double& ua, double& ub) {
-  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | (s.hi << 20), s.c2, ((uint32_t)purpose | (draw << 8)) | ((s.hi << 12) & 0xff000000u)), make_uint2(s.k0, s.k1));
+  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, ((uint32_t)purpose | (draw << 8)) | s.c3hi), make_uint2(s.k0, s.k1));
   ua = u64_to_unit(r.x, r.y);
   ub = u64_to_unit(r.z, r.w);
 }
 // first uniform (52 bits, words x,y) + the raw second half (words z,w) of the block: models that split the second half into
 // two 32-bit uniforms (LevySvModel: Poisson count + first jump) read it in this form
 __device__ __forceinline__ void philox_u1raw(const Stream& s, uint32_t i, int t, int purpose, uint32_t draw, double& ua, uint2& zw) {
-  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | (s.hi << 20), s.c2, ((uint32_t)purpose | (draw << 8)) | ((s.hi << 12) & 0xff000000u)), make_uint2(s.k0, s.k1));
+  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, ((uint32_t)purpose | (draw << 8)) | s.c3hi), make_uint2(s.k0, s.k1));
   ua = u64_to_unit(r.x, r.y);
   zw = make_uint2(r.z, r.w);
 }
 // 32-bit uniform in the open interval (0,1): (x + 0.5) * 2^-32 (exact in fp64; R's own unif_rand() has 32-bit resolution)
 __device__ __forceinline__ double u32_to_unit(uint32_t x) { return (__uint2double_rn(x) + 0.5) * 0x1p-32; }
 __device__ __forceinline__ double philox_u1(const Stream& s, uint32_t i, int t, int purpose, uint32_t draw) {
-  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | (s.hi << 20), s.c2, ((uint32_t)purpose | (draw << 8)) | ((s.hi << 12) & 0xff000000u)), make_uint2(s.k0, s.k1));
+  uint4 r = philox4x32_10(make_uint4(i, (uint32_t)t | s.c1hi, s.c2, ((uint32_t)purpose | (draw << 8)) | s.c3hi), make_uint2(s.k0, s.k1));
   return u64_to_unit(r.x, r.y);
 }
 // ---------------------------------------------------------------- transcendental maps of the RNG specification

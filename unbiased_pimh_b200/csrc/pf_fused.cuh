@@ -229,7 +229,9 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     int nq1 = 0;                                           // entries in this warp's queue (warp-uniform)
     uint4* jq = Model::JUMP_LIST ? p.jq + (size_t)ws * pf_jq_stride(Npad) + (size_t)(tid >> 5) * 32 * ((N + NT - 1) / NT) : nullptr;   // a warp owns 32 x ceil(N / NT) particles
     if (draw_res && tid == 0) sm.dscr2[0] = -rng_log(philox_u1(stream, N, t, CPIMH_P_RESAMPLE, 0));   // E_N, read after the scan's barriers
-    if (draw_res || (need_shared_u && jump_list)) {
+    if constexpr (!Model::JUMP_LIST) {
+      if (draw_res) for (int i = tid, ip = kp0; i < N; i += NT, ip += NTP) sm.S[ip] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));   // exponential spacing E_i
+    } else if (draw_res || (need_shared_u && jump_list)) {
       int e = 0;
       const int lane = tid & 31;
       for (int i0 = tid - lane; i0 < N; i0 += NT, e++) {   // warp-uniform trip count: the queue append votes with all 32 lanes
