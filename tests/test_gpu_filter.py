@@ -307,3 +307,17 @@ def test_chain_iteration_index_has_twenty_bits(up, oracle, golden):
         assert np.max(np.abs(r["logz_t"][0] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ and int(r["path_index"][0]) == o["path_index"]
         lz[it] = r["logz"][0]
     assert len(set(lz.values())) == 4
+
+
+def test_levy_sv_observation_no_particle_explains(up, oracle, golden):
+    """levy_sv forms its weights as exp(a) v^(-1/2) with a <= 0 and no maximum subtracted; when every a is below -600 (an absurd
+    observation) the kernel falls back to the maximum-relative form: log Z stays finite and equal to the oracle's."""
+    th = golden["sv_theta_mle"]
+    y = golden["sv_y"][:6].copy()
+    y[3, 0] = 250.0                                   # (y - mu - beta v)^2 / (2 v) ~ 1e4 for every particle
+    r = up.cpf_batch(512, up.get_levy_sv(), th, y, 2, seed=8, logz_t=True)
+    ocfg = oracle.make_config(oracle.MODEL_LEVY_SV, 2, 1, 512, 6, theta=th)
+    for b in range(2):
+        o = oracle.cpf(ocfg, y, seed=8, filter_id=b)
+        assert np.all(np.isfinite(r["logz_t"][b])) and o["logz_t"][3] < -600
+        assert np.max(np.abs(r["logz_t"][b] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ and int(r["path_index"][b]) == o["path_index"]

@@ -313,10 +313,18 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       for (int q = 0; q < D; q++) xnew[(size_t)q * Npad + k] = x[q];
       double lw;
       if constexpr (Model::SPLIT_W) {
-        if (split_w) { double f; Model::weight_parts(c, x, y, lw, f); sm.C[kp] = f; }
+        if (split_w) {
+          // a <= 0 by construction (Model::SPLIT_W): exp(a) cannot overflow, so the weight is formed right here with max = 0
+          // and the separate weight pass is skipped; if EVERY a is below -600 (an observation no particle explains) the pass
+          // below redoes the weights against the true maximum
+          double f; Model::weight_parts(c, x, y, lw, f);
+          const double w = exp(lw) * f;
+          sm.C[kp] = w;
+          if (!(CPIMH_EXP & 2)) p.wscr[(size_t)ws * Npad + k] = w;
+        }
         else lw = Model::logw(c, x, y);
       } else lw = Model::logw(c, x, y);
-      sm.S[kp] = lw;
+      if (!split_w) sm.S[kp] = lw;
       m = fmax(m, lw);
       if (dense) hist_a[(size_t)(t - 1) * Npad + k] = a;
       if (tree) {                                      // src/tree.cpp:39-42, 90-94
@@ -473,7 +481,21 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     m = block_max(m, sm.dscr);
     double sloc = 0.0;
     double* wscr = p.wscr + (size_t)ws * Npad;             // this step's unnormalised weights, for an exact-order repeat of the next step
-    if (split_w) { for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP) { double w = exp(sm.S[kp] - m) * sm.C[kp]; sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
+    if (split_w) {
+      if constexpr (Model::SPLIT_W) {
+        if (m >= -600.0) m = 0.0;                          // the weights are already in C and wscr (finish_particle)
+        else {                                             // all weights would underflow: redo them relative to the maximum
+          for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP) {
+            double x[D], a, f;
+#pragma unroll
+            for (int q = 0; q < D; q++) x[q] = xnew[(size_t)q * Npad + k];
+            Model::weight_parts(c, x, y, a, f);
+            const double w = exp(a - m) * f;
+            sm.C[kp] = w; wscr[k] = w;
+          }
+        }
+      }
+    }
     else { for (int k = tid, kp = kp0; k < N; k += NT, kp += NTP) { double w = exp(sm.S[kp] - m); sm.C[kp] = w; if (!(CPIMH_EXP & 2)) wscr[k] = w; sloc += w; } }
     // the sum is evaluated as one fixed tree, whatever the CTA size (common.cuh block_sum_canonical)
     const double s = (CPIMH_EXP & 1) ? block_sum(sloc, sm.dscr) : block_sum_canonical([&](int, int kp) { return sm.C[kp]; }, N, sm.dscr);
