@@ -212,7 +212,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // somewhere in the CTA), it runs a second time with the reference's own operation order (exact): see "ancestors" below.
     bool exact = false;
     for (;;) {
-    double sumw = 1.0, margin_r = 0.0;
+    double sumw = 1.0;
     m = -INFINITY;
     if (tid == 0 && !exact) sm.iscr[35] = 0;             // near-knot flag (set by check_knots, read by vote_repeat); the repeat pass ignores it
     // block-wide vote at a barrier the step has anyway; true => repeat the step in exact order
@@ -276,7 +276,6 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
       // non-negative terms differ by at most 2 gamma_N of the total, likewise the two u_k; 12 (N + 2) 2^-53 sum(w) bounds the
       // sum of all those differences (DESIGN.md "Exact ancestors").
       if (tid == 0) sm.dscr2[2] = exact ? 0.0 : (double)(N + 2) * 0x1.8p-50 * sumw;      // read after the barrier below
-      margin_r = exact ? 0.0 : (double)(N + 2) * 0x1.8p-50 * sumw;
       if (!inj_res) sumw = sumw / (sm.S[pad16(N - 1)] + sm.dscr2[0]);   // total = P_{N-1} + E_N
       // every 32nd sorted uniform gets a full search; the others then search only between their neighbours' results
       const int nrows = (N + 31) >> 5;
@@ -296,7 +295,7 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
     // 10^4 steps at N = 4096) the CTA repeats the step with normalised weights and left-to-right sums by one thread.
     auto check_knots = [&](int a, double u) {
       if (CPIMH_EXP & 4) return;
-      const double prev = sm.C[pad16(a > 0 ? a - 1 : 0)], cur = sm.C[pad16(a)], margin = (CPIMH_EXP & 16) ? margin_r : sm.dscr2[2];      // C carries a +infinity sentinel at N
+      const double prev = sm.C[pad16(a > 0 ? a - 1 : 0)], cur = sm.C[pad16(a)], margin = sm.dscr2[2];      // C carries a +infinity sentinel at N
       if ((a > 0 && u - prev < margin) || (cur - u <= margin)) sm.iscr[35] = 1;
     };
     auto ancestor_of = [&](int k, int kp) -> int {
