@@ -49,11 +49,13 @@ def craft_sorted_uniforms(rng, w, ncraft):
     return np.sort(np.array(e)), hits
 
 
-CASES = [("ar1", 256, 0), ("gss", 1000, 0), ("ar3", 2048, 0), ("levy_sv", 4096, 0), ("levy_sv", 4096, 1024), ("sk", 512, 0), ("ar1", 37, 0)]
+CASES = [("ar1", 256, 0, {}), ("gss", 1000, 0, {}), ("ar3", 2048, 0, {}), ("levy_sv", 4096, 0, {}), ("levy_sv", 4096, 1024, {}), ("sk", 512, 0, {}), ("ar1", 37, 0, {}),
+         # the general (non-lean) instantiation: ancestor tree as the path store, and the reference's random_shuffle switched on
+         ("levy_sv", 2048, 0, {"store_paths": 3}), ("gss", 600, 0, {"store_paths": 3}), ("ar1", 500, 0, {"shuffle": 1}), ("levy_sv", 1024, 0, {"shuffle": 1})]
 
 
-@pytest.mark.parametrize("name,N,threads", CASES)
-def test_uniforms_on_cdf_knots_give_reference_ancestors(up, oracle, golden, name, N, threads):
+@pytest.mark.parametrize("name,N,threads,kw", CASES)
+def test_uniforms_on_cdf_knots_give_reference_ancestors(up, oracle, golden, name, N, threads, kw):
     rng = np.random.default_rng(N + threads)
     A = np.array([[1, 0, 0, 0], [0, 1, 2, 0]], dtype=float)
     model, theta, obs = {
@@ -65,7 +67,7 @@ def test_uniforms_on_cdf_knots_give_reference_ancestors(up, oracle, golden, name
     }[name]
     B, seed = 2, 99
     # 1. the normalised weights after step 1 (a T = 1 filter; step 1 never resamples)
-    pb1 = up.PfBatch(model, theta, obs[:1], N, B, threads_per_filter=threads)
+    pb1 = up.PfBatch(model, theta, obs[:1], N, B, threads_per_filter=threads, **kw)
     pb1.run(B, seed)
     pb1.fetch()
     W = [pb1.fetch_all_particles(b, exp_path=False)["weights"] for b in range(B)]
@@ -78,9 +80,12 @@ def test_uniforms_on_cdf_knots_give_reference_ancestors(up, oracle, golden, name
     for b in range(B):
         res[b, 1] = E[b]
     # 3. the T = 2 filter (same Philox streams => same step 1) with those uniforms injected
-    pb2 = up.PfBatch(model, theta, obs[:2], N, B, threads_per_filter=threads)
+    pb2 = up.PfBatch(model, theta, obs[:2], N, B, threads_per_filter=threads, **kw)
     pb2.record_ancestors(True)
-    pb2.set_noise(B, {"resample": res})
+    nz = {"resample": res}
+    if kw.get("shuffle"):            # uniforms that make std::random_shuffle the identity (u_i -> j = i): ancestors stay comparable
+        nz["shuffle"] = np.broadcast_to((np.arange(1, N) + 0.5) / np.arange(2, N + 1), (B, 2, N - 1)).copy()
+    pb2.set_noise(B, nz)
     pb2.run(B, seed)
     pb2.fetch()
     rep = pb2.fetch_exact_repeats(B)
