@@ -10,6 +10,7 @@
 // State and path storage are the same dense history hist_x[t][i][0..d) (array of rows: a particle's d doubles are
 // contiguous, which is also R's d x N column-major layout) + hist_a[t][i].
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "host_common.h"
@@ -22,7 +23,7 @@ namespace cpimh {
 
 
 struct WideParams {
-  int N, T, D, B, GX, G, gshift, pgrid, substeps;   // GX = number of warp groups (softmax blocks), G = 1 << gshift particles each
+  int N, T, D, B, GX, G, pgrid, substeps;   // GX = number of warp groups (softmax blocks), G <= 32 particles each (any G, not only powers of two)
   unsigned long long seed, first_filter;
   const double* obs;          // [T][D]
   double F, sx, sy, isy, cst;     // isy = 1 / sy
@@ -66,8 +67,16 @@ __global__ void wide_init_kernel(WideParams p) {
 }
 
 // ------------------------------------------------------------------ one time step for all particles of all filters
+#ifndef WIDE_MINB
+#define WIDE_MINB 8
+#endif
+#ifndef WIDE_UNROLL
+#define WIDE_UNROLL 1
+#endif
+#define WIDE_PRAGMA_(x) _Pragma(#x)
+#define WIDE_PRAGMA_UNROLL(n) WIDE_PRAGMA_(unroll n)
 template <int C, bool TWO>
-__global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, int t, int ident, int prep_next) {
+__global__ void __launch_bounds__(128, WIDE_MINB) wide_propagate_kernel(WideParams p, int t, int ident, int prep_next) {
   constexpr int D = 32 * C;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int N = p.N, G = p.G;
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
   const double scale = ident ? 0.0 : (TWO ? GCb[p.GX - 1] / p.ptot[b] : (p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b]));   // u = sumw e_k  /  (sumw / total) P_k
   // persistent warps: group g = G consecutive particles; the grid covers the machine once and strides over the groups
   for (int grp = blockIdx.x * nwarp + warp; grp < p.GX; grp += gridDim.x * nwarp) {
-    const long long base = (long long)grp << p.gshift;
+    const long long base = (long long)grp * G;
     // ancestors of this group's particles: lanes search in parallel (src/multinomial.cpp:25-28 rule)
     const long long k = base + lane;
     const bool mine = lane < G && k < N;
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
         if (gs >= p.GX) gs = p.GX - 1;
         double acc = gs > 0 ? GCb[gs - 1] : 0.0;
         const double f = facb[gs];
-        const long long j0 = (long long)gs << p.gshift;
+        const long long j0 = (long long)gs * G;
         const int cnt = (int)min((long long)G, (long long)N - j0);
         a = (int)j0 + cnt - 1;
         for (int j = 0; j < cnt; j++) {                            // knots inside the group, left to right (src/multinomial.cpp:25-28 rule)
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(128, 8) wide_propagate_kernel(WideParams p, in
       if (p.anc_rec) p.anc_rec[((size_t)b * p.T + (t - 1)) * N + k] = a;
     }
     double mylw = -INFINITY;
-#pragma unroll 2
+WIDE_PRAGMA_UNROLL(WIDE_UNROLL)
     for (int j = 0; j < G && base + j < N; j++) {
       const int aj = __shfl_sync(0xffffffffu, a, j);
       const long long kk = base + j;
@@ -194,14 +203,14 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y, N = p.N;
-  const int gshift = p.gshift;                      // softmax block = one warp group of wide_propagate
+  const int G = p.G;                                // softmax block = one warp group of wide_propagate
   double m = -INFINITY;
   for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[(size_t)b * p.GX + i]);
   m = block_max(m, scr);
   // element ranges are aligned to propagate blocks
   const int bper = (p.GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER;
   const int c0 = rank * bper, c1 = min(p.GX, c0 + bper);
-  const long long lo = (long long)c0 << gshift, hi = min((long long)N, (long long)c1 << gshift);
+  const long long lo = (long long)c0 * G, hi = min((long long)N, (long long)c1 * G);
   double* Cb = p.C + (size_t)b * N;
   double* Sb = p.S + (size_t)b * N;
   const bool ladder = prep && !p.inj_resample;
@@ -235,7 +244,7 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
 #pragma unroll
     for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; r[e] = q < n ? Wb[base + q] : 0.0; }
 #pragma unroll
-    for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) buf[q] = (r[e] * fac[(int)((base + q - lo) >> gshift)]) / s; }   // normweights (R/CPF.R:63)
+    for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) buf[q] = (r[e] * fac[(int)(base + q - lo) / G]) / s; }   // normweights (R/CPF.R:63)
     __syncthreads();
     block_scan_inplace<false>(buf, n, scr);
 #pragma unroll
@@ -327,7 +336,7 @@ __global__ void wide_path_kernel(WideParams p) {
 struct WideFilter {
   cpimh_config cfg;
   int64_t maxB, lastB, launches, bytes;
-  int GX, G, gshift, pgrid, record_anc;
+  int GX, G, pgrid, record_anc;
   std::vector<double> obs_host;
   DevBuf ptot;
   DevBuf obs, hist_x, hist_a, lw, lw2, GC, GP, fac, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
@@ -335,16 +344,19 @@ struct WideFilter {
   bool have_inj[4];
 };
 
-static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* gshift, int* GX) {
-  // particles per warp group: enough groups that the persistent propagate grid balances well (>= ~4 groups per warp slot),
-  // at most 32 so the per-group ancestor search stays one pass
-  // (measured on B200, N = 65536: G = 8 beats G = 2 by 30 % -- the 16-step binary search in the global CDF is paid once
-  // per group by up to 32 lanes in parallel, so small groups are dominated by its latency)
+static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* GX) {
+  // particles per warp group: enough groups that the propagate grid balances (>= ~1.5 groups per resident warp slot), at most
+  // 32 so the per-group ancestor search stays one pass.  Any G in 1..32 works (the kernels multiply / divide by G); measured
+  // on B200 at N = 65536, B = 1 (tools/ab_wide.py, CPIMH_WIDE_G): G = 8 / 12 / 14 / 16 / 24 / 28 / 32 give
+  // 0.87 / 0.97 / 1.01 / 1.04 / 1.01 / 1.05 / 0.99 e9 particle-steps/s -- flat from 14 up (the kernel is issue-bound, not
+  // occupancy-bound: profiles/r2_lorenz64_propagate_ncu_summary.txt), so the power of two is kept; G = 8 beats G = 2 by 30 %
+  // (the binary search in the CDF is paid once per group by up to 32 lanes in parallel).
   long long target = (long long)num_sms * 48;
   long long g = ((long long)c.nparticles * B + target - 1) / target;
-  int G_ = 1, sh = 0;
-  while (G_ < 32 && G_ < g) { G_ <<= 1; sh++; }
-  *G = G_; *gshift = sh;
+  int G_ = 1;
+  while (G_ < 32 && G_ < g) G_ <<= 1;
+  if (const char* e = getenv("CPIMH_WIDE_G")) { const int v = atoi(e); if (v >= 1 && v <= 32) G_ = v; }   // tuning aid only
+  *G = G_;
   *GX = (int)(((long long)c.nparticles + G_ - 1) / G_);
 }
 
@@ -362,8 +374,8 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   WideFilter* h = new WideFilter();
   h->cfg = cfg; h->maxB = max_filters; h->lastB = 0; h->launches = 0; h->bytes = 0; h->record_anc = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
-  wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->gshift, &h->GX);
-  h->pgrid = prop.multiProcessorCount * 8;                  // at least one resident wave of wide_propagate CTAs
+  wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->GX);
+  h->pgrid = prop.multiProcessorCount * WIDE_MINB;          // at least one resident wave of wide_propagate CTAs
   CPIMH_REQUIRE((h->GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER <= WIDE_MAX_BLOCKS_PER_CTA, "N too large for the cluster scan");
   const size_t B = (size_t)max_filters, N = cfg.nparticles, T = cfg.nobs, D = cfg.dim;
   size_t free_b = 0, total_b = 0;
@@ -475,7 +487,7 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   const cpimh_config& c = h->cfg;
   WideParams p;
   memset(&p, 0, sizeof(p));
-  p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.GX = h->GX; p.G = h->G; p.gshift = h->gshift; p.pgrid = h->pgrid; p.substeps = c.substeps < 1 ? 1 : c.substeps;
+  p.N = c.nparticles; p.T = c.nobs; p.D = c.dim; p.B = (int)B; p.GX = h->GX; p.G = h->G; p.pgrid = h->pgrid; p.substeps = c.substeps < 1 ? 1 : c.substeps;
   p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>();
   p.F = c.theta[0]; p.sx = c.theta[1]; p.sy = c.theta[2]; p.isy = 1.0 / c.theta[2];
