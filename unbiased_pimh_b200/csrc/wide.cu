@@ -1,12 +1,15 @@
 // wide.cu -- the bootstrap filter for WIDE states (Lorenz 96, d = 32 or 64; BASELINE config 5: d = 64, N = 65536,
 // T = 500, path storage on): one filter spans the whole GPU.  Same step as pf_fused.cuh (R/CPF.R:35-67) but split at
 // the two grid-wide dependencies:
-//   wide_propagate      warp per particle: ancestor search in the CDF, 512-byte coalesced gather of the ancestor's state,
-//                       RK4 on shuffles (lorenz_wide.cuh), process noise, measurement density; then block-local softmax
-//                       numerators exp(lw - m_block), block sums, and the next step's exponential spacings -log(u)
-//   wide_weights_scan   one 8-CTA thread-block cluster per filter: global max, rescale blocks by exp(m_block - m),
-//                       normalise, log Z increment, chunk scans (CDF and sorted-uniform ladder) with carries exchanged
-//                       through distributed shared memory
+//   wide_propagate      warp per GROUP of G <= 32 consecutive particles: ancestor search, 512-byte coalesced gather of the
+//                       ancestor's state, RK4 on shuffles (lorenz_wide.cuh), process noise, measurement density; then
+//                       group-local softmax numerators exp(lw - m_group), group sums, the next step's spacings -log(u).
+//                       Philox path (two-level CDF): 1024-thread CTAs, one per SM; each CTA's prologue rebuilds the step's
+//                       group table (factors exp(m_group - m), CDF over groups, ladder over groups, log Z of the previous
+//                       step) in its shared memory from the previous launch's group records -- one launch per time step.
+//   wide_weights_scan   one 8-CTA thread-block cluster per filter: the per-PARTICLE normalised CDF (carries exchanged
+//                       through distributed shared memory); once after step T for the final path pick, and between steps
+//                       only on the injected-uniform parity path.
 // State and path storage are the same dense history hist_x[t][i][0..d) (array of rows: a particle's d doubles are
 // contiguous, which is also R's d x N column-major layout) + hist_a[t][i].
 #include <math.h>
@@ -30,12 +33,18 @@ struct WideParams {
   double* hist_x; int* hist_a;
   double* lw; double* C; double* S;
   // two-level CDF (round 2): per-group inclusive sums instead of per-particle scans; lw is double-buffered by step parity
-  double* lw2; double* GC; double* GP; double* fac; int two_level;
-  double* pmax; double* psum; double* pv; double* mstep; double* ptot;
+  double* lw2; int two_level;
+  double* pmax; double* psum; double* pv; double* mstep; double* ptot;   // pmax / psum / pv: [2][B][GX], indexed by the parity of the step that wrote them
+  size_t maxB;                // stride of the parity dimension (filters allocated)
   double* logz_t; double* logz; double* traj; int* path_index;
   const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_path;
   int* anc_rec;
 };
+
+
+// group records (max, sum of numerators, sum of spacings) of step t live in half (t & 1): a fused launch reads step t-1's half
+// in its prologue while its faster CTAs already write step t's
+__device__ __forceinline__ size_t wide_rec(const WideParams& p, int t, int b) { return ((size_t)(t & 1) * p.maxB + (size_t)b) * (size_t)p.GX; }
 
 __device__ __forceinline__ int g_count_le_w(const double* c, int n, double u) {
   int lo = 0, hi = n;
@@ -75,12 +84,45 @@ __global__ void wide_init_kernel(WideParams p) {
 #endif
 #define WIDE_PRAGMA_(x) _Pragma(#x)
 #define WIDE_PRAGMA_UNROLL(n) WIDE_PRAGMA_(unroll n)
+// TWO (the two-level CDF: the Philox path when the group table fits shared memory): 1024-thread CTAs, one per SM; every CTA first rebuilds the
+// step's group table (factors, inclusive CDF over groups, inclusive ladder over groups) from the previous launch's group
+// records in ITS OWN shared memory -- redundant across CTAs (3 * GX doubles read from L2, two scans: ~3 us) but it removes
+// the separate one-CTA scan launch (~10 us with its gap while 147 SMs idle) and turns the per-group binary search from 13
+// dependent L2 loads into shared-memory loads.
+// group table in shared memory: 3 * GX doubles must fit beside the static arrays (227 KB per CTA)
+#define WIDE_MAX_GROUPS 8192
 template <int C, bool TWO>
-__global__ void __launch_bounds__(128, WIDE_MINB) wide_propagate_kernel(WideParams p, int t, int ident, int prep_next) {
+__global__ void __launch_bounds__(TWO ? 1024 : 128, TWO ? 1 : WIDE_MINB) wide_propagate_kernel(WideParams p, int t, int ident, int prep_next) {
   constexpr int D = 32 * C;
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int N = p.N, G = p.G;
   const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
+  extern __shared__ __align__(16) unsigned char wide_raw[];
+  double* const tab = reinterpret_cast<double*>(wide_raw);      // TWO: [GX] CDF over groups | [GX] ladder over groups | [GX] factors
+  __shared__ double scr[34];
+  if (TWO && t >= 2) {
+    const int GX = p.GX;
+    double* gc = tab; double* gp = tab + GX; double* gf = tab + 2 * (size_t)GX;
+    const size_t ro = wide_rec(p, t - 1, b);
+    double m = -INFINITY;
+    for (int g = threadIdx.x; g < GX; g += blockDim.x) m = fmax(m, p.pmax[ro + g]);
+    m = block_max(m, scr);
+    for (int g = threadIdx.x; g < GX; g += blockDim.x) {
+      const double mc = p.pmax[ro + g];
+      const double f = (mc == -INFINITY) ? 0.0 : exp(mc - m);
+      gf[g] = f;
+      gc[g] = p.psum[ro + g] * f;
+      gp[g] = p.pv[ro + g];
+    }
+    __syncthreads();
+    block_scan_inplace<false>(gc, GX, scr);
+    if (!ident) block_scan_inplace<false>(gp, GX, scr);
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0) p.logz_t[(size_t)b * p.T + (t - 2)] = log(gc[GX - 1] / (double)N) + m;   // log Z of step t-1 (R/CPF.R:66)
+      if (!ident) scr[32] = gp[GX - 1] - rng_log(philox_u1(s, (unsigned)N, t, CPIMH_P_RESAMPLE, 0));   // the ladder's last spacing
+    }
+    __syncthreads();
+  }
   const double* Cb = p.C + (size_t)b * N;
   const double* Sb = p.S + (size_t)b * N;
   const double* xold = p.hist_x + ((size_t)b * (p.T + 1) + (t - 1)) * N * D;
@@ -92,14 +134,14 @@ __global__ void __launch_bounds__(128, WIDE_MINB) wide_propagate_kernel(WidePara
 #pragma unroll
   for (int c = 0; c < C; c++) yv[c] = y[lane * C + c];
   const double h = 0.05 / (double)p.substeps;
-  // TWO: the CDF is kept as inclusive sums GC of the G-particle groups (wide_group_scan_kernel) + the group-scaled numerators
+  // TWO: the CDF is kept as inclusive sums GC of the G-particle groups (the prologue above) + the group-scaled numerators
   // lw of the previous step (factor fac per group); likewise the sorted-uniform ladder as group sums GP + the spacings S
-  const double* GCb = TWO ? p.GC + (size_t)b * p.GX : nullptr;
-  const double* GPb = TWO ? p.GP + (size_t)b * p.GX : nullptr;
-  const double* facb = TWO ? p.fac + (size_t)b * p.GX : nullptr;
+  const double* GCb = tab;
+  const double* GPb = tab + p.GX;
+  const double* facb = tab + 2 * (size_t)p.GX;
   const double* lwold = (TWO ? ((t & 1) ? p.lw2 : p.lw) : p.lw) + (size_t)b * N;           // written by step t-1
   double* lwnew = (TWO ? ((t & 1) ? p.lw : p.lw2) : p.lw) + (size_t)b * N;
-  const double scale = ident ? 0.0 : (TWO ? GCb[p.GX - 1] / p.ptot[b] : (p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b]));   // u = sumw e_k  /  (sumw / total) P_k
+  const double scale = ident ? 0.0 : (TWO ? GCb[p.GX - 1] / scr[32] : (p.inj_resample ? Cb[N - 1] : Cb[N - 1] / p.ptot[b]));   // u = sumw e_k  /  (sumw / total) P_k
   // persistent warps: group g = G consecutive particles; the grid covers the machine once and strides over the groups
   for (int grp = blockIdx.x * nwarp + warp; grp < p.GX; grp += gridDim.x * nwarp) {
     const long long base = (long long)grp * G;
@@ -179,9 +221,10 @@ WIDE_PRAGMA_UNROLL(WIDE_UNROLL)
     }
     const double wsum = warp_sum(w), vsum = warp_sum(v);
     if (lane == 0) {
-      p.pmax[(size_t)b * p.GX + grp] = mg;
-      p.psum[(size_t)b * p.GX + grp] = wsum;
-      p.pv[(size_t)b * p.GX + grp] = vsum;
+      const size_t wo = wide_rec(p, t, b) + grp;
+      p.pmax[wo] = mg;
+      p.psum[wo] = wsum;
+      p.pv[wo] = vsum;
     }
   }
 }
@@ -204,8 +247,9 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y, N = p.N;
   const int G = p.G;                                // softmax block = one warp group of wide_propagate
+  const size_t ro = wide_rec(p, t_done, b);
   double m = -INFINITY;
-  for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[(size_t)b * p.GX + i]);
+  for (int i = threadIdx.x; i < p.GX; i += blockDim.x) m = fmax(m, p.pmax[ro + i]);
   m = block_max(m, scr);
   // element ranges are aligned to propagate blocks
   const int bper = (p.GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER;
@@ -216,11 +260,11 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   const bool ladder = prep && !p.inj_resample;
   double sw = 0.0, sv = 0.0;
   for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-    const double mc = p.pmax[(size_t)b * p.GX + c];
+    const double mc = p.pmax[ro + c];
     const double f = (mc == -INFINITY) ? 0.0 : exp(mc - m);
     fac[c - c0] = f;
-    sw += p.psum[(size_t)b * p.GX + c] * f;
-    sv += p.pv[(size_t)b * p.GX + c];
+    sw += p.psum[ro + c] * f;
+    sv += p.pv[ro + c];
   }
   sw = block_sum(sw, scr);
   sv = block_sum(sv, scr);
@@ -270,44 +314,6 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   }
 }
 
-// ------------------------------------------------------------------ two-level variant of the step's normalisation (round 2):
-// one CTA per filter turns the per-group maxima / sums that wide_propagate left into (a) log Z_t, (b) the factor exp(m_g - m) of
-// every group, (c) the inclusive CDF over GROUPS and (d) the inclusive ladder sums over groups.  The per-particle CDF and ladder
-// are never materialised: wide_propagate<.., true> searches the group table and then walks the G weights of one group.
-// 4096 groups instead of 65536 particles, no cluster, no per-particle pass: ~5 us instead of ~23 us per step at N = 65536.
-#define WIDE_MAX_GROUPS 8192
-__global__ void __launch_bounds__(1024, 1) wide_group_scan_kernel(WideParams p, int t_done, int prep) {
-  extern __shared__ __align__(16) unsigned char raw[];
-  double* bw = reinterpret_cast<double*>(raw);      // [GX] group weights -> inclusive CDF
-  double* bv = bw + p.GX;                           // [GX] group spacing sums -> inclusive ladder
-  __shared__ double scr[32];
-  const int b = blockIdx.x, GX = p.GX, N = p.N;
-  double m = -INFINITY;
-  for (int g = threadIdx.x; g < GX; g += blockDim.x) m = fmax(m, p.pmax[(size_t)b * GX + g]);
-  m = block_max(m, scr);
-  for (int g = threadIdx.x; g < GX; g += blockDim.x) {
-    const double mc = p.pmax[(size_t)b * GX + g];
-    const double f = (mc == -INFINITY) ? 0.0 : exp(mc - m);
-    p.fac[(size_t)b * GX + g] = f;
-    bw[g] = p.psum[(size_t)b * GX + g] * f;
-    bv[g] = p.pv[(size_t)b * GX + g];
-  }
-  __syncthreads();
-  block_scan_inplace<false>(bw, GX, scr);
-  if (prep) block_scan_inplace<false>(bv, GX, scr);
-  for (int g = threadIdx.x; g < GX; g += blockDim.x) {
-    p.GC[(size_t)b * GX + g] = bw[g];
-    if (prep) p.GP[(size_t)b * GX + g] = bv[g];
-  }
-  if (threadIdx.x == 0) {
-    p.logz_t[(size_t)b * p.T + (t_done - 1)] = log(bw[GX - 1] / (double)N) + m;   // R/CPF.R:66
-    if (prep) {
-      const Stream st = make_stream(p.seed, p.first_filter + (unsigned long long)b);
-      p.ptot[b] = bv[GX - 1] - rng_log(philox_u1(st, (unsigned)N, t_done + 1, CPIMH_P_RESAMPLE, 0));
-    }
-  }
-}
-
 // ------------------------------------------------------------------ final path: systematic(normw, 1, u) + get_path (R/CPF.R:69)
 template <int C>
 __global__ void wide_path_kernel(WideParams p) {
@@ -339,23 +345,19 @@ struct WideFilter {
   int GX, G, pgrid, record_anc;
   std::vector<double> obs_host;
   DevBuf ptot;
-  DevBuf obs, hist_x, hist_a, lw, lw2, GC, GP, fac, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
+  DevBuf obs, hist_x, hist_a, lw, lw2, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
   DevBuf inj_init, inj_trans, inj_resample, inj_path;
   bool have_inj[4];
 };
 
 static void wide_geometry(const cpimh_config& c, int64_t B, int num_sms, int* G, int* GX) {
-  // particles per warp group: enough groups that the propagate grid balances (>= ~1.5 groups per resident warp slot), at most
-  // 32 so the per-group ancestor search stays one pass.  Any G in 1..32 works (the kernels multiply / divide by G); measured
-  // on B200 at N = 65536, B = 1 (tools/ab_wide.py, CPIMH_WIDE_G): G = 8 / 12 / 14 / 16 / 24 / 28 / 32 give
-  // 0.87 / 0.97 / 1.01 / 1.04 / 1.01 / 1.05 / 0.99 e9 particle-steps/s -- flat from 14 up (the kernel is issue-bound, not
-  // occupancy-bound: profiles/r2_lorenz64_propagate_ncu_summary.txt), so the power of two is kept; G = 8 beats G = 2 by 30 %
-  // (the binary search in the CDF is paid once per group by up to 32 lanes in parallel).
-  long long target = (long long)num_sms * 48;
-  long long g = ((long long)c.nparticles * B + target - 1) / target;
-  int G_ = 1;
-  while (G_ < 32 && G_ < g) G_ <<= 1;
-  if (const char* e = getenv("CPIMH_WIDE_G")) { const int v = atoi(e); if (v >= 1 && v <= 32) G_ = v; }   // tuning aid only
+  // particles per warp group: the smallest G for which every group of every filter has a resident warp in ONE wave of the
+  // fused propagate kernel (32 warps per SM), at most 32 so the per-group ancestor search stays one pass.  Any G in 1..32
+  // works (the kernels multiply / divide by G): N = 65536, B = 1 on 148 SMs gives G = 14, 4682 groups on 4736 warps.
+  const long long slots = (long long)num_sms * 32;
+  long long g = ((long long)c.nparticles * B + slots - 1) / slots;
+  if (const char* e = getenv("CPIMH_WIDE_G")) { const int v = atoi(e); if (v >= 1 && v <= 32) g = v; }   // tuning aid only (tools/ab_wide.py)
+  const int G_ = (int)(g < 1 ? 1 : (g > 32 ? 32 : g));
   *G = G_;
   *GX = (int)(((long long)c.nparticles + G_ - 1) / G_);
 }
@@ -388,14 +390,11 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   if (!rc) rc = A(h->hist_a, sizeof(int) * B * T * N);
   if (!rc) rc = A(h->lw, sizeof(double) * B * N);
   if (!rc) rc = A(h->lw2, sizeof(double) * B * N);
-  if (!rc) rc = A(h->GC, sizeof(double) * B * h->GX);
-  if (!rc) rc = A(h->GP, sizeof(double) * B * h->GX);
-  if (!rc) rc = A(h->fac, sizeof(double) * B * h->GX);
   if (!rc) rc = A(h->C, sizeof(double) * B * N);
   if (!rc) rc = A(h->S, sizeof(double) * B * N);
-  if (!rc) rc = A(h->pmax, sizeof(double) * B * h->GX);
-  if (!rc) rc = A(h->psum, sizeof(double) * B * h->GX);
-  if (!rc) rc = A(h->pv, sizeof(double) * B * h->GX);
+  if (!rc) rc = A(h->pmax, sizeof(double) * 2 * B * h->GX);
+  if (!rc) rc = A(h->psum, sizeof(double) * 2 * B * h->GX);
+  if (!rc) rc = A(h->pv, sizeof(double) * 2 * B * h->GX);
   if (!rc) rc = A(h->mstep, sizeof(double) * B);
   if (!rc) rc = A(h->ptot, sizeof(double) * B);
   if (!rc) rc = A(h->logz_t, sizeof(double) * B * T);
@@ -409,7 +408,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
 
 void wide_destroy(WideFilter* h) {
   if (!h) return;
-  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->lw2, &h->GC, &h->GP, &h->fac, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
+  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->lw2, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
                    &h->path_index, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
@@ -458,23 +457,23 @@ static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   auto is_ident = [&](int t) { return (t == 1) || isnan(h->obs_host[(size_t)(t - 2) * p.D]); };   // R/CPF.R:38-40
   const size_t wsmem = (WIDE_TILE + WIDE_MAX_BLOCKS_PER_CTA) * sizeof(double);
   CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_weights_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-  const size_t gsmem = 2 * (size_t)p.GX * sizeof(double);
-  if (p.two_level) CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_group_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+  const size_t fsmem = 3 * (size_t)p.GX * sizeof(double);
+  if (p.two_level) CPIMH_CUDA_CHECK(cudaFuncSetAttribute(wide_propagate_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  const dim3 gf((unsigned)((p.GX + 31) / 32), (unsigned)B);            // two-level: 32 warps per CTA, one group per warp
   for (int t = 1; t <= T; t++) {
     const int ident = is_ident(t);
-    if (t >= 2) {
-      if (p.two_level) wide_group_scan_kernel<<<B, 1024, gsmem, s>>>(p, t - 1, ident ? 0 : 1);
-      else wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, t - 1, ident ? 0 : 1);
+    if (t >= 2 && !p.two_level) {
+      wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, t - 1, ident ? 0 : 1);
       h->launches += 1;
     }
     const int prep_next = (t < T && !is_ident(t + 1)) ? 1 : 0;
-    if (p.two_level) wide_propagate_kernel<C, true><<<gp, 128, 0, s>>>(p, t, ident, prep_next);
+    if (p.two_level) wide_propagate_kernel<C, true><<<gf, 1024, fsmem, s>>>(p, t, ident, prep_next);
     else wide_propagate_kernel<C, false><<<gp, 128, 0, s>>>(p, t, ident, prep_next);
     h->launches++;
   }
   // the last step's weights as a normalised per-particle CDF: the final path pick (R/CPF.R:69) and log Z_T
   WideParams pl = p;
-  if (p.two_level && (T & 1) == 0) pl.lw = p.lw2;           // step T wrote the buffer of its parity
+  if (p.two_level && (T & 1) == 0) pl.lw = p.lw2;           // step T wrote the buffer of its parity (its log Z_T comes from this scan)
   wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(pl, T, 0);
   wide_path_kernel<C><<<B, 32, 0, s>>>(p);
   h->launches += 2;
@@ -495,10 +494,10 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   for (int i = 0; i < c.dim; i++) hl += log(c.theta[2]);                               // src/mvnorm.cpp:120-121
   p.cst = -(hl) - (c.dim * CPIMH_HALF_LOG_2PI_TRUNC);
   p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.lw = h->lw.as<double>(); p.C = h->C.as<double>(); p.S = h->S.as<double>();
-  p.lw2 = h->lw2.as<double>(); p.GC = h->GC.as<double>(); p.GP = h->GP.as<double>(); p.fac = h->fac.as<double>();
+  p.lw2 = h->lw2.as<double>();
   // the two-level CDF serves the Philox path; injected sorted uniforms (parity runs) keep the per-particle scans
   p.two_level = (!h->have_inj[2] && h->GX <= WIDE_MAX_GROUPS) ? 1 : 0;
-  p.pmax = h->pmax.as<double>(); p.psum = h->psum.as<double>(); p.pv = h->pv.as<double>(); p.mstep = h->mstep.as<double>(); p.ptot = h->ptot.as<double>();
+  p.pmax = h->pmax.as<double>(); p.psum = h->psum.as<double>(); p.pv = h->pv.as<double>(); p.mstep = h->mstep.as<double>(); p.ptot = h->ptot.as<double>(); p.maxB = (size_t)h->maxB;
   p.logz_t = h->logz_t.as<double>(); p.logz = h->logz.as<double>(); p.traj = h->traj.as<double>(); p.path_index = h->path_index.as<int>();
   p.inj_init = h->have_inj[0] ? h->inj_init.as<double>() : nullptr;
   p.inj_trans = h->have_inj[1] ? h->inj_trans.as<double>() : nullptr;
