@@ -104,19 +104,37 @@ __global__ void __launch_bounds__(TWO ? 1024 : 128, TWO ? 1 : WIDE_MINB) wide_pr
     const int GX = p.GX;
     double* gc = tab; double* gp = tab + GX; double* gf = tab + 2 * (size_t)GX;
     const size_t ro = wide_rec(p, t - 1, b);
+    // every thread owns a contiguous chunk of <= 8 groups: running sums inside the chunk, one warp scan of the chunk totals,
+    // one scan of the 32 warp totals, offsets added in place (both tables in the same passes)
+    const int cpt = (GX + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int g0 = min(GX, (int)threadIdx.x * cpt), g1 = min(GX, g0 + cpt);
     double m = -INFINITY;
-    for (int g = threadIdx.x; g < GX; g += blockDim.x) m = fmax(m, p.pmax[ro + g]);
+    for (int g = g0; g < g1; g++) m = fmax(m, p.pmax[ro + g]);
     m = block_max(m, scr);
-    for (int g = threadIdx.x; g < GX; g += blockDim.x) {
+    double aw = 0.0, av = 0.0;
+    for (int g = g0; g < g1; g++) {
       const double mc = p.pmax[ro + g];
       const double f = (mc == -INFINITY) ? 0.0 : exp(mc - m);
       gf[g] = f;
-      gc[g] = p.psum[ro + g] * f;
-      gp[g] = p.pv[ro + g];
+      aw += p.psum[ro + g] * f;
+      av += p.pv[ro + g];
+      gc[g] = aw;
+      gp[g] = av;
+    }
+    const double iw = warp_incl_scan(aw, lane), iv = warp_incl_scan(av, lane);
+    double ew = __shfl_up_sync(0xffffffffu, iw, 1), ev = __shfl_up_sync(0xffffffffu, iv, 1);     // exclusive over the warp's threads
+    if (lane == 0) { ew = 0.0; ev = 0.0; }
+    __shared__ double wtot[2][32];
+    if (lane == 31) { wtot[0][warp] = iw; wtot[1][warp] = iv; }
+    __syncthreads();
+    {
+      const double ww = lane < nwarp ? wtot[0][lane] : 0.0, wv = lane < nwarp ? wtot[1][lane] : 0.0;
+      const double cw = warp_incl_scan(ww, lane), cv = warp_incl_scan(wv, lane);
+      const double ow = (warp > 0 ? __shfl_sync(0xffffffffu, cw, (warp + 31) & 31) : 0.0) + ew;
+      const double ov = (warp > 0 ? __shfl_sync(0xffffffffu, cv, (warp + 31) & 31) : 0.0) + ev;
+      for (int g = g0; g < g1; g++) { gc[g] += ow; gp[g] += ov; }
     }
     __syncthreads();
-    block_scan_inplace<false>(gc, GX, scr);
-    if (!ident) block_scan_inplace<false>(gp, GX, scr);
     if (threadIdx.x == 0) {
       if (blockIdx.x == 0) p.logz_t[(size_t)b * p.T + (t - 2)] = log(gc[GX - 1] / (double)N) + m;   // log Z of step t-1 (R/CPF.R:66)
       if (!ident) scr[32] = gp[GX - 1] - rng_log(philox_u1(s, (unsigned)N, t, CPIMH_P_RESAMPLE, 0));   // the ladder's last spacing
