@@ -78,17 +78,39 @@ struct ArModel {
   static constexpr bool JUMP_LIST = false;
   static constexpr bool HAS_DTRANS = true;
   static constexpr bool SPLIT_W = false;
+  // y = A x with A[i][j] = alpha^(1 + |i - j|) (src/create_A_.cpp:10, R/model_get_ar.R:13).  For D >= 3 the product uses the
+  // structure of A instead of its D*D entries: with L_i = sum_{j<i} alpha^(i-j) x_j = alpha (x_{i-1} + L_{i-1}) and
+  // U_i = sum_{j>i} alpha^(j-i) x_j = alpha (x_{i+1} + U_{i+1}),  y_i = alpha (x_i + L_i + U_i): 7D - 4 operations and no table
+  // loads instead of D*D multiply-adds and D*D shared-memory loads (D = 10: 66 against 200 instructions; rounding differs from
+  // the dense product by a few ulp, far inside the 1e-10 of the floating-point parity tests).
+  __device__ static void apply_A(const ModelCtx& c, const double* x, double* y) {
+    if (D < 3) {
+#pragma unroll
+      for (int r = 0; r < D; r++) {
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < D; l++) s += c.pre[r + l * D] * x[l];
+        y[r] = s;
+      }
+    } else {
+      const double a = c.pre[0];                  // A[0][0] = alpha
+      double lo[D];
+      double L = 0.0, U = 0.0;
+      lo[0] = 0.0;
+#pragma unroll
+      for (int i = 1; i < D; i++) { L = a * (x[i - 1] + L); lo[i] = L; }
+      y[D - 1] = a * (x[D - 1] + lo[D - 1]);
+#pragma unroll
+      for (int i = D - 2; i >= 0; i--) { U = a * (x[i + 1] + U); y[i] = a * ((x[i] + lo[i]) + U); }
+    }
+  }
   // dtransition = dmvnorm_transpose_cholesky(A x, next_x, I): R/model_get_ar.R:28-30, src/mvnorm.cpp:113-132
   __device__ static double dtrans(const ModelCtx& c, const double* next, const double* x, int, double) {
+    double m[D];
+    apply_A(c, x, m);
     double sq = 0.0;
 #pragma unroll
-    for (int r = 0; r < D; r++) {
-      double s = 0.0;
-#pragma unroll
-      for (int l = 0; l < D; l++) s += c.pre[r + l * D] * x[l];
-      const double e = s - next[r];
-      sq += e * e;
-    }
+    for (int r = 0; r < D; r++) { const double e = m[r] - next[r]; sq += e * e; }
     return -0.5 * sq + (-0.0 - (double)D * 0.9189385);
   }
   __device__ static double step_const(const ModelCtx&, int) { return 0.0; }
@@ -114,13 +136,7 @@ struct ArModel {
 #pragma unroll
       for (int k = 0; k < D; k++) z[k] = trans_row(c, t, k)[i];
     } else normals(c, i, t, CPIMH_P_TRANS, z);
-#pragma unroll
-    for (int r = 0; r < D; r++) {
-      double s = 0.0;
-#pragma unroll
-      for (int l = 0; l < D; l++) s += c.pre[r + l * D] * x[l];
-      y[r] = s;
-    }
+    apply_A(c, x, y);
 #pragma unroll
     for (int r = 0; r < D; r++) x[r] = y[r] + z[r];
     return 0;
