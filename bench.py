@@ -449,7 +449,11 @@ def main():
             roof, sec = roofline_of(wl, r, peak, which, counts, issue_peak, name)
             cfg_table[name] = {"workload": wl["name"], "value": r["value"], "ms_per_step": r["ms_per_step"], "e2e": r["e2e"]["value"], "frac": roof["frac"],
                                "algorithmic_bytes_per_particle_step": roof["algorithmic_bytes_per_particle_step"], "path_storage": roof["path_storage"],
-                               "issue_frac": sec["frac"] if sec else None, "threads_per_filter": r["eff"]["threads_per_filter"], "ctas_per_sm": r["eff"]["ctas_per_sm"]}
+                               "issue_frac": sec["frac"] if sec else None}
+            if name == "cfg5":     # the wide filter: warp per group of G particles, 1024-thread CTAs, one launch per time step
+                cfg_table[name].update({"particles_per_warp_group": r["eff"]["threads_per_filter"], "warp_groups": r["eff"]["ctas_per_sm"]})
+            else:
+                cfg_table[name].update({"threads_per_filter": r["eff"]["threads_per_filter"], "ctas_per_sm": r["eff"]["ctas_per_sm"]})
 
     if rank == 0:
         eff = main_res["eff"]

@@ -185,21 +185,28 @@ int api_plan_geometry(const cpimh_config& c, const ModelEntry* e, bool chains, i
   return CPIMH_OK;
 }
 
-// Tail launch: when the last wave of a batch would leave most SMs with one CTA instead of two, those filters run
-// faster as one 1024-thread CTA per SM.  Returns tail->threads = 0 when no such variant applies.
+// Tail launch: when the last wave of a batch would leave the SMs with one CTA instead of two or three, those filters run faster
+// as ONE wide CTA per SM.  Measured on B200 (tools/tail_geometry.py: levy_sv, N = 4096, 136 filters on 148 SMs, T = 300):
+// 128 / 256 / 512 / 1024 threads per filter 20.9 / 8.7 / 6.6 / 7.0 ms -- 512 threads (128 registers per thread, half the
+// barrier width) beat 1024 up to N = 4096; above that the 1024-thread CTA wins on particles per thread.
+// Returns tail->threads = 0 when no such variant applies.
 int api_plan_tail_geometry(const cpimh_config& c, const ModelEntry* e, int npre, const Geometry& main, Geometry* tail) {
   *tail = main;
   tail->threads = 0;
   if (main.variant == PF_VARIANT_1024x1 || c.threads_per_filter > 0 || main.blocks_per_sm < 2 || c.nparticles < 2048) return CPIMH_OK;
-  Geometry t = main;
-  t.variant = PF_VARIANT_1024x1; t.threads = 1024;
-  t.smem = pf_smem_bytes(t.Npad, t.M, npre, t.path_mode, c.shuffle);
-  int bps = 0;
-  int rc = e->occupancy_pf(t.variant, t.threads, t.smem, &bps);
-  if (rc) return rc;
-  if (bps < 1) return CPIMH_OK;
-  t.blocks_per_sm = 1;
-  *tail = t;
+  const int candidates[2] = {(c.nparticles <= 4096 && main.variant < PF_VARIANT_512x2) ? PF_VARIANT_512x2 : PF_VARIANT_1024x1, PF_VARIANT_1024x1};
+  for (int k = 0; k < 2; k++) {
+    Geometry t = main;
+    t.variant = candidates[k]; t.threads = pf_variant_threads(t.variant);
+    t.smem = pf_smem_bytes(t.Npad, t.M, npre, t.path_mode, c.shuffle);
+    int bps = 0;
+    int rc = e->occupancy_pf(t.variant, t.threads, t.smem, &bps);
+    if (rc) return rc;
+    if (bps < 1) continue;
+    t.blocks_per_sm = 1;
+    *tail = t;
+    return CPIMH_OK;
+  }
   return CPIMH_OK;
 }
 
@@ -406,7 +413,7 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   p.inj_resample = h->have_inj[2] ? h->inj_resample.as<double>() : nullptr;
   p.inj_shuffle = h->have_inj[3] ? h->inj_shuffle.as<double>() : nullptr;
   p.inj_path = h->have_inj[4] ? h->inj_path.as<double>() : nullptr;
-  // whole waves with the main geometry; a short last wave (at most one filter per SM) as 1024-thread CTAs
+  // whole waves with the main geometry; a short last wave (at most one filter per SM) as one wide CTA per SM
   int64_t main_B = B, tail_B = 0;
   if (h->geo_tail.threads > 0 && B > h->grid) {
     const int64_t rem = B % h->grid;
