@@ -66,3 +66,62 @@ def test_wide_full_size_properties(up):
     assert np.array_equal(a["logz_t"], b["logz_t"]) and np.array_equal(a["trajectory"], b["trajectory"])
     assert a["trajectory"].shape == (1, d, T + 1) and np.all(np.abs(a["trajectory"]) < 50)
     pb.close()
+
+
+def test_wide_philox_parity_with_missing_observation(up, oracle):
+    """The Philox (two-level CDF) path through an NA row: weights 0 at that step, no resampling at the next one
+    (R/CPF.R:38-40, R/model_get_lorenz.R:39-40) -- the launch after the NA step must still write log Z of the NA step."""
+    d, N, T, seed = 64, 5000, 8, 5
+    y = np.random.default_rng(3).normal(size=(T, d)) * 2 + 2
+    y[3, :] = np.nan
+    r = up.cpf_batch(N, up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5], y, 1, seed=seed, logz_t=True)
+    ocfg = oracle.make_config(oracle.MODEL_LORENZ, d, d, N, T, theta=[8.0, 0.5, 1.0], integrator=0, substeps=1)
+    o = oracle.cpf(ocfg, y, seed=seed, filter_id=0)
+    assert r["logz_t"][0][3] == 0.0
+    assert np.allclose(r["logz_t"][0], o["logz_t"], rtol=1e-10, atol=1e-300)
+    assert int(r["path_index"][0]) == o["path_index"]
+    assert np.allclose(r["trajectory"][0], o["trajectory"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("N,B,G", [(20000, 3, 0), (1000, 1, 5), (1000, 2, 32), (4097, 1, 14)])
+def test_wide_group_sizes(up, oracle, monkeypatch, N, B, G):
+    """Any group size 1..32 (not only powers of two; the last group ragged): G = 0 takes the library's own choice
+    (13 for 3 x 20000 particles on 148 SMs), the others force it through the tuning knob."""
+    if G:
+        monkeypatch.setenv("CPIMH_WIDE_G", str(G))
+    d, T, seed = 64, 5, 11
+    y = np.random.default_rng(N).normal(size=(T, d)) * 2 + 2
+    pb = up.PfBatch(up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5], y, N, B)
+    eff = pb.effective_config()
+    if G:
+        assert eff["threads_per_filter"] == G                      # wide filter: particles per warp group
+    else:
+        assert eff["threads_per_filter"] not in (1, 2, 4, 8, 16, 32)
+    pb.run(B, seed, first_filter=2)
+    r = pb.fetch(logz_t=True, path_index=True)
+    pb.close()
+    ocfg = oracle.make_config(oracle.MODEL_LORENZ, d, d, N, T, theta=[8.0, 0.5, 1.0], integrator=0, substeps=1)
+    for b in range(B):
+        o = oracle.cpf(ocfg, y, seed=seed, filter_id=2 + b)
+        assert np.allclose(r["logz_t"][b], o["logz_t"], rtol=1e-10, atol=0)
+        assert int(r["path_index"][b]) == o["path_index"]
+        assert np.allclose(r["trajectory"][b], o["trajectory"], rtol=1e-9, atol=1e-9)
+
+
+def test_wide_more_groups_than_the_shared_memory_table_holds(up):
+    """N = 300 000 gives 9375 groups of 32 > the 8192 a CTA's shared memory holds: the per-particle cluster scan runs
+    between the steps instead.  Properties only (ancestors sorted and in range, finite log Z, reproducible)."""
+    d, N, T = 64, 300000, 4
+    y = np.random.default_rng(2).normal(size=(T, d)) * 1.5 + 2
+    pb = up.PfBatch(up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5], y, N, 1)
+    assert pb.effective_config()["ctas_per_sm"] > 8192             # wide filter: number of warp groups
+    pb.record_ancestors(True)
+    pb.run(1, 7)
+    a = pb.fetch(logz_t=True, path_index=True)
+    anc = pb.fetch_ancestors(0)
+    assert np.array_equal(anc[0], np.arange(N)) and anc.min() >= 0 and anc.max() < N and np.all(np.diff(anc[1:], axis=1) >= 0)
+    assert np.all(np.isfinite(a["logz_t"]))
+    pb.run(1, 7)
+    b = pb.fetch(logz_t=True, path_index=True)
+    assert np.array_equal(a["logz_t"], b["logz_t"]) and np.array_equal(a["trajectory"], b["trajectory"])
+    pb.close()
