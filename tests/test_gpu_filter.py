@@ -321,3 +321,25 @@ def test_levy_sv_observation_no_particle_explains(up, oracle, golden):
         o = oracle.cpf(ocfg, y, seed=8, filter_id=b)
         assert np.all(np.isfinite(r["logz_t"][b])) and o["logz_t"][3] < -600
         assert np.max(np.abs(r["logz_t"][b] - o["logz_t"]) / np.abs(o["logz_t"])) < RTOL_LOGZ and int(r["path_index"][b]) == o["path_index"]
+
+
+@pytest.mark.parametrize("name,N,extra", [("gss", 256, 100), ("gss", 256, 0), ("levy_sv", 2048, 5), ("ar3", 512, 301)])
+def test_one_shot_entry_over_several_waves_is_pipelined_and_matches_the_handle_api(up, golden, name, N, extra):
+    """More filters than resident CTAs: the one-shot entry runs groups of whole waves (+ the tail launch) while it copies the
+    finished groups' results to the caller; every output must equal the handle API's run of the same batch, bit for bit."""
+    model, theta, obs = {
+        "gss": (up.get_gss(), [], golden["gss_y"][:100]),          # 1.6 KB of results per filter: 7 waves are copied in two groups
+        "levy_sv": (up.get_levy_sv(), golden["sv_theta_mle"], golden["sv_y"][:6]),
+        "ar3": (up.get_ar(3), [0.4, 1.0], np.random.default_rng(3).normal(size=(8, 3))),
+    }[name]
+    pb = up.PfBatch(model, theta, obs, N, 8)
+    grid = pb.effective_config()["ctas_per_sm"] * 148
+    pb.close()
+    B = (7 if name == "gss" else 2) * grid + extra
+    pb = up.PfBatch(model, theta, obs, N, B)
+    pb.run(B, 21, first_filter=4)
+    ref = pb.fetch(logz_t=True, path_index=True)
+    pb.close()
+    r = up.cpf_batch(N, model, theta, obs, B, seed=21, first_filter=4, logz_t=True)
+    for k in ("logz", "logz_t", "trajectory", "path_index"):
+        assert np.array_equal(r[k], ref[k]), k

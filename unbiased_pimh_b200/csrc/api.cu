@@ -392,14 +392,12 @@ void api_fill_pf_params(const cpimh_config& c, const Geometry& g, int npre, PfPa
 }  // namespace cpimh
 extern "C" {
 
-int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, void* stream) {
-  CPIMH_REQUIRE(h, "null handle");
-  if (h->wide) { int rcw = wide_run(h->wide, B, seed, first_filter, (cudaStream_t)stream); if (!rcw) h->lastB = B; return rcw; }
-  CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
-  const cpimh_config& c = h->cfg;
-  PfParams p;
-  api_fill_pf_params(c, h->geo, h->npre, &p);
-  p.B = B; p.seed = seed; p.first_filter = first_filter;
+// launch parameters of one run of the handle's batch (filters are addressed by their position b in the batch: Philox stream
+// first_filter + b, outputs at index b)
+static void pf_run_params(cpimh_pf* h, uint64_t seed, uint64_t first_filter, PfParams* pp) {
+  PfParams& p = *pp;
+  api_fill_pf_params(h->cfg, h->geo, h->npre, &p);
+  p.seed = seed; p.first_filter = first_filter;
   p.obs = h->obs.as<double>(); p.theta = h->theta.as<double>(); p.pre = h->pre.as<double>();
   p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.ascr = h->ascr.as<int>();
   p.wscr = h->wscr.as<double>(); p.exact_repeats = h->exact.as<int>(); p.jq = h->jq.as<uint4>();
@@ -413,27 +411,39 @@ int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, v
   p.inj_resample = h->have_inj[2] ? h->inj_resample.as<double>() : nullptr;
   p.inj_shuffle = h->have_inj[3] ? h->inj_shuffle.as<double>() : nullptr;
   p.inj_path = h->have_inj[4] ? h->inj_path.as<double>() : nullptr;
-  // whole waves with the main geometry; a short last wave (at most one filter per SM) as one wide CTA per SM
-  int64_t main_B = B, tail_B = 0;
+}
+// whole waves run with the main geometry; a short last wave (at most one filter per SM) as one wide CTA per SM
+static void pf_split_tail(const cpimh_pf* h, int64_t B, int64_t* main_B, int64_t* tail_B) {
+  *main_B = B; *tail_B = 0;
   if (h->geo_tail.threads > 0 && B > h->grid) {
     const int64_t rem = B % h->grid;
-    if (rem > 0 && rem <= h->geo.num_sms) { tail_B = rem; main_B = B - rem; }
+    if (rem > 0 && rem <= h->geo.num_sms) { *tail_B = rem; *main_B = B - rem; }
   }
+}
+// filters [b0, b0 + nb) of the batch as one launch (tail: the wide-CTA geometry)
+static int pf_launch_range(cpimh_pf* h, PfParams p, int64_t b0, int64_t nb, bool tail, cudaStream_t stream) {
+  const Geometry& g = tail ? h->geo_tail : h->geo;
   PfLaunch L;
-  L.threads = h->geo.threads; L.smem = h->geo.smem; L.variant = h->geo.variant;
-  L.grid = (int)(main_B < h->grid ? main_B : h->grid);
-  p.B = main_B; p.b0 = 0;
-  int rc = h->entry->launch_pf(p, L, (cudaStream_t)stream);
+  L.threads = g.threads; L.smem = g.smem; L.variant = g.variant;
+  L.grid = (int)(tail ? nb : (nb < h->grid ? nb : h->grid));
+  p.B = nb; p.b0 = b0;
+  int rc = h->entry->launch_pf(p, L, stream);
+  if (!rc) h->launches += 1;
+  return rc;
+}
+
+int cpimh_pf_run(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter, void* stream) {
+  CPIMH_REQUIRE(h, "null handle");
+  if (h->wide) { int rcw = wide_run(h->wide, B, seed, first_filter, (cudaStream_t)stream); if (!rcw) h->lastB = B; return rcw; }
+  CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
+  PfParams p;
+  pf_run_params(h, seed, first_filter, &p);
+  int64_t main_B, tail_B;
+  pf_split_tail(h, B, &main_B, &tail_B);
+  int rc = pf_launch_range(h, p, 0, main_B, false, (cudaStream_t)stream);
+  if (!rc && tail_B > 0) rc = pf_launch_range(h, p, main_B, tail_B, true, (cudaStream_t)stream);
   if (rc) return rc;
-  if (tail_B > 0) {
-    PfLaunch Lt;
-    Lt.threads = h->geo_tail.threads; Lt.smem = h->geo_tail.smem; Lt.variant = h->geo_tail.variant; Lt.grid = (int)tail_B;
-    p.B = tail_B; p.b0 = main_B;
-    rc = h->entry->launch_pf(p, Lt, (cudaStream_t)stream);
-    if (rc) return rc;
-    h->launches += 1;
-  }
-  h->launches += 1; h->lastB = B;
+  h->lastB = B;
   return CPIMH_OK;
 }
 
@@ -578,6 +588,73 @@ int cpimh_release_cached(void) {
   return cpimh_ccpf_release_cached();
 }
 
+// One-shot entry, several waves: the batch runs as up to four groups of whole waves (+ the tail launch) on one stream while the
+// finished groups' results are copied to the caller's (pageable) buffers on a second one, so that only the last group's copy
+// is exposed (ar(10), 16 384 filters: 132 MB of trajectories, 22 ms of a 140 ms call).
+static cudaStream_t g_pipe_run = nullptr, g_pipe_copy = nullptr;
+static int g_pipe_device = -1;
+static int pf_run_fetch_pipelined(cpimh_pf* h, int64_t B, uint64_t seed, uint64_t first_filter,
+                                  double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
+  CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
+  CPIMH_REQUIRE(!trajectory || h->geo.path_mode != PATH_NONE, "trajectories need store_paths != 0");
+  int dev = 0;
+  CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev != g_pipe_device) {                                      // streams belong to the device that was current when they were made
+    CPIMH_CUDA_CHECK(cudaStreamCreateWithFlags(&g_pipe_run, cudaStreamNonBlocking));
+    CPIMH_CUDA_CHECK(cudaStreamCreateWithFlags(&g_pipe_copy, cudaStreamNonBlocking));
+    g_pipe_device = dev;
+  }
+  const cpimh_config& c = h->cfg;
+  PfParams p;
+  pf_run_params(h, seed, first_filter, &p);
+  int64_t main_B, tail_B;
+  pf_split_tail(h, B, &main_B, &tail_B);
+  struct Group { int64_t b0, nb; bool tail; cudaEvent_t done; };
+  std::vector<Group> groups;
+  const int64_t waves = (main_B + h->grid - 1) / h->grid;
+  // a group boundary costs a partly idle wave end, so groups are only formed where there is something to hide: one per 16 MB
+  // of results, at most four
+  const size_t per_filter = sizeof(double) * ((logz ? 1 : 0) + (logz_t ? (size_t)c.nobs : 0) + (trajectory ? (size_t)(c.nobs + 1) * c.dim : 0)) + (path_index ? sizeof(int) : 0);
+  int64_t ngroups = (int64_t)((per_filter * (size_t)main_B) >> 24);
+  if (ngroups > 4) ngroups = 4;
+  if (ngroups > waves) ngroups = waves;
+  if (ngroups < 1) ngroups = 1;
+  for (int64_t g = 0, w0 = 0; g < ngroups; g++) {
+    const int64_t w1 = waves * (g + 1) / ngroups;
+    const int64_t b0 = w0 * h->grid, b1 = (w1 * h->grid < main_B) ? w1 * h->grid : main_B;
+    if (b1 > b0) groups.push_back({b0, b1 - b0, false, nullptr});
+    w0 = w1;
+  }
+  if (tail_B > 0) groups.push_back({main_B, tail_B, true, nullptr});
+  CPIMH_CUDA_CHECK(cudaDeviceSynchronize());                       // observations / noise uploads of the legacy stream are complete
+  int rc = CPIMH_OK;
+  for (auto& g : groups) {
+    if (!rc) rc = pf_launch_range(h, p, g.b0, g.nb, g.tail, g_pipe_run);
+    if (!rc && cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = CPIMH_ERR_CUDA; }
+    if (!rc && cudaEventRecord(g.done, g_pipe_run) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = CPIMH_ERR_CUDA; }
+  }
+  const size_t T = (size_t)c.nobs, D = (size_t)c.dim;
+  auto copy = [&](void* dst, const void* src, size_t bytes) {
+    if (!rc && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_pipe_copy) != cudaSuccess) { set_error("device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError())); rc = CPIMH_ERR_CUDA; }
+  };
+  for (auto& g : groups) {
+    if (rc) break;
+    if (cudaStreamWaitEvent(g_pipe_copy, g.done, 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = CPIMH_ERR_CUDA; break; }
+    const size_t b0 = (size_t)g.b0, nb = (size_t)g.nb;
+    if (logz) copy(logz + b0, h->logz.as<double>() + b0, sizeof(double) * nb);
+    if (logz_t) copy(logz_t + b0 * T, h->logz_t.as<double>() + b0 * T, sizeof(double) * nb * T);
+    if (trajectory) copy(trajectory + b0 * (T + 1) * D, h->traj.as<double>() + b0 * (T + 1) * D, sizeof(double) * nb * (T + 1) * D);
+    if (path_index) copy(path_index + b0, h->path_index.as<int>() + b0, sizeof(int) * nb);
+  }
+  cudaStreamSynchronize(g_pipe_run);
+  cudaStreamSynchronize(g_pipe_copy);
+  for (auto& g : groups) if (g.done) cudaEventDestroy(g.done);
+  if (rc) return rc;
+  CPIMH_CUDA_CHECK(cudaGetLastError());
+  h->lastB = B;
+  return check_status(h->status.as<int>(), B, g_pipe_copy);      // a failed filter invalidates the call (its outputs were copied but are not returned as valid)
+}
+
 static int pf_batch_cached(const cpimh_config* cfg, const double* obs_host, int64_t B, uint64_t seed, uint64_t first_filter,
                            const cpimh_noise* noise_host, double* logz, double* logz_t, double* trajectory, int32_t* path_index, double* exp_path) {
   CPIMH_REQUIRE(cfg && obs_host, "null argument");
@@ -598,8 +675,11 @@ static int pf_batch_cached(const cpimh_config* cfg, const double* obs_host, int6
     if (!rc) rc = cpimh_pf_record_ancestors(h, 0);
     if (!rc && !h->wide) rc = cpimh_pf_all_particles(h, exp_path ? 1 : 0);
     if (!rc && h->wide && exp_path) { set_error("all-particle outputs are not available for the wide (d = 32/64) filter"); rc = CPIMH_ERR_INVALID; }
-    if (!rc) rc = cpimh_pf_run(h, B, seed, first_filter, nullptr);
-    if (!rc) rc = cpimh_pf_fetch(h, B, nullptr, logz, logz_t, trajectory, path_index);
+    if (!rc && !h->wide && !exp_path && B > h->grid) rc = pf_run_fetch_pipelined(h, B, seed, first_filter, logz, logz_t, trajectory, path_index);
+    else {
+      if (!rc) rc = cpimh_pf_run(h, B, seed, first_filter, nullptr);
+      if (!rc) rc = cpimh_pf_fetch(h, B, nullptr, logz, logz_t, trajectory, path_index);
+    }
     if (!rc && exp_path) rc = cpimh_pf_fetch_exp_paths(h, B, nullptr, exp_path);
     if (rc != CPIMH_ERR_TREE_OVERFLOW) {
       if (rc) { cpimh_pf_destroy(g_cached); g_cached = nullptr; g_cached_B = 0; }   // do not keep a handle in an unknown state
