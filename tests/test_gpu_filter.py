@@ -343,3 +343,50 @@ def test_one_shot_entry_over_several_waves_is_pipelined_and_matches_the_handle_a
     r = up.cpf_batch(N, model, theta, obs, B, seed=21, first_filter=4, logz_t=True)
     for k in ("logz", "logz_t", "trajectory", "path_index"):
         assert np.array_equal(r[k], ref[k]), k
+
+
+@pytest.mark.parametrize("name,N", [("levy_sv", 4096), ("gss", 2000), ("ar1", 1025), ("ar1", 37)])
+def test_shuffled_ancestors_philox_parity(up, oracle, golden, name, N):
+    """cfg.shuffle = 1 (std::random_shuffle of the ancestors, src/multinomial.cpp:6-10,29-30) with Philox uniforms: the
+    kernel replays the N - 1 swaps in parallel (every final position traced back to its origin); ancestors must equal the
+    oracle's one-swap-after-the-other loop at every step."""
+    c = model_cases(up, oracle, golden)[name]
+    obs = c["obs"][:6]
+    B, seed = 2, 77
+    pb = up.PfBatch(c["model"], c["theta"], obs, N, B, shuffle=1)
+    pb.record_ancestors(True)
+    pb.run(B, seed, first_filter=1)
+    r = pb.fetch(logz_t=True, path_index=True)
+    okw = {k: v for k, v in c["okw"].items() if k != "sk_max_events"}
+    ocfg = oracle.make_config(c["oid"], c["d"], c["dy"], N, obs.shape[0], theta=c["otheta"], shuffle=1, **okw)
+    for b in range(B):
+        o = oracle.cpf(ocfg, obs, seed=seed, filter_id=1 + b, want_ancestors=True)
+        anc = pb.fetch_ancestors(b)
+        assert np.array_equal(anc, o["ancestors"]), (name, b, int(np.sum(anc != o["ancestors"])))
+        assert not np.all(np.diff(anc[1]) >= 0)                                   # really shuffled
+        assert int(r["path_index"][b]) == o["path_index"]
+    pb.close()
+
+
+@pytest.mark.parametrize("kind", ["all_to_front", "shift_by_one", "identity", "random"])
+def test_shuffle_replay_adversarial_draws(up, oracle, golden, kind):
+    """Injected shuffle uniforms that stress the parallel replay: every swap with position 0 (one bucket of N - 1 entries: the
+    one-thread fallback), j_i = i - 1 (a hop chain of length N from the last position), j_i = i (no swap at all)."""
+    N, T, B = 1500, 3, 2                     # >= 1024: the parallel replay (smaller filters swap serially)
+    c = model_cases(up, oracle, golden)["ar1"]
+    obs = c["obs"][:T]
+    rng = np.random.default_rng(5)
+    ocfg = oracle.make_config(c["oid"], c["d"], c["dy"], N, T, theta=c["otheta"], shuffle=1, **c["okw"])
+    nz = injected_noise(rng, oracle, ocfg, B, N, T, 1)
+    i = np.arange(1, N)
+    u = {"all_to_front": np.zeros(N - 1), "shift_by_one": (i - 0.5) / (i + 1), "identity": (i + 0.5) / (i + 1), "random": rng.random(N - 1)}[kind]
+    nz["shuffle"] = np.broadcast_to(u, (B, T, N - 1)).copy()
+    pb = up.PfBatch(c["model"], c["theta"], obs, N, B, shuffle=1)
+    pb.record_ancestors(True)
+    pb.set_noise(B, nz)
+    pb.run(B, 0)
+    pb.fetch()
+    for b in range(B):
+        o = oracle.cpf(ocfg, obs, noise={k: v[b] for k, v in nz.items()}, want_ancestors=True)
+        assert np.array_equal(pb.fetch_ancestors(b), o["ancestors"]), (kind, b)
+    pb.close()

@@ -353,9 +353,59 @@ __device__ void run_filter(const PfParams& p, const PfSmem& sm, long long ws, co
         int j = (int)floor(u * (double)(i + 1));
         jidx[i] = j > i ? i : j;
       }
+      // The N-1 swaps are a serial chain on the array; replayed in parallel instead by tracing every FINAL position back to
+      // the original position its content came from.  Swap i touches positions i and j_i <= i, so going back in time from
+      // position cur with swaps < m still to undo: if some swap i in (cur, m) has j_i == cur, the content sat at position i
+      // before it and no earlier swap touches i: origin i (the largest such i); else swap cur itself moved it from j_cur:
+      // continue from there with m = cur.  The swaps that hit a position are kept as buckets sorted descending (counting
+      // sort + insertion sort of buckets of expected length <= ln N); ~1 hop per position for uniform draws.  Scratch: the
+      // CDF and ladder arrays, both dead once the ancestors sit in bpar.  Buckets longer than 32 (only injected uniforms can
+      // do that) and filters of fewer than 1024 particles use the one-thread loop.
+      int* start = jidx + N;                               // [N + 1] bucket offsets (ladder array, second half)
+      int* items = reinterpret_cast<int*>(sm.C.ptr());     // [N] swap indices grouped by the position they hit
+      int* outp = items + N;                               // [N] fill cursors, then the permuted ancestors
+      for (int q = tid; q <= N; q += NT) start[q] = 0;
       __syncthreads();
-      if (tid == 0)
-        for (int i = 1; i < N; i++) { int j = jidx[i]; int tmp = sm.bpar[i]; sm.bpar[i] = sm.bpar[j]; sm.bpar[j] = tmp; }
+      for (int i = 1 + tid; i < N; i += NT) { const int j = jidx[i]; if (j != i) atomicAdd(&start[j], 1); }
+      __syncthreads();
+      const int cpt = (N + NT - 1) / NT;
+      const int q0 = min(N, tid * cpt), q1 = min(N, q0 + cpt);
+      int tot = 0, longest = 0;
+      for (int q = q0; q < q1; q++) { const int cnt = start[q]; longest = max(longest, cnt); tot += cnt; }
+      int total = 0;
+      int off = block_excl_scan_int(tot, sm.iscr.ptr(), &total);
+      if (__syncthreads_or(longest > 32 || N < 1024)) {     // small N: the 6 passes + barriers cost more than N serial swaps (gss N = 256: 1.4x)
+        if (tid == 0)
+          for (int i = 1; i < N; i++) { int j = jidx[i]; int tmp = sm.bpar[i]; sm.bpar[i] = sm.bpar[j]; sm.bpar[j] = tmp; }
+      } else {
+        for (int q = q0; q < q1; q++) { const int cnt = start[q]; start[q] = off; outp[q] = off; off += cnt; }
+        if (tid == 0) start[N] = total;
+        __syncthreads();
+        for (int i = 1 + tid; i < N; i += NT) { const int j = jidx[i]; if (j != i) items[atomicAdd(&outp[j], 1)] = i; }
+        __syncthreads();
+        for (int q = tid; q < N; q += NT) {
+          const int b0 = start[q], b1 = start[q + 1];
+          for (int x = b0 + 1; x < b1; x++) {
+            const int v = items[x];
+            int y = x - 1;
+            while (y >= b0 && items[y] < v) { items[y + 1] = items[y]; y--; }
+            items[y + 1] = v;
+          }
+        }
+        __syncthreads();
+        for (int q = tid; q < N; q += NT) {
+          int cur = q, m = N, origin;
+          for (;;) {
+            int found = -1;
+            for (int x = start[cur], xe = start[cur + 1]; x < xe; x++) { const int it = items[x]; if (it < m) { found = it; break; } }
+            if (found >= 0) { origin = found; break; }
+            if (cur >= 1 && cur < m) { m = cur; cur = jidx[cur]; } else { origin = cur; break; }
+          }
+          outp[q] = sm.bpar[origin];
+        }
+        __syncthreads();
+        for (int q = tid; q < N; q += NT) sm.bpar[q] = outp[q];
+      }
       __syncthreads();
     }
     bool done = false;
