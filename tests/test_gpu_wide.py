@@ -125,3 +125,63 @@ def test_wide_more_groups_than_the_shared_memory_table_holds(up):
     b = pb.fetch(logz_t=True, path_index=True)
     assert np.array_equal(a["logz_t"], b["logz_t"]) and np.array_equal(a["trajectory"], b["trajectory"])
     pb.close()
+
+
+def _wide_run(up, y, N, B, seed, noise=None, d=64):
+    pb = up.PfBatch(up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5], y, N, B)
+    pb.record_ancestors(True)
+    if noise is not None:
+        pb.set_noise(B, noise)
+    pb.run(B, seed, first_filter=3)
+    r = pb.fetch(logz_t=True, path_index=True)
+    r["anc"] = np.stack([pb.fetch_ancestors(b) for b in range(B)])
+    r["rep"] = pb.fetch_exact_repeats(B)
+    pb.close()
+    return r
+
+
+@pytest.mark.parametrize("N,B", [(5000, 2), (65536, 1)])
+def test_wide_reference_order_mode_equals_the_fast_pass(up, monkeypatch, N, B):
+    """Exact ancestors, wide filter: the fast pass (group-table CDF, parallel sums) checks every chosen knot against the uniform
+    +- a rounding margin; a filter that trips the check is rerun with cumsum(normweights) in the reference's left-to-right
+    order (src/multinomial.cpp:17).  On random draws nothing trips, and forcing the reference-order mode must give the same
+    ancestors, path and trajectory (log Z: another summation order, 1e-13)."""
+    T = 6 if N < 10000 else 4
+    y = np.random.default_rng(N).normal(size=(T, 64)) * 2 + 2
+    fast = _wide_run(up, y, N, B, 19)
+    assert not fast["rep"].any()
+    monkeypatch.setenv("CPIMH_WIDE_EXACT", "1")
+    ref = _wide_run(up, y, N, B, 19)
+    assert np.array_equal(fast["anc"], ref["anc"])
+    assert np.array_equal(fast["path_index"], ref["path_index"]) and np.array_equal(fast["trajectory"], ref["trajectory"])
+    assert np.allclose(fast["logz_t"], ref["logz_t"], rtol=1e-13, atol=0)
+
+
+def test_wide_uniform_on_a_cdf_knot_reruns_in_reference_order(up, oracle, monkeypatch):
+    """Sorted uniforms placed ON (or one ulp beside) knots of the step-1 CDF: the fast pass must flag the filter, and what the
+    handle then returns must be the reference-order run, bit for bit.  (The knots come from the oracle's weights, equal to the
+    kernel's to ~1e-15: far inside the margin, so the check trips; the kernel's own last bits decide the crafted ancestors.)"""
+    from tests.test_gpu_exact_ancestors import craft_sorted_uniforms
+    d, N, B = 64, 2000, 2
+    rng = np.random.default_rng(8)
+    y = rng.normal(size=(2, d)) * 2 + 2
+    nz = dict(init=rng.normal(size=(B, d, N)), trans=rng.normal(size=(B, 2, d, N)), resample=np.zeros((B, 2, N)), path_u=rng.random(B))
+    nz["resample"][:, 0, :] = 0.5
+    ocfg1 = oracle.make_config(oracle.MODEL_LORENZ, d, d, N, 1, theta=[8.0, 0.5, 1.0], integrator=0, substeps=1)
+    ncraft = 40
+    for b in range(B):
+        n1 = {"init": nz["init"][b], "trans": nz["trans"][b][:1], "resample": nz["resample"][b][:1], "path_u": nz["path_u"][b]}
+        w = oracle.cpf(ocfg1, y[:1], noise=n1, all_particles=True)["normweights"]
+        e, hits = craft_sorted_uniforms(rng, w, ncraft)
+        assert hits >= 10
+        nz["resample"][b, 1] = e
+    got = _wide_run(up, y, N, B, 0, noise=nz)
+    assert got["rep"].all(), "a uniform on a knot must send the filter through the reference-order pass"
+    monkeypatch.setenv("CPIMH_WIDE_EXACT", "1")
+    ref = _wide_run(up, y, N, B, 0, noise=nz)
+    assert np.array_equal(got["anc"], ref["anc"]) and np.array_equal(got["trajectory"], ref["trajectory"])
+    assert np.array_equal(got["logz_t"], ref["logz_t"])
+    ocfg = oracle.make_config(oracle.MODEL_LORENZ, d, d, N, 2, theta=[8.0, 0.5, 1.0], integrator=0, substeps=1)
+    for b in range(B):
+        o = oracle.cpf(ocfg, y, noise={k: v[b] for k, v in nz.items()}, want_ancestors=True)
+        assert int(np.sum(got["anc"][b][1] != o["ancestors"][1])) <= ncraft        # only crafted draws may land on the other side

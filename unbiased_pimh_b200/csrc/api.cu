@@ -529,7 +529,7 @@ int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* e
 
 int cpimh_pf_fetch_exact_repeats(cpimh_pf* h, int64_t B, void* stream, int32_t* repeats) {
   CPIMH_REQUIRE(h && repeats, "null argument");
-  CPIMH_REQUIRE(!h->wide, "not available for the wide (d = 32/64) filter");
+  if (h->wide) return wide_fetch_exact_repeats(h->wide, B, (cudaStream_t)stream, repeats);
   CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
   cudaStream_t s = (cudaStream_t)stream;
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(repeats, h->exact.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, s));

@@ -39,6 +39,9 @@ struct WideParams {
   double* logz_t; double* logz; double* traj; int* path_index;
   const double* inj_init; const double* inj_trans; const double* inj_resample; const double* inj_path;
   int* anc_rec;
+  // exact ancestors (DESIGN.md "Exact ancestors"): the fast pass flags a filter when a uniform lies within rounding distance
+  // (margin_rel * sum of the weights) of a CDF knot; the host then reruns the batch with exact = 1 (reference-order CDF)
+  int* near; double margin_rel; int exact;
 };
 
 
@@ -170,7 +173,13 @@ __global__ void __launch_bounds__(TWO ? 1024 : 128, TWO ? 1 : WIDE_MINB) wide_pr
     if (mine) {
       if (ident) a = (int)k;
       else if (!TWO) {
-        a = g_count_le_w(Cb, N, scale * Sb[k]);
+        const double u = scale * Sb[k];
+        a = g_count_le_w(Cb, N, u);
+        if (!p.exact) {                                            // exact = 1: Cb IS the reference-order CDF, nothing to check
+          const double mar = p.margin_rel * Cb[N - 1];
+          const double cur = a < N ? Cb[a] : INFINITY, below = a > 0 ? Cb[a - 1] : -INFINITY;
+          if (cur - u <= mar || u - below < mar) p.near[b] = 1;
+        }
         if (a >= N) a = N - 1;
       }
     }
@@ -187,10 +196,16 @@ __global__ void __launch_bounds__(TWO ? 1024 : 128, TWO ? 1 : WIDE_MINB) wide_pr
         const long long j0 = (long long)gs * G;
         const int cnt = (int)min((long long)G, (long long)N - j0);
         a = (int)j0 + cnt - 1;
+        double below = acc;
+        bool hit = false;
         for (int j = 0; j < cnt; j++) {                            // knots inside the group, left to right (src/multinomial.cpp:25-28 rule)
-          acc += lwold[j0 + j] * f;
-          if (acc > u) { a = (int)j0 + j; break; }
+          const double nxt = acc + lwold[j0 + j] * f;
+          if (nxt > u) { a = (int)j0 + j; below = acc; acc = nxt; hit = true; break; }
+          acc = nxt;
         }
+        // the two knots that decided a, against u +- the rounding margin of a CDF summed in another order than the reference's
+        const double mar = p.margin_rel * GCb[p.GX - 1];
+        if (!hit || acc - u <= mar || (a > 0 && u - below < mar)) p.near[b] = 1;
       }
     }
     if (mine) {
@@ -255,7 +270,7 @@ WIDE_PRAGMA_UNROLL(WIDE_UNROLL)
 #define WIDE_TILE 8192       // elements scanned per pass in shared memory (64 KB)
 #define WIDE_MAX_BLOCKS_PER_CTA 8192
 __global__ void __cluster_dims__(WIDE_CLUSTER, 1, 1) __launch_bounds__(1024, 1)
-wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
+wide_weights_scan_kernel(WideParams p, int t_done, int prep, int exact) {
   extern __shared__ __align__(16) unsigned char raw[];
   double* buf = reinterpret_cast<double*>(raw);     // [WIDE_TILE]
   double* fac = buf + WIDE_TILE;                    // [blocks of this CTA] exp(m_c - m)
@@ -308,10 +323,15 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
 #pragma unroll
     for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) buf[q] = (r[e] * fac[(int)(base + q - lo) / G]) / s; }   // normweights (R/CPF.R:63)
     __syncthreads();
-    block_scan_inplace<false>(buf, n, scr);
+    if (exact) {                                    // the normalised weights themselves: wide_seq_cumsum_kernel sums them left to right
 #pragma unroll
-    for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) Cb[base + q] = buf[q] + run; }
-    run += buf[n - 1];
+      for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) Cb[base + q] = buf[q]; }
+    } else {
+      block_scan_inplace<false>(buf, n, scr);
+#pragma unroll
+      for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) Cb[base + q] = buf[q] + run; }
+      run += buf[n - 1];
+    }
     __syncthreads();
     if (ladder) {
 #pragma unroll
@@ -332,6 +352,26 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep) {
   }
 }
 
+// ------------------------------------------------------------------ exact mode: cumsum(normweights) in the reference's order
+// (Rcpp::cumsum, src/multinomial.cpp:17 / the running sum of src/systematic.cpp:13-19): one lane adds left to right, the
+// warp stages tiles through shared memory.  ~0.4 ms for N = 65536 -- only filters that flagged a near-knot uniform come here.
+__global__ void wide_seq_cumsum_kernel(WideParams p) {
+  __shared__ double tile[1024];
+  const int b = blockIdx.x, lane = threadIdx.x, N = p.N;
+  double* Cb = p.C + (size_t)b * N;
+  double acc = 0.0;
+  for (int base = 0; base < N; base += 1024) {
+    const int n = min(1024, N - base);
+    for (int q = lane; q < n; q += 32) tile[q] = Cb[base + q];
+    __syncwarp();
+    if (lane == 0)
+      for (int q = 0; q < n; q++) { acc += tile[q]; tile[q] = acc; }
+    __syncwarp();
+    for (int q = lane; q < n; q += 32) Cb[base + q] = tile[q];
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------ final path: systematic(normw, 1, u) + get_path (R/CPF.R:69)
 template <int C>
 __global__ void wide_path_kernel(WideParams p) {
@@ -339,7 +379,13 @@ __global__ void wide_path_kernel(WideParams p) {
   const int b = blockIdx.x, lane = threadIdx.x, N = p.N, T = p.T;
   const Stream s = make_stream(p.seed, p.first_filter + (unsigned long long)b);
   const double u = p.inj_path ? p.inj_path[b] : philox_u1(s, 0, T + 1, CPIMH_P_PATH, 0);
-  int k = g_count_lt_w(p.C + (size_t)b * N, N, u);
+  const double* Cb = p.C + (size_t)b * N;
+  int k = g_count_lt_w(Cb, N, u);
+  if (!p.exact && lane == 0) {                      // `while (csw < u)` (src/systematic.cpp:15): knots k - 1 (< u) and k (>= u)
+    const double mar = p.margin_rel * Cb[N - 1];
+    const double cur = k < N ? Cb[k] : INFINITY, below = k > 0 ? Cb[k - 1] : -INFINITY;
+    if (cur - u < mar || u - below <= mar) p.near[b] = 1;
+  }
   if (k >= N) k = N - 1;
   if (lane == 0) {
     p.path_index[b] = k;
@@ -361,6 +407,12 @@ struct WideFilter {
   cpimh_config cfg;
   int64_t maxB, lastB, launches, bytes;
   int GX, G, pgrid, record_anc;
+  // exact ancestors: near-knot flags of the last fast pass, the arguments to rerun it with, and whether that has been settled
+  DevBuf near;
+  std::vector<int> near_host;
+  uint64_t last_seed = 0, last_first = 0;
+  int force_exact = 0, last_exact = 0, resolved = 1;
+  int64_t exact_reruns = 0;
   std::vector<double> obs_host;
   DevBuf ptot;
   DevBuf obs, hist_x, hist_a, lw, lw2, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
@@ -394,6 +446,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   WideFilter* h = new WideFilter();
   h->cfg = cfg; h->maxB = max_filters; h->lastB = 0; h->launches = 0; h->bytes = 0; h->record_anc = 0;
   memset(h->have_inj, 0, sizeof(h->have_inj));
+  if (const char* e = getenv("CPIMH_WIDE_EXACT")) h->force_exact = atoi(e) ? 1 : 0;      // test aid: every run in the reference-order mode
   wide_geometry(cfg, max_filters, prop.multiProcessorCount, &h->G, &h->GX);
   h->pgrid = prop.multiProcessorCount * WIDE_MINB;          // at least one resident wave of wide_propagate CTAs
   CPIMH_REQUIRE((h->GX + WIDE_CLUSTER - 1) / WIDE_CLUSTER <= WIDE_MAX_BLOCKS_PER_CTA, "N too large for the cluster scan");
@@ -410,6 +463,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
   if (!rc) rc = A(h->lw2, sizeof(double) * B * N);
   if (!rc) rc = A(h->C, sizeof(double) * B * N);
   if (!rc) rc = A(h->S, sizeof(double) * B * N);
+  if (!rc) rc = A(h->near, sizeof(int) * B);
   if (!rc) rc = A(h->pmax, sizeof(double) * 2 * B * h->GX);
   if (!rc) rc = A(h->psum, sizeof(double) * 2 * B * h->GX);
   if (!rc) rc = A(h->pv, sizeof(double) * 2 * B * h->GX);
@@ -426,7 +480,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
 
 void wide_destroy(WideFilter* h) {
   if (!h) return;
-  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->lw2, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
+  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->lw2, &h->near, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
                    &h->path_index, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
@@ -481,7 +535,8 @@ static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   for (int t = 1; t <= T; t++) {
     const int ident = is_ident(t);
     if (t >= 2 && !p.two_level) {
-      wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, t - 1, ident ? 0 : 1);
+      wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(p, t - 1, ident ? 0 : 1, p.exact);
+      if (p.exact && !ident) { wide_seq_cumsum_kernel<<<B, 32, 0, s>>>(p); h->launches += 1; }
       h->launches += 1;
     }
     const int prep_next = (t < T && !is_ident(t + 1)) ? 1 : 0;
@@ -492,14 +547,15 @@ static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   // the last step's weights as a normalised per-particle CDF: the final path pick (R/CPF.R:69) and log Z_T
   WideParams pl = p;
   if (p.two_level && (T & 1) == 0) pl.lw = p.lw2;           // step T wrote the buffer of its parity (its log Z_T comes from this scan)
-  wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(pl, T, 0);
+  wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(pl, T, 0, p.exact);
+  if (p.exact) { wide_seq_cumsum_kernel<<<B, 32, 0, s>>>(p); h->launches += 1; }
   wide_path_kernel<C><<<B, 32, 0, s>>>(p);
   h->launches += 2;
   CPIMH_CUDA_CHECK(cudaGetLastError());
   return CPIMH_OK;
 }
 
-int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cudaStream_t s) {
+static int wide_launch(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, int exact, cudaStream_t s) {
   CPIMH_REQUIRE(B >= 1 && B <= h->maxB, "nfilters %lld outside [1, %lld]", (long long)B, (long long)h->maxB);
   const cpimh_config& c = h->cfg;
   WideParams p;
@@ -514,7 +570,10 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   p.hist_x = h->hist_x.as<double>(); p.hist_a = h->hist_a.as<int>(); p.lw = h->lw.as<double>(); p.C = h->C.as<double>(); p.S = h->S.as<double>();
   p.lw2 = h->lw2.as<double>();
   // the two-level CDF serves the Philox path; injected sorted uniforms (parity runs) keep the per-particle scans
-  p.two_level = (!h->have_inj[2] && h->GX <= WIDE_MAX_GROUPS) ? 1 : 0;
+  p.two_level = (!exact && !h->have_inj[2] && h->GX <= WIDE_MAX_GROUPS) ? 1 : 0;
+  p.exact = exact; p.near = h->near.as<int>();
+  p.margin_rel = 12.0 * ((double)c.nparticles + 2.0) * 0x1p-53;      // as pf_fused.cuh check_knots: both CDFs are sums of N terms, relative error <= (N - 1) 2^-53 each
+  if (!exact) CPIMH_CUDA_CHECK(cudaMemsetAsync(h->near.p, 0, sizeof(int) * (size_t)B, s));
   p.pmax = h->pmax.as<double>(); p.psum = h->psum.as<double>(); p.pv = h->pv.as<double>(); p.mstep = h->mstep.as<double>(); p.ptot = h->ptot.as<double>(); p.maxB = (size_t)h->maxB;
   p.logz_t = h->logz_t.as<double>(); p.logz = h->logz.as<double>(); p.traj = h->traj.as<double>(); p.path_index = h->path_index.as<int>();
   p.inj_init = h->have_inj[0] ? h->inj_init.as<double>() : nullptr;
@@ -524,12 +583,46 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   p.anc_rec = h->record_anc ? h->anc_rec.as<int>() : nullptr;
   int rc = c.dim == 64 ? wide_run_t<2>(h, p, s) : wide_run_t<1>(h, p, s);
   if (rc) return rc;
-  h->lastB = B;
+  h->lastB = B; h->last_seed = seed; h->last_first = first_filter; h->last_exact = exact;
+  return CPIMH_OK;
+}
+
+int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cudaStream_t s) {
+  h->resolved = 0;
+  h->near_host.assign((size_t)B, 0);
+  return wide_launch(h, B, seed, first_filter, h->force_exact, s);
+}
+
+// Before any result leaves the handle: if the fast pass met a uniform within rounding distance of a CDF knot (its ancestor
+// could differ from the reference's left-to-right CDF), the batch is run again with that CDF (same Philox streams, same
+// injected noise: every other draw is unchanged).  Expected once per ~10^3-10^4 config-5 filters.
+static int wide_resolve(WideFilter* h, cudaStream_t s) {
+  if (h->resolved) return CPIMH_OK;
+  if (!h->last_exact) {
+    CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->near_host.data(), h->near.p, sizeof(int) * (size_t)h->lastB, cudaMemcpyDeviceToHost, s));
+    CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+    bool any = false;
+    for (int64_t b = 0; b < h->lastB; b++) any = any || h->near_host[(size_t)b] != 0;
+    if (any) {
+      int rc = wide_launch(h, h->lastB, h->last_seed, h->last_first, 1, s);
+      if (rc) return rc;
+      h->exact_reruns += 1;
+    }
+  }
+  h->resolved = 1;
+  return CPIMH_OK;
+}
+int wide_fetch_exact_repeats(WideFilter* h, int64_t B, cudaStream_t s, int32_t* repeats) {
+  CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
+  int rc = wide_resolve(h, s);
+  if (rc) return rc;
+  for (int64_t b = 0; b < B; b++) repeats[b] = h->near_host[(size_t)b];      // 1: this filter sent the batch through the exact-order pass
   return CPIMH_OK;
 }
 
 int wide_fetch(WideFilter* h, int64_t B, cudaStream_t s, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
   CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
+  { int rcr = wide_resolve(h, s); if (rcr) return rcr; }
   const cpimh_config& c = h->cfg;
   if (logz) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz, h->logz.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
   if (logz_t) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz_t, h->logz_t.p, sizeof(double) * (size_t)B * c.nobs, cudaMemcpyDeviceToHost, s));
@@ -542,6 +635,7 @@ int wide_fetch(WideFilter* h, int64_t B, cudaStream_t s, double* logz, double* l
 int wide_fetch_ancestors(WideFilter* h, int64_t b, cudaStream_t s, int32_t* anc) {
   CPIMH_REQUIRE(h->record_anc, "call cpimh_pf_record_ancestors(h, 1) before cpimh_pf_run");
   CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
+  { int rcr = wide_resolve(h, s); if (rcr) return rcr; }
   const size_t n = (size_t)h->cfg.nobs * h->cfg.nparticles;
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(anc, h->anc_rec.as<int>() + (size_t)b * n, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -550,7 +644,7 @@ int wide_fetch_ancestors(WideFilter* h, int64_t b, cudaStream_t s, int32_t* anc)
 
 int64_t wide_launch_count(const WideFilter* h) { return h->launches; }
 int64_t wide_device_bytes(const WideFilter* h) { return h->bytes; }
-void wide_device_outputs(WideFilter* h, double** d_logz, double** d_traj) { if (d_logz) *d_logz = h->logz.as<double>(); if (d_traj) *d_traj = h->traj.as<double>(); }
+void wide_device_outputs(WideFilter* h, double** d_logz, double** d_traj) { wide_resolve(h, nullptr); if (d_logz) *d_logz = h->logz.as<double>(); if (d_traj) *d_traj = h->traj.as<double>(); }
 void wide_effective(const WideFilter* h, cpimh_config* out) { *out = h->cfg; out->tree_capacity = 0; out->threads_per_filter = h->G; out->store_paths = 2; out->reserved = h->GX; }
 
 }  // namespace cpimh
