@@ -224,6 +224,25 @@ def test_adaptive_pf_matches_oracle(up, oracle, golden, name, ess, systematic):
         assert 0 < g["resampled"].mean() < 1
 
 
+@pytest.mark.parametrize("name,N", [("gss", 128), ("sv", 2000), ("ar3", 1000)])
+@pytest.mark.parametrize("ess,systematic", [(1.0, False), (0.6, True)])
+def test_adaptive_pf_reference_order_mode_equals_the_fast_pass(up, golden, monkeypatch, name, N, ess, systematic):
+    """Exact ancestors in pf(): the fast pass checks every chosen knot of its parallel-scan CDF against the uniform +- a rounding
+    margin and reruns a flagged batch with cumsum(normweights) left to right (src/multinomial.cpp:17, src/systematic.cpp:13-19).
+    On random draws nothing is flagged, and forcing the reference-order mode must return the same bits."""
+    if name == "gss":
+        m, th, y = up.get_gss(), [], golden["gss_y"][:40]
+    elif name == "sv":
+        m, th, y = up.get_levy_sv(), golden["sv_theta_mle"], golden["sv_y"][:25]
+    else:
+        m, th, y = up.get_ar(3), TH_AR, np.random.default_rng(4).normal(size=(30, 3))
+    fast = up.pf_batch(y, th, m, N, 4, ess_threshold=ess, systematic=systematic, seed=5, first_filter=1, ancestors=True)
+    monkeypatch.setenv("CPIMH_APF_EXACT", "1")
+    ref = up.pf_batch(y, th, m, N, 4, ess_threshold=ess, systematic=systematic, seed=5, first_filter=1, ancestors=True)
+    for k in ("ancestors", "resampled", "path", "loglik_t", "pf_means"):
+        assert np.array_equal(fast[k], ref[k]), k
+
+
 def test_adaptive_pf_likelihood_is_unbiased(up, golden):
     """exp(loglik) is an unbiased estimator of the likelihood: log-mean-exp over 4000 filters matches the Kalman value."""
     y = golden["lgssm_y"]

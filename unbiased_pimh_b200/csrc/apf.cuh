@@ -32,6 +32,9 @@ struct ApfParams {
   int* resampled;              // [B][T] or null
   int* anc_rec;                // [B][T][N] or null
   int* status;                 // [B]
+  // exact ancestors (DESIGN.md "Exact ancestors"): the fast pass flags a filter whose uniform lies within margin_rel * sum(w)
+  // of a CDF knot; the host then reruns the batch with exact = 1 (cumsum(normweights) by one thread, left to right)
+  int exact; int* near; double margin_rel;
 };
 struct ApfSmem { double* C; double* S; double* LW; double* theta; double* pre; double* dscr; int* iscr; int theta_off, pre_off; };
 __host__ __device__ inline size_t apf_smem_bytes(int Npad, int npre) {
@@ -66,6 +69,24 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
   c.n_trans = 0; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
   int st = 0;
   if (tid == 0) sm.iscr[32] = 0;
+  bool near = false;
+  // CDF of the normalised weights: parallel scan, or (exact) the reference's running sum (src/multinomial.cpp:17, src/systematic.cpp:13-19)
+  auto weight_cdf = [&]() {
+    if (p.exact) { __syncthreads(); if (tid == 0) sequential_cumsum_p(sm.C, N); __syncthreads(); }
+    else block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
+  };
+  // the two knots that decided ancestor a (rule `u < cdf[j-1]`, src/multinomial.cpp:25-27) against u +- the rounding margin
+  auto knots_le = [&](int a, double u) {
+    const double mar = p.margin_rel * sm.C[pad16(N - 1)];
+    const double cur = a < N ? sm.C[pad16(a)] : INFINITY, below = a > 0 ? sm.C[pad16(a - 1)] : -INFINITY;
+    if (cur - u <= mar || u - below < mar) near = true;
+  };
+  // rule `while (csw < u)` (src/systematic.cpp:15)
+  auto knots_lt = [&](int a, double u) {
+    const double mar = p.margin_rel * sm.C[pad16(N - 1)];
+    const double cur = a < N ? sm.C[pad16(a)] : INFINITY, below = a > 0 ? sm.C[pad16(a - 1)] : -INFINITY;
+    if (cur - u < mar || u - below <= mar) near = true;
+  };
   const double lw0 = log(1.0 / (double)N);
   for (int i = tid; i < N; i += NT) {                    // R/CPF.R:113-119
     double x[D];
@@ -123,20 +144,24 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
       if (!p.systematic) {
         for (int i = tid; i <= N; i += NT) sm.S[pad16(i)] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
         __syncthreads();
-        block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
+        weight_cdf();
         block_scan_chunked<false>(sm.S, nullptr, N + 1, sm.dscr);
         const double scale = sm.C[pad16(N - 1)] / sm.S[pad16(N)];
         for (int k = tid; k < N; k += NT) {
-          int a = count_le_p(sm.C, 0, N, scale * sm.S[pad16(k)]);
+          const double u = scale * sm.S[pad16(k)];
+          int a = count_le_p(sm.C, 0, N, u);
+          if (!p.exact) knots_le(a, u);
           if (a >= N) { a = N - 1; st |= 512; }
           arow[k] = a;
         }
       } else {                                           // systematic_resampling_n(normweights, N, u): src/systematic.cpp:7-32
         __syncthreads();
-        block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
+        weight_cdf();
         const double u = philox_u1(stream, 0, t, CPIMH_P_AS, 0) / (double)N;
         for (int k = tid; k < N; k += NT) {
-          int a = count_lt_p(sm.C, N, u + (double)k * (1.0 / (double)N));
+          const double uk = u + (double)k * (1.0 / (double)N);
+          int a = count_lt_p(sm.C, N, uk);
+          if (!p.exact) knots_lt(a, uk);
           if (a >= N) { a = N - 1; st |= 512; }
           arow[k] = a;
         }
@@ -146,7 +171,7 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
     } else {
       for (int k = tid; k < N; k += NT) { arow[k] = k; sm.LW[k] = log(sm.C[pad16(k)]); }
       __syncthreads();
-      if (t == T) block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);           // the final draw needs the CDF
+      if (t == T) weight_cdf();                                                    // the final draw needs the CDF
     }
     // ---- the tree keeps the resampled particles (:148-149)
     for (int k = tid; k < N; k += NT) {
@@ -160,8 +185,11 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
   // ---- sample(1:N, 1, prob = normweights) (:152) by inversion of the last CDF, then Tree$get_path
   if (st) atomicOr(&sm.iscr[32], st);
   __syncthreads();
-  int kidx = count_lt_p(sm.C, N, philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0));
+  const double upath = philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0);
+  int kidx = count_lt_p(sm.C, N, upath);
+  if (!p.exact) knots_lt(kidx, upath);
   if (kidx >= N) kidx = N - 1;
+  if (near && p.near) p.near[b] = 1;
   const int flags = sm.iscr[32];
   if (tid == 0) {
     p.loglik[b] = cum;

@@ -2,6 +2,7 @@
 // kernel apf.cuh) and the conditional particle filters: CPF(ref_trajectory, with_as)
 // (R/CPF.R:14-78), CPF_coupled (R/CPF_coupled.R:14-112), the CCPF kernels (R/pf_kernels.R:236-265) and
 // coupled_ccpf_chains + H_bar (R/debiasing_algorithm.R:23-111, 284-316).  Kernels: ccpf.cuh.
+#include <stdlib.h>
 #include <cstring>
 #include <chrono>
 #include <cstdlib>
@@ -393,8 +394,8 @@ int cpimh_pf_adaptive_batch(const cpimh_config* cfg_in, const double* obs_host, 
   const int64_t resident = (int64_t)bps * prop.multiProcessorCount;
   const int grid = (int)(B < resident ? B : resident);
   const size_t PD = (size_t)(T + 1) * D;
-  DevBuf obs, theta, dpre, hx, ha, pr, ll, llt, pm, pa, rs, an, stt;
-  struct Rel { DevBuf* b[13]; ~Rel() { for (auto x : b) x->release(); } } rel{{&obs, &theta, &dpre, &hx, &ha, &pr, &ll, &llt, &pm, &pa, &rs, &an, &stt}};
+  DevBuf obs, theta, dpre, hx, ha, pr, ll, llt, pm, pa, rs, an, stt, nr;
+  struct Rel { DevBuf* b[14]; ~Rel() { for (auto x : b) x->release(); } } rel{{&obs, &theta, &dpre, &hx, &ha, &pr, &ll, &llt, &pm, &pa, &rs, &an, &stt, &nr}};
   rc = obs.alloc(sizeof(double) * (size_t)T * c.dim_y);
   if (!rc) rc = theta.alloc(sizeof(double) * CPIMH_MAX_THETA);
   if (!rc) rc = dpre.alloc(sizeof(double) * (pre.size() + 1));
@@ -407,6 +408,7 @@ int cpimh_pf_adaptive_batch(const cpimh_config* cfg_in, const double* obs_host, 
   if (!rc) rc = pa.alloc(sizeof(double) * B * PD);
   if (!rc) rc = rs.alloc(sizeof(int) * B * T);
   if (!rc) rc = stt.alloc(sizeof(int) * B);
+  if (!rc) rc = nr.alloc(sizeof(int) * B);
   if (!rc && ancestors) rc = an.alloc(sizeof(int) * (size_t)B * T * N);
   if (rc) return rc;
   CPIMH_CUDA_CHECK(cudaMemcpy(theta.p, c.theta, sizeof(double) * CPIMH_MAX_THETA, cudaMemcpyHostToDevice));
@@ -424,10 +426,25 @@ int cpimh_pf_adaptive_batch(const cpimh_config* cfg_in, const double* obs_host, 
   p.resampled = rs.as<int>(); p.anc_rec = ancestors ? an.as<int>() : nullptr; p.status = stt.as<int>();
   ApfLaunch L;
   L.grid = grid; L.threads = threads; L.smem = smem;
-  rc = e->launch_apf(p, L, nullptr);
-  if (rc) return rc;
-  CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
+  // exact ancestors: a fast pass whose filters flag uniforms within rounding distance of a CDF knot; if any did, the batch
+  // runs again with the reference-order CDF (same Philox streams: every other draw is unchanged)
+  p.near = nr.as<int>();
+  p.margin_rel = 12.0 * ((double)N + 2.0) * 0x1p-53;
+  const char* force = getenv("CPIMH_APF_EXACT");                    // test aid: reference-order mode from the start
+  p.exact = (force && atoi(force)) ? 1 : 0;
   std::vector<int> st((size_t)B);
+  for (int pass = 0; pass < 2; pass++) {
+    CPIMH_CUDA_CHECK(cudaMemset(nr.p, 0, sizeof(int) * B));
+    rc = e->launch_apf(p, L, nullptr);
+    if (rc) return rc;
+    CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
+    if (p.exact) break;
+    CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), nr.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    bool any = false;
+    for (int64_t b = 0; b < B; b++) any = any || st[(size_t)b] != 0;
+    if (!any) break;
+    p.exact = 1;
+  }
   CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), stt.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
   for (int64_t b = 0; b < B; b++)
     if (st[(size_t)b]) { set_error("adaptive filter %lld failed with status %d", (long long)b, st[(size_t)b]); return st[(size_t)b]; }
