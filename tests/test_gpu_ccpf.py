@@ -321,3 +321,48 @@ def test_rheeglynn_estimator_with_geometric_truncation(up, oracle, golden):
     # the R-shaped front end draws the truncation itself and returns it
     e = up.rheeglynn_estimator(y, model, th, {"nparticles": N, "with_as": False, "lambda": 0.3}, seed=5)
     assert e["estimate"].shape == (1, T + 1) and e["truncation"] >= 0 and e["iteration"] <= max(e["truncation"], 0) and np.all(np.isfinite(e["estimate"]))
+
+
+@pytest.mark.parametrize("name,N,with_as", [("ar1", 64, True), ("gss", 500, True), ("sv", 1000, False), ("ar3", 100, False)])
+def test_conditional_filters_reference_order_mode_equals_the_fast_pass_and_the_oracle(up, oracle, golden, monkeypatch, name, N, with_as):
+    """Exact ancestors in the conditional filters: the fast pass compares every chosen knot (of the CDFs of w, of mu = nu / alpha,
+    of the two residuals, of the ancestor-sampling weights) and every coupling uniform against alpha with a rounding margin; a
+    flagged call runs again with alpha, mu, the residuals and all cumsums in the reference's order
+    (src/coupledresamplingindexmatching.cpp:13-24, src/multinomial.cpp:17,40-41).  On random draws nothing is flagged; the
+    forced reference-order mode must give the fast pass's ancestors and paths, and the oracle's."""
+    if name == "ar1":
+        m, th, y, oc = up.get_ar(1), TH_AR, golden["lgssm_y"][:50], (oracle.MODEL_AR, 1, 1)
+    elif name == "ar3":
+        m, th, y, oc = up.get_ar(3), TH_AR, np.random.default_rng(4).normal(size=(30, 3)), (oracle.MODEL_AR, 3, 3)
+    elif name == "gss":
+        m, th, y, oc = up.get_gss(), [], golden["gss_y"][:40], (oracle.MODEL_GSS, 1, 1)
+    else:
+        m, th, y, oc = up.get_levy_sv(), golden["sv_theta_mle"], golden["sv_y"][:30], (oracle.MODEL_LEVY_SV, 2, 1)
+    cfg = oracle.make_config(oc[0], oc[1], oc[2], N, y.shape[0], theta=th)
+    refs = _refs(oracle, cfg, y, 9, 4)
+    fast1 = up.ccpf_batch(N, m, th, y, refs[:2], with_as=with_as, seed=31, first_filter=2, ancestors=True)
+    fast2 = up.ccpf_batch(N, m, th, y, refs[:2], refs[2:], with_as=with_as, seed=32, first_filter=5, ancestors=True)
+    monkeypatch.setenv("CPIMH_CCPF_EXACT", "1")
+    ex1 = up.ccpf_batch(N, m, th, y, refs[:2], with_as=with_as, seed=31, first_filter=2, ancestors=True)
+    ex2 = up.ccpf_batch(N, m, th, y, refs[:2], refs[2:], with_as=with_as, seed=32, first_filter=5, ancestors=True)
+    for f, e in ((fast1, ex1), (fast2, ex2)):
+        for k in ("ancestors", "path_index", "trajectory1", "logz"):
+            assert np.array_equal(f[k], e[k]), k
+    assert np.array_equal(fast2["trajectory2"], ex2["trajectory2"])
+    for b in range(2):
+        o = oracle.ccpf(cfg, y, refs[b], refs[2 + b], with_as=with_as, seed=32, filter_id=5 + b, want_ancestors=True)
+        assert np.array_equal(ex2["ancestors"][b, 0], o["ancestors1"]) and np.array_equal(ex2["ancestors"][b, 1], o["ancestors2"])
+        assert list(ex2["path_index"][b]) == o["path_index"]
+
+
+def test_ccpf_chains_reference_order_mode(up, oracle, golden, monkeypatch):
+    y = golden["lgssm_y"]
+    kw = dict(K=5, k=2, with_as=True, seed=12, first_replicate=3, max_iterations=400)
+    fast = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 64, 60, **kw)
+    monkeypatch.setenv("CPIMH_CCPF_EXACT", "1")
+    ex = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 64, 60, **kw)
+    assert np.array_equal(fast["meetingtime"], ex["meetingtime"]) and np.array_equal(fast["iteration"], ex["iteration"])
+    assert np.array_equal(fast["hbar"], ex["hbar"]) and fast["nfilters"] == ex["nfilters"]
+    cfg = oracle.make_config(oracle.MODEL_AR, 1, 1, 64, 100, theta=TH_AR)
+    o = oracle.coupled_ccpf_batch(cfg, y, 12, 3, 60, k=2, K=5, with_as=True, max_iterations=400)
+    assert np.array_equal(ex["meetingtime"], o["meetingtime"]) and np.allclose(ex["hbar"][:, 0, :], o["hbar"], rtol=1e-9, atol=1e-9)

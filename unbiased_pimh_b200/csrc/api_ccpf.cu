@@ -17,9 +17,10 @@ struct CcpfWork {
   const ModelEntry* entry = nullptr;
   int Npad = 0, npre = 0, threads = 0, grid_max = 0;
   size_t smem = 0;
-  DevBuf obs, theta, pre, hist_x, hist_a;
+  DevBuf obs, theta, pre, hist_x, hist_a, near;   // near: one word, set by a fast pass that met a uniform within rounding distance of a CDF knot
   int64_t launches = 0;
-  ~CcpfWork() { obs.release(); theta.release(); pre.release(); hist_x.release(); hist_a.release(); }
+  int64_t exact_reruns = 0;
+  ~CcpfWork() { obs.release(); theta.release(); pre.release(); hist_x.release(); hist_a.release(); near.release(); }
 };
 
 static int ccpf_work_init(CcpfWork* w, const cpimh_config* cfg_in, const double* obs_host, int64_t max_filters) {
@@ -57,6 +58,7 @@ static int ccpf_work_init(CcpfWork* w, const cpimh_config* cfg_in, const double*
   if (!rc) rc = w->pre.alloc(sizeof(double) * (pre.size() + 1));
   if (!rc) rc = w->hist_x.alloc(sizeof(double) * (size_t)w->grid_max * 2 * (T + 1) * D * w->Npad);
   if (!rc) rc = w->hist_a.alloc(sizeof(int) * (size_t)w->grid_max * 2 * T * w->Npad);
+  if (!rc) rc = w->near.alloc(sizeof(int));
   if (rc) return rc;
   CPIMH_CUDA_CHECK(cudaMemcpy(w->theta.p, c.theta, sizeof(double) * CPIMH_MAX_THETA, cudaMemcpyHostToDevice));
   if (!pre.empty()) CPIMH_CUDA_CHECK(cudaMemcpy(w->pre.p, pre.data(), sizeof(double) * pre.size(), cudaMemcpyHostToDevice));
@@ -71,6 +73,9 @@ static void ccpf_fill(const CcpfWork& w, CcpfParams* p) {
   p->npre = w.npre; p->integrator = c.integrator; p->substeps = c.substeps;
   p->hist_x = w.hist_x.as<double>(); p->hist_a = w.hist_a.as<int>();
   p->n_init = api_n_init(c); p->n_trans = api_n_trans(c); p->sk_M = c.sk_max_events;
+  p->near = w.near.as<int>(); p->margin_rel = 12.0 * ((double)c.nparticles + 2.0) * 0x1p-53;
+  const char* force = getenv("CPIMH_CCPF_EXACT");                 // test aid: reference-order mode from the start
+  p->exact = (force && atoi(force)) ? 1 : 0;
 }
 static int ccpf_launch(CcpfWork& w, const CcpfParams& p, cudaStream_t s) {
   CcpfLaunch L;
@@ -180,9 +185,19 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B,
   p.traj1 = t1.as<double>(); p.traj2 = t2.as<double>(); p.logz = lz.as<double>(); p.path_index = pidx.as<int>();
   p.status = status.as<int>(); p.anc_rec = ancestors ? anc.as<int>() : nullptr;
   if (want_exp) { p.exp1 = ex1.as<double>(); p.exp2 = ex2.as<double>(); }
-  rc = ccpf_launch(w, p, nullptr);
-  if (rc) return rc;
-  CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
+  // exact ancestors: fast pass; if it met a uniform within rounding distance of a CDF knot (or of alpha), the whole batch runs
+  // again with every sum in the reference's order (same Philox streams and injected noise: all other draws unchanged)
+  for (int pass = 0; pass < 2; pass++) {
+    CPIMH_CUDA_CHECK(cudaMemset(w.near.p, 0, sizeof(int)));
+    rc = ccpf_launch(w, p, nullptr);
+    if (rc) return rc;
+    CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
+    int flagged = 0;
+    CPIMH_CUDA_CHECK(cudaMemcpy(&flagged, w.near.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (p.exact || !flagged) break;
+    p.exact = 1;
+    w.exact_reruns++;
+  }
   std::vector<int> st((size_t)B);
   CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), status.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
   for (int64_t b = 0; b < B; b++)
@@ -208,7 +223,7 @@ struct CcChainCache {
   DevBuf e1, e2, ne1, ne2, accHe, accDe, hbar_rb, sums_rb;
   void release() {
     DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &cnt, &nf, &sums, &pst1, &pst2, &trunc,
-                     &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb, &w.obs, &w.theta, &w.pre, &w.hist_x, &w.hist_a};
+                     &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb, &w.obs, &w.theta, &w.pre, &w.hist_x, &w.hist_a, &w.near};
     for (auto x : all) x->release();
     if (pf) { cpimh_pf_destroy(pf); pf = nullptr; pf_R = 0; }
   }
@@ -233,8 +248,23 @@ int cpimh_rheeglynn(const cpimh_config* cfg, const double* obs_host, int64_t R, 
   CPIMH_REQUIRE(lambda == 0.0 || (lambda > 0.0 && lambda < 1.0 && truncation), "lambda must be 0, or in (0, 1) with one truncation variable per replicate");
   return coupled_ccpf_impl(cfg, obs_host, R, seed, first_replicate, 0, 0, max_iterations, with_as, lambda, lambda > 0.0 ? truncation : nullptr, o);
 }
+static int coupled_ccpf_pass(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
+                             int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o,
+                             int exact, int* flagged);
+// exact ancestors: a fast pass, and -- if any conditional filter of any replicate met a uniform within rounding distance of a
+// CDF knot or of the coupling probability -- the call once more in reference order (expected once per several thousand calls)
 static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
                              int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o) {
+  const char* force = getenv("CPIMH_CCPF_EXACT");
+  int flagged = 0;
+  int rc = coupled_ccpf_pass(cfg, obs_host, R, seed, first_replicate, k, K, max_iterations, with_as, rg_lambda, truncation, o, (force && atoi(force)) ? 1 : 0, &flagged);
+  if (rc || !flagged) return rc;
+  g_cc.w.exact_reruns++;
+  return coupled_ccpf_pass(cfg, obs_host, R, seed, first_replicate, k, K, max_iterations, with_as, rg_lambda, truncation, o, 1, &flagged);
+}
+static int coupled_ccpf_pass(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
+                             int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o,
+                             int exact, int* flagged) {
   CPIMH_REQUIRE(cfg && obs_host && o, "null argument");
   CPIMH_REQUIRE(R >= 1, "nreplicates must be >= 1");
   CPIMH_REQUIRE(k >= 0 && K >= k, "need 0 <= k <= K (got k=%d K=%d)", k, K);
@@ -328,6 +358,8 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
   p.ref1 = g.st1.as<double>(); p.ref2 = g.st2.as<double>();
   p.traj1 = g.n1.as<double>(); p.traj2 = g.n2.as<double>(); p.logz = g.nlz.as<double>(); p.status = g.nst.as<int>();
   if (rb) { p.exp1 = g.ne1.as<double>(); p.exp2 = g.ne2.as<double>(); }
+  p.exact = exact;
+  CPIMH_CUDA_CHECK(cudaMemsetAsync(w.near.p, 0, sizeof(int), s));
   // ---- the chains: one persistent kernel, every resident CTA runs whole replicates (ccpf.cuh ccpf_chains_kernel)
   CcpfLaunch L;
   L.threads = w.threads; L.smem = w.smem; L.grid = (int)(R < w.grid_max ? R : w.grid_max);
@@ -341,7 +373,10 @@ static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, in
   const double t_out = now();
   std::vector<int> stv((size_t)R);
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(stv.data(), g.status.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(flagged, w.near.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (exact) *flagged = 0;
+  if (*flagged) return CPIMH_OK;                       // the caller runs the reference-order pass; nothing of this one is returned
   for (int64_t r = 0; r < R; r++)
     if (stv[(size_t)r] && stv[(size_t)r] != CPIMH_ERR_NOT_MET) { set_error("replicate %lld failed with status %d", (long long)r, stv[(size_t)r]); return stv[(size_t)r]; }
   std::vector<double> hs(2 * (size_t)PD + 2);

@@ -40,6 +40,11 @@ struct CcpfParams {
   double* exp1; double* exp2;  // [slot][T+1][D] or null: weighted average of all N paths (CPF_RB, R/rheeglynn_estimator_RB.R:50-56)
   const double* inj_init; const double* inj_trans;
   int n_init, n_trans, sk_M;
+  // exact ancestors (DESIGN.md "Exact ancestors"): the fast pass sets near[0] when a uniform lies within margin_rel of a CDF knot
+  // (or of the coupling probability alpha); the host then runs the call again with exact = 1: alpha, mu = nu / alpha, the
+  // residuals (w - nu) / (1 - alpha) and every cumsum in the reference's order (src/coupledresamplingindexmatching.cpp:13-24,
+  // src/multinomial.cpp:17,40-41) by one thread
+  int exact; int* near; double margin_rel;
 };
 
 struct CcpfSmem {
@@ -72,24 +77,64 @@ __device__ __forceinline__ CcpfSmem ccpf_carve(int Npad, int npre) {
 
 __device__ __forceinline__ int clampN(int a, int N) { return a >= N ? N - 1 : a; }
 
-// indexmatching_cpp(w1, w2, ndraws = 1) with the uniforms (uc, ud): coupled with probability alpha = sum min(w1, w2),
-// then one draw from mu, else one common-uniform draw from the two residuals.  Destroys A and Bv.  All threads call.
-__device__ inline void im_single_draw(double* A, double* Bv, int N, double uc, double ud, double* dscr, int& a1, int& a2) {
+// in-place CDF of a padded array: parallel scan, or (exact) the reference's left-to-right running sum.  All threads call.
+__device__ __forceinline__ void cc_cdf(double* A, int N, bool exact, double* dscr) {
+  if (exact) { __syncthreads(); if (threadIdx.x == 0) sequential_cumsum_p(A, N); __syncthreads(); }
+  else block_scan_chunked<false>(A, nullptr, N, dscr);
+}
+// sum of v over the CTA: parallel tree, or (exact) A[0] + A[1] + ... by one thread (Rcpp sugar sum)
+__device__ __forceinline__ double cc_sum_min(const double* A, const double* Bv, int N, bool exact, double* dscr) {
   const int tid = threadIdx.x, NT = blockDim.x;
+  if (exact) {
+    __syncthreads();
+    if (tid == 0) { double acc = 0.0; for (int k = 0; k < N; k++) acc += fmin(A[pad16(k)], Bv[pad16(k)]); dscr[0] = acc; }
+    __syncthreads();
+    const double r = dscr[0];
+    __syncthreads();
+    return r;
+  }
   double al = 0.0;
   for (int k = tid; k < N; k += NT) al += fmin(A[pad16(k)], Bv[pad16(k)]);
-  al = block_sum(al, dscr);
+  return block_sum(al, dscr);
+}
+// the two knots that decided index a against u +- the rounding margin; LE: rule `u < cdf[j-1]` (src/multinomial.cpp:25-27),
+// else `while (csw < u)` (src/systematic.cpp:15)
+template <bool LE>
+__device__ __forceinline__ bool cc_near(const double* C, int N, int a, double u, double margin_rel) {
+  const double mar = margin_rel * C[pad16(N - 1)];
+  const double cur = a < N ? C[pad16(a)] : INFINITY, below = a > 0 ? C[pad16(a - 1)] : -INFINITY;
+  return LE ? (cur - u <= mar || u - below < mar) : (cur - u < mar || u - below <= mar);
+}
+
+// indexmatching_cpp(w1, w2, ndraws = 1) with the uniforms (uc, ud): coupled with probability alpha = sum min(w1, w2),
+// then one draw from mu, else one common-uniform draw from the two residuals.  Destroys A and Bv.  All threads call.
+__device__ inline void im_single_draw(double* A, double* Bv, int N, double uc, double ud, double* dscr, int& a1, int& a2,
+                                      bool exact, double margin_rel, bool& near) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const double al = cc_sum_min(A, Bv, N, exact, dscr);
+  if (!exact && fabs(uc - al) <= margin_rel) near = true;
   if (uc < al) {
-    for (int k = tid; k < N; k += NT) A[pad16(k)] = fmin(A[pad16(k)], Bv[pad16(k)]);
+    for (int k = tid; k < N; k += NT) { const double nu = fmin(A[pad16(k)], Bv[pad16(k)]); A[pad16(k)] = exact ? nu / al : nu; }
     __syncthreads();
-    block_scan_chunked<false>(A, nullptr, N, dscr);
-    a1 = a2 = clampN(count_le_p(A, 0, N, ud * A[pad16(N - 1)]), N);
+    cc_cdf(A, N, exact, dscr);
+    const double u = ud * A[pad16(N - 1)];
+    const int a = count_le_p(A, 0, N, u);
+    if (!exact && cc_near<true>(A, N, a, u, margin_rel)) near = true;
+    a1 = a2 = clampN(a, N);
   } else {
-    for (int k = tid; k < N; k += NT) { const double nu = fmin(A[pad16(k)], Bv[pad16(k)]); A[pad16(k)] -= nu; Bv[pad16(k)] -= nu; }
+    const double den = 1.0 - al;
+    for (int k = tid; k < N; k += NT) {
+      const double nu = fmin(A[pad16(k)], Bv[pad16(k)]);
+      A[pad16(k)] = exact ? (A[pad16(k)] - nu) / den : A[pad16(k)] - nu;
+      Bv[pad16(k)] = exact ? (Bv[pad16(k)] - nu) / den : Bv[pad16(k)] - nu;
+    }
     __syncthreads();
-    block_scan_chunked<true>(A, Bv, N, dscr);
-    a1 = clampN(count_le_p(A, 0, N, ud * A[pad16(N - 1)]), N);
-    a2 = clampN(count_le_p(Bv, 0, N, ud * Bv[pad16(N - 1)]), N);
+    if (exact) { cc_cdf(A, N, true, dscr); cc_cdf(Bv, N, true, dscr); }
+    else block_scan_chunked<true>(A, Bv, N, dscr);
+    const double u1 = ud * A[pad16(N - 1)], u2 = ud * Bv[pad16(N - 1)];
+    const int b1 = count_le_p(A, 0, N, u1), b2 = count_le_p(Bv, 0, N, u2);
+    if (!exact && (cc_near<true>(A, N, b1, u1, margin_rel) || cc_near<true>(Bv, N, b2, u2, margin_rel))) near = true;
+    a1 = clampN(b1, N); a2 = clampN(b2, N);
   }
   __syncthreads();
 }
@@ -118,6 +163,8 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   c.n_trans = p.n_trans; c.sk_M = p.sk_M; c.integrator = p.integrator; c.substeps = p.substeps;
   int st = 0;
   if (tid == 0) sm.iscr[32] = 0;
+  const bool exact = p.exact != 0;
+  bool near = false;
 
   // ---------------- initialisation (R/CPF.R:19-28, R/CPF_coupled.R:22-33): common init noise, last particle = ref[, 1]
   for (int i = tid; i < N; i += NT) {
@@ -176,11 +223,13 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
         double ua, ub;
         philox_u2(stream, 0, t, CPIMH_P_AS, 0, ua, ub);
         if (nsys == 1) {
-          block_scan_chunked<false>(Lk[0], nullptr, N, sm.dscr);
-          aref[0] = clampN(count_lt_p(Lk[0], N, ua), N);                       // systematic_resampling_n(w_as, 1, u)
+          cc_cdf(Lk[0], N, exact, sm.dscr);
+          const int a = count_lt_p(Lk[0], N, ua);                              // systematic_resampling_n(w_as, 1, u)
+          if (!exact && cc_near<false>(Lk[0], N, a, ua, p.margin_rel)) near = true;
+          aref[0] = clampN(a, N);
           __syncthreads();
         } else {
-          im_single_draw(Lk[0], Lk[1], N, ua, ub, sm.dscr, aref[0], aref[1]);  // CR_indexmatching(w_as1, w_as2, ntrials = 1)
+          im_single_draw(Lk[0], Lk[1], N, ua, ub, sm.dscr, aref[0], aref[1], exact, p.margin_rel, near);  // CR_indexmatching(w_as1, w_as2, ntrials = 1)
         }
       }
     }
@@ -190,32 +239,44 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
       for (int i = tid; i <= nd + 1; i += NT) sm.P[pad16(i)] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
       if (nsys == 1) {
         __syncthreads();
-        block_scan_chunked<false>(sm.C1, nullptr, N, sm.dscr);
+        cc_cdf(sm.C1, N, exact, sm.dscr);
         block_scan_chunked<false>(sm.P, nullptr, nd + 1, sm.dscr);
         const double scale = sm.C1[pad16(N - 1)] / sm.P[pad16(nd)];
         for (int k = tid; k < nd; k += NT) {
-          int a = count_le_p(sm.C1, 0, N, scale * sm.P[pad16(k)]);
+          const double u = scale * sm.P[pad16(k)];
+          int a = count_le_p(sm.C1, 0, N, u);
+          if (!exact && cc_near<true>(sm.C1, N, a, u, p.margin_rel)) near = true;
           if (a >= N) { a = N - 1; st |= 512; }
           arow[0][k] = a;
         }
       } else {
-        double al = 0.0;                                                     // coupledresamplingindexmatching.cpp:13-21
-        for (int k = tid; k < N; k += NT) {
-          const double nu = fmin(sm.C1[pad16(k)], sm.C2[pad16(k)]);
-          sm.V[pad16(k)] = nu; sm.C1[pad16(k)] -= nu; sm.C2[pad16(k)] -= nu;
-          al += nu;
+        const double al = cc_sum_min(sm.C1, sm.C2, N, exact, sm.dscr);       // coupledresamplingindexmatching.cpp:13-21
+        {
+          const double den = 1.0 - al;
+          for (int k = tid; k < N; k += NT) {
+            const double nu = fmin(sm.C1[pad16(k)], sm.C2[pad16(k)]);
+            if (exact) {                                                     // mu = nu / alpha, R = (w - nu) / (1 - alpha)  (:22-24)
+              sm.V[pad16(k)] = nu / al;
+              sm.C1[pad16(k)] = al < 1.0 ? (sm.C1[pad16(k)] - nu) / den : 0.0;
+              sm.C2[pad16(k)] = al < 1.0 ? (sm.C2[pad16(k)] - nu) / den : 0.0;
+            } else { sm.V[pad16(k)] = nu; sm.C1[pad16(k)] -= nu; sm.C2[pad16(k)] -= nu; }
+          }
         }
-        al = block_sum(al, sm.dscr);
         // coupled flags (:26-33) and each index's rank inside its group: thread `tid` owns a contiguous chunk of indices
         const int chunk = (nd + NT - 1) / NT, i0 = min(nd, tid * chunk), i1 = min(nd, i0 + chunk);
         int cnt = 0;
-        for (int i = i0; i < i1; i++) { const int f = philox_u1(stream, i, t, CPIMH_P_COUPLE, 0) < al; sm.R[i] = f; cnt += f; }
+        for (int i = i0; i < i1; i++) {
+          const double uc = philox_u1(stream, i, t, CPIMH_P_COUPLE, 0);
+          const int f = uc < al;
+          if (!exact && fabs(uc - al) <= p.margin_rel) near = true;
+          sm.R[i] = f; cnt += f;
+        }
         int nc;
         int jc = block_excl_scan_int(cnt, sm.iscr, &nc);
         int jr = i0 - jc;
         for (int i = i0; i < i1; i++) { if (sm.R[i]) sm.R[i] = jc++; else sm.R[i] = ~(jr++); }
-        block_scan_chunked<true>(sm.C1, sm.C2, N, sm.dscr);
-        block_scan_chunked<false>(sm.V, nullptr, N, sm.dscr);
+        if (exact) { cc_cdf(sm.C1, N, true, sm.dscr); cc_cdf(sm.C2, N, true, sm.dscr); cc_cdf(sm.V, N, true, sm.dscr); }
+        else { block_scan_chunked<true>(sm.C1, sm.C2, N, sm.dscr); block_scan_chunked<false>(sm.V, nullptr, N, sm.dscr); }
         block_scan_chunked<false>(sm.P, nullptr, nd + 2, sm.dscr);
         const double Pnc = sm.P[pad16(nc)], den = sm.P[pad16(nd + 1)] - Pnc;
         const double totV = sm.V[pad16(N - 1)], tot1 = sm.C1[pad16(N - 1)], tot2 = sm.C2[pad16(N - 1)];
@@ -223,11 +284,15 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
           const int r = sm.R[k];
           int a1, a2;
           if (r >= 0) {                                                      // :36-38 common draw from mu = nu / alpha
-            a1 = a2 = clampN(count_le_p(sm.V, 0, N, (sm.P[pad16(r)] / Pnc) * totV), N);
+            const double u = (sm.P[pad16(r)] / Pnc) * totV;
+            const int a = count_le_p(sm.V, 0, N, u);
+            if (!exact && cc_near<true>(sm.V, N, a, u, p.margin_rel)) near = true;
+            a1 = a2 = clampN(a, N);
           } else {                                                           // :40-42 residuals with a common uniform
             const double u = (sm.P[pad16(nc + 1 + (~r))] - Pnc) / den;
-            a1 = clampN(count_le_p(sm.C1, 0, N, u * tot1), N);
-            a2 = clampN(count_le_p(sm.C2, 0, N, u * tot2), N);
+            const int b1 = count_le_p(sm.C1, 0, N, u * tot1), b2 = count_le_p(sm.C2, 0, N, u * tot2);
+            if (!exact && (cc_near<true>(sm.C1, N, b1, u * tot1, p.margin_rel) || cc_near<true>(sm.C2, N, b2, u * tot2, p.margin_rel))) near = true;
+            a1 = clampN(b1, N); a2 = clampN(b2, N);
           }
           arow[0][k] = a1; arow[1][k] = a2;
         }
@@ -310,11 +375,14 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   philox_u2(stream, 0, T + 1, CPIMH_P_PATH, 0, ua, ub);
   int kidx[2] = {0, 0};
   if (nsys == 1) {
-    block_scan_chunked<false>(sm.C1, nullptr, N, sm.dscr);
-    kidx[0] = clampN(count_lt_p(sm.C1, N, ua), N);
+    cc_cdf(sm.C1, N, exact, sm.dscr);
+    const int a = count_lt_p(sm.C1, N, ua);
+    if (!exact && cc_near<false>(sm.C1, N, a, ua, p.margin_rel)) near = true;
+    kidx[0] = clampN(a, N);
   } else {
-    im_single_draw(sm.C1, sm.C2, N, ua, ub, sm.dscr, kidx[0], kidx[1]);
+    im_single_draw(sm.C1, sm.C2, N, ua, ub, sm.dscr, kidx[0], kidx[1], exact, p.margin_rel, near);
   }
+  if (near && p.near) p.near[0] = 1;
   const int flags = sm.iscr[32];
   if (tid == 0) {
     p.logz[slot] = logz_sum;
