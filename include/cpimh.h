@@ -144,6 +144,15 @@ int cpimh_pf_device_exp_paths(cpimh_pf* h, double** d_exp_path);   /* [B][T+1][d
 /* number of time steps each filter of the last run repeated with sequential-order sums because a sorted uniform came within
  * rounding distance of a CDF knot (DESIGN.md "Exact ancestors"): repeats [B] */
 int cpimh_pf_fetch_exact_repeats(cpimh_pf* h, int64_t nfilters, void* stream, int32_t* repeats);
+/* Wide filter (Lorenz 96, d = 32 / 64) only: the fused filter settles a near-knot step inside the kernel, one filter across the
+ * GPU cannot (at N = 65536 a uniform comes within the worst-case rounding bound of a knot about once per step, and settling it
+ * needs the reference's serial sum).  on = 1: every step uses cumsum(normweights) in the reference's order (src/multinomial.cpp:17),
+ * ~6x slower; on = 0 (default): fast pass, cpimh_pf_fetch_exact_repeats then reports per filter whether any draw was that close. */
+int cpimh_pf_exact_mode(cpimh_pf* h, int on);
+/* Conditional filters (cpimh_ccpf_batch, cpimh_coupled_ccpf, cpimh_rheeglynn) and pf() (cpimh_pf_adaptive_batch) repeat a step in
+ * the reference's operation order when a uniform comes within rounding distance of a CDF knot (or of the coupling probability);
+ * this returns how many steps the last such call repeated (diagnostic). */
+int64_t cpimh_last_exact_repeats(void);
 int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status);   /* [B] per-filter status of the last run (0 = ok) */
 /* kernels launched by this handle so far (bench.py's gpu_launches) and bytes of HBM it holds */
 int64_t cpimh_pf_launch_count(const cpimh_pf* h);

@@ -227,9 +227,9 @@ def test_adaptive_pf_matches_oracle(up, oracle, golden, name, ess, systematic):
 @pytest.mark.parametrize("name,N", [("gss", 128), ("sv", 2000), ("ar3", 1000)])
 @pytest.mark.parametrize("ess,systematic", [(1.0, False), (0.6, True)])
 def test_adaptive_pf_reference_order_mode_equals_the_fast_pass(up, golden, monkeypatch, name, N, ess, systematic):
-    """Exact ancestors in pf(): the fast pass checks every chosen knot of its parallel-scan CDF against the uniform +- a rounding
-    margin and reruns a flagged batch with cumsum(normweights) left to right (src/multinomial.cpp:17, src/systematic.cpp:13-19).
-    On random draws nothing is flagged, and forcing the reference-order mode must return the same bits."""
+    """Exact ancestors in pf(): every chosen knot of the parallel-scan CDF is compared with the uniform +- a rounding margin; a
+    step that trips the check is repeated inside the kernel with cumsum(normweights) left to right (src/multinomial.cpp:17,
+    src/systematic.cpp:13-19).  On random draws nothing trips, and forcing the reference-order mode must return the same bits."""
     if name == "gss":
         m, th, y = up.get_gss(), [], golden["gss_y"][:40]
     elif name == "sv":
@@ -237,10 +237,18 @@ def test_adaptive_pf_reference_order_mode_equals_the_fast_pass(up, golden, monke
     else:
         m, th, y = up.get_ar(3), TH_AR, np.random.default_rng(4).normal(size=(30, 3))
     fast = up.pf_batch(y, th, m, N, 4, ess_threshold=ess, systematic=systematic, seed=5, first_filter=1, ancestors=True)
+    assert up.lib().cpimh_last_exact_repeats() == 0
+    # a margin widened 10^9-fold makes many steps look near a knot: each is repeated in reference order inside the kernel and
+    # must come out with the same ancestors (the repeat restores the weights, redraws the same uniforms, sums left to right)
+    monkeypatch.setenv("CPIMH_EXACT_MARGIN_SCALE", "1e9")
+    rep = up.pf_batch(y, th, m, N, 4, ess_threshold=ess, systematic=systematic, seed=5, first_filter=1, ancestors=True)
+    assert up.lib().cpimh_last_exact_repeats() > 0
+    monkeypatch.delenv("CPIMH_EXACT_MARGIN_SCALE")
     monkeypatch.setenv("CPIMH_APF_EXACT", "1")
     ref = up.pf_batch(y, th, m, N, 4, ess_threshold=ess, systematic=systematic, seed=5, first_filter=1, ancestors=True)
     for k in ("ancestors", "resampled", "path", "loglik_t", "pf_means"):
         assert np.array_equal(fast[k], ref[k]), k
+        assert np.array_equal(rep[k], ref[k]), k
 
 
 def test_adaptive_pf_likelihood_is_unbiased(up, golden):
@@ -327,7 +335,7 @@ def test_rheeglynn_estimator_with_geometric_truncation(up, oracle, golden):
 def test_conditional_filters_reference_order_mode_equals_the_fast_pass_and_the_oracle(up, oracle, golden, monkeypatch, name, N, with_as):
     """Exact ancestors in the conditional filters: the fast pass compares every chosen knot (of the CDFs of w, of mu = nu / alpha,
     of the two residuals, of the ancestor-sampling weights) and every coupling uniform against alpha with a rounding margin; a
-    flagged call runs again with alpha, mu, the residuals and all cumsums in the reference's order
+    step that trips the check is repeated inside the kernel with alpha, mu, the residuals and all cumsums in the reference's order
     (src/coupledresamplingindexmatching.cpp:13-24, src/multinomial.cpp:17,40-41).  On random draws nothing is flagged; the
     forced reference-order mode must give the fast pass's ancestors and paths, and the oracle's."""
     if name == "ar1":
@@ -342,13 +350,20 @@ def test_conditional_filters_reference_order_mode_equals_the_fast_pass_and_the_o
     refs = _refs(oracle, cfg, y, 9, 4)
     fast1 = up.ccpf_batch(N, m, th, y, refs[:2], with_as=with_as, seed=31, first_filter=2, ancestors=True)
     fast2 = up.ccpf_batch(N, m, th, y, refs[:2], refs[2:], with_as=with_as, seed=32, first_filter=5, ancestors=True)
+    assert up.lib().cpimh_last_exact_repeats() == 0
+    monkeypatch.setenv("CPIMH_EXACT_MARGIN_SCALE", "1e9")           # many steps now trip the check and are repeated in reference order
+    rep1 = up.ccpf_batch(N, m, th, y, refs[:2], with_as=with_as, seed=31, first_filter=2, ancestors=True)
+    n1 = up.lib().cpimh_last_exact_repeats()
+    rep2 = up.ccpf_batch(N, m, th, y, refs[:2], refs[2:], with_as=with_as, seed=32, first_filter=5, ancestors=True)
+    assert n1 > 0 and up.lib().cpimh_last_exact_repeats() > 0
+    monkeypatch.delenv("CPIMH_EXACT_MARGIN_SCALE")
     monkeypatch.setenv("CPIMH_CCPF_EXACT", "1")
     ex1 = up.ccpf_batch(N, m, th, y, refs[:2], with_as=with_as, seed=31, first_filter=2, ancestors=True)
     ex2 = up.ccpf_batch(N, m, th, y, refs[:2], refs[2:], with_as=with_as, seed=32, first_filter=5, ancestors=True)
-    for f, e in ((fast1, ex1), (fast2, ex2)):
+    for f, e in ((fast1, ex1), (fast2, ex2), (rep1, ex1), (rep2, ex2)):
         for k in ("ancestors", "path_index", "trajectory1", "logz"):
             assert np.array_equal(f[k], e[k]), k
-    assert np.array_equal(fast2["trajectory2"], ex2["trajectory2"])
+    assert np.array_equal(fast2["trajectory2"], ex2["trajectory2"]) and np.array_equal(rep2["trajectory2"], ex2["trajectory2"])
     for b in range(2):
         o = oracle.ccpf(cfg, y, refs[b], refs[2 + b], with_as=with_as, seed=32, filter_id=5 + b, want_ancestors=True)
         assert np.array_equal(ex2["ancestors"][b, 0], o["ancestors1"]) and np.array_equal(ex2["ancestors"][b, 1], o["ancestors2"])
@@ -359,6 +374,11 @@ def test_ccpf_chains_reference_order_mode(up, oracle, golden, monkeypatch):
     y = golden["lgssm_y"]
     kw = dict(K=5, k=2, with_as=True, seed=12, first_replicate=3, max_iterations=400)
     fast = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 64, 60, **kw)
+    monkeypatch.setenv("CPIMH_EXACT_MARGIN_SCALE", "1e9")
+    rep = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 64, 60, **kw)
+    assert up.lib().cpimh_last_exact_repeats() > 0
+    assert np.array_equal(fast["meetingtime"], rep["meetingtime"]) and np.array_equal(fast["hbar"], rep["hbar"])
+    monkeypatch.delenv("CPIMH_EXACT_MARGIN_SCALE")
     monkeypatch.setenv("CPIMH_CCPF_EXACT", "1")
     ex = up.coupled_ccpf_chains_batch(up.get_ar(1), TH_AR, y, 64, 60, **kw)
     assert np.array_equal(fast["meetingtime"], ex["meetingtime"]) and np.array_equal(fast["iteration"], ex["iteration"])

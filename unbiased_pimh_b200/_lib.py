@@ -54,6 +54,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.cpimh_last_error.restype = C.c_char_p
         L.cpimh_pf_launch_count.restype = C.c_int64
+        L.cpimh_last_exact_repeats.restype = C.c_int64
         L.cpimh_pf_device_bytes.restype = C.c_int64
         L.cpimh_chains_launch_count.restype = C.c_int64
         L.cpimh_chains_filters_launched.restype = C.c_int64

@@ -32,8 +32,9 @@ struct ApfParams {
   int* resampled;              // [B][T] or null
   int* anc_rec;                // [B][T][N] or null
   int* status;                 // [B]
-  // exact ancestors (DESIGN.md "Exact ancestors"): the fast pass flags a filter whose uniform lies within margin_rel * sum(w)
-  // of a CDF knot; the host then reruns the batch with exact = 1 (cumsum(normweights) by one thread, left to right)
+  // exact ancestors (DESIGN.md "Exact ancestors"): a step whose uniform lies within margin_rel * sum(w) of a CDF knot is repeated
+  // inside the kernel with cumsum(normweights) by one thread, left to right; exact = 1 takes that order from the start (test aid);
+  // near[b] counts the repeated steps of filter b
   int exact; int* near; double margin_rel;
 };
 struct ApfSmem { double* C; double* S; double* LW; double* theta; double* pre; double* dscr; int* iscr; int theta_off, pre_off; };
@@ -70,10 +71,19 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
   int st = 0;
   if (tid == 0) sm.iscr[32] = 0;
   bool near = false;
-  // CDF of the normalised weights: parallel scan, or (exact) the reference's running sum (src/multinomial.cpp:17, src/systematic.cpp:13-19)
-  auto weight_cdf = [&]() {
-    if (p.exact) { __syncthreads(); if (tid == 0) sequential_cumsum_p(sm.C, N); __syncthreads(); }
+  int repeats = 0;
+  bool cdf_exact = false;                              // whether sm.C currently holds the reference-order CDF
+  // CDF of the normalised weights: parallel scan, or (ex) the reference's running sum (src/multinomial.cpp:17, src/systematic.cpp:13-19)
+  auto weight_cdf = [&](bool ex) {
+    if (ex) { __syncthreads(); if (tid == 0) sequential_cumsum_p(sm.C, N); __syncthreads(); }
     else block_scan_chunked<false>(sm.C, nullptr, N, sm.dscr);
+    cdf_exact = ex;
+  };
+  // a flagged pass: put the normalised weights (stashed in LW, which is dead while a step resamples) back
+  auto restore_weights = [&]() {
+    __syncthreads();
+    for (int k = tid; k < N; k += NT) sm.C[pad16(k)] = sm.LW[k];
+    repeats++;
   };
   // the two knots that decided ancestor a (rule `u < cdf[j-1]`, src/multinomial.cpp:25-27) against u +- the rounding margin
   auto knots_le = [&](int a, double u) {
@@ -141,37 +151,44 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
     if (tid == 0 && p.resampled) p.resampled[(size_t)b * T + (t - 1)] = resample ? 1 : 0;
     // ---- resample (:136-147)
     if (resample) {
-      if (!p.systematic) {
-        for (int i = tid; i <= N; i += NT) sm.S[pad16(i)] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
-        __syncthreads();
-        weight_cdf();
-        block_scan_chunked<false>(sm.S, nullptr, N + 1, sm.dscr);
-        const double scale = sm.C[pad16(N - 1)] / sm.S[pad16(N)];
-        for (int k = tid; k < N; k += NT) {
-          const double u = scale * sm.S[pad16(k)];
-          int a = count_le_p(sm.C, 0, N, u);
-          if (!p.exact) knots_le(a, u);
-          if (a >= N) { a = N - 1; st |= 512; }
-          arow[k] = a;
+      for (int k = tid; k < N; k += NT) sm.LW[k] = sm.C[pad16(k)];          // stash: LW is reset below
+      bool ex = p.exact != 0;
+      for (;;) {
+        near = false;
+        if (!p.systematic) {
+          for (int i = tid; i <= N; i += NT) sm.S[pad16(i)] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
+          __syncthreads();
+          weight_cdf(ex);
+          block_scan_chunked<false>(sm.S, nullptr, N + 1, sm.dscr);
+          const double scale = sm.C[pad16(N - 1)] / sm.S[pad16(N)];
+          for (int k = tid; k < N; k += NT) {
+            const double u = scale * sm.S[pad16(k)];
+            int a = count_le_p(sm.C, 0, N, u);
+            if (!ex) knots_le(a, u);
+            if (a >= N) { a = N - 1; st |= 512; }
+            arow[k] = a;
+          }
+        } else {                                         // systematic_resampling_n(normweights, N, u): src/systematic.cpp:7-32
+          __syncthreads();
+          weight_cdf(ex);
+          const double u = philox_u1(stream, 0, t, CPIMH_P_AS, 0) / (double)N;
+          for (int k = tid; k < N; k += NT) {
+            const double uk = u + (double)k * (1.0 / (double)N);
+            int a = count_lt_p(sm.C, N, uk);
+            if (!ex) knots_lt(a, uk);
+            if (a >= N) { a = N - 1; st |= 512; }
+            arow[k] = a;
+          }
         }
-      } else {                                           // systematic_resampling_n(normweights, N, u): src/systematic.cpp:7-32
-        __syncthreads();
-        weight_cdf();
-        const double u = philox_u1(stream, 0, t, CPIMH_P_AS, 0) / (double)N;
-        for (int k = tid; k < N; k += NT) {
-          const double uk = u + (double)k * (1.0 / (double)N);
-          int a = count_lt_p(sm.C, N, uk);
-          if (!p.exact) knots_lt(a, uk);
-          if (a >= N) { a = N - 1; st |= 512; }
-          arow[k] = a;
-        }
+        if (!ex && __syncthreads_or(near ? 1 : 0)) { ex = true; restore_weights(); continue; }   // repeat this step in reference order
+        break;
       }
       __syncthreads();
-      for (int k = tid; k < N; k += NT) sm.LW[k] = lw0;
+      if (t < T) for (int k = tid; k < N; k += NT) sm.LW[k] = lw0;          // t == T: the stash serves the final draw
     } else {
-      for (int k = tid; k < N; k += NT) { arow[k] = k; sm.LW[k] = log(sm.C[pad16(k)]); }
+      for (int k = tid; k < N; k += NT) { arow[k] = k; sm.LW[k] = (t < T) ? log(sm.C[pad16(k)]) : sm.C[pad16(k)]; }
       __syncthreads();
-      if (t == T) weight_cdf();                                                    // the final draw needs the CDF
+      if (t == T) weight_cdf(p.exact != 0);                                  // the final draw needs the CDF
     }
     // ---- the tree keeps the resampled particles (:148-149)
     for (int k = tid; k < N; k += NT) {
@@ -187,9 +204,15 @@ __device__ void run_apf(const ApfParams& p, const ApfSmem& sm, long long ws, con
   __syncthreads();
   const double upath = philox_u1(stream, 0, T + 1, CPIMH_P_PATH, 0);
   int kidx = count_lt_p(sm.C, N, upath);
-  if (!p.exact) knots_lt(kidx, upath);
+  near = false;
+  if (!cdf_exact) knots_lt(kidx, upath);
+  if (!cdf_exact && __syncthreads_or(near ? 1 : 0)) {    // the final draw in reference order
+    restore_weights();
+    weight_cdf(true);
+    kidx = count_lt_p(sm.C, N, upath);
+  }
   if (kidx >= N) kidx = N - 1;
-  if (near && p.near) p.near[b] = 1;
+  if (tid == 0 && p.near) p.near[b] = repeats;
   const int flags = sm.iscr[32];
   if (tid == 0) {
     p.loglik[b] = cum;

@@ -527,6 +527,12 @@ int cpimh_pf_fetch_all_particles(cpimh_pf* h, int64_t b, void* stream, double* e
   return api_all_particles(a, s, exp_path, trajectories, normweights);
 }
 
+int cpimh_pf_exact_mode(cpimh_pf* h, int on) {
+  CPIMH_REQUIRE(h, "null handle");
+  if (h->wide) wide_exact_mode(h->wide, on);        // the fused filter is always exact (in-kernel repeat of a flagged step)
+  return CPIMH_OK;
+}
+
 int cpimh_pf_fetch_exact_repeats(cpimh_pf* h, int64_t B, void* stream, int32_t* repeats) {
   CPIMH_REQUIRE(h && repeats, "null argument");
   if (h->wide) return wide_fetch_exact_repeats(h->wide, B, (cudaStream_t)stream, repeats);

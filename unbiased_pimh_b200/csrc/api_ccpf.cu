@@ -12,15 +12,18 @@
 
 namespace cpimh {
 
+// steps the last conditional / adaptive filter call repeated in reference order (diagnostic; cpimh_last_exact_repeats)
+static int64_t g_last_exact_repeats = 0;
+static double margin_scale() { const char* e = getenv("CPIMH_EXACT_MARGIN_SCALE"); const double v = e ? atof(e) : 1.0; return v > 0.0 ? v : 1.0; }   // test aid: widen the knot margin so that repeats happen on random draws
+
 struct CcpfWork {
   cpimh_config cfg;
   const ModelEntry* entry = nullptr;
   int Npad = 0, npre = 0, threads = 0, grid_max = 0;
   size_t smem = 0;
-  DevBuf obs, theta, pre, hist_x, hist_a, near;   // near: one word, set by a fast pass that met a uniform within rounding distance of a CDF knot
+  DevBuf obs, theta, pre, hist_x, hist_a, near, wsave;   // near: one word counting the steps repeated in reference order; wsave: the step's normalised weights
   int64_t launches = 0;
-  int64_t exact_reruns = 0;
-  ~CcpfWork() { obs.release(); theta.release(); pre.release(); hist_x.release(); hist_a.release(); near.release(); }
+  ~CcpfWork() { obs.release(); theta.release(); pre.release(); hist_x.release(); hist_a.release(); near.release(); wsave.release(); }
 };
 
 static int ccpf_work_init(CcpfWork* w, const cpimh_config* cfg_in, const double* obs_host, int64_t max_filters) {
@@ -59,6 +62,7 @@ static int ccpf_work_init(CcpfWork* w, const cpimh_config* cfg_in, const double*
   if (!rc) rc = w->hist_x.alloc(sizeof(double) * (size_t)w->grid_max * 2 * (T + 1) * D * w->Npad);
   if (!rc) rc = w->hist_a.alloc(sizeof(int) * (size_t)w->grid_max * 2 * T * w->Npad);
   if (!rc) rc = w->near.alloc(sizeof(int));
+  if (!rc) rc = w->wsave.alloc(sizeof(double) * (size_t)w->grid_max * 2 * w->Npad);
   if (rc) return rc;
   CPIMH_CUDA_CHECK(cudaMemcpy(w->theta.p, c.theta, sizeof(double) * CPIMH_MAX_THETA, cudaMemcpyHostToDevice));
   if (!pre.empty()) CPIMH_CUDA_CHECK(cudaMemcpy(w->pre.p, pre.data(), sizeof(double) * pre.size(), cudaMemcpyHostToDevice));
@@ -73,7 +77,7 @@ static void ccpf_fill(const CcpfWork& w, CcpfParams* p) {
   p->npre = w.npre; p->integrator = c.integrator; p->substeps = c.substeps;
   p->hist_x = w.hist_x.as<double>(); p->hist_a = w.hist_a.as<int>();
   p->n_init = api_n_init(c); p->n_trans = api_n_trans(c); p->sk_M = c.sk_max_events;
-  p->near = w.near.as<int>(); p->margin_rel = 12.0 * ((double)c.nparticles + 2.0) * 0x1p-53;
+  p->near = w.near.as<int>(); p->wsave = w.wsave.as<double>(); p->margin_rel = 12.0 * ((double)c.nparticles + 2.0) * 0x1p-53 * margin_scale();
   const char* force = getenv("CPIMH_CCPF_EXACT");                 // test aid: reference-order mode from the start
   p->exact = (force && atoi(force)) ? 1 : 0;
 }
@@ -185,19 +189,13 @@ int cpimh_ccpf_batch(const cpimh_config* cfg, const double* obs_host, int64_t B,
   p.traj1 = t1.as<double>(); p.traj2 = t2.as<double>(); p.logz = lz.as<double>(); p.path_index = pidx.as<int>();
   p.status = status.as<int>(); p.anc_rec = ancestors ? anc.as<int>() : nullptr;
   if (want_exp) { p.exp1 = ex1.as<double>(); p.exp2 = ex2.as<double>(); }
-  // exact ancestors: fast pass; if it met a uniform within rounding distance of a CDF knot (or of alpha), the whole batch runs
-  // again with every sum in the reference's order (same Philox streams and injected noise: all other draws unchanged)
-  for (int pass = 0; pass < 2; pass++) {
-    CPIMH_CUDA_CHECK(cudaMemset(w.near.p, 0, sizeof(int)));
-    rc = ccpf_launch(w, p, nullptr);
-    if (rc) return rc;
-    CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
-    int flagged = 0;
-    CPIMH_CUDA_CHECK(cudaMemcpy(&flagged, w.near.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (p.exact || !flagged) break;
-    p.exact = 1;
-    w.exact_reruns++;
-  }
+  // exact ancestors: a step with a uniform within rounding distance of a CDF knot (or of alpha) is repeated in reference order
+  // inside the kernel (ccpf.cuh); near counts those steps
+  CPIMH_CUDA_CHECK(cudaMemset(w.near.p, 0, sizeof(int)));
+  rc = ccpf_launch(w, p, nullptr);
+  if (rc) return rc;
+  CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
+  { int nrep = 0; CPIMH_CUDA_CHECK(cudaMemcpy(&nrep, w.near.p, sizeof(int), cudaMemcpyDeviceToHost)); g_last_exact_repeats = nrep; }
   std::vector<int> st((size_t)B);
   CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), status.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
   for (int64_t b = 0; b < B; b++)
@@ -223,7 +221,7 @@ struct CcChainCache {
   DevBuf e1, e2, ne1, ne2, accHe, accDe, hbar_rb, sums_rb;
   void release() {
     DevBuf* all[] = {&st1, &st2, &n1, &n2, &lz1, &lz2, &nlz, &nst, &single, &iter, &tau, &status, &accH, &accD, &hbar, &bc, &cnt, &nf, &sums, &pst1, &pst2, &trunc,
-                     &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb, &w.obs, &w.theta, &w.pre, &w.hist_x, &w.hist_a, &w.near};
+                     &e1, &e2, &ne1, &ne2, &accHe, &accDe, &hbar_rb, &sums_rb, &w.obs, &w.theta, &w.pre, &w.hist_x, &w.hist_a, &w.near, &w.wsave};
     for (auto x : all) x->release();
     if (pf) { cpimh_pf_destroy(pf); pf = nullptr; pf_R = 0; }
   }
@@ -248,23 +246,8 @@ int cpimh_rheeglynn(const cpimh_config* cfg, const double* obs_host, int64_t R, 
   CPIMH_REQUIRE(lambda == 0.0 || (lambda > 0.0 && lambda < 1.0 && truncation), "lambda must be 0, or in (0, 1) with one truncation variable per replicate");
   return coupled_ccpf_impl(cfg, obs_host, R, seed, first_replicate, 0, 0, max_iterations, with_as, lambda, lambda > 0.0 ? truncation : nullptr, o);
 }
-static int coupled_ccpf_pass(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
-                             int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o,
-                             int exact, int* flagged);
-// exact ancestors: a fast pass, and -- if any conditional filter of any replicate met a uniform within rounding distance of a
-// CDF knot or of the coupling probability -- the call once more in reference order (expected once per several thousand calls)
 static int coupled_ccpf_impl(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
                              int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o) {
-  const char* force = getenv("CPIMH_CCPF_EXACT");
-  int flagged = 0;
-  int rc = coupled_ccpf_pass(cfg, obs_host, R, seed, first_replicate, k, K, max_iterations, with_as, rg_lambda, truncation, o, (force && atoi(force)) ? 1 : 0, &flagged);
-  if (rc || !flagged) return rc;
-  g_cc.w.exact_reruns++;
-  return coupled_ccpf_pass(cfg, obs_host, R, seed, first_replicate, k, K, max_iterations, with_as, rg_lambda, truncation, o, 1, &flagged);
-}
-static int coupled_ccpf_pass(const cpimh_config* cfg, const double* obs_host, int64_t R, uint64_t seed, uint32_t first_replicate,
-                             int k, int K, int max_iterations, int with_as, double rg_lambda, const int32_t* truncation, cpimh_chain_out* o,
-                             int exact, int* flagged) {
   CPIMH_REQUIRE(cfg && obs_host && o, "null argument");
   CPIMH_REQUIRE(R >= 1, "nreplicates must be >= 1");
   CPIMH_REQUIRE(k >= 0 && K >= k, "need 0 <= k <= K (got k=%d K=%d)", k, K);
@@ -358,7 +341,6 @@ static int coupled_ccpf_pass(const cpimh_config* cfg, const double* obs_host, in
   p.ref1 = g.st1.as<double>(); p.ref2 = g.st2.as<double>();
   p.traj1 = g.n1.as<double>(); p.traj2 = g.n2.as<double>(); p.logz = g.nlz.as<double>(); p.status = g.nst.as<int>();
   if (rb) { p.exp1 = g.ne1.as<double>(); p.exp2 = g.ne2.as<double>(); }
-  p.exact = exact;
   CPIMH_CUDA_CHECK(cudaMemsetAsync(w.near.p, 0, sizeof(int), s));
   // ---- the chains: one persistent kernel, every resident CTA runs whole replicates (ccpf.cuh ccpf_chains_kernel)
   CcpfLaunch L;
@@ -373,10 +355,10 @@ static int coupled_ccpf_pass(const cpimh_config* cfg, const double* obs_host, in
   const double t_out = now();
   std::vector<int> stv((size_t)R);
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(stv.data(), g.status.p, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, s));
-  CPIMH_CUDA_CHECK(cudaMemcpyAsync(flagged, w.near.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  int nrep = 0;
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(&nrep, w.near.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
-  if (exact) *flagged = 0;
-  if (*flagged) return CPIMH_OK;                       // the caller runs the reference-order pass; nothing of this one is returned
+  g_last_exact_repeats = nrep;
   for (int64_t r = 0; r < R; r++)
     if (stv[(size_t)r] && stv[(size_t)r] != CPIMH_ERR_NOT_MET) { set_error("replicate %lld failed with status %d", (long long)r, stv[(size_t)r]); return stv[(size_t)r]; }
   std::vector<double> hs(2 * (size_t)PD + 2);
@@ -461,25 +443,19 @@ int cpimh_pf_adaptive_batch(const cpimh_config* cfg_in, const double* obs_host, 
   p.resampled = rs.as<int>(); p.anc_rec = ancestors ? an.as<int>() : nullptr; p.status = stt.as<int>();
   ApfLaunch L;
   L.grid = grid; L.threads = threads; L.smem = smem;
-  // exact ancestors: a fast pass whose filters flag uniforms within rounding distance of a CDF knot; if any did, the batch
-  // runs again with the reference-order CDF (same Philox streams: every other draw is unchanged)
+  // exact ancestors: a step with a uniform within rounding distance of a CDF knot is repeated in reference order inside the kernel
   p.near = nr.as<int>();
-  p.margin_rel = 12.0 * ((double)N + 2.0) * 0x1p-53;
+  p.margin_rel = 12.0 * ((double)N + 2.0) * 0x1p-53 * margin_scale();
+  CPIMH_CUDA_CHECK(cudaMemset(nr.p, 0, sizeof(int) * B));
   const char* force = getenv("CPIMH_APF_EXACT");                    // test aid: reference-order mode from the start
   p.exact = (force && atoi(force)) ? 1 : 0;
+  rc = e->launch_apf(p, L, nullptr);
+  if (rc) return rc;
+  CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
   std::vector<int> st((size_t)B);
-  for (int pass = 0; pass < 2; pass++) {
-    CPIMH_CUDA_CHECK(cudaMemset(nr.p, 0, sizeof(int) * B));
-    rc = e->launch_apf(p, L, nullptr);
-    if (rc) return rc;
-    CPIMH_CUDA_CHECK(cudaDeviceSynchronize());
-    if (p.exact) break;
-    CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), nr.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
-    bool any = false;
-    for (int64_t b = 0; b < B; b++) any = any || st[(size_t)b] != 0;
-    if (!any) break;
-    p.exact = 1;
-  }
+  CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), nr.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
+  g_last_exact_repeats = 0;
+  for (int64_t b = 0; b < B; b++) g_last_exact_repeats += st[(size_t)b];
   CPIMH_CUDA_CHECK(cudaMemcpy(st.data(), stt.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
   for (int64_t b = 0; b < B; b++)
     if (st[(size_t)b]) { set_error("adaptive filter %lld failed with status %d", (long long)b, st[(size_t)b]); return st[(size_t)b]; }
@@ -491,5 +467,7 @@ int cpimh_pf_adaptive_batch(const cpimh_config* cfg_in, const double* obs_host, 
   if (ancestors) CPIMH_CUDA_CHECK(cudaMemcpy(ancestors, an.p, an.bytes, cudaMemcpyDeviceToHost));
   return CPIMH_OK;
 }
+
+int64_t cpimh_last_exact_repeats(void) { return g_last_exact_repeats; }
 
 }  // extern "C"

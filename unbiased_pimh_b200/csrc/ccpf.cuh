@@ -40,11 +40,12 @@ struct CcpfParams {
   double* exp1; double* exp2;  // [slot][T+1][D] or null: weighted average of all N paths (CPF_RB, R/rheeglynn_estimator_RB.R:50-56)
   const double* inj_init; const double* inj_trans;
   int n_init, n_trans, sk_M;
-  // exact ancestors (DESIGN.md "Exact ancestors"): the fast pass sets near[0] when a uniform lies within margin_rel of a CDF knot
-  // (or of the coupling probability alpha); the host then runs the call again with exact = 1: alpha, mu = nu / alpha, the
+  // exact ancestors (DESIGN.md "Exact ancestors"): a step in which a uniform lies within margin_rel of a CDF knot (or of the
+  // coupling probability alpha) is repeated inside the kernel in reference order (near[0] counts the repeats): alpha, mu = nu / alpha, the
   // residuals (w - nu) / (1 - alpha) and every cumsum in the reference's order (src/coupledresamplingindexmatching.cpp:13-24,
   // src/multinomial.cpp:17,40-41) by one thread
   int exact; int* near; double margin_rel;
+  double* wsave;               // [ws][2][Npad] the step's normalised weights (L2-resident scratch, read only by a repeat)
 };
 
 struct CcpfSmem {
@@ -165,6 +166,8 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   if (tid == 0) sm.iscr[32] = 0;
   const bool exact = p.exact != 0;
   bool near = false;
+  int repeats = 0;
+  double* wsave[2] = {p.wsave + (size_t)ws * 2 * Npad, p.wsave + ((size_t)ws * 2 + 1) * Npad};
 
   // ---------------- initialisation (R/CPF.R:19-28, R/CPF_coupled.R:22-33): common init noise, last particle = ref[, 1]
   for (int i = tid; i < N; i += NT) {
@@ -195,8 +198,16 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
       for (int k = tid; k < N; k += NT) Wk[s][pad16(k)] = Wk[s][pad16(k)] / ssum[s];
     __syncthreads();
 
-    // ---- ancestor of the reference particle: R/CPF.R:47-57, R/CPF_coupled.R:64-84
+    // the normalised weights, kept for a repeat of this step: the CDFs below overwrite them in place
+#pragma unroll
+    for (int s = 0; s < nsys; s++)
+      for (int k = tid; k < N; k += NT) wsave[s][k] = Wk[s][pad16(k)];
     int aref[2] = {N - 1, N - 1};
+    bool ex = exact;
+    for (;;) {                                                               // second pass only after a near-knot draw (reference order)
+    near = false;
+    aref[0] = aref[1] = N - 1;
+    // ---- ancestor of the reference particle: R/CPF.R:47-57, R/CPF_coupled.R:64-84
     if constexpr (Model::HAS_DTRANS) {
       if (p.with_as) {
 #pragma unroll
@@ -223,13 +234,13 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
         double ua, ub;
         philox_u2(stream, 0, t, CPIMH_P_AS, 0, ua, ub);
         if (nsys == 1) {
-          cc_cdf(Lk[0], N, exact, sm.dscr);
+          cc_cdf(Lk[0], N, ex, sm.dscr);
           const int a = count_lt_p(Lk[0], N, ua);                              // systematic_resampling_n(w_as, 1, u)
-          if (!exact && cc_near<false>(Lk[0], N, a, ua, p.margin_rel)) near = true;
+          if (!ex && cc_near<false>(Lk[0], N, a, ua, p.margin_rel)) near = true;
           aref[0] = clampN(a, N);
           __syncthreads();
         } else {
-          im_single_draw(Lk[0], Lk[1], N, ua, ub, sm.dscr, aref[0], aref[1], exact, p.margin_rel, near);  // CR_indexmatching(w_as1, w_as2, ntrials = 1)
+          im_single_draw(Lk[0], Lk[1], N, ua, ub, sm.dscr, aref[0], aref[1], ex, p.margin_rel, near);  // CR_indexmatching(w_as1, w_as2, ntrials = 1)
         }
       }
     }
@@ -239,23 +250,23 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
       for (int i = tid; i <= nd + 1; i += NT) sm.P[pad16(i)] = -rng_log(philox_u1(stream, i, t, CPIMH_P_RESAMPLE, 0));
       if (nsys == 1) {
         __syncthreads();
-        cc_cdf(sm.C1, N, exact, sm.dscr);
+        cc_cdf(sm.C1, N, ex, sm.dscr);
         block_scan_chunked<false>(sm.P, nullptr, nd + 1, sm.dscr);
         const double scale = sm.C1[pad16(N - 1)] / sm.P[pad16(nd)];
         for (int k = tid; k < nd; k += NT) {
           const double u = scale * sm.P[pad16(k)];
           int a = count_le_p(sm.C1, 0, N, u);
-          if (!exact && cc_near<true>(sm.C1, N, a, u, p.margin_rel)) near = true;
+          if (!ex && cc_near<true>(sm.C1, N, a, u, p.margin_rel)) near = true;
           if (a >= N) { a = N - 1; st |= 512; }
           arow[0][k] = a;
         }
       } else {
-        const double al = cc_sum_min(sm.C1, sm.C2, N, exact, sm.dscr);       // coupledresamplingindexmatching.cpp:13-21
+        const double al = cc_sum_min(sm.C1, sm.C2, N, ex, sm.dscr);       // coupledresamplingindexmatching.cpp:13-21
         {
           const double den = 1.0 - al;
           for (int k = tid; k < N; k += NT) {
             const double nu = fmin(sm.C1[pad16(k)], sm.C2[pad16(k)]);
-            if (exact) {                                                     // mu = nu / alpha, R = (w - nu) / (1 - alpha)  (:22-24)
+            if (ex) {                                                     // mu = nu / alpha, R = (w - nu) / (1 - alpha)  (:22-24)
               sm.V[pad16(k)] = nu / al;
               sm.C1[pad16(k)] = al < 1.0 ? (sm.C1[pad16(k)] - nu) / den : 0.0;
               sm.C2[pad16(k)] = al < 1.0 ? (sm.C2[pad16(k)] - nu) / den : 0.0;
@@ -268,14 +279,14 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
         for (int i = i0; i < i1; i++) {
           const double uc = philox_u1(stream, i, t, CPIMH_P_COUPLE, 0);
           const int f = uc < al;
-          if (!exact && fabs(uc - al) <= p.margin_rel) near = true;
+          if (!ex && fabs(uc - al) <= p.margin_rel) near = true;
           sm.R[i] = f; cnt += f;
         }
         int nc;
         int jc = block_excl_scan_int(cnt, sm.iscr, &nc);
         int jr = i0 - jc;
         for (int i = i0; i < i1; i++) { if (sm.R[i]) sm.R[i] = jc++; else sm.R[i] = ~(jr++); }
-        if (exact) { cc_cdf(sm.C1, N, true, sm.dscr); cc_cdf(sm.C2, N, true, sm.dscr); cc_cdf(sm.V, N, true, sm.dscr); }
+        if (ex) { cc_cdf(sm.C1, N, true, sm.dscr); cc_cdf(sm.C2, N, true, sm.dscr); cc_cdf(sm.V, N, true, sm.dscr); }
         else { block_scan_chunked<true>(sm.C1, sm.C2, N, sm.dscr); block_scan_chunked<false>(sm.V, nullptr, N, sm.dscr); }
         block_scan_chunked<false>(sm.P, nullptr, nd + 2, sm.dscr);
         const double Pnc = sm.P[pad16(nc)], den = sm.P[pad16(nd + 1)] - Pnc;
@@ -286,12 +297,12 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
           if (r >= 0) {                                                      // :36-38 common draw from mu = nu / alpha
             const double u = (sm.P[pad16(r)] / Pnc) * totV;
             const int a = count_le_p(sm.V, 0, N, u);
-            if (!exact && cc_near<true>(sm.V, N, a, u, p.margin_rel)) near = true;
+            if (!ex && cc_near<true>(sm.V, N, a, u, p.margin_rel)) near = true;
             a1 = a2 = clampN(a, N);
           } else {                                                           // :40-42 residuals with a common uniform
             const double u = (sm.P[pad16(nc + 1 + (~r))] - Pnc) / den;
             const int b1 = count_le_p(sm.C1, 0, N, u * tot1), b2 = count_le_p(sm.C2, 0, N, u * tot2);
-            if (!exact && (cc_near<true>(sm.C1, N, b1, u * tot1, p.margin_rel) || cc_near<true>(sm.C2, N, b2, u * tot2, p.margin_rel))) near = true;
+            if (!ex && (cc_near<true>(sm.C1, N, b1, u * tot1, p.margin_rel) || cc_near<true>(sm.C2, N, b2, u * tot2, p.margin_rel))) near = true;
             a1 = clampN(b1, N); a2 = clampN(b2, N);
           }
           arow[0][k] = a1; arow[1][k] = a2;
@@ -301,6 +312,16 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
 #pragma unroll
       for (int s = 0; s < nsys; s++)
         for (int k = tid; k < nd; k += NT) arow[s][k] = k;
+    }
+    if (!ex && __syncthreads_or(near ? 1 : 0)) {
+      ex = true; repeats++;
+#pragma unroll
+      for (int s = 0; s < nsys; s++)
+        for (int k = tid; k < N; k += NT) Wk[s][pad16(k)] = wsave[s][k];
+      __syncthreads();
+      continue;
+    }
+    break;
     }
     if (tid == 0) {
 #pragma unroll
@@ -374,15 +395,30 @@ __device__ void run_ccpf(const CcpfParams& p, const CcpfSmem& sm, long long ws, 
   double ua, ub;
   philox_u2(stream, 0, T + 1, CPIMH_P_PATH, 0, ua, ub);
   int kidx[2] = {0, 0};
-  if (nsys == 1) {
-    cc_cdf(sm.C1, N, exact, sm.dscr);
-    const int a = count_lt_p(sm.C1, N, ua);
-    if (!exact && cc_near<false>(sm.C1, N, a, ua, p.margin_rel)) near = true;
-    kidx[0] = clampN(a, N);
-  } else {
-    im_single_draw(sm.C1, sm.C2, N, ua, ub, sm.dscr, kidx[0], kidx[1], exact, p.margin_rel, near);
+#pragma unroll
+  for (int s = 0; s < nsys; s++)
+    for (int k = tid; k < N; k += NT) wsave[s][k] = Wk[s][pad16(k)];
+  for (bool ex = exact;;) {
+    near = false;
+    if (nsys == 1) {
+      cc_cdf(sm.C1, N, ex, sm.dscr);
+      const int a = count_lt_p(sm.C1, N, ua);
+      if (!ex && cc_near<false>(sm.C1, N, a, ua, p.margin_rel)) near = true;
+      kidx[0] = clampN(a, N);
+    } else {
+      im_single_draw(sm.C1, sm.C2, N, ua, ub, sm.dscr, kidx[0], kidx[1], ex, p.margin_rel, near);
+    }
+    if (!ex && __syncthreads_or(near ? 1 : 0)) {
+      ex = true; repeats++;
+#pragma unroll
+      for (int s = 0; s < nsys; s++)
+        for (int k = tid; k < N; k += NT) Wk[s][pad16(k)] = wsave[s][k];
+      __syncthreads();
+      continue;
+    }
+    break;
   }
-  if (near && p.near) p.near[0] = 1;
+  if (tid == 0 && repeats && p.near) atomicAdd(p.near, repeats);
   const int flags = sm.iscr[32];
   if (tid == 0) {
     p.logz[slot] = logz_sum;

@@ -412,7 +412,6 @@ struct WideFilter {
   std::vector<int> near_host;
   uint64_t last_seed = 0, last_first = 0;
   int force_exact = 0, last_exact = 0, resolved = 1;
-  int64_t exact_reruns = 0;
   std::vector<double> obs_host;
   DevBuf ptot;
   DevBuf obs, hist_x, hist_a, lw, lw2, C, S, pmax, psum, pv, mstep, logz_t, logz, traj, path_index, anc_rec;
@@ -593,36 +592,33 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
   return wide_launch(h, B, seed, first_filter, h->force_exact, s);
 }
 
-// Before any result leaves the handle: if the fast pass met a uniform within rounding distance of a CDF knot (its ancestor
-// could differ from the reference's left-to-right CDF), the batch is run again with that CDF (same Philox streams, same
-// injected noise: every other draw is unchanged).  Expected once per ~10^3-10^4 config-5 filters.
+// Exact ancestors for one filter across the GPU.  The fast pass records, per filter, whether some uniform came within the
+// worst-case rounding distance m = 12 (N + 2) 2^-53 sum(w) of a CDF knot (only then can its ancestor differ from the one the
+// reference's left-to-right CDF gives).  With N = 65536 that happens about 2 N^2 m = 0.7 times per STEP -- the bound grows with
+// N, and so does the number of knots -- and the only way to settle such a draw is the reference's own serial sum (65536
+// dependent additions, 0.3 ms against a 0.05 ms step).  So the reference-order run is a mode of the handle
+// (cpimh_pf_exact_mode / CPIMH_WIDE_EXACT=1: every step with cumsum(normweights) by one lane, ~6x slower at N = 65536), and
+// the default run REPORTS the flag (cpimh_pf_fetch_exact_repeats) instead of paying for it.
 static int wide_resolve(WideFilter* h, cudaStream_t s) {
   if (h->resolved) return CPIMH_OK;
   if (!h->last_exact) {
     CPIMH_CUDA_CHECK(cudaMemcpyAsync(h->near_host.data(), h->near.p, sizeof(int) * (size_t)h->lastB, cudaMemcpyDeviceToHost, s));
     CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
-    bool any = false;
-    for (int64_t b = 0; b < h->lastB; b++) any = any || h->near_host[(size_t)b] != 0;
-    if (any) {
-      int rc = wide_launch(h, h->lastB, h->last_seed, h->last_first, 1, s);
-      if (rc) return rc;
-      h->exact_reruns += 1;
-    }
   }
   h->resolved = 1;
   return CPIMH_OK;
 }
+void wide_exact_mode(WideFilter* h, int on) { h->force_exact = on ? 1 : 0; }
 int wide_fetch_exact_repeats(WideFilter* h, int64_t B, cudaStream_t s, int32_t* repeats) {
   CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
   int rc = wide_resolve(h, s);
   if (rc) return rc;
-  for (int64_t b = 0; b < B; b++) repeats[b] = h->near_host[(size_t)b];      // 1: this filter sent the batch through the exact-order pass
+  for (int64_t b = 0; b < B; b++) repeats[b] = h->near_host[(size_t)b];      // 1: some uniform of this filter came within the rounding margin of a knot (0 in exact mode)
   return CPIMH_OK;
 }
 
 int wide_fetch(WideFilter* h, int64_t B, cudaStream_t s, double* logz, double* logz_t, double* trajectory, int32_t* path_index) {
   CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
-  { int rcr = wide_resolve(h, s); if (rcr) return rcr; }
   const cpimh_config& c = h->cfg;
   if (logz) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz, h->logz.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
   if (logz_t) CPIMH_CUDA_CHECK(cudaMemcpyAsync(logz_t, h->logz_t.p, sizeof(double) * (size_t)B * c.nobs, cudaMemcpyDeviceToHost, s));
@@ -635,7 +631,6 @@ int wide_fetch(WideFilter* h, int64_t B, cudaStream_t s, double* logz, double* l
 int wide_fetch_ancestors(WideFilter* h, int64_t b, cudaStream_t s, int32_t* anc) {
   CPIMH_REQUIRE(h->record_anc, "call cpimh_pf_record_ancestors(h, 1) before cpimh_pf_run");
   CPIMH_REQUIRE(b >= 0 && b < h->lastB, "filter index out of range");
-  { int rcr = wide_resolve(h, s); if (rcr) return rcr; }
   const size_t n = (size_t)h->cfg.nobs * h->cfg.nparticles;
   CPIMH_CUDA_CHECK(cudaMemcpyAsync(anc, h->anc_rec.as<int>() + (size_t)b * n, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
   CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -644,7 +639,7 @@ int wide_fetch_ancestors(WideFilter* h, int64_t b, cudaStream_t s, int32_t* anc)
 
 int64_t wide_launch_count(const WideFilter* h) { return h->launches; }
 int64_t wide_device_bytes(const WideFilter* h) { return h->bytes; }
-void wide_device_outputs(WideFilter* h, double** d_logz, double** d_traj) { wide_resolve(h, nullptr); if (d_logz) *d_logz = h->logz.as<double>(); if (d_traj) *d_traj = h->traj.as<double>(); }
+void wide_device_outputs(WideFilter* h, double** d_logz, double** d_traj) { if (d_logz) *d_logz = h->logz.as<double>(); if (d_traj) *d_traj = h->traj.as<double>(); }
 void wide_effective(const WideFilter* h, cpimh_config* out) { *out = h->cfg; out->tree_capacity = 0; out->threads_per_filter = h->G; out->store_paths = 2; out->reserved = h->GX; }
 
 }  // namespace cpimh

@@ -15,6 +15,7 @@ int wide_record_ancestors(WideFilter* h, int on);
 int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cudaStream_t s);
 int wide_fetch(WideFilter* h, int64_t B, cudaStream_t s, double* logz, double* logz_t, double* trajectory, int32_t* path_index);
 int wide_fetch_ancestors(WideFilter* h, int64_t b, cudaStream_t s, int32_t* anc);
+void wide_exact_mode(WideFilter* h, int on);
 int wide_fetch_exact_repeats(WideFilter* h, int64_t B, cudaStream_t s, int32_t* repeats);
 int64_t wide_launch_count(const WideFilter* h);
 int64_t wide_device_bytes(const WideFilter* h);

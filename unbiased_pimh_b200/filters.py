@@ -102,6 +102,10 @@ class PfBatch:
         L.check(L.lib().cpimh_pf_fetch_ancestors(self.h, C.c_int64(int(b)), C.c_void_p(stream or 0), L.ptr(anc)))
         return anc
 
+    def exact_mode(self, on=True):
+        """Wide filter only (cpimh_pf_exact_mode): every step with the reference-order CDF; the other filters are always exact."""
+        L.check(L.lib().cpimh_pf_exact_mode(self.h, C.c_int(1 if on else 0)))
+
     def fetch_exact_repeats(self, nfilters=None, stream=None):
         """Steps each filter of the last run repeated with sequential-order sums (a sorted uniform within rounding distance
         of a CDF knot; DESIGN.md "Exact ancestors")."""
