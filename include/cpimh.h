@@ -147,7 +147,7 @@ int cpimh_pf_fetch_exact_repeats(cpimh_pf* h, int64_t nfilters, void* stream, in
 /* Wide filter (Lorenz 96, d = 32 / 64) only: the fused filter settles a near-knot step inside the kernel, one filter across the
  * GPU cannot (at N = 65536 a uniform comes within the worst-case rounding bound of a knot about once per step, and settling it
  * needs the reference's serial sum).  on = 1: every step uses cumsum(normweights) in the reference's order (src/multinomial.cpp:17),
- * ~6x slower; on = 0 (default): fast pass, cpimh_pf_fetch_exact_repeats then reports per filter whether any draw was that close. */
+ * ~12x slower at N = 65536; on = 0 (default): fast pass, cpimh_pf_fetch_exact_repeats then reports per filter whether any draw was that close. */
 int cpimh_pf_exact_mode(cpimh_pf* h, int on);
 /* Conditional filters (cpimh_ccpf_batch, cpimh_coupled_ccpf, cpimh_rheeglynn) and pf() (cpimh_pf_adaptive_batch) repeat a step in
  * the reference's operation order when a uniform comes within rounding distance of a CDF knot (or of the coupling probability);

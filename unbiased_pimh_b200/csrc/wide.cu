@@ -597,7 +597,7 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
 // reference's left-to-right CDF gives).  With N = 65536 that happens about 2 N^2 m = 0.7 times per STEP -- the bound grows with
 // N, and so does the number of knots -- and the only way to settle such a draw is the reference's own serial sum (65536
 // dependent additions, 0.3 ms against a 0.05 ms step).  So the reference-order run is a mode of the handle
-// (cpimh_pf_exact_mode / CPIMH_WIDE_EXACT=1: every step with cumsum(normweights) by one lane, ~6x slower at N = 65536), and
+// (cpimh_pf_exact_mode / CPIMH_WIDE_EXACT=1: every step with cumsum(normweights) by one lane, ~12x slower at N = 65536), and
 // the default run REPORTS the flag (cpimh_pf_fetch_exact_repeats) instead of paying for it.
 static int wide_resolve(WideFilter* h, cudaStream_t s) {
   if (h->resolved) return CPIMH_OK;
