@@ -38,7 +38,7 @@ static int ccpf_work_init(CcpfWork* w, const cpimh_config* cfg_in, const double*
   int dev = 0;
   CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
   cudaDeviceProp prop;
-  CPIMH_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  CPIMH_CUDA_CHECK(cached_device_properties(&prop, dev));
   CPIMH_REQUIRE(prop.major >= 10, "libcpimh is built for sm_100a (Blackwell); device %d is sm_%d%d", dev, prop.major, prop.minor);
   std::vector<double> pre = api_precompute(c);
   w->npre = (int)pre.size();
@@ -395,7 +395,7 @@ int cpimh_pf_adaptive_batch(const cpimh_config* cfg_in, const double* obs_host, 
   int dev = 0;
   CPIMH_CUDA_CHECK(cudaGetDevice(&dev));
   cudaDeviceProp prop;
-  CPIMH_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  CPIMH_CUDA_CHECK(cached_device_properties(&prop, dev));
   CPIMH_REQUIRE(prop.major >= 10, "libcpimh is built for sm_100a (Blackwell); device %d is sm_%d%d", dev, prop.major, prop.minor);
   std::vector<double> pre = api_precompute(c);
   const int N = c.nparticles, T = c.nobs, D = c.dim, Npad = (N + 31) & ~31;

@@ -5,6 +5,16 @@
 
 namespace cpimh {
 
+// cudaGetDeviceProperties costs milliseconds (it queries every attribute); the one-shot entries ask once per device
+inline cudaError_t cached_device_properties(cudaDeviceProp* out, int dev) {
+  static cudaDeviceProp props[64];
+  static bool have[64] = {false};
+  if (dev < 0 || dev >= 64) return cudaGetDeviceProperties(out, dev);
+  if (!have[dev]) { cudaError_t e = cudaGetDeviceProperties(&props[dev], dev); if (e != cudaSuccess) return e; have[dev] = true; }
+  *out = props[dev];
+  return cudaSuccess;
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
