@@ -192,3 +192,18 @@ def test_wide_uniform_on_a_cdf_knot_is_flagged_and_settled_by_the_reference_orde
         o = oracle.cpf(ocfg, y, noise={k: v[b] for k, v in nz.items()}, want_ancestors=True)
         assert int(np.sum(ref["anc"][b][1] != o["ancestors"][1])) <= ncraft        # only crafted draws may land on the other side
         assert int(np.sum(fast["anc"][b][1] != ref["anc"][b][1])) <= ncraft
+
+
+@pytest.mark.parametrize("d,N", [(64, 300), (32, 1000)])
+def test_wide_all_particle_average_matches_oracle(up, oracle, d, N):
+    """all_particles = TRUE (R/CPF.R:73-76) for the wide filter: the weighted average of all N paths, walked from the leaves."""
+    T, B, seed = 9, 2, 13
+    y = np.random.default_rng(d + N).normal(size=(T, d)) * 2 + 2
+    r = up.cpf_batch(N, up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5], y, B, seed=seed, first_filter=2, all_particles=True)
+    ocfg = oracle.make_config(oracle.MODEL_LORENZ, d, d, N, T, theta=[8.0, 0.5, 1.0], integrator=0, substeps=1)
+    for b in range(B):
+        o = oracle.cpf(ocfg, y, seed=seed, filter_id=2 + b, all_particles=True)
+        assert np.allclose(r["exp_path"][b], o["exp_path"], rtol=1e-9, atol=1e-9)
+        assert np.allclose(r["trajectory"][b], o["trajectory"], rtol=1e-9, atol=1e-9)
+    again = up.cpf_batch(N, up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5], y, B, seed=seed, first_filter=2, all_particles=True)
+    assert np.array_equal(again["exp_path"], r["exp_path"])                         # fixed summation order

@@ -320,7 +320,7 @@ int cpimh_pf_destroy(cpimh_pf* h) {
 
 int cpimh_pf_all_particles(cpimh_pf* h, int on) {
   CPIMH_REQUIRE(h, "null handle");
-  CPIMH_REQUIRE(!h->wide, "all-particle outputs are not available for the wide (d = 32/64) filter");
+  if (h->wide) return wide_all_particles(h->wide, on);
   CPIMH_REQUIRE(!on || h->geo.path_mode != PATH_NONE, "all-particle outputs need store_paths != 0");
   h->all_particles = on ? 1 : 0;
   if (on) return h->exp_path.alloc(sizeof(double) * (size_t)h->maxB * (h->cfg.nobs + 1) * h->cfg.dim, &h->bytes);
@@ -495,7 +495,8 @@ int cpimh_pf_fetch_ancestors(cpimh_pf* h, int64_t b, void* stream, int32_t* ance
 
 int cpimh_pf_fetch_exp_paths(cpimh_pf* h, int64_t B, void* stream, double* exp_path) {
   CPIMH_REQUIRE(h && exp_path, "null argument");
-  CPIMH_REQUIRE(!h->wide && h->all_particles, "call cpimh_pf_all_particles(h, 1) before cpimh_pf_run");
+  if (h->wide) return wide_fetch_exp_paths(h->wide, B, (cudaStream_t)stream, exp_path);
+  CPIMH_REQUIRE(h->all_particles, "call cpimh_pf_all_particles(h, 1) before cpimh_pf_run");
   CPIMH_REQUIRE(B >= 0 && B <= h->lastB, "filter count out of range");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = check_status(h->status.as<int>(), B, s);
@@ -552,7 +553,8 @@ int cpimh_pf_device_status(cpimh_pf* h, int32_t** d_status) {
 
 int cpimh_pf_device_exp_paths(cpimh_pf* h, double** d_exp_path) {
   CPIMH_REQUIRE(h && d_exp_path, "null argument");
-  CPIMH_REQUIRE(!h->wide && h->all_particles, "call cpimh_pf_all_particles(h, 1) first");
+  if (h->wide) { *d_exp_path = wide_device_exp_paths(h->wide); CPIMH_REQUIRE(*d_exp_path, "call cpimh_pf_all_particles(h, 1) first"); return CPIMH_OK; }
+  CPIMH_REQUIRE(h->all_particles, "call cpimh_pf_all_particles(h, 1) first");
   *d_exp_path = h->exp_path.as<double>();
   return CPIMH_OK;
 }
@@ -679,8 +681,7 @@ static int pf_batch_cached(const cpimh_config* cfg, const double* obs_host, int6
     rc = cpimh_pf_set_observations(h, obs_host);
     if (!rc) rc = cpimh_pf_set_noise(h, B, noise_host);                 // NULL clears noise left by an earlier call
     if (!rc) rc = cpimh_pf_record_ancestors(h, 0);
-    if (!rc && !h->wide) rc = cpimh_pf_all_particles(h, exp_path ? 1 : 0);
-    if (!rc && h->wide && exp_path) { set_error("all-particle outputs are not available for the wide (d = 32/64) filter"); rc = CPIMH_ERR_INVALID; }
+    if (!rc) rc = cpimh_pf_all_particles(h, exp_path ? 1 : 0);
     if (!rc && !h->wide && !exp_path && B > h->grid) rc = pf_run_fetch_pipelined(h, B, seed, first_filter, logz, logz_t, trajectory, path_index);
     else {
       if (!rc) rc = cpimh_pf_run(h, B, seed, first_filter, nullptr);

@@ -42,6 +42,8 @@ struct WideParams {
   // exact ancestors (DESIGN.md "Exact ancestors"): the fast pass flags a filter when a uniform lies within rounding distance
   // (margin_rel * sum of the weights) of a CDF knot; the host then reruns the batch with exact = 1 (reference-order CDF)
   int* near; double margin_rel; int exact;
+  // all-particle average (R/CPF.R:73-76): normalised weights of step T, walkers, per-CTA partial sums, output [B][T+1][D]
+  double* normw; int* walk; double* partial; double* exp_path;
 };
 
 
@@ -323,6 +325,10 @@ wide_weights_scan_kernel(WideParams p, int t_done, int prep, int exact) {
 #pragma unroll
     for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) buf[q] = (r[e] * fac[(int)(base + q - lo) / G]) / s; }   // normweights (R/CPF.R:63)
     __syncthreads();
+    if (p.normw) {
+#pragma unroll
+      for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) p.normw[(size_t)b * N + base + q] = buf[q]; }
+    }
     if (exact) {                                    // the normalised weights themselves: wide_seq_cumsum_kernel sums them left to right
 #pragma unroll
       for (int e = 0; e < EPT; e++) { const int q = threadIdx.x + e * 1024; if (q < n) Cb[base + q] = buf[q]; }
@@ -402,13 +408,55 @@ __global__ void wide_path_kernel(WideParams p) {
   }
 }
 
+// ------------------------------------------------------------------ all_particles = TRUE (R/CPF.R:73-76): the weighted average of
+// ALL N paths, exp_path[step] = sum_n normw[n] * x_step[path of particle n].  N walkers start at the leaves and move to their
+// ancestors step by step; per step a warp accumulates its particles' 512-byte rows in a fixed order, CTAs reduce through shared
+// memory, and a second kernel adds the per-CTA partial sums in CTA order: the result does not depend on scheduling.
+#define WIDE_EXP_WARPS 8
+template <int C>
+__global__ void __launch_bounds__(32 * WIDE_EXP_WARPS) wide_exp_step_kernel(WideParams p, int step) {
+  constexpr int D = 32 * C;
+  __shared__ double part[WIDE_EXP_WARPS][D];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = p.N, T = p.T;
+  const double* row0 = p.hist_x + ((size_t)b * (T + 1) + step) * N * D;
+  const int* anc = step > 0 ? p.hist_a + ((size_t)b * T + (step - 1)) * N : nullptr;
+  const double* w = p.normw + (size_t)b * N;
+  int* walk = p.walk + (size_t)b * N;
+  double acc[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) acc[c] = 0.0;
+  for (int n = blockIdx.x * WIDE_EXP_WARPS + warp; n < N; n += gridDim.x * WIDE_EXP_WARPS) {
+    int j = n;
+    if (step < T) { j = lane == 0 ? walk[n] : 0; j = __shfl_sync(0xffffffffu, j, 0); }   // one lane reads: it also overwrites the entry below
+    const double wn = w[n];
+#pragma unroll
+    for (int c = 0; c < C; c++) acc[c] += wn * row0[(size_t)j * D + lane * C + c];
+    if (anc && lane == 0) walk[n] = anc[j];
+  }
+#pragma unroll
+  for (int c = 0; c < C; c++) part[warp][lane * C + c] = acc[c];
+  __syncthreads();
+  for (int q = threadIdx.x; q < D; q += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < WIDE_EXP_WARPS; k++) s += part[k][q];
+    p.partial[((size_t)b * gridDim.x + blockIdx.x) * D + q] = s;
+  }
+}
+__global__ void wide_exp_reduce_kernel(WideParams p, int step, int nparts) {
+  const int b = blockIdx.x, q = threadIdx.x, D = p.D;
+  double s = 0.0;
+  for (int k = 0; k < nparts; k++) s += p.partial[((size_t)b * nparts + k) * D + q];
+  p.exp_path[((size_t)b * (p.T + 1) + step) * D + q] = s;
+}
+
 // ================================================================== host side
 struct WideFilter {
   cpimh_config cfg;
   int64_t maxB, lastB, launches, bytes;
   int GX, G, pgrid, record_anc;
   // exact ancestors: near-knot flags of the last fast pass, the arguments to rerun it with, and whether that has been settled
-  DevBuf near;
+  DevBuf near, normw, walk, partial, exp_path;
+  int all_particles = 0, exp_parts = 0;
   std::vector<int> near_host;
   uint64_t last_seed = 0, last_first = 0;
   int force_exact = 0, last_exact = 0, resolved = 1;
@@ -479,7 +527,7 @@ int wide_create(const cpimh_config& cfg, int64_t max_filters, WideFilter** out) 
 
 void wide_destroy(WideFilter* h) {
   if (!h) return;
-  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->lw2, &h->near, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
+  DevBuf* all[] = {&h->ptot, &h->obs, &h->hist_x, &h->hist_a, &h->lw, &h->lw2, &h->near, &h->normw, &h->walk, &h->partial, &h->exp_path, &h->C, &h->S, &h->pmax, &h->psum, &h->pv, &h->mstep, &h->logz_t, &h->logz, &h->traj,
                    &h->path_index, &h->anc_rec, &h->inj_init, &h->inj_trans, &h->inj_resample, &h->inj_path};
   for (auto b : all) b->release();
   delete h;
@@ -546,10 +594,21 @@ static int wide_run_t(WideFilter* h, const WideParams& p, cudaStream_t s) {
   // the last step's weights as a normalised per-particle CDF: the final path pick (R/CPF.R:69) and log Z_T
   WideParams pl = p;
   if (p.two_level && (T & 1) == 0) pl.lw = p.lw2;           // step T wrote the buffer of its parity (its log Z_T comes from this scan)
+  pl.normw = h->all_particles ? h->normw.as<double>() : nullptr;
   wide_weights_scan_kernel<<<gw, 1024, wsmem, s>>>(pl, T, 0, p.exact);
   if (p.exact) { wide_seq_cumsum_kernel<<<B, 32, 0, s>>>(p); h->launches += 1; }
   wide_path_kernel<C><<<B, 32, 0, s>>>(p);
   h->launches += 2;
+  if (h->all_particles) {
+    WideParams pe = p;
+    pe.normw = h->normw.as<double>(); pe.walk = h->walk.as<int>(); pe.partial = h->partial.as<double>(); pe.exp_path = h->exp_path.as<double>();
+    const dim3 ge((unsigned)h->exp_parts, (unsigned)B);
+    for (int step = T; step >= 0; step--) {
+      wide_exp_step_kernel<C><<<ge, 32 * WIDE_EXP_WARPS, 0, s>>>(pe, step);
+      wide_exp_reduce_kernel<<<B, p.D, 0, s>>>(pe, step, h->exp_parts);
+    }
+    h->launches += 2 * (T + 1);
+  }
   CPIMH_CUDA_CHECK(cudaGetLastError());
   return CPIMH_OK;
 }
@@ -609,6 +668,27 @@ static int wide_resolve(WideFilter* h, cudaStream_t s) {
   return CPIMH_OK;
 }
 void wide_exact_mode(WideFilter* h, int on) { h->force_exact = on ? 1 : 0; }
+int wide_all_particles(WideFilter* h, int on) {
+  h->all_particles = on ? 1 : 0;
+  if (!on) return CPIMH_OK;
+  const size_t B = (size_t)h->maxB, N = h->cfg.nparticles, T = h->cfg.nobs, D = h->cfg.dim;
+  int parts = (int)((N + WIDE_EXP_WARPS - 1) / WIDE_EXP_WARPS);
+  if (parts > 592) parts = 592;                                    // 4 CTAs of 8 warps per SM
+  h->exp_parts = parts;
+  int rc = h->normw.alloc(sizeof(double) * B * N, &h->bytes);
+  if (!rc) rc = h->walk.alloc(sizeof(int) * B * N, &h->bytes);
+  if (!rc) rc = h->partial.alloc(sizeof(double) * B * (size_t)parts * D, &h->bytes);
+  if (!rc) rc = h->exp_path.alloc(sizeof(double) * B * (T + 1) * D, &h->bytes);
+  return rc;
+}
+int wide_fetch_exp_paths(WideFilter* h, int64_t B, cudaStream_t s, double* exp_path) {
+  CPIMH_REQUIRE(h->all_particles, "call cpimh_pf_all_particles(h, 1) before cpimh_pf_run");
+  CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
+  CPIMH_CUDA_CHECK(cudaMemcpyAsync(exp_path, h->exp_path.p, sizeof(double) * (size_t)B * (h->cfg.nobs + 1) * h->cfg.dim, cudaMemcpyDeviceToHost, s));
+  CPIMH_CUDA_CHECK(cudaStreamSynchronize(s));
+  return CPIMH_OK;
+}
+double* wide_device_exp_paths(WideFilter* h) { return h->all_particles ? h->exp_path.as<double>() : nullptr; }
 int wide_fetch_exact_repeats(WideFilter* h, int64_t B, cudaStream_t s, int32_t* repeats) {
   CPIMH_REQUIRE(B >= 1 && B <= h->lastB, "nfilters %lld exceeds the last run (%lld)", (long long)B, (long long)h->lastB);
   int rc = wide_resolve(h, s);

@@ -16,6 +16,9 @@ int wide_run(WideFilter* h, int64_t B, uint64_t seed, uint64_t first_filter, cud
 int wide_fetch(WideFilter* h, int64_t B, cudaStream_t s, double* logz, double* logz_t, double* trajectory, int32_t* path_index);
 int wide_fetch_ancestors(WideFilter* h, int64_t b, cudaStream_t s, int32_t* anc);
 void wide_exact_mode(WideFilter* h, int on);
+int wide_all_particles(WideFilter* h, int on);
+int wide_fetch_exp_paths(WideFilter* h, int64_t B, cudaStream_t s, double* exp_path);
+double* wide_device_exp_paths(WideFilter* h);
 int wide_fetch_exact_repeats(WideFilter* h, int64_t B, cudaStream_t s, int32_t* repeats);
 int64_t wide_launch_count(const WideFilter* h);
 int64_t wide_device_bytes(const WideFilter* h);
