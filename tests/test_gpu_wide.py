@@ -207,3 +207,20 @@ def test_wide_all_particle_average_matches_oracle(up, oracle, d, N):
         assert np.allclose(r["trajectory"][b], o["trajectory"], rtol=1e-9, atol=1e-9)
     again = up.cpf_batch(N, up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5], y, B, seed=seed, first_filter=2, all_particles=True)
     assert np.array_equal(again["exp_path"], r["exp_path"])                         # fixed summation order
+
+
+def test_r_shaped_pimh_chains_on_the_wide_filter(up):
+    """get_pimh_kernels / coupled_pimh_chains (R/pf_kernels.R:88-145, R/debiasing_algorithm.R:140-265) with Lorenz 96 d = 64:
+    every proposal is one wide filter; also with all_particles = TRUE (the Rao-Blackwellised state)."""
+    d, N, T = 64, 2000, 4
+    y = np.random.default_rng(21).normal(size=(T, d)) * 1.5 + 2
+    model, th = up.get_lorenz(1.0, d, "rk4", 1), [8.0, 0.5]
+    up.set_seed(11)
+    ker = up.get_pimh_kernels(False, model=model, theta=th, observations=y)
+    c = up.coupled_pimh_chains(ker["single_kernel"], ker["coupled_kernel"], ker["pimh_init"], N, K=2, max_iterations=200)
+    assert c["finished"] and c["meetingtime"] >= 1 and c["samples1"].shape[1] == T + 1
+    hb = up.H_bar(c, k=1, K=2)
+    assert np.all(np.isfinite(hb))
+    kap = up.get_pimh_kernels(False, all_particles=True, model=model, theta=th, observations=y)
+    c2 = up.coupled_pimh_chains(kap["single_kernel"], kap["coupled_kernel"], kap["pimh_init"], N, K=2, max_iterations=200)
+    assert c2["finished"] and c2["exp_samples1"].shape == c2["samples1"].shape and np.all(np.isfinite(c2["exp_samples1"]))

@@ -182,6 +182,9 @@ def CPF(nparticles, model, theta, observations, ref_trajectory=None, with_as=Fal
     if not all_particles:
         r = cpf_batch(nparticles, model, theta, observations, 1, seed=seed, first_filter=filter_id, noise=noise, **kw)
         return {"trajectory": np.ascontiguousarray(r["trajectory"][0]), "logz": float(r["logz"][0])}
+    if model.dimension >= 32:     # wide filter (one filter across the GPU): the one-shot entry computes the all-particle average
+        r = cpf_batch(nparticles, model, theta, observations, 1, seed=seed, first_filter=filter_id, all_particles=True, **kw)
+        return {"trajectory": np.ascontiguousarray(r["trajectory"][0]), "exp_path": np.ascontiguousarray(r["exp_path"][0]), "logz": float(r["logz"][0])}
     pb = PfBatch(model, theta, observations, nparticles, 1, **kw)
     try:
         if noise:
