@@ -4,7 +4,7 @@
 OUT=$1; LIB=$2; shift 2
 ARGS=${@:-levy_sv 4096 50 444}
 export CPIMH_LIB=$(realpath $LIB)
-ncu --set full --clock-control none --import-source on -k regex:pf_batch_kernel -c 1 -f -o gpurun_out/$OUT python tools/prof_pf.py $ARGS > gpurun_out/$OUT.ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:${KREGEX:-pf_batch_kernel} -c 1 -f -o gpurun_out/$OUT python ${PROF_SCRIPT:-tools/prof_pf.py} $ARGS > gpurun_out/$OUT.ncu.log 2>&1
 ncu -i gpurun_out/$OUT.ncu-rep --page raw --csv > gpurun_out/$OUT.raw.csv 2>/dev/null
 ncu -i gpurun_out/$OUT.ncu-rep --page source --print-source cuda,sass --csv > gpurun_out/$OUT.src.csv 2>/dev/null
 python tools/ncu_hot.py gpurun_out/$OUT.src.csv 70 > gpurun_out/$OUT.hot.txt 2>&1
